@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""Headline benchmark: images/sec at 640x640 batch inference (BASELINE.json `metric`).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [...]                         # the reference's CPU path (oracle port)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one pass of the hot path (u8 batch -> network -> sigmoid/clamp -> path-C decode -> [B,100,6]
+boxes, + for N>1 the NCCL all-gather of the box lists) over one synthetic batch of 32 images per GPU
+(configs[1]; at N=8 this is configs[2], batch-256 sharded 32/GPU => weak scaling).
+
+`value`  : inputs resident in HBM, timed with CUDA events on the launching stream, max over ranks.
+`e2e`    : the same step through the C-ABI host entry point cf_detect_topk_host with pinned HOST
+           buffers (H2D of the u8 batch and D2H of the boxes inside the timed region).
+`roofline`: the dominant kernel class, algorithmic bytes (cf_work_model x batch) / CUDA-event time of
+           that class's launches, against MEASURED_PEAKS.json.
+`cpu_baseline` / `--impl reference`: the oracle port of the reference's CPU path on the host cores.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG_NAME = "lightweight-face-detection-centernet_b200"
+WEIGHTS = os.path.join(ROOT, "tests", "golden", "weights_e100.npz")
+METRIC = "images/sec at 640x640 batch inference"
+UNIT = "images/s"
+H = W = 640
+PER_GPU_BATCH = 32
+K_TOP = 100
+CLASS_NAMES = {1: "pointwise_gemm", 2: "depthwise", 3: "stem", 4: "heads", 5: "decode_topk"}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="images per GPU per step")
+    ap.add_argument("--pw", type=int, default=int(os.environ.get("CENTERFACE_B200_PW", -1)),
+                    help="point-wise engine: 0 fp32 SIMT, 1 tcgen05 3xTF32, 2 tcgen05 1xTF32 (default: library default)")
+    ap.add_argument("--cpu-sample", type=int, default=4, help="images per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def synthetic_batch(n, seed):
+    """SURVEY.md 8d throughput inputs: seeded u8 uniform noise [n,H,W,3] (backbone cost is content
+    independent; random-noise heat-maps still exercise the full peak/top-k decode)."""
+    rng = np.random.RandomState(seed)
+    return rng.randint(0, 256, size=(n, H, W, 3), dtype=np.uint8)
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU path (oracle port; the reference is Python on ATen and cannot
+# travel to the GPU box) on all host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_run(steps, warmup, sample):
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import centerface_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = O.load_weights(WEIGHTS)
+    u8 = synthetic_batch(sample, 0)
+
+    def step():
+        x = torch.from_numpy(np.stack([O.normalize_u8(i) for i in u8]))  # centerface.py:32-34
+        o = O.forward(sd, x)                                             # model/centernet.py:263-280
+        dets, _ = O.ctdet_decode(O.sigmoid_clamp(o["hm"]), o["wh"], o["reg"], K=K_TOP)  # centerface_ext.py:52-82
+        return dets
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return {"value": sample * steps / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{steps} steps x {sample} images of the 640x640 batch-{PER_GPU_BATCH} workload "
+                      f"(normalise + forward + sigmoid/clamp + ctdet_decode K={K_TOP}), torch {torch.__version__} CPU, "
+                      f"{cores} logical cores"}, dt / steps * 1e3
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(a.steps, 6))
+    warm = max(1, min(a.warmup, 2))
+    cb, ms = cpu_reference_run(steps, warm, a.cpu_sample)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"batch-{PER_GPU_BATCH} 640x640 (configs[1]), bounded sample of {a.cpu_sample} images per step",
+                       "h": H, "w": W, "decode": f"path C top-{K_TOP}"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md)
+# ---------------------------------------------------------------------------------------------
+class Clocks:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], False
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop:
+            try:
+                r = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5)
+                if r.returncode == 0 and r.stdout.strip():
+                    self.rows.append([c.strip() for c in r.stdout.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *exc):
+        self.stop = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d["bf16_tflops_sustained"], "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------
+# this repo's arm
+# ---------------------------------------------------------------------------------------------
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    pkg = importlib.import_module(PKG_NAME)
+    L = pkg._lib
+    sh = importlib.import_module(PKG_NAME + ".sharding")
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus:
+        raise SystemExit(f"--gpus {a.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {a.gpus}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this arm has no CPU fallback (use --impl reference for the CPU path)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    if rank == 0:
+        pkg.build()
+    if world > 1:
+        dist.barrier()
+    B = a.batch
+    pw = a.pw if a.pw >= 0 else L.CF_PW_SIMT
+    eng = pkg.Engine(WEIGHTS, max_batch=B, max_h=H, max_w=W, device=local, pw_engine=pw)
+    dev = torch.device(f"cuda:{local}")
+
+    # rotating input buffers (4 x 39 MB > 126 MB L2); each step also streams ~12 GB of activations
+    n_rot = 4
+    host = [torch.from_numpy(synthetic_batch(B, 1000 * rank + i)).pin_memory() for i in range(n_rot)]
+    devin = [h.to(dev) for h in host]
+    out_dets = torch.empty((B, K_TOP, 6), dtype=torch.float32).pin_memory()
+    out_inds = torch.empty((B, K_TOP), dtype=torch.int32).pin_memory()
+    n_total = B * world
+
+    def step_resident(i):
+        eng.forward(devin[i % n_rot])
+        dets, _ = eng.decode_topk(K_TOP)
+        return sh.gather_detections(dets, n_total=n_total)  # NCCL all-gather of the final box list (N>1)
+
+    def step_e2e(i):
+        eng.detect_topk_host(host[i % n_rot], K_TOP, out_dets, out_inds)  # H2D + net + decode + D2H, synchronous
+        if world > 1:
+            return sh.gather_detections(out_dets.to(dev, non_blocking=True), n_total=n_total)
+        return out_dets
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        sync()
+        l0 = eng.launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        sync()
+        dev_ms = e0.elapsed_time(e1)
+        t = torch.tensor([dev_ms, wall * 1e3], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t[0].item(), t[1].item(), eng.launches - l0
+
+    warm = max(a.warmup, 3)
+    with Clocks(local) as clk:
+        dev_ms, _, launches = timed(step_resident, a.steps, warm)
+        e2e_steps = max(3, min(a.steps, 10))
+        _, e2e_wall_ms, _ = timed(step_e2e, e2e_steps, 2)
+    clocks = clk.summary()
+
+    ms_per_step = dev_ms / a.steps
+    value = n_total / (ms_per_step * 1e-3)
+    e2e_value = n_total / (e2e_wall_ms / e2e_steps * 1e-3)
+
+    # per-class roofline, measured live with CUDA events on the launching stream (rank 0's GPU)
+    hbm, tf, peak_src = peaks()
+    classes = {}
+    eng.forward(devin[0])
+    eng.decode_topk(K_TOP)
+    torch.cuda.synchronize()
+    for cls, name in CLASS_NAMES.items():
+        ms, n = eng.time_class(cls, iters=5)
+        by, fl = L.work_model(H, W, L.CF_IN_U8_HWC, cls)
+        classes[name] = {"ms_per_step": ms, "launches": n, "alg_bytes": by * B, "alg_flops": fl * B,
+                         "gbs": by * B / (ms * 1e-3) / 1e9, "tflops": fl * B / (ms * 1e-3) / 1e12}
+    net_ms = sum(c["ms_per_step"] for k, c in classes.items())
+    for c in classes.values():
+        c["share"] = c["ms_per_step"] / net_ms
+    top = max(classes, key=lambda k: classes[k]["ms_per_step"])
+    tc = classes[top]
+    roofline = {"kernel": top, "bound": "hbm", "achieved": tc["gbs"], "peak": hbm, "unit": "GB/s", "frac": tc["gbs"] / hbm,
+                "traffic": None, "peak_source": peak_src, "launches": tc["launches"], "ms": tc["ms_per_step"],
+                "alg_bytes_per_step": tc["alg_bytes"], "share_of_step": tc["share"],
+                "tensor_frac_of_sustained_bf16": tc["tflops"] / tf,
+                "classes": {k: {"ms": round(v["ms_per_step"], 4), "share": round(v["share"], 4), "GBps": round(v["gbs"], 1),
+                                "frac_hbm": round(v["gbs"] / hbm, 4), "TFLOPs": round(v["tflops"], 2), "launches": v["launches"]}
+                            for k, v in classes.items()}}
+    by_all, fl_all = L.work_model(H, W, L.CF_IN_U8_HWC, 0)
+    roofline["whole_step"] = {"alg_bytes_per_image": by_all, "alg_flops_per_image": fl_all,
+                              "GBps": by_all * B / (ms_per_step * 1e-3) / 1e9,
+                              "frac_hbm": by_all * B / (ms_per_step * 1e-3) / 1e9 / hbm,
+                              "TFLOPs": fl_all * B / (ms_per_step * 1e-3) / 1e12}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cpu_baseline, _ = cpu_reference_run(3, 1, a.cpu_sample)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": warm,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32" if pw == 0 else ("tf32x3" if pw == 1 else "tf32"), "data": "synthetic",
+                "config": {"workload": f"batch-{B} 640x640 per GPU ({'configs[1]' if world == 1 else 'configs[2] sharding'}), "
+                                       f"u8 BGR input, network + sigmoid/clamp + path-C top-{K_TOP} decode"
+                                       + (", NCCL all-gather of [B,100,6] boxes" if world > 1 else ""),
+                           "global_batch": n_total, "h": H, "w": W, "pw_engine": pw,
+                           "l2": f"{n_rot} rotating input batches ({n_rot * B * H * W * 3 / 1e6:.0f} MB) and "
+                                 f"{by_all * B / 1e9:.1f} GB of activation traffic per step, both > 126 MB L2",
+                           "parallelism": f"dp{world}"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * H * W * 3,
+                        "d2h_bytes_per_step": B * K_TOP * (6 * 4 + 4), "api": "cf_detect_topk_host (pinned host buffers)",
+                        "steps": e2e_steps},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline}
+        if cpu_baseline is not None:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,150 @@
+/*
+ * centerface_b200.h -- C ABI of the B200-native CenterFace inference engine.
+ *
+ * This is the drop-in boundary for ONE hot path of nvlong21/Lightweight-face-detection-CenterNet:
+ *     image batch -> backbone + FPN + heads -> heat-map decode -> boxes.
+ * The reference has no native code and therefore no FFI of its own; each entry point below
+ * names the reference Python interface (file:line in the reference repository) it replaces.
+ * The reference-side binding (a ctypes stub) is shown in INTEGRATION.md and shipped as
+ * lightweight-face-detection-centernet_b200/_lib.py.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a raw device or host address as documented;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream);
+ *   - every call returns 0 on success or a negative CF_E* code; cf_last_error() returns a
+ *     thread-local, human readable message for the most recent failure on this thread;
+ *   - a handle owns all of its device buffers (sized at cf_create for max_batch/max_h/max_w);
+ *     one handle per GPU / per host thread; calls on one handle are not re-entrant;
+ *   - nothing here falls back to the CPU: without a usable sm_100 device cf_create fails.
+ */
+#ifndef CENTERFACE_B200_H_
+#define CENTERFACE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CF_ABI_VERSION 1
+
+/* error codes */
+#define CF_OK 0
+#define CF_EINVAL (-1)   /* bad argument / shape / state         */
+#define CF_ECUDA (-2)    /* a CUDA runtime or driver call failed */
+#define CF_EWEIGHTS (-3) /* malformed weight blob                */
+#define CF_ENODEV (-4)   /* no sm_100 class device               */
+#define CF_ECAP (-5)     /* a capacity given at cf_create was exceeded */
+
+/* input formats for cf_forward */
+#define CF_IN_F32_NCHW 0 /* normalised fp32 [B,3,H,W]: the tensor the reference feeds
+                            EfficientNet.forward (model/centernet.py:263)               */
+#define CF_IN_U8_HWC 1   /* raw BGR u8 [B,H,W,3] already at network size; the /255,
+                            mean/std step of centerface.py:32-34 is fused into the stem */
+
+/* GEMM engine for the point-wise (1x1) convolutions */
+#define CF_PW_SIMT 0      /* fp32 FFMA tiles (validation engine)                          */
+#define CF_PW_TCGEN05 1   /* tcgen05.mma kind::tf32, 3-pass split (fp32-class accuracy)   */
+#define CF_PW_TCGEN05_1P 2 /* tcgen05.mma kind::tf32 single pass (throughput mode)        */
+
+/* decode variants for cf_decode_threshold */
+#define CF_DECODE_A 0 /* centerface.py:73-109   : offsets unused, landmarks, clip to (H,W)   */
+#define CF_DECODE_B 1 /* eval_widerface.py:92-110: swapped offsets, no landmarks             */
+
+typedef struct cf_engine cf_engine; /* opaque */
+
+/* ---- life cycle ----------------------------------------------------------------------
+ * Replaces CenterFace.__init__ (centerface.py:16-27): efficientnet_b0() construction,
+ * checkpoint load and .cuda().  `weights` is a HOST pointer to the packed fp32 blob written
+ * by lightweight-face-detection-centernet_b200/weights.py::pack_weights (BatchNorms folded,
+ * heads collapsed, kernel-ready layouts); it is copied to the device and may be freed after
+ * the call.  `max_h`,`max_w` are network-input sizes (multiples of 32).                  */
+int cf_create(const void* weights, size_t weights_bytes, int device, int max_batch, int max_h,
+              int max_w, int pw_engine, cf_engine** out);
+int cf_destroy(cf_engine* e);
+
+/* thread-local message of the last failure on the calling thread ("" if none) */
+const char* cf_last_error(void);
+int cf_abi_version(void);
+/* size in bytes the packed blob must have (so the packer and the engine cannot drift) */
+size_t cf_weights_blob_bytes(void);
+
+/* ---- network -------------------------------------------------------------------------
+ * Replaces `self.net(img)[0]` (centerface.py:41) / `model(img_batch)[0]`
+ * (eval_widerface.py:84) == EfficientNet.forward (model/centernet.py:263-280).
+ * `input` is a DEVICE pointer in `in_format`.  Results stay in handle-owned device buffers,
+ * fetched with cf_heads().  Asynchronous on `stream`.                                    */
+int cf_forward(cf_engine* e, const void* input, int in_format, int batch, int h, int w, void* stream);
+
+/* Device pointers to the head maps of the last cf_forward, fp32 planar (NCHW) like the
+ * reference's output dict {'hm','wh','lm','reg'} (model/centernet.py:277-280):
+ * hm [B,1,h/4,w/4] raw logits, wh [B,2,..], lm [B,10,..], reg [B,2,..]; hm_sig is
+ * clamp(sigmoid(hm),1e-4,1-1e-4) (centerface.py:43, eval_widerface.py:85).  Any may be NULL. */
+int cf_heads(cf_engine* e, float** hm, float** wh, float** lm, float** reg, float** hm_sig);
+
+/* Debug/parity taps: device pointer + shape of an intermediate NHWC fp32 activation.
+ * name in {"stem","layer0".."layer6","conv_last","fpn"}.                                  */
+int cf_tap(cf_engine* e, const char* name, float** ptr, int* h, int* w, int* c);
+
+/* ---- decode, path C ------------------------------------------------------------------
+ * Replaces ctdet_decode (centerface_ext.py:52-82) with _nms/_topk/_gather_feat fused:
+ * 3x3 peak keep -> per-image top-K (score desc, flat index asc) -> wh/reg gather -> boxes.
+ * All pointers are DEVICE pointers: heat [B,1,h,w] post-sigmoid, wh/reg [B,2,h,w] (reg may
+ * be NULL -> +0.5 centres), out_dets [B,K,6] = x1,y1,x2,y2,score,class(0) in output-map
+ * units, out_inds [B,K] int32 flat indices (may be NULL).  `scratch` is a device buffer of
+ * at least B*h*w floats (cf_decode_topk uses the engine's own).  K <= 1024 and K <= h*w. */
+int cf_ctdet_decode(const float* heat, const float* wh, const float* reg, int batch, int h, int w,
+                    int K, float* out_dets, int32_t* out_inds, float* scratch, void* stream);
+/* same, on the heads of the last cf_forward */
+int cf_decode_topk(cf_engine* e, int K, float* out_dets, int32_t* out_inds, void* stream);
+
+/* ---- decode, paths A and B -----------------------------------------------------------
+ * Replaces CenterFace.decode + nms (centerface.py:73-151) / eval_widerface.decode + nms
+ * (eval_widerface.py:92-152) and, when scale_w/scale_h are non-zero, the float32 floor
+ * division back to source pixels (centerface.py:55-58).
+ * DEVICE pointers: hm_sig [B,1,h,w], wh/reg [B,2,h,w], lm [B,10,h,w] (variant A only);
+ * out_dets [B,cap,5], out_lms [B,cap,10] (NULL for variant B), out_counts [B] int32 =
+ * number of kept boxes; if more than `cap` pixels pass the threshold in some image its
+ * count is set to -(number of candidates) and that image's rows are undefined.
+ * size_h,size_w: the clipping size the reference passes as `size`.  cap <= 4096.          */
+int cf_decode_threshold(const float* hm_sig, const float* wh, const float* reg, const float* lm,
+                        int batch, int h, int w, int variant, float threshold, float nms_threshold,
+                        int size_h, int size_w, float scale_w, float scale_h, int cap,
+                        float* out_dets, float* out_lms, int32_t* out_counts, void* stream);
+
+/* ---- end-to-end convenience (HOST buffers) -------------------------------------------
+ * One call = H2D copy of a raw u8 BGR batch [B,h,w,3] (already at network size), network,
+ * path-C decode, D2H copy of [B,K,6] boxes (+ optional [B,K] indices).  Synchronous.
+ * This is the call the `e2e` figure of bench.py times.                                    */
+int cf_detect_topk_host(cf_engine* e, const uint8_t* images, int batch, int h, int w, int K,
+                        float* out_dets, int32_t* out_inds);
+
+/* Same for the threshold paths: the body of CenterFace.__call__ after cv2.resize
+ * (centerface.py:32-62) for variant A, or of get_detections (eval_widerface.py:83-89) for
+ * variant B, on a HOST u8 BGR batch [B,h,w,3].  Host outputs as in cf_decode_threshold.    */
+int cf_detect_threshold_host(cf_engine* e, const uint8_t* images, int batch, int h, int w, int variant,
+                             float threshold, float nms_threshold, float scale_w, float scale_h, int cap,
+                             float* out_dets, float* out_lms, int32_t* out_counts);
+
+/* ---- instrumentation -----------------------------------------------------------------
+ * Number of kernels this library launched on behalf of the handle since creation.        */
+long long cf_launch_count(cf_engine* e);
+/* Algorithmic bytes / flops of ONE image at (h,w) for kernel class `which`
+ * (0 = network = 1+2+3+4, 1 = point-wise GEMMs, 2 = depth-wise, 3 = stem, 4 = heads,
+ * 5 = path-C decode).  Bytes: every conv reads its un-padded input once and writes its output
+ * once in the engine's fp32 storage (+ residual / low-res re-reads); weights (5 MB per LAUNCH,
+ * not per image) are not counted.  Flops: 2*MAC of the REFERENCE graph (model/centernet.py),
+ * i.e. the four un-collapsed heads.  in_format selects the stem's input bytes.            */
+int cf_work_model(int h, int w, int in_format, int which, double* bytes, double* flops);
+/* Run only one layer class `iters` times on the current activations (for per-kernel
+ * CUDA-event timing in bench.py). which as above.                                        */
+int cf_replay_class(cf_engine* e, int which, int iters, void* stream);
+/* cf_replay_class bracketed by CUDA events on `stream`; *ms = mean device time of ONE replay of
+ * the class, *launches = kernels per replay.  Synchronises the stream.                    */
+int cf_time_class(cf_engine* e, int which, int iters, void* stream, float* ms, int* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CENTERFACE_B200_H_ */

@@ -1,0 +1,119 @@
+// Shared helpers for the CenterFace B200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+
+#include "../../include/centerface_b200.h"
+
+namespace cf {
+
+// ---- thread-local error string ---------------------------------------------------------
+inline std::string& err_slot() {
+    static thread_local std::string s;
+    return s;
+}
+inline int fail(int code, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
+inline int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    err_slot() = buf;
+    return code;
+}
+
+#define CF_CUDA(expr)                                                                         \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return cf::fail(CF_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                            __FILE__, __LINE__);                                              \
+    } while (0)
+
+#define CF_CHECK(cond, code, ...)                      \
+    do {                                               \
+        if (!(cond)) return cf::fail(code, __VA_ARGS__); \
+    } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// ---- device math -----------------------------------------------------------------------
+// Swish (model/centernet.py:39-40) x*sigmoid(x) = x/(1+e^-x): MUFU.EX2 + MUFU.RCP, ~4 ulp.
+// x -> -inf gives -0, x -> +inf gives x; no NaN is produced for finite x.
+__device__ __forceinline__ float swishf(float x) { return __fdividef(x, 1.f + __expf(-x)); }
+
+__device__ __forceinline__ float4 swish4(float4 v) {
+    return make_float4(swishf(v.x), swishf(v.y), swishf(v.z), swishf(v.w));
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+__device__ __forceinline__ void fma4(float4& acc, float a, float4 w) {
+    acc.x = fmaf(a, w.x, acc.x);
+    acc.y = fmaf(a, w.y, acc.y);
+    acc.z = fmaf(a, w.z, acc.z);
+    acc.w = fmaf(a, w.w, acc.w);
+}
+__device__ __forceinline__ void fma44(float4& acc, float4 a, float4 w) {
+    acc.x = fmaf(a.x, w.x, acc.x);
+    acc.y = fmaf(a.y, w.y, acc.y);
+    acc.z = fmaf(a.z, w.z, acc.z);
+    acc.w = fmaf(a.w, w.w, acc.w);
+}
+
+// Epilogue kinds shared by the SIMT and tcgen05 point-wise GEMMs.
+enum Epi : int {
+    EPI_LINEAR = 0,      // project conv, model/centernet.py:118
+    EPI_SWISH = 1,       // expand conv + Swish, :110
+    EPI_RESIDUAL = 2,    // project + skip add, :137
+    EPI_BIAS_SWISH = 3,  // conv_last: conv + folded BN + Swish, :178-184
+    EPI_IDAUP = 4,       // IDAUp: relu(BN(lateral)) + relu(BN(convT2x2 dw(low))), :186-204
+};
+
+struct EpiArgs {
+    const float* res;   // [M,N]    residual (EPI_RESIDUAL)
+    const float* bias;  // [N]      folded BN shift (BIAS_SWISH, IDAUP lateral)
+    const float* low;   // [B,Ho/2,Wo/2,N] low-res input of the transposed conv (IDAUP)
+    const float* su;    // [N][2][2] folded up-sample scale (IDAUP)
+    const float* tu;    // [N]      folded up-sample shift (IDAUP)
+    int Ho, Wo;         // output map size (IDAUP: m -> (b,y,x))
+};
+
+template <int EPI>
+__device__ __forceinline__ float4 apply_epi(float4 acc, int m, int n, int N, const EpiArgs& ea) {
+    if (EPI == EPI_SWISH) return swish4(acc);
+    if (EPI == EPI_RESIDUAL) {
+        float4 r = ldg4(ea.res + (size_t)m * N + n);
+        return make_float4(acc.x + r.x, acc.y + r.y, acc.z + r.z, acc.w + r.w);
+    }
+    if (EPI == EPI_BIAS_SWISH) {
+        float4 b = ldg4(ea.bias + n);
+        return swish4(make_float4(acc.x + b.x, acc.y + b.y, acc.z + b.z, acc.w + b.w));
+    }
+    if (EPI == EPI_IDAUP) {
+        int x = m % ea.Wo;
+        int t = m / ea.Wo;
+        int y = t % ea.Ho;
+        int b = t / ea.Ho;
+        int Hl = ea.Ho >> 1, Wl = ea.Wo >> 1;
+        float4 lo = ldg4(ea.low + ((size_t)(b * Hl + (y >> 1)) * Wl + (x >> 1)) * N + n);
+        int q = (y & 1) * 2 + (x & 1);
+        float4 bb = ldg4(ea.bias + n), tt = ldg4(ea.tu + n);
+        float s0 = __ldg(ea.su + (n + 0) * 4 + q), s1 = __ldg(ea.su + (n + 1) * 4 + q);
+        float s2 = __ldg(ea.su + (n + 2) * 4 + q), s3 = __ldg(ea.su + (n + 3) * 4 + q);
+        float4 o;
+        o.x = fmaxf(fmaf(lo.x, s0, tt.x), 0.f) + fmaxf(acc.x + bb.x, 0.f);
+        o.y = fmaxf(fmaf(lo.y, s1, tt.y), 0.f) + fmaxf(acc.y + bb.y, 0.f);
+        o.z = fmaxf(fmaf(lo.z, s2, tt.z), 0.f) + fmaxf(acc.z + bb.z, 0.f);
+        o.w = fmaxf(fmaf(lo.w, s3, tt.w), 0.f) + fmaxf(acc.w + bb.w, 0.f);
+        return o;
+    }
+    return acc;
+}
+
+}  // namespace cf

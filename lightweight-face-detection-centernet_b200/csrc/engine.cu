@@ -1,0 +1,673 @@
+// C-ABI implementation of the B200-native CenterFace engine (see include/centerface_b200.h).
+//
+// Path: EfficientNet.forward (model/centernet.py:263-280) -> sigmoid+clamp
+// (centerface.py:43) -> decode (centerface_ext.py:52-82 | centerface.py:73-151 |
+// eval_widerface.py:92-152).  Activations live in HBM as NHWC fp32 (pixels are GEMM rows, the
+// channel axis is contiguous so every kernel moves float4s); see DESIGN.md for the layout.
+//
+// There is no CPU fallback in this file: every entry point either launches kernels on an
+// sm_100 device or fails with an error code.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+
+#include <functional>
+#include <vector>
+
+#include "common.cuh"
+#include "k_conv.cuh"
+#include "k_decode.cuh"
+#include "k_pw_simt.cuh"
+#include "k_pw_tc.cuh"
+#include "net.hpp"
+
+using namespace cf;
+
+namespace {
+
+enum WorkClass { CLS_ALL = 0, CLS_PW = 1, CLS_DW = 2, CLS_STEM = 3, CLS_HEADS = 4, CLS_DECODE = 5 };
+
+struct Step {
+    int cls;
+    std::function<cudaError_t(cudaStream_t)> run;
+};
+
+struct EntrySpec {
+    std::string name;
+    uint64_t count;
+};
+
+// The packed-blob contract shared with weights.py::pack_weights (names, float counts, order).
+std::vector<EntrySpec> expected_entries() {
+    std::vector<EntrySpec> v;
+    v.push_back({"stem.w", 27 * 32});  // [(ky*3+kx)*3+ci][co]
+    v.push_back({"lut", 768});         // [c][256] u8 -> normalised fp32 (centerface.py:32-34)
+    for (int i = 0; i < 12; ++i) {
+        const MBBlock& b = kBlocks[i];
+        const std::string p = "b" + std::to_string(i);
+        if (b.t != 1) v.push_back({p + ".exp", (uint64_t)b.cin * b.hid()});  // [K=cin][N=hid]
+        v.push_back({p + ".dw", (uint64_t)b.k * b.k * b.hid()});             // [k*k][hid]
+        v.push_back({p + ".proj", (uint64_t)b.hid() * b.cout});              // [K=hid][N=cout]
+    }
+    v.push_back({"clast.w", 320 * 24});  // BN scale folded
+    v.push_back({"clast.b", 24});
+    const int skip_c[3] = {96, 32, 24};
+    for (int j = 0; j < 3; ++j) {
+        const std::string p = "up" + std::to_string(j + 1);
+        v.push_back({p + ".w", (uint64_t)skip_c[j] * 24});  // lateral 1x1, BN scale folded
+        v.push_back({p + ".b", 24});
+        v.push_back({p + ".su", 24 * 4});  // [c][a][b] transposed-conv tap * BN scale
+        v.push_back({p + ".tu", 24});
+    }
+    v.push_back({"heads.w", 216 * 16});  // [(ky*3+kx)*24+ci][16]
+    v.push_back({"heads.b", 16});
+    return v;
+}
+
+constexpr uint64_t kEntryAlignFloats = 32;  // 128-byte aligned entries (float4 / TMA friendly)
+inline uint64_t round_up(uint64_t a, uint64_t b) { return (a + b - 1) / b * b; }
+
+size_t blob_bytes() {
+    const auto ents = expected_entries();
+    uint64_t tab = sizeof(BlobHeader) + ents.size() * sizeof(BlobEntry);
+    tab = round_up(tab, 128);
+    uint64_t fl = 0;
+    for (auto& e : ents) fl += round_up(e.count, kEntryAlignFloats);
+    return (size_t)(tab + fl * 4);
+}
+
+}  // namespace
+
+struct cf_engine {
+    int device = 0;
+    int max_batch = 0, max_h = 0, max_w = 0;
+    int pw_engine = CF_PW_SIMT;
+    float* d_w = nullptr;
+    std::map<std::string, const float*> w;
+    // activations (NHWC fp32)
+    float* stem = nullptr;
+    float* hidA = nullptr;  // expand output
+    float* hidB = nullptr;  // depth-wise output
+    float* blk[12] = {};
+    float* clast = nullptr;
+    float* up[3] = {};
+    // heads (planar) + decode scratch
+    float *hm = nullptr, *wh = nullptr, *lm = nullptr, *reg = nullptr, *hm_sig = nullptr, *peak = nullptr;
+    // staging for the host entry points
+    uint8_t* in_u8 = nullptr;
+    float* o_dets = nullptr;
+    float* o_lms = nullptr;
+    int32_t* o_inds = nullptr;
+    int32_t* o_counts = nullptr;
+    size_t o_dets_floats = 0, o_lms_floats = 0, o_inds_n = 0;
+    cudaStream_t stream = nullptr;  // used by the *_host entry points
+    // last forward
+    int B = 0, H = 0, W = 0, fmt = -1;
+    const void* in = nullptr;
+    std::vector<Step> plan;
+    long long launches = 0;
+    PwTcState tc;  // tensor maps etc. of the tcgen05 engine
+};
+
+namespace {
+
+int run_steps(cf_engine* e, int which, cudaStream_t s) {
+    for (auto& st : e->plan) {
+        if (which != CLS_ALL && st.cls != which) continue;
+        if (st.cls == CLS_DECODE && which == CLS_ALL) continue;  // decode is launched by its own entry points
+        cudaError_t err = st.run(s);
+        if (err != cudaSuccess) return fail(CF_ECUDA, "kernel launch failed: %s", cudaGetErrorString(err));
+        ++e->launches;
+    }
+    return CF_OK;
+}
+
+template <int EPI>
+cudaError_t launch_pw_simt(const float* A, const float* Wkn, float* out, int M, int K, int N, EpiArgs ea,
+                           cudaStream_t s) {
+    if (N >= 64) {
+        dim3 g(cdiv(M, 128), cdiv(N, 64));
+        k_pw_simt<64, EPI><<<g, 256, 0, s>>>(A, Wkn, out, M, K, N, ea);
+    } else if (N > 16) {
+        dim3 g(cdiv(M, 128), cdiv(N, 32));
+        k_pw_simt<32, EPI><<<g, 256, 0, s>>>(A, Wkn, out, M, K, N, ea);
+    } else {
+        dim3 g(cdiv(M, 128), 1);
+        k_pw_simt<16, EPI><<<g, 256, 0, s>>>(A, Wkn, out, M, K, N, ea);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pw(cf_engine* e, int epi, const float* A, const float* Wkn, float* out, int M, int K, int N,
+                      EpiArgs ea, cudaStream_t s) {
+    if (e->pw_engine != CF_PW_SIMT) return launch_pw_tc(e->tc, e->pw_engine == CF_PW_TCGEN05 ? 3 : 1, epi, A, Wkn, out, M, K, N, ea, s);
+    switch (epi) {
+        case EPI_LINEAR: return launch_pw_simt<EPI_LINEAR>(A, Wkn, out, M, K, N, ea, s);
+        case EPI_SWISH: return launch_pw_simt<EPI_SWISH>(A, Wkn, out, M, K, N, ea, s);
+        case EPI_RESIDUAL: return launch_pw_simt<EPI_RESIDUAL>(A, Wkn, out, M, K, N, ea, s);
+        case EPI_BIAS_SWISH: return launch_pw_simt<EPI_BIAS_SWISH>(A, Wkn, out, M, K, N, ea, s);
+        default: return launch_pw_simt<EPI_IDAUP>(A, Wkn, out, M, K, N, ea, s);
+    }
+}
+
+template <int KS, int S>
+cudaError_t launch_dw_t(const float* in, const float* w, float* out, int B, int Hi, int Wi, int C, int Ho, int Wo,
+                        cudaStream_t s) {
+    constexpr int XT = 4;
+    const int tiles_x = cdiv(Wo, 4 * XT), tiles_y = cdiv(Ho, 8);
+    k_dw<KS, S, XT><<<B * tiles_x * tiles_y, 256, 0, s>>>(in, w, out, B, Hi, Wi, C, Ho, Wo, tiles_x, tiles_y);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dw(int ks, int st, const float* in, const float* w, float* out, int B, int Hi, int Wi, int C,
+                      int Ho, int Wo, cudaStream_t s) {
+    if (ks == 3 && st == 1) return launch_dw_t<3, 1>(in, w, out, B, Hi, Wi, C, Ho, Wo, s);
+    if (ks == 3 && st == 2) return launch_dw_t<3, 2>(in, w, out, B, Hi, Wi, C, Ho, Wo, s);
+    if (ks == 5 && st == 1) return launch_dw_t<5, 1>(in, w, out, B, Hi, Wi, C, Ho, Wo, s);
+    return launch_dw_t<5, 2>(in, w, out, B, Hi, Wi, C, Ho, Wo, s);
+}
+
+// Build the launch list of EfficientNet.forward (model/centernet.py:263-280) for one batch shape.
+void build_plan(cf_engine* e, const void* input, int fmt, int B, int H, int W) {
+    e->plan.clear();
+    auto& P = e->plan;
+    const int H2 = H / 2, W2 = W / 2;
+    // first_conv, :224
+    {
+        const float* w = e->w["stem.w"];
+        const float* lut = e->w["lut"];
+        float* out = e->stem;
+        const long long thr = (long long)B * H2 * W2 * 4;
+        const unsigned grid = (unsigned)((thr + 255) / 256);
+        if (fmt == CF_IN_U8_HWC)
+            P.push_back({CLS_STEM, [=](cudaStream_t s) {
+                             k_stem<1><<<grid, 256, 0, s>>>(input, w, lut, out, B, H, W);
+                             return cudaGetLastError();
+                         }});
+        else
+            P.push_back({CLS_STEM, [=](cudaStream_t s) {
+                             k_stem<0><<<grid, 256, 0, s>>>(input, w, lut, out, B, H, W);
+                             return cudaGetLastError();
+                         }});
+    }
+    // layer0..layer6, :225-235 -> MBConvBlock.forward :128-140
+    const float* x = e->stem;
+    int h = H2, wd = W2;
+    for (int i = 0; i < 12; ++i) {
+        const MBBlock& b = kBlocks[i];
+        const std::string p = "b" + std::to_string(i);
+        const int hid = b.hid();
+        const float* dw_in = x;
+        if (b.t != 1) {
+            const float* wexp = e->w[p + ".exp"];
+            float* o = e->hidA;
+            const int M = B * h * wd, K = b.cin;
+            P.push_back({CLS_PW, [=](cudaStream_t s) { return launch_pw(e, EPI_SWISH, x, wexp, o, M, K, hid, EpiArgs{}, s); }});
+            dw_in = e->hidA;
+        }
+        const int ho = h / b.s, wo = wd / b.s;
+        {
+            const float* wdw = e->w[p + ".dw"];
+            float* o = e->hidB;
+            const int ks = b.k, st = b.s, hi = h, wi = wd;
+            P.push_back({CLS_DW, [=](cudaStream_t s) { return launch_dw(ks, st, dw_in, wdw, o, B, hi, wi, hid, ho, wo, s); }});
+        }
+        {
+            const float* wpr = e->w[p + ".proj"];
+            const float* a = e->hidB;
+            float* o = e->blk[i];
+            const int M = B * ho * wo, N = b.cout;
+            EpiArgs ea{};
+            int epi = EPI_LINEAR;
+            if (b.residual()) {
+                epi = EPI_RESIDUAL;
+                ea.res = x;
+            }
+            P.push_back({CLS_PW, [=](cudaStream_t s) { return launch_pw(e, epi, a, wpr, o, M, hid, N, ea, s); }});
+        }
+        x = e->blk[i];
+        h = ho;
+        wd = wo;
+    }
+    // conv_last, :236 (conv 1x1 + folded BN + Swish)
+    {
+        const float* a = e->blk[11];
+        const float* wl = e->w["clast.w"];
+        EpiArgs ea{};
+        ea.bias = e->w["clast.b"];
+        float* o = e->clast;
+        const int M = B * h * wd;
+        P.push_back({CLS_PW, [=](cudaStream_t s) { return launch_pw(e, EPI_BIAS_SWISH, a, wl, o, M, 320, 24, ea, s); }});
+    }
+    // up1..up3, :237-239, :270-272 -> IDAUp.forward :200-204
+    const float* low = e->clast;
+    const int skip_blk[3] = {8, 4, 2};  // x4, x2, x1
+    const int skip_c[3] = {96, 32, 24};
+    for (int j = 0; j < 3; ++j) {
+        h *= 2;
+        wd *= 2;
+        const std::string p = "up" + std::to_string(j + 1);
+        EpiArgs ea{};
+        ea.bias = e->w[p + ".b"];
+        ea.low = low;
+        ea.su = e->w[p + ".su"];
+        ea.tu = e->w[p + ".tu"];
+        ea.Ho = h;
+        ea.Wo = wd;
+        const float* a = e->blk[skip_blk[j]];
+        const float* wl = e->w[p + ".w"];
+        float* o = e->up[j];
+        const int M = B * h * wd, K = skip_c[j];
+        P.push_back({CLS_PW, [=](cudaStream_t s) { return launch_pw(e, EPI_IDAUP, a, wl, o, M, K, 24, ea, s); }});
+        low = e->up[j];
+    }
+    // heads, :240-261, :277-279 (+ sigmoid/clamp of centerface.py:43)
+    {
+        const float* a = e->up[2];
+        const float* wh_ = e->w["heads.w"];
+        const float* bh = e->w["heads.b"];
+        const int hh = h, ww = wd;
+        P.push_back({CLS_HEADS, [=](cudaStream_t s) {
+                         dim3 g(cdiv(ww, 32), cdiv(hh, 16), B);
+                         k_heads<<<g, 128, HEADS_SMEM, s>>>(a, wh_, bh, e->hm, e->wh, e->lm, e->reg, e->hm_sig, B, hh, ww);
+                         return cudaGetLastError();
+                     }});
+    }
+    // path-C decode on the heads (entered through cf_decode_topk; listed for cf_replay_class)
+    {
+        const int hh = h, ww = wd;
+        P.push_back({CLS_DECODE, [=](cudaStream_t s) {
+                         const long long n = (long long)B * hh * ww;
+                         k_peak_mask<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(e->hm_sig, e->peak, B, hh, ww);
+                         return cudaGetLastError();
+                     }});
+        P.push_back({CLS_DECODE, [=](cudaStream_t s) {
+                         k_topk<<<B, 1024, 0, s>>>(e->peak, e->wh, e->reg, hh, ww, 100, e->o_dets, e->o_inds);
+                         return cudaGetLastError();
+                     }});
+    }
+    e->in = input;
+    e->fmt = fmt;
+    e->B = B;
+    e->H = H;
+    e->W = W;
+}
+
+int dalloc(float** p, size_t floats) {
+    CF_CUDA(cudaMalloc((void**)p, floats * sizeof(float)));
+    return CF_OK;
+}
+
+int check_decode_args(int batch, int h, int w) {
+    CF_CHECK(batch > 0 && h > 0 && w > 0, CF_EINVAL, "decode: batch=%d h=%d w=%d must be positive", batch, h, w);
+    CF_CHECK((long long)h * w < (1ll << 24), CF_EINVAL, "decode: map %dx%d too large (flat index must be < 2^24)", h, w);
+    return CF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* cf_last_error(void) { return err_slot().c_str(); }
+int cf_abi_version(void) { return CF_ABI_VERSION; }
+size_t cf_weights_blob_bytes(void) { return blob_bytes(); }
+
+int cf_create(const void* weights, size_t weights_bytes, int device, int max_batch, int max_h, int max_w,
+              int pw_engine, cf_engine** out) {
+    CF_CHECK(out != nullptr, CF_EINVAL, "cf_create: out is NULL");
+    *out = nullptr;
+    CF_CHECK(weights != nullptr, CF_EINVAL, "cf_create: weights is NULL");
+    CF_CHECK(max_batch >= 1 && max_h >= 32 && max_w >= 32 && max_h % 32 == 0 && max_w % 32 == 0, CF_EINVAL,
+             "cf_create: max_batch=%d max_h=%d max_w=%d (sizes must be positive multiples of 32)", max_batch, max_h, max_w);
+    CF_CHECK(pw_engine >= CF_PW_SIMT && pw_engine <= CF_PW_TCGEN05_1P, CF_EINVAL, "cf_create: unknown pw_engine %d", pw_engine);
+    CF_CHECK(weights_bytes == blob_bytes(), CF_EWEIGHTS, "cf_create: blob is %zu bytes, expected %zu", weights_bytes, blob_bytes());
+    Blob blob;
+    std::string why;
+    CF_CHECK(blob.parse(weights, weights_bytes, why), CF_EWEIGHTS, "cf_create: %s", why.c_str());
+
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) return fail(CF_ENODEV, "cf_create: no CUDA device (%s)", cudaGetErrorString(ce));
+    CF_CHECK(device >= 0 && device < ndev, CF_EINVAL, "cf_create: device %d out of range (have %d)", device, ndev);
+    cudaDeviceProp prop;
+    CF_CUDA(cudaGetDeviceProperties(&prop, device));
+    CF_CHECK(prop.major == 10, CF_ENODEV, "cf_create: device %d is sm_%d%d; this library is built for sm_100a only", device,
+             prop.major, prop.minor);
+    CF_CUDA(cudaSetDevice(device));
+
+    cf_engine* e = new cf_engine();
+    e->device = device;
+    e->max_batch = max_batch;
+    e->max_h = max_h;
+    e->max_w = max_w;
+    e->pw_engine = pw_engine;
+    int rc = CF_OK;
+    auto bail = [&](int code) {
+        cf_destroy(e);
+        return code;
+    };
+
+    // weights: upload the payload once, resolve every expected entry
+    {
+        BlobHeader hd;
+        memcpy(&hd, weights, sizeof hd);
+        CF_CUDA(cudaMalloc((void**)&e->d_w, hd.payload_floats * 4));
+        CF_CUDA(cudaMemcpy(e->d_w, blob.payload, hd.payload_floats * 4, cudaMemcpyHostToDevice));
+        for (auto& en : expected_entries()) {
+            const float* hp = blob.get(en.name, en.count, why);
+            if (!hp) return bail(fail(CF_EWEIGHTS, "cf_create: %s", why.c_str()));
+            const uint64_t off = (uint64_t)(hp - blob.payload);
+            if (off % kEntryAlignFloats != 0) return bail(fail(CF_EWEIGHTS, "cf_create: entry %s is not 128-byte aligned", en.name.c_str()));
+            e->w[en.name] = e->d_w + off;
+        }
+    }
+
+    const size_t Bm = (size_t)max_batch;
+    const size_t px2 = (size_t)(max_h / 2) * (max_w / 2);
+    // largest hidden tensor: layer1.0 expand output, 96 channels at stride 2
+    size_t hid_max = 0, dwo_max = 0;
+    {
+        size_t h = max_h / 2, w = max_w / 2;
+        for (int i = 0; i < 12; ++i) {
+            const MBBlock& b = kBlocks[i];
+            hid_max = std::max(hid_max, h * w * (size_t)b.hid());
+            h /= b.s;
+            w /= b.s;
+            dwo_max = std::max(dwo_max, h * w * (size_t)b.hid());
+        }
+    }
+    if ((rc = dalloc(&e->stem, Bm * px2 * 32))) return bail(rc);
+    if ((rc = dalloc(&e->hidA, Bm * hid_max))) return bail(rc);
+    if ((rc = dalloc(&e->hidB, Bm * dwo_max))) return bail(rc);
+    {
+        size_t h = max_h / 2, w = max_w / 2;
+        for (int i = 0; i < 12; ++i) {
+            h /= kBlocks[i].s;
+            w /= kBlocks[i].s;
+            if ((rc = dalloc(&e->blk[i], Bm * h * w * kBlocks[i].cout))) return bail(rc);
+        }
+        if ((rc = dalloc(&e->clast, Bm * h * w * 24))) return bail(rc);
+        for (int j = 0; j < 3; ++j) {
+            h *= 2;
+            w *= 2;
+            if ((rc = dalloc(&e->up[j], Bm * h * w * 24))) return bail(rc);
+        }
+        const size_t px4 = h * w;
+        if ((rc = dalloc(&e->hm, Bm * px4))) return bail(rc);
+        if ((rc = dalloc(&e->wh, Bm * px4 * 2))) return bail(rc);
+        if ((rc = dalloc(&e->lm, Bm * px4 * 10))) return bail(rc);
+        if ((rc = dalloc(&e->reg, Bm * px4 * 2))) return bail(rc);
+        if ((rc = dalloc(&e->hm_sig, Bm * px4))) return bail(rc);
+        if ((rc = dalloc(&e->peak, Bm * px4))) return bail(rc);
+    }
+    e->o_dets_floats = Bm * (size_t)THRESH_MAX_CAP * 6;  // covers [B,K<=1024,6] and [B,cap<=4096,5]
+    e->o_lms_floats = Bm * (size_t)THRESH_MAX_CAP * 10;
+    e->o_inds_n = Bm * 1024;
+    if ((rc = dalloc(&e->o_dets, e->o_dets_floats))) return bail(rc);
+    if ((rc = dalloc(&e->o_lms, e->o_lms_floats))) return bail(rc);
+    if (cudaMalloc((void**)&e->o_inds, e->o_inds_n * 4) != cudaSuccess ||
+        cudaMalloc((void**)&e->o_counts, Bm * 4) != cudaSuccess ||
+        cudaMalloc((void**)&e->in_u8, Bm * (size_t)max_h * max_w * 3) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess)
+        return bail(fail(CF_ECUDA, "cf_create: staging allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
+
+    if (cudaFuncSetAttribute(k_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, HEADS_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(k_thresh_nms, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)thresh_smem_bytes(THRESH_MAX_CAP)) != cudaSuccess)
+        return bail(fail(CF_ECUDA, "cf_create: cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError())));
+    if (pw_engine != CF_PW_SIMT) {
+        if ((rc = pw_tc_init(e->tc, device))) return bail(rc);
+    }
+    *out = e;
+    return CF_OK;
+}
+
+int cf_destroy(cf_engine* e) {
+    if (!e) return CF_OK;
+    cudaSetDevice(e->device);
+    pw_tc_destroy(e->tc);
+    float* bufs[] = {e->d_w, e->stem, e->hidA, e->hidB, e->clast, e->up[0], e->up[1], e->up[2], e->hm, e->wh,
+                     e->lm,  e->reg,  e->hm_sig, e->peak, e->o_dets, e->o_lms};
+    for (float* p : bufs)
+        if (p) cudaFree(p);
+    for (float* p : e->blk)
+        if (p) cudaFree(p);
+    if (e->o_inds) cudaFree(e->o_inds);
+    if (e->o_counts) cudaFree(e->o_counts);
+    if (e->in_u8) cudaFree(e->in_u8);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+    return CF_OK;
+}
+
+int cf_forward(cf_engine* e, const void* input, int in_format, int batch, int h, int w, void* stream) {
+    CF_CHECK(e != nullptr && input != nullptr, CF_EINVAL, "cf_forward: NULL engine or input");
+    CF_CHECK(in_format == CF_IN_F32_NCHW || in_format == CF_IN_U8_HWC, CF_EINVAL, "cf_forward: unknown in_format %d", in_format);
+    CF_CHECK(batch >= 1 && batch <= e->max_batch, CF_ECAP, "cf_forward: batch %d outside [1,%d]", batch, e->max_batch);
+    // EfficientNet needs H,W multiples of 32 (five stride-2 stages; centerface.py:69 guarantees it)
+    CF_CHECK(h >= 32 && w >= 32 && h % 32 == 0 && w % 32 == 0, CF_EINVAL, "cf_forward: h=%d w=%d must be positive multiples of 32", h, w);
+    CF_CHECK((size_t)h * w <= (size_t)e->max_h * e->max_w, CF_ECAP, "cf_forward: %dx%d exceeds the %dx%d the engine was created for", h, w,
+             e->max_h, e->max_w);
+    CF_CUDA(cudaSetDevice(e->device));
+    if (e->plan.empty() || e->in != input || e->fmt != in_format || e->B != batch || e->H != h || e->W != w)
+        build_plan(e, input, in_format, batch, h, w);
+    return run_steps(e, CLS_ALL, (cudaStream_t)stream);
+}
+
+int cf_heads(cf_engine* e, float** hm, float** wh, float** lm, float** reg, float** hm_sig) {
+    CF_CHECK(e != nullptr, CF_EINVAL, "cf_heads: NULL engine");
+    CF_CHECK(e->B > 0, CF_EINVAL, "cf_heads: no cf_forward has run on this engine");
+    if (hm) *hm = e->hm;
+    if (wh) *wh = e->wh;
+    if (lm) *lm = e->lm;
+    if (reg) *reg = e->reg;
+    if (hm_sig) *hm_sig = e->hm_sig;
+    return CF_OK;
+}
+
+int cf_tap(cf_engine* e, const char* name, float** ptr, int* h, int* w, int* c) {
+    CF_CHECK(e != nullptr && name != nullptr && ptr != nullptr, CF_EINVAL, "cf_tap: NULL argument");
+    CF_CHECK(e->B > 0, CF_EINVAL, "cf_tap: no cf_forward has run on this engine");
+    const std::string n(name);
+    int hh = e->H / 2, ww = e->W / 2, cc = 32;
+    float* p = nullptr;
+    if (n == "stem") p = e->stem;
+    for (int i = 0; i < 12 && !p; ++i) {
+        hh /= kBlocks[i].s;
+        ww /= kBlocks[i].s;
+        cc = kBlocks[i].cout;
+        if (n == "layer" + std::to_string(kLayerOfBlock[i]) && i == kLastBlockOfLayer[kLayerOfBlock[i]]) p = e->blk[i];
+        if (n == "block" + std::to_string(i)) p = e->blk[i];
+    }
+    if (!p) {
+        hh = e->H / 32;
+        ww = e->W / 32;
+        cc = 24;
+        if (n == "conv_last") p = e->clast;
+        else if (n == "up1") p = e->up[0], hh *= 2, ww *= 2;
+        else if (n == "up2") p = e->up[1], hh *= 4, ww *= 4;
+        else if (n == "fpn" || n == "up3") p = e->up[2], hh *= 8, ww *= 8;
+    }
+    CF_CHECK(p != nullptr, CF_EINVAL, "cf_tap: unknown tap '%s'", name);
+    *ptr = p;
+    if (h) *h = hh;
+    if (w) *w = ww;
+    if (c) *c = cc;
+    return CF_OK;
+}
+
+int cf_ctdet_decode(const float* heat, const float* wh, const float* reg, int batch, int h, int w, int K,
+                    float* out_dets, int32_t* out_inds, float* scratch, void* stream) {
+    CF_CHECK(heat && wh && out_dets && scratch, CF_EINVAL, "cf_ctdet_decode: NULL pointer");
+    int rc = check_decode_args(batch, h, w);
+    if (rc) return rc;
+    CF_CHECK(K >= 1 && K <= 1024 && K <= h * w, CF_EINVAL, "cf_ctdet_decode: K=%d outside [1,min(1024,h*w)]", K);
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long n = (long long)batch * h * w;
+    k_peak_mask<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(heat, scratch, batch, h, w);
+    k_topk<<<batch, 1024, 0, s>>>(scratch, wh, reg, h, w, K, out_dets, out_inds);
+    CF_CUDA(cudaGetLastError());
+    return CF_OK;
+}
+
+int cf_decode_topk(cf_engine* e, int K, float* out_dets, int32_t* out_inds, void* stream) {
+    CF_CHECK(e != nullptr, CF_EINVAL, "cf_decode_topk: NULL engine");
+    CF_CHECK(e->B > 0, CF_EINVAL, "cf_decode_topk: no cf_forward has run on this engine");
+    int rc = cf_ctdet_decode(e->hm_sig, e->wh, e->reg, e->B, e->H / 4, e->W / 4, K, out_dets, out_inds, e->peak, stream);
+    if (rc == CF_OK) e->launches += 2;
+    return rc;
+}
+
+int cf_decode_threshold(const float* hm_sig, const float* wh, const float* reg, const float* lm, int batch, int h,
+                        int w, int variant, float threshold, float nms_threshold, int size_h, int size_w,
+                        float scale_w, float scale_h, int cap, float* out_dets, float* out_lms,
+                        int32_t* out_counts, void* stream) {
+    CF_CHECK(hm_sig && wh && out_dets && out_counts, CF_EINVAL, "cf_decode_threshold: NULL pointer");
+    CF_CHECK(variant == CF_DECODE_A || variant == CF_DECODE_B, CF_EINVAL, "cf_decode_threshold: unknown variant %d", variant);
+    CF_CHECK(variant != CF_DECODE_B || reg != nullptr, CF_EINVAL, "cf_decode_threshold: variant B needs reg");
+    int rc = check_decode_args(batch, h, w);
+    if (rc) return rc;
+    CF_CHECK(cap >= 1 && cap <= THRESH_MAX_CAP, CF_EINVAL, "cf_decode_threshold: cap=%d outside [1,%d]", cap, THRESH_MAX_CAP);
+    int capP = 1;
+    while (capP < cap) capP <<= 1;
+    static thread_local int attr_dev = -1;
+    int dev = 0;
+    CF_CUDA(cudaGetDevice(&dev));
+    if (attr_dev != dev) {
+        CF_CUDA(cudaFuncSetAttribute(k_thresh_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)thresh_smem_bytes(THRESH_MAX_CAP)));
+        attr_dev = dev;
+    }
+    k_thresh_nms<<<batch, 1024, thresh_smem_bytes(capP), (cudaStream_t)stream>>>(
+        hm_sig, wh, reg, lm, h, w, variant, threshold, nms_threshold, size_h, size_w, scale_w, scale_h, cap, capP, out_dets,
+        out_lms, out_counts);
+    CF_CUDA(cudaGetLastError());
+    return CF_OK;
+}
+
+int cf_detect_topk_host(cf_engine* e, const uint8_t* images, int batch, int h, int w, int K, float* out_dets,
+                        int32_t* out_inds) {
+    CF_CHECK(e && images && out_dets, CF_EINVAL, "cf_detect_topk_host: NULL argument");
+    CF_CHECK(batch >= 1 && batch <= e->max_batch, CF_ECAP, "cf_detect_topk_host: batch %d outside [1,%d]", batch, e->max_batch);
+    CF_CHECK(K >= 1 && K <= 1024, CF_EINVAL, "cf_detect_topk_host: K=%d outside [1,1024]", K);
+    CF_CUDA(cudaSetDevice(e->device));
+    cudaStream_t s = e->stream;
+    CF_CUDA(cudaMemcpyAsync(e->in_u8, images, (size_t)batch * h * w * 3, cudaMemcpyHostToDevice, s));
+    int rc = cf_forward(e, e->in_u8, CF_IN_U8_HWC, batch, h, w, s);
+    if (rc) return rc;
+    if ((rc = cf_decode_topk(e, K, e->o_dets, e->o_inds, s))) return rc;
+    CF_CUDA(cudaMemcpyAsync(out_dets, e->o_dets, (size_t)batch * K * 6 * 4, cudaMemcpyDeviceToHost, s));
+    if (out_inds) CF_CUDA(cudaMemcpyAsync(out_inds, e->o_inds, (size_t)batch * K * 4, cudaMemcpyDeviceToHost, s));
+    CF_CUDA(cudaStreamSynchronize(s));
+    return CF_OK;
+}
+
+int cf_detect_threshold_host(cf_engine* e, const uint8_t* images, int batch, int h, int w, int variant,
+                             float threshold, float nms_threshold, float scale_w, float scale_h, int cap,
+                             float* out_dets, float* out_lms, int32_t* out_counts) {
+    CF_CHECK(e && images && out_dets && out_counts, CF_EINVAL, "cf_detect_threshold_host: NULL argument");
+    CF_CHECK(batch >= 1 && batch <= e->max_batch, CF_ECAP, "cf_detect_threshold_host: batch %d outside [1,%d]", batch, e->max_batch);
+    CF_CUDA(cudaSetDevice(e->device));
+    cudaStream_t s = e->stream;
+    CF_CUDA(cudaMemcpyAsync(e->in_u8, images, (size_t)batch * h * w * 3, cudaMemcpyHostToDevice, s));
+    int rc = cf_forward(e, e->in_u8, CF_IN_U8_HWC, batch, h, w, s);
+    if (rc) return rc;
+    // `size` as the reference passes it: (H',W') in centerface.py:51, fixed (640,640) in eval_widerface.py:88
+    const int size_h = variant == CF_DECODE_B ? 640 : h, size_w = variant == CF_DECODE_B ? 640 : w;
+    rc = cf_decode_threshold(e->hm_sig, e->wh, e->reg, e->lm, batch, h / 4, w / 4, variant, threshold, nms_threshold, size_h,
+                             size_w, scale_w, scale_h, cap, e->o_dets, out_lms ? e->o_lms : nullptr, e->o_counts, s);
+    if (rc) return rc;
+    ++e->launches;
+    CF_CUDA(cudaMemcpyAsync(out_counts, e->o_counts, (size_t)batch * 4, cudaMemcpyDeviceToHost, s));
+    CF_CUDA(cudaMemcpyAsync(out_dets, e->o_dets, (size_t)batch * cap * 5 * 4, cudaMemcpyDeviceToHost, s));
+    if (out_lms) CF_CUDA(cudaMemcpyAsync(out_lms, e->o_lms, (size_t)batch * cap * 10 * 4, cudaMemcpyDeviceToHost, s));
+    CF_CUDA(cudaStreamSynchronize(s));
+    return CF_OK;
+}
+
+long long cf_launch_count(cf_engine* e) { return e ? e->launches : 0; }
+
+int cf_work_model(int h, int w, int in_format, int which, double* bytes, double* flops) {
+    CF_CHECK(h >= 32 && w >= 32 && h % 32 == 0 && w % 32 == 0, CF_EINVAL, "cf_work_model: h=%d w=%d must be multiples of 32", h, w);
+    CF_CHECK(which >= CLS_ALL && which <= CLS_DECODE, CF_EINVAL, "cf_work_model: unknown class %d", which);
+    double by[6] = {}, fl[6] = {};
+    const double F = 4.0;  // fp32 storage
+    double hh = h / 2, ww = w / 2;
+    by[CLS_STEM] = (double)h * w * 3 * (in_format == CF_IN_U8_HWC ? 1.0 : F) + hh * ww * 32 * F;
+    fl[CLS_STEM] = 2.0 * hh * ww * 32 * 27;
+    for (int i = 0; i < 12; ++i) {
+        const MBBlock& b = kBlocks[i];
+        const double hid = b.hid();
+        if (b.t != 1) {
+            by[CLS_PW] += hh * ww * (b.cin + hid) * F;
+            fl[CLS_PW] += 2.0 * hh * ww * b.cin * hid;
+        }
+        const double ho = hh / b.s, wo = ww / b.s;
+        by[CLS_DW] += (hh * ww + ho * wo) * hid * F;
+        fl[CLS_DW] += 2.0 * ho * wo * hid * b.k * b.k;
+        by[CLS_PW] += ho * wo * (hid + b.cout + (b.residual() ? b.cout : 0)) * F;
+        fl[CLS_PW] += 2.0 * ho * wo * hid * b.cout;
+        hh = ho;
+        ww = wo;
+    }
+    by[CLS_PW] += hh * ww * (320 + 24) * F;
+    fl[CLS_PW] += 2.0 * hh * ww * 320 * 24;
+    const int skip_c[3] = {96, 32, 24};
+    for (int j = 0; j < 3; ++j) {
+        const double lo = hh * ww;
+        hh *= 2;
+        ww *= 2;
+        by[CLS_PW] += (hh * ww * (skip_c[j] + 24) + lo * 24) * F;
+        fl[CLS_PW] += 2.0 * hh * ww * (skip_c[j] * 24 + 24);
+    }
+    by[CLS_HEADS] = hh * ww * (24 + 16) * F;                       // FPN map in; 15 head planes + hm_sig out
+    fl[CLS_HEADS] = 2.0 * hh * ww * (4 * 24 * 24 * 9 + 24 * 15);   // reference graph: four 3x3 24->24 + 1x1s
+    by[CLS_DECODE] = hh * ww * 5 * F + 100 * 6 * F;                // hm, wh, reg in; [K,6] out (centerface_ext.py:52-82)
+    fl[CLS_DECODE] = 0;
+    for (int c = CLS_PW; c <= CLS_HEADS; ++c) {
+        by[CLS_ALL] += by[c];
+        fl[CLS_ALL] += fl[c];
+    }
+    if (bytes) *bytes = by[which];
+    if (flops) *flops = fl[which];
+    return CF_OK;
+}
+
+int cf_replay_class(cf_engine* e, int which, int iters, void* stream) {
+    CF_CHECK(e != nullptr, CF_EINVAL, "cf_replay_class: NULL engine");
+    CF_CHECK(!e->plan.empty(), CF_EINVAL, "cf_replay_class: no cf_forward has run on this engine");
+    CF_CHECK(which >= CLS_ALL && which <= CLS_DECODE && iters >= 1, CF_EINVAL, "cf_replay_class: which=%d iters=%d", which, iters);
+    CF_CUDA(cudaSetDevice(e->device));
+    for (int i = 0; i < iters; ++i) {
+        int rc = run_steps(e, which, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return CF_OK;
+}
+
+int cf_time_class(cf_engine* e, int which, int iters, void* stream, float* ms, int* launches) {
+    CF_CHECK(e != nullptr && ms != nullptr, CF_EINVAL, "cf_time_class: NULL argument");
+    CF_CHECK(!e->plan.empty(), CF_EINVAL, "cf_time_class: no cf_forward has run on this engine");
+    CF_CUDA(cudaSetDevice(e->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaEvent_t a, b;
+    CF_CUDA(cudaEventCreate(&a));
+    CF_CUDA(cudaEventCreate(&b));
+    const long long before = e->launches;
+    int rc = cf_replay_class(e, which, 1, stream);  // warm
+    const int per = (int)(e->launches - before);
+    if (rc == CF_OK) {
+        cudaEventRecord(a, s);
+        rc = cf_replay_class(e, which, iters, stream);
+        cudaEventRecord(b, s);
+        cudaError_t ce = cudaEventSynchronize(b);
+        if (rc == CF_OK && ce != cudaSuccess) rc = fail(CF_ECUDA, "cf_time_class: %s", cudaGetErrorString(ce));
+        float t = 0.f;
+        cudaEventElapsedTime(&t, a, b);
+        *ms = t / (float)iters;
+        if (launches) *launches = per;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,231 @@
+// Direct-convolution kernels: stem (dense 3x3 s2), depth-wise 3x3/5x5, collapsed heads 3x3.
+// Activations are NHWC fp32.  HBM-bound work: coalesced float4 traffic along the channel axis,
+// weights staged in shared memory, zero padding folded into index math (ZeroPad2d,
+// model/centernet.py:63, is never materialised).
+#pragma once
+#include "common.cuh"
+
+namespace cf {
+
+// ----------------------------------------------------------------------------------------
+// K1 stem: ZeroPad2d(0,1,0,1) + conv3x3 s2 3->32 (no bias) + Swish   (model/centernet.py:224)
+//   FMT 0: fp32 NCHW normalised input (what EfficientNet.forward receives)
+//   FMT 1: u8 HWC BGR input; /255, -mean, /std (centerface.py:32-34) applied through a
+//          768-entry table built on the host with the reference's own fp32 ops (bit-exact).
+// One thread = one output pixel x 8 output channels {4g..4g+3, 16+4g..16+4g+3}, so each
+// quad of threads writes two full 64-byte runs of the 128-byte NHWC pixel.
+// ----------------------------------------------------------------------------------------
+template <int FMT>
+__global__ void __launch_bounds__(256) k_stem(const void* __restrict__ in, const float* __restrict__ w,
+                                              const float* __restrict__ lut, float* __restrict__ out,
+                                              int B, int H, int W) {
+    __shared__ __align__(16) float w_s[27 * 32];
+    __shared__ float lut_s[FMT == 1 ? 768 : 1];
+    for (int i = threadIdx.x; i < 27 * 32; i += 256) w_s[i] = w[i];
+    if (FMT == 1)
+        for (int i = threadIdx.x; i < 768; i += 256) lut_s[i] = lut[i];
+    __syncthreads();
+
+    const int Ho = H >> 1, Wo = W >> 1;
+    const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
+    const int g = (int)(gid & 3);
+    const long long pix = gid >> 2;
+    if (pix >= (long long)B * Ho * Wo) return;
+    const int xo = (int)(pix % Wo);
+    const int yo = (int)((pix / Wo) % Ho);
+    const int b = (int)(pix / ((long long)Wo * Ho));
+
+    float4 a0 = make_float4(0, 0, 0, 0), a1 = a0;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int iy = 2 * yo + ky;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int ix = 2 * xo + kx;
+            float v[3] = {0.f, 0.f, 0.f};
+            if (iy < H && ix < W) {
+                if (FMT == 1) {
+                    const uint8_t* p = (const uint8_t*)in + ((size_t)(b * H + iy) * W + ix) * 3;
+                    v[0] = lut_s[p[0]];
+                    v[1] = lut_s[256 + p[1]];
+                    v[2] = lut_s[512 + p[2]];
+                } else {
+                    const float* p = (const float*)in + ((size_t)(b * 3) * H + iy) * W + ix;
+                    v[0] = __ldg(p);
+                    v[1] = __ldg(p + (size_t)H * W);
+                    v[2] = __ldg(p + 2 * (size_t)H * W);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float* wr = w_s + ((ky * 3 + kx) * 3 + c) * 32 + 4 * g;
+                fma4(a0, v[c], *reinterpret_cast<const float4*>(wr));
+                fma4(a1, v[c], *reinterpret_cast<const float4*>(wr + 16));
+            }
+        }
+    }
+    float* o = out + (size_t)pix * 32 + 4 * g;
+    st4(o, swish4(a0));
+    st4(o + 16, swish4(a1));
+}
+
+// ----------------------------------------------------------------------------------------
+// K3 depth-wise KSxKS stride S + Swish   (ConvReLU with groups=hidden, model/centernet.py:112)
+// Padding (model/centernet.py:68-70): total p = KS-S, lo = p/2 on left/top, rest right/bottom.
+// Thread = XT consecutive output pixels along x for one float4 of channels; the input row
+// window is loaded once per kernel row and reused across the XT outputs in registers, the
+// vertical reuse comes from L1 (a CTA covers a TYx(TX*XT) pixel tile).
+// w layout: [KS*KS][C].
+// ----------------------------------------------------------------------------------------
+template <int KS, int S, int XT>
+__global__ void __launch_bounds__(256) k_dw(const float* __restrict__ in, const float* __restrict__ w,
+                                            float* __restrict__ out, int B, int Hi, int Wi, int C,
+                                            int Ho, int Wo, int tiles_x, int tiles_y) {
+    constexpr int LO = (KS - S) / 2;
+    constexpr int WIN = (XT - 1) * S + KS;  // input columns feeding XT outputs
+    constexpr int TXS = 4;                  // strips per tile row  -> tile width  = 4*XT
+    constexpr int TY = 8;                   // tile height
+    const int C4 = C >> 2;
+    int bid = blockIdx.x;
+    const int tx0 = (bid % tiles_x) * (TXS * XT);
+    bid /= tiles_x;
+    const int ty0 = (bid % tiles_y) * TY;
+    const int b = bid / tiles_y;
+
+    const int items = TXS * TY * C4;
+    for (int it = threadIdx.x; it < items; it += 256) {
+        const int c4 = it % C4;
+        const int p = it / C4;
+        const int xo0 = tx0 + (p % TXS) * XT;
+        const int yo = ty0 + p / TXS;
+        if (yo >= Ho || xo0 >= Wo) continue;
+        float4 acc[XT];
+#pragma unroll
+        for (int j = 0; j < XT; ++j) acc[j] = make_float4(0, 0, 0, 0);
+        const int ix0 = xo0 * S - LO;
+#pragma unroll
+        for (int ky = 0; ky < KS; ++ky) {
+            const int iy = yo * S - LO + ky;
+            if (iy < 0 || iy >= Hi) continue;
+            const float* row = in + ((size_t)(b * Hi + iy) * Wi) * C + c4 * 4;
+            float4 win[WIN];
+#pragma unroll
+            for (int i = 0; i < WIN; ++i) {
+                const int ix = ix0 + i;
+                win[i] = (ix >= 0 && ix < Wi) ? ldg4(row + (size_t)ix * C) : make_float4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int kx = 0; kx < KS; ++kx) {
+                const float4 wv = ldg4(w + (size_t)(ky * KS + kx) * C + c4 * 4);
+#pragma unroll
+                for (int j = 0; j < XT; ++j) fma44(acc[j], win[j * S + kx], wv);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < XT; ++j) {
+            const int xo = xo0 + j;
+            if (xo < Wo) st4(out + ((size_t)(b * Ho + yo) * Wo + xo) * C + c4 * 4, swish4(acc[j]));
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// K5 heads.  The reference runs, per head, conv3x3(24->24)+b0 then conv1x1(24->c)+b1 with no
+// non-linearity between (model/centernet.py:249-256), so all four heads collapse exactly
+// (up to fp rounding) into ONE 3x3 conv 24->15: W' = W1.W0, b' = W1.b0 + b1,
+// computed in fp64 by the packer.  Output channel order: hm, wh0, wh1, lm0..9, reg0, reg1, pad.
+// Outputs are written planar (NCHW) like the reference's dict, plus
+// hm_sig = clamp(sigmoid(hm), 1e-4, 1-1e-4) (centerface.py:43) for the decoders.
+// CTA = 128 threads, 32x16 output pixels; thread = 4 pixels (x = sx + 8p) x 16 outputs.
+// smem: input tile [18][34][28] (pixel stride 28 floats -> conflict-free LDS.128) + weights.
+// ----------------------------------------------------------------------------------------
+constexpr int HEADS_PS = 28;  // padded pixel stride in floats
+constexpr int HEADS_SMEM = (18 * 34 * HEADS_PS + 216 * 16 + 16) * 4;
+
+__global__ void __launch_bounds__(128) k_heads(const float* __restrict__ in, const float* __restrict__ w,
+                                               const float* __restrict__ bias, float* __restrict__ hm,
+                                               float* __restrict__ wh, float* __restrict__ lm,
+                                               float* __restrict__ reg, float* __restrict__ hm_sig,
+                                               int B, int H, int W) {
+    extern __shared__ __align__(16) float sm[];
+    float* tile = sm;                        // [18][34][28]
+    float* ws = sm + 18 * 34 * HEADS_PS;     // [9][24][16]
+    float* bs = ws + 216 * 16;               // [16]
+    const int tid = threadIdx.x;
+    const int x00 = blockIdx.x * 32, y00 = blockIdx.y * 16, b = blockIdx.z;
+
+    for (int i = tid; i < 216 * 16 / 4; i += 128) st4(ws + i * 4, ldg4(w + i * 4));
+    if (tid < 16) bs[tid] = bias[tid];
+    for (int i = tid; i < 18 * 34 * 6; i += 128) {
+        const int c4 = i % 6;
+        const int px = (i / 6) % 34;
+        const int py = i / (6 * 34);
+        const int gy = y00 + py - 1, gx = x00 + px - 1;
+        float4 v = make_float4(0, 0, 0, 0);
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = ldg4(in + ((size_t)(b * H + gy) * W + gx) * 24 + c4 * 4);
+        st4(tile + (py * 34 + px) * HEADS_PS + c4 * 4, v);
+    }
+    __syncthreads();
+
+    const int sx = tid & 7, sy = tid >> 3;
+    float4 acc[4][4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[p][q] = make_float4(0, 0, 0, 0);
+
+    for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const float* trow = tile + ((sy + ky) * 34 + sx + kx) * HEADS_PS;
+            const float* wt = ws + (ky * 3 + kx) * 24 * 16;
+#pragma unroll
+            for (int c4 = 0; c4 < 6; ++c4) {
+                float4 a[4];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) a[p] = *reinterpret_cast<const float4*>(trow + p * 8 * HEADS_PS + c4 * 4);
+#pragma unroll
+                for (int ci = 0; ci < 4; ++ci) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 wv = *reinterpret_cast<const float4*>(wt + (c4 * 4 + ci) * 16 + q * 4);
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) {
+                            const float av = ci == 0 ? a[p].x : ci == 1 ? a[p].y : ci == 2 ? a[p].z : a[p].w;
+                            fma4(acc[p][q], av, wv);
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    const int y = y00 + sy;
+    if (y >= H) return;
+    const size_t plane = (size_t)H * W;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int x = x00 + sx + 8 * p;
+        if (x >= W) continue;
+        float o[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            o[q * 4 + 0] = acc[p][q].x + bs[q * 4 + 0];
+            o[q * 4 + 1] = acc[p][q].y + bs[q * 4 + 1];
+            o[q * 4 + 2] = acc[p][q].z + bs[q * 4 + 2];
+            o[q * 4 + 3] = acc[p][q].w + bs[q * 4 + 3];
+        }
+        const size_t pix = (size_t)y * W + x;
+        hm[(size_t)b * plane + pix] = o[0];
+        const float s = 1.f / (1.f + expf(-o[0]));
+        hm_sig[(size_t)b * plane + pix] = fminf(fmaxf(s, 1e-4f), 1.f - 1e-4f);
+        wh[((size_t)b * 2 + 0) * plane + pix] = o[1];
+        wh[((size_t)b * 2 + 1) * plane + pix] = o[2];
+#pragma unroll
+        for (int j = 0; j < 10; ++j) lm[((size_t)b * 10 + j) * plane + pix] = o[3 + j];
+        reg[((size_t)b * 2 + 0) * plane + pix] = o[13];
+        reg[((size_t)b * 2 + 1) * plane + pix] = o[14];
+    }
+}
+
+}  // namespace cf

@@ -1,0 +1,322 @@
+// Heat-map decode kernels.
+//   path C: _nms + _topk + _gather_feat + ctdet_decode      (centerface_ext.py:11-82)
+//   paths A/B: threshold decode + greedy IoU NMS + //scale  (centerface.py:73-151, :55-58;
+//                                                            eval_widerface.py:92-152)
+// HBM/latency-bound integer and compare work: one CTA per image, shared-memory radix select
+// and bitonic sort, warp-ballot ordered compaction.  Orders are total (no unspecified ties):
+//   path C   : (score desc, flat index asc)
+//   paths A/B: (score desc, flat index desc)  == stable ascending argsort reversed.
+#pragma once
+#include "common.cuh"
+
+namespace cf {
+
+// monotone float -> uint key (works for negative inputs too)
+__device__ __forceinline__ uint32_t fkey(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float fkey_inv(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// ---- K6: 3x3 peak keep (max_pool2d pads with -inf: border pixels only see in-bounds
+//      neighbours; equal plateau neighbours are all kept), centerface_ext.py:44-50 -----
+__global__ void __launch_bounds__(256) k_peak_mask(const float* __restrict__ heat, float* __restrict__ pk,
+                                                   int B, int H, int W) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= (long long)B * H * W) return;
+    const int x = (int)(i % W);
+    const int y = (int)((i / W) % H);
+    const float* img = heat + (i - (long long)y * W - x);
+    const float v = __ldg(img + y * W + x);
+    bool keep = true;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+        const int yy = y + dy;
+        if (yy < 0 || yy >= H) continue;
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+            const int xx = x + dx;
+            if (xx < 0 || xx >= W) continue;
+            keep = keep && !(__ldg(img + yy * W + xx) > v);
+        }
+    }
+    pk[i] = keep ? v : v * 0.f;  // heat * keep.float()
+}
+
+// in-place bitonic sort, descending, n = power of two, keys in shared memory
+__device__ __forceinline__ void bitonic_desc(unsigned long long* keys, int n) {
+    for (int k = 2; k <= n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long a = keys[i], b = keys[ixj];
+                    const bool desc = (i & k) == 0;
+                    if (desc ? (a < b) : (a > b)) {
+                        keys[i] = b;
+                        keys[ixj] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ---- K7+K8: per-image top-K of the peak map + gather + box assembly ------------------
+// grid = B, block = 1024.  4-pass MSB radix select of the K-th largest score, ordered
+// (lowest index first) admission of ties at the threshold, bitonic sort of the K winners.
+__global__ void __launch_bounds__(1024) k_topk(const float* __restrict__ pk, const float* __restrict__ wh,
+                                               const float* __restrict__ reg, int H, int W, int K,
+                                               float* __restrict__ dets, int32_t* __restrict__ inds) {
+    __shared__ unsigned hist[256];
+    __shared__ unsigned long long buf[1024];
+    __shared__ unsigned wcnt[32];
+    __shared__ unsigned s_prefix, s_krem, s_cnt;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int HW = H * W;
+    const int b = blockIdx.x;
+    const float* p = pk + (size_t)b * HW;
+
+    unsigned prefix = 0, mask = 0, krem = K;
+    for (int pass = 3; pass >= 0; --pass) {
+        if (tid < 256) hist[tid] = 0;
+        __syncthreads();
+        for (int i = tid; i < HW; i += 1024) {
+            const uint32_t key = fkey(__ldg(p + i));
+            if ((key & mask) == prefix) atomicAdd(&hist[(key >> (8 * pass)) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned cum = 0;
+            int sel = 0;
+            for (int bin = 255; bin >= 0; --bin) {
+                if (cum + hist[bin] >= krem) {
+                    sel = bin;
+                    break;
+                }
+                cum += hist[bin];
+            }
+            s_krem = krem - cum;
+            s_prefix = prefix | ((unsigned)sel << (8 * pass));
+        }
+        __syncthreads();
+        krem = s_krem;
+        prefix = s_prefix;
+        mask |= 0xFFu << (8 * pass);
+    }
+    const uint32_t T = prefix;         // key of the K-th largest score
+    const unsigned G = K - krem;       // winners strictly above T; krem ties admitted by index
+
+    if (tid == 0) s_cnt = 0;
+    for (int i = tid; i < 1024; i += 1024) buf[i] = 0ull;
+    __syncthreads();
+    unsigned eq_run = 0;
+    for (int base = 0; base < HW; base += 1024) {
+        const int i = base + tid;
+        const bool valid = i < HW;
+        const uint32_t key = valid ? fkey(__ldg(p + i)) : 0u;
+        const bool gt = valid && key > T;
+        const bool eq = valid && key == T;
+        if (gt) {
+            const unsigned slot = atomicAdd(&s_cnt, 1u);
+            buf[slot] = ((unsigned long long)key << 32) | (0xFFFFFFFFu - (unsigned)i);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, eq);
+        if (lane == 0) wcnt[warp] = __popc(m);
+        __syncthreads();
+        unsigned woff = 0, tot = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < 32; ++w2) {
+            const unsigned c = wcnt[w2];
+            woff += (w2 < warp) ? c : 0u;
+            tot += c;
+        }
+        const unsigned rank = eq_run + woff + __popc(m & ((1u << lane) - 1u));
+        if (eq && rank < krem) buf[G + rank] = ((unsigned long long)key << 32) | (0xFFFFFFFFu - (unsigned)i);
+        eq_run += tot;
+        __syncthreads();
+    }
+    int P = 1;
+    while (P < K) P <<= 1;
+    bitonic_desc(buf, P);
+
+    for (int r = tid; r < K; r += 1024) {
+        const unsigned long long c = buf[r];
+        const int idx = (int)(0xFFFFFFFFu - (unsigned)(c & 0xFFFFFFFFull));
+        const float score = fkey_inv((uint32_t)(c >> 32));
+        float xs = (float)(idx % W), ys = (float)(idx / W);  // centerface_ext.py:18-19
+        if (reg) {
+            xs = __fadd_rn(xs, __ldg(reg + ((size_t)b * 2 + 0) * HW + idx));  // :62
+            ys = __fadd_rn(ys, __ldg(reg + ((size_t)b * 2 + 1) * HW + idx));  // :63
+        } else {
+            xs += 0.5f;
+            ys += 0.5f;
+        }
+        const float hw = __ldg(wh + ((size_t)b * 2 + 0) * HW + idx) / 2.f;
+        const float hh = __ldg(wh + ((size_t)b * 2 + 1) * HW + idx) / 2.f;
+        float* d = dets + ((size_t)b * K + r) * 6;
+        d[0] = __fsub_rn(xs, hw);
+        d[1] = __fsub_rn(ys, hh);
+        d[2] = __fadd_rn(xs, hw);
+        d[3] = __fadd_rn(ys, hh);
+        d[4] = score;
+        d[5] = 0.f;
+        if (inds) inds[(size_t)b * K + r] = idx;
+    }
+}
+
+// numpy float32 floor_divide (npy_floor_dividef -> npy_divmodf), used by centerface.py:56-58
+__device__ __forceinline__ float np_floordiv(float a, float b) {
+    if (b == 0.f) return a / b;
+    float mod = fmodf(a, b);
+    float div = __fdiv_rn(__fsub_rn(a, mod), b);
+    if (mod != 0.f) {
+        if ((b < 0.f) != (mod < 0.f)) div = __fsub_rn(div, 1.0f);
+    }
+    if (div != 0.f) {
+        float fl = floorf(div);
+        if (__fsub_rn(div, fl) > 0.5f) fl = __fadd_rn(fl, 1.0f);
+        return fl;
+    }
+    return copysignf(0.f, __fdiv_rn(a, b));
+}
+
+// ---- K9: threshold decode + greedy NMS (paths A and B), one CTA per image ------------
+// dynamic smem: cand u64[capP] | box float4[capP] | area float[capP] | keep int[capP] | supp u8[capP]
+constexpr int THRESH_MAX_CAP = 4096;
+__host__ __device__ inline size_t thresh_smem_bytes(int capP) { return (size_t)capP * (8 + 16 + 4 + 4 + 1) + 16; }
+
+__global__ void __launch_bounds__(1024) k_thresh_nms(const float* __restrict__ hm, const float* __restrict__ wh,
+                                                      const float* __restrict__ reg, const float* __restrict__ lm,
+                                                      int H, int W, int variant, float thr, float nms_thr,
+                                                      int size_h, int size_w, float scale_w, float scale_h,
+                                                      int cap, int capP, float* __restrict__ out_dets,
+                                                      float* __restrict__ out_lms, int32_t* __restrict__ out_counts) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    unsigned long long* cand = reinterpret_cast<unsigned long long*>(smraw);
+    float4* box = reinterpret_cast<float4*>(cand + capP);
+    float* area = reinterpret_cast<float*>(box + capP);
+    int* keep = reinterpret_cast<int*>(area + capP);
+    unsigned char* supp = reinterpret_cast<unsigned char*>(keep + capP);
+    __shared__ unsigned s_cnt;
+    __shared__ int s_nk;
+    const int tid = threadIdx.x;
+    const int HW = H * W;
+    const int b = blockIdx.x;
+    const float* hmb = hm + (size_t)b * HW;
+
+    if (tid == 0) s_cnt = 0;
+    for (int i = tid; i < capP; i += 1024) cand[i] = 0ull;
+    __syncthreads();
+    for (int i = tid; i < HW; i += 1024) {
+        const float s = __ldg(hmb + i);
+        if (s > thr) {  // np.where(heatmap > thr): float32 compare
+            const unsigned slot = atomicAdd(&s_cnt, 1u);
+            if (slot < (unsigned)cap) cand[slot] = ((unsigned long long)__float_as_uint(s) << 32) | (unsigned)i;
+        }
+    }
+    __syncthreads();
+    const int n = (int)s_cnt;
+    if (n > cap) {
+        if (tid == 0) out_counts[b] = -n;
+        return;
+    }
+    int P = 1;
+    while (P < n) P <<= 1;
+    bitonic_desc(cand, P);
+
+    // boxes in the reference's mixed float32/float64 arithmetic, rounded once to float32
+    for (int j = tid; j < n; j += 1024) {
+        const unsigned long long c = cand[j];
+        const int idx = (int)(c & 0xFFFFFFFFull);
+        const int row = idx / W, col = idx % W;
+        const float s0 = __fmul_rn(__ldg(wh + ((size_t)b * 2 + 0) * HW + idx), 4.f);
+        const float s1 = __fmul_rn(__ldg(wh + ((size_t)b * 2 + 1) * HW + idx), 4.f);
+        double cx = (double)col, cy = (double)row;
+        if (variant == CF_DECODE_B) {  // eval_widerface.py:102: offsets swapped
+            cx += (double)__ldg(reg + ((size_t)b * 2 + 1) * HW + idx);
+            cy += (double)__ldg(reg + ((size_t)b * 2 + 0) * HW + idx);
+        }
+        double x1 = (cx + 0.5) * 4.0 - (double)(s0 / 2.f);
+        double y1 = (cy + 0.5) * 4.0 - (double)(s1 / 2.f);
+        x1 = x1 > 0.0 ? x1 : 0.0;  // max(0, .)
+        y1 = y1 > 0.0 ? y1 : 0.0;
+        x1 = (double)size_w < x1 ? (double)size_w : x1;  // min(x1, size[1])
+        y1 = (double)size_h < y1 ? (double)size_h : y1;
+        double x2 = x1 + (double)s0, y2 = y1 + (double)s1;
+        x2 = (double)size_w < x2 ? (double)size_w : x2;
+        y2 = (double)size_h < y2 ? (double)size_h : y2;
+        const float fx1 = __double2float_rn(x1), fy1 = __double2float_rn(y1);
+        const float fx2 = __double2float_rn(x2), fy2 = __double2float_rn(y2);
+        box[j] = make_float4(fx1, fy1, fx2, fy2);
+        area[j] = __fmul_rn(__fadd_rn(__fsub_rn(fx2, fx1), 1.f), __fadd_rn(__fsub_rn(fy2, fy1), 1.f));
+        supp[j] = 0;
+    }
+    if (tid == 0) s_nk = 0;
+    __syncthreads();
+
+    // greedy suppression in score order (centerface.py:123-149)
+    for (int i = 0; i < n; ++i) {
+        if (supp[i]) continue;  // uniform: last write to supp[i] is behind a barrier
+        if (tid == 0) keep[s_nk++] = i;
+        const float4 bi = box[i];
+        const float ai = area[i];
+        for (int j = i + 1 + tid; j < n; j += 1024) {
+            if (supp[j]) continue;
+            const float4 bj = box[j];
+            const float xx1 = fmaxf(bi.x, bj.x), yy1 = fmaxf(bi.y, bj.y);
+            const float xx2 = fminf(bi.z, bj.z), yy2 = fminf(bi.w, bj.w);
+            float w = __fadd_rn(__fsub_rn(xx2, xx1), 1.f);
+            float h = __fadd_rn(__fsub_rn(yy2, yy1), 1.f);
+            w = w > 0.f ? w : 0.f;
+            h = h > 0.f ? h : 0.f;
+            const float inter = __fmul_rn(w, h);
+            const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ai, area[j]), inter));
+            if (ovr >= nms_thr) supp[j] = 1;
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    const int nk = s_nk;
+    const bool resc = (scale_w != 0.f) && (scale_h != 0.f);
+    for (int r = tid; r < nk; r += 1024) {
+        const int i = keep[r];
+        const unsigned long long c = cand[i];
+        const int idx = (int)(c & 0xFFFFFFFFull);
+        float4 bx = box[i];
+        if (resc) {
+            bx.x = np_floordiv(bx.x, scale_w);
+            bx.z = np_floordiv(bx.z, scale_w);
+            bx.y = np_floordiv(bx.y, scale_h);
+            bx.w = np_floordiv(bx.w, scale_h);
+        }
+        float* d = out_dets + ((size_t)b * cap + r) * 5;
+        d[0] = bx.x;
+        d[1] = bx.y;
+        d[2] = bx.z;
+        d[3] = bx.w;
+        d[4] = __uint_as_float((uint32_t)(c >> 32));
+        if (variant == CF_DECODE_A && out_lms && lm) {
+            const int row = idx / W, col = idx % W;
+            float* l = out_lms + ((size_t)b * cap + r) * 10;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {  // centerface.py:97-98
+                const double lx = ((double)__ldg(lm + ((size_t)b * 10 + 2 * j) * HW + idx) + (double)col + 0.5) * 4.0;
+                const double ly = ((double)__ldg(lm + ((size_t)b * 10 + 2 * j + 1) * HW + idx) + (double)row + 0.5) * 4.0;
+                float fx = __double2float_rn(lx), fy = __double2float_rn(ly);
+                if (resc) {
+                    fx = np_floordiv(fx, scale_w);
+                    fy = np_floordiv(fy, scale_h);
+                }
+                l[2 * j] = fx;
+                l[2 * j + 1] = fy;
+            }
+        }
+    }
+    if (tid == 0) out_counts[b] = nk;
+}
+
+}  // namespace cf

@@ -1,0 +1,210 @@
+"""Python handle over the C ABI (one ``cf_engine`` per GPU).  PyTorch is used only for device
+memory, streams and zero-copy views of the engine's buffers."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from .weights import load_state_dict, pack_weights
+
+
+class _DevView:
+    """Expose a raw device pointer through __cuda_array_interface__ so torch can wrap it."""
+
+    def __init__(self, ptr, shape, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2}
+
+
+def _host_ptr(a):
+    """numpy array or (pinned) torch CPU tensor -> (address, keepalive)."""
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data, a
+    assert a.device.type == "cpu" and a.is_contiguous()
+    return a.data_ptr(), a
+
+
+class Engine:
+    """Owns a ``cf_engine``: weights on the device + activation buffers for ``max_batch`` images of
+    ``max_h x max_w``.  Replaces efficientnet_b0() + load_state_dict + .cuda()
+    (centerface.py:19-24)."""
+
+    def __init__(self, weights, max_batch=1, max_h=640, max_w=640, device=0, pw_engine=L.CF_PW_SIMT):
+        self.lib = L.load()
+        if isinstance(weights, (str, bytes)) and not isinstance(weights, bytes):
+            weights = load_state_dict(weights)
+        blob = weights if isinstance(weights, bytes) else pack_weights(weights)
+        if len(blob) != self.lib.cf_weights_blob_bytes():
+            raise L.CenterFaceError(f"weight blob is {len(blob)} bytes, library expects {self.lib.cf_weights_blob_bytes()}")
+        self.device = int(device)
+        self.max_batch, self.max_h, self.max_w = int(max_batch), int(max_h), int(max_w)
+        self.pw_engine = int(pw_engine)
+        h = C.c_void_p()
+        buf = C.create_string_buffer(blob, len(blob))
+        L.check(self.lib.cf_create(C.cast(buf, C.c_void_p), len(blob), self.device, self.max_batch, self.max_h,
+                                   self.max_w, self.pw_engine, C.byref(h)), "cf_create")
+        self.h = h
+        self.shape = None  # (B,H,W) of the last forward
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cf_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- device-side API (torch tensors on this engine's GPU) -------------------------------
+    def _stream(self):
+        import torch
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def forward(self, x):
+        """EfficientNet.forward (model/centernet.py:263-280).  x: cuda float32 [B,3,H,W] (normalised,
+        what the reference feeds its net) or cuda uint8 [B,H,W,3] raw BGR (normalisation fused)."""
+        import torch
+        assert x.is_cuda and x.device.index == self.device and x.is_contiguous()
+        if x.dtype == torch.uint8:
+            B, H, W, c = x.shape
+            fmt = L.CF_IN_U8_HWC
+        else:
+            assert x.dtype == torch.float32
+            B, c, H, W = x.shape
+            fmt = L.CF_IN_F32_NCHW
+        assert c == 3
+        L.check(self.lib.cf_forward(self.h, C.c_void_p(x.data_ptr()), fmt, B, H, W, self._stream()), "cf_forward")
+        self._keep = x
+        self.shape = (B, H, W)
+
+    def heads(self):
+        """Zero-copy views of the reference's output dict (+ 'hm_sig'), model/centernet.py:277-280."""
+        import torch
+        p = [C.c_void_p() for _ in range(5)]
+        L.check(self.lib.cf_heads(self.h, *[C.byref(q) for q in p]), "cf_heads")
+        B, H, W = self.shape
+        h4, w4 = H // 4, W // 4
+        dev = f"cuda:{self.device}"
+        out = {}
+        for name, q, c in zip(("hm", "wh", "lm", "reg", "hm_sig"), p, (1, 2, 10, 2, 1)):
+            out[name] = torch.as_tensor(_DevView(q.value, (B, c, h4, w4)), device=dev)
+        return out
+
+    def tap(self, name):
+        """NHWC fp32 view [B,h,w,c] of an intermediate activation (parity taps)."""
+        import torch
+        p, h, w, c = C.c_void_p(), C.c_int32(), C.c_int32(), C.c_int32()
+        L.check(self.lib.cf_tap(self.h, name.encode(), C.byref(p), C.byref(h), C.byref(w), C.byref(c)), "cf_tap")
+        return torch.as_tensor(_DevView(p.value, (self.shape[0], h.value, w.value, c.value)), device=f"cuda:{self.device}")
+
+    def decode_topk(self, K=100):
+        """ctdet_decode (centerface_ext.py:52-82) on the heads of the last forward -> dets [B,K,6], inds [B,K]."""
+        import torch
+        B = self.shape[0]
+        dev = f"cuda:{self.device}"
+        dets = torch.empty((B, K, 6), dtype=torch.float32, device=dev)
+        inds = torch.empty((B, K), dtype=torch.int32, device=dev)
+        L.check(self.lib.cf_decode_topk(self.h, K, C.c_void_p(dets.data_ptr()), C.c_void_p(inds.data_ptr()),
+                                        self._stream()), "cf_decode_topk")
+        return dets, inds
+
+    def time_class(self, which, iters=5):
+        """Mean device ms of one replay of a kernel class on the last forward's activations."""
+        ms, n = C.c_float(), C.c_int32()
+        L.check(self.lib.cf_time_class(self.h, which, iters, self._stream(), C.byref(ms), C.byref(n)), "cf_time_class")
+        return ms.value, n.value
+
+    @property
+    def launches(self):
+        return int(self.lib.cf_launch_count(self.h))
+
+    # ---- host-side API (numpy / pinned buffers; the calls the e2e figure times) --------------
+    def detect_topk_host(self, images, K=100, out_dets=None, out_inds=None):
+        """u8 BGR [B,H,W,3] host batch at network size -> dets [B,K,6], inds [B,K] (host)."""
+        B, H, W, c = images.shape
+        assert c == 3
+        if out_dets is None:
+            out_dets = np.empty((B, K, 6), np.float32)
+        if out_inds is None:
+            out_inds = np.empty((B, K), np.int32)
+        ip, k0 = _host_ptr(images)
+        dp, k1 = _host_ptr(out_dets)
+        np_, k2 = _host_ptr(out_inds)
+        L.check(self.lib.cf_detect_topk_host(self.h, C.c_void_p(ip), B, H, W, K, C.c_void_p(dp), C.c_void_p(np_)),
+                "cf_detect_topk_host")
+        self.shape = (B, H, W)
+        return out_dets, out_inds
+
+    def detect_threshold_host(self, images, variant, threshold, nms_threshold=0.3, scale_w=0.0, scale_h=0.0,
+                              cap=1024, landmarks=True):
+        """u8 BGR [B,H,W,3] host batch -> list of (dets [n,5], lms [n,10] | None) per image.
+        Variant A = CenterFace.decode+nms (+ //scale), variant B = eval_widerface.decode+nms."""
+        B, H, W, c = images.shape
+        assert c == 3
+        want_lms = landmarks and variant == L.CF_DECODE_A
+        while True:
+            dets = np.empty((B, cap, 5), np.float32)
+            lms = np.empty((B, cap, 10), np.float32) if want_lms else None
+            counts = np.empty((B,), np.int32)
+            ip, _k = _host_ptr(images)
+            L.check(self.lib.cf_detect_threshold_host(
+                self.h, C.c_void_p(ip), B, H, W, variant, threshold, nms_threshold, scale_w, scale_h, cap,
+                C.c_void_p(dets.ctypes.data), C.c_void_p(lms.ctypes.data) if want_lms else None,
+                C.c_void_p(counts.ctypes.data)), "cf_detect_threshold_host")
+            self.shape = (B, H, W)
+            if (counts >= 0).all():
+                break
+            need = int(-counts.min())
+            if need > L.MAX_CAP:
+                raise L.CenterFaceError(f"{need} pixels above the threshold in one image; the decode kernel caps at {L.MAX_CAP}")
+            cap = L.MAX_CAP
+        return [(dets[i, :counts[i]].copy(), lms[i, :counts[i]].copy() if want_lms else None) for i in range(B)]
+
+
+def ctdet_decode(heat, wh, reg=None, cat_spec_wh=False, K=100, return_inds=False):
+    """Drop-in for centerface_ext.ctdet_decode (centerface_ext.py:52): cuda fp32 tensors
+    heat [B,1,h,w] (post-sigmoid), wh/reg [B,2,h,w] -> detections [B,K,6]."""
+    import torch
+    assert not cat_spec_wh, "single-class model: cat_spec_wh is not used by the reference path"
+    lib = L.load()
+    assert heat.is_cuda and heat.dtype == torch.float32 and heat.shape[1] == 1
+    heat, wh = heat.contiguous(), wh.contiguous()
+    reg = reg.contiguous() if reg is not None else None
+    B, _, h, w = heat.shape
+    dets = torch.empty((B, K, 6), dtype=torch.float32, device=heat.device)
+    inds = torch.empty((B, K), dtype=torch.int32, device=heat.device)
+    scratch = torch.empty((B, h, w), dtype=torch.float32, device=heat.device)
+    with torch.cuda.device(heat.device):
+        L.check(lib.cf_ctdet_decode(C.c_void_p(heat.data_ptr()), C.c_void_p(wh.data_ptr()),
+                                    C.c_void_p(reg.data_ptr()) if reg is not None else None, B, h, w, K,
+                                    C.c_void_p(dets.data_ptr()), C.c_void_p(inds.data_ptr()),
+                                    C.c_void_p(scratch.data_ptr()),
+                                    C.c_void_p(torch.cuda.current_stream(heat.device).cuda_stream)), "cf_ctdet_decode")
+    return (dets, inds) if return_inds else dets
+
+
+def decode_threshold(hm_sig, wh, reg, lm, variant, threshold, nms_threshold=0.3, size=(640, 640), scale_w=0.0,
+                     scale_h=0.0, cap=1024):
+    """Device-side paths A/B on cuda tensors hm_sig [B,1,h,w], wh/reg [B,2,h,w], lm [B,10,h,w]|None
+    -> (dets [B,cap,5], lms [B,cap,10]|None, counts [B]) cuda tensors."""
+    import torch
+    lib = L.load()
+    B, _, h, w = hm_sig.shape
+    dev = hm_sig.device
+    dets = torch.empty((B, cap, 5), dtype=torch.float32, device=dev)
+    lms = torch.empty((B, cap, 10), dtype=torch.float32, device=dev) if (lm is not None and variant == L.CF_DECODE_A) else None
+    counts = torch.empty((B,), dtype=torch.int32, device=dev)
+    for t in (hm_sig, wh, reg, lm):
+        assert t is None or (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32)
+    p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
+    with torch.cuda.device(dev):
+        L.check(lib.cf_decode_threshold(p(hm_sig), p(wh), p(reg), p(lm), B, h, w, variant, threshold, nms_threshold,
+                                        size[0], size[1], scale_w, scale_h, cap, p(dets), p(lms), p(counts),
+                                        C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "cf_decode_threshold")
+    return dets, lms, counts

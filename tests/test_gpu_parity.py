@@ -1,0 +1,276 @@
+"""Parity tests proper (B200): the CUDA path, called through the C ABI, against the oracle and the
+committed golden vectors of the reference.
+
+Tolerances (BASELINE.json north_star): sigmoid heat-map <= 1e-3, emitted boxes IoU >= 0.999,
+top-k indices bit-exact; decode kernels fed the reference's own head maps are bit-exact in every
+output word.  The fp32 engine is held to a much tighter bar than the contract (see each test)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import IMGS
+
+pytestmark = pytest.mark.gpu
+
+HM_SIG_TOL = 1e-3      # contract
+HM_LOGIT_TOL_FP32 = 2e-4   # what the fp32 engine is held to (oracle noise floor is ~3e-6..1e-5)
+
+
+@pytest.fixture(scope="module")
+def eng(pkg, weights_path):
+    e = pkg.Engine(weights_path, max_batch=8, max_h=640, max_w=640, device=0, pw_engine=pkg.CF_PW_SIMT)
+    yield e
+    e.close()
+
+
+def _x640(oracle, f5_640, names):
+    return torch.from_numpy(np.stack([oracle.normalize_u8(f5_640[n]) for n in names])).cuda()
+
+
+# ---------------------------------------------------------------------------------------------
+# decode kernels on the reference's own head maps: bit-exact
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", ["27", "17"])
+def test_path_c_bit_exact_on_golden_heads(pkg, oracle, golden, n):
+    g = lambda k: torch.from_numpy(golden[f"f5_640/{n}/{k}"])[None].cuda()  # noqa: E731
+    hm = oracle.sigmoid_clamp(torch.from_numpy(golden[f"f5_640/{n}/hm"])[None]).cuda()
+    dets, inds = pkg.ctdet_decode(hm, g("wh"), g("reg"), K=100, return_inds=True)
+    assert np.array_equal(inds[0].cpu().numpy(), golden[f"f5_640/{n}/pathC_inds"])
+    assert np.array_equal(dets[0].cpu().numpy(), golden[f"f5_640/{n}/pathC_dets"])
+
+
+@pytest.mark.parametrize("n", ["27", "17"])
+def test_paths_a_b_bit_exact_on_golden_heads(pkg, oracle, golden, n):
+    g = lambda k: torch.from_numpy(golden[f"f5_640/{n}/{k}"])[None].cuda()  # noqa: E731
+    hm = oracle.sigmoid_clamp(torch.from_numpy(golden[f"f5_640/{n}/hm"])[None]).cuda()
+    d, l, c = pkg.decode_threshold(hm, g("wh"), g("reg"), g("lm"), pkg.CF_DECODE_A, 0.3, 0.3, (640, 640), cap=1024)
+    k = int(c.item())
+    assert k == len(golden[f"f5_640/{n}/pathA_dets"])
+    assert np.array_equal(d[0, :k].cpu().numpy(), golden[f"f5_640/{n}/pathA_dets"])
+    assert np.array_equal(l[0, :k].cpu().numpy(), golden[f"f5_640/{n}/pathA_lms"])
+    d, _, c = pkg.decode_threshold(hm, g("wh"), g("reg"), None, pkg.CF_DECODE_B, 0.35, 0.3, (640, 640), cap=1024)
+    k = int(c.item())
+    assert np.array_equal(d[0, :k].cpu().numpy(), golden[f"f5_640/{n}/pathB_dets"])
+
+
+def test_decode_batch_of_oracle_heads(pkg, oracle, oracle_heads_640):
+    """All five images as one ragged-content batch, K=100 and K=7, with and without reg."""
+    hm = torch.cat([oracle.sigmoid_clamp(oracle_heads_640[n]["hm"]) for n in IMGS])
+    wh = torch.cat([oracle_heads_640[n]["wh"] for n in IMGS])
+    reg = torch.cat([oracle_heads_640[n]["reg"] for n in IMGS])
+    for K in (100, 7, 1):
+        for r in (reg, None):
+            want, wi = oracle.ctdet_decode(hm, wh, r, K=K)
+            got, gi = pkg.ctdet_decode(hm.cuda(), wh.cuda(), None if r is None else r.cuda(), K=K, return_inds=True)
+            assert np.array_equal(gi.cpu().numpy(), wi.numpy().astype(np.int32))
+            assert torch.equal(got.cpu(), want)
+
+
+def test_decode_ties_constant_map_and_few_peaks(pkg, oracle):
+    """Edge cases of the total order: a constant map (every pixel a plateau peak, K ties resolved by
+    lowest flat index), a map with fewer than K peaks (the rest are 0-valued non-peaks), non-square."""
+    h, w = 24, 40
+    heat = torch.full((2, 1, h, w), 0.5)
+    heat[1] = 1e-4
+    heat[1, 0, 3, 5] = 0.8
+    heat[1, 0, 20, 39] = 0.8  # equal scores: lower flat index first
+    heat[1, 0, 10, 10] = 0.6
+    g = torch.Generator().manual_seed(3)
+    wh = torch.rand(2, 2, h, w, generator=g) * 10
+    reg = torch.rand(2, 2, h, w, generator=g)
+    want, wi = oracle.ctdet_decode(heat, wh, reg, K=50)
+    got, gi = pkg.ctdet_decode(heat.cuda(), wh.cuda(), reg.cuda(), K=50, return_inds=True)
+    assert gi[0].tolist() == list(range(50))
+    assert np.array_equal(gi.cpu().numpy(), wi.numpy().astype(np.int32))
+    assert torch.equal(got.cpu(), want)
+
+
+def test_threshold_paths_edge_cases(pkg, oracle):
+    """No candidate -> count 0; cap overflow -> negative count; equal scores -> documented order;
+    rescale floor-division equals numpy's."""
+    h = w = 32
+    hm = torch.full((3, 1, h, w), 1e-4)
+    hm[1, 0, 4:8, 4:8] = 0.9     # 16 equal-score candidates
+    hm[2] = 0.5                  # 1024 candidates > cap
+    g = torch.Generator().manual_seed(5)
+    wh = torch.rand(3, 2, h, w, generator=g) * 6 + 1
+    reg = torch.rand(3, 2, h, w, generator=g)
+    lm = torch.randn(3, 10, h, w, generator=g)
+    d, l, c = pkg.decode_threshold(hm.cuda(), wh.cuda(), reg.cuda(), lm.cuda(), pkg.CF_DECODE_A, 0.3, 0.3, (128, 128), cap=512)
+    c = c.cpu().numpy()
+    assert c[0] == 0 and c[2] == -1024
+    wa, wl = oracle.decode_a(hm[1:2].numpy(), wh[1:2].numpy(), reg[1:2].numpy(), lm[1:2].numpy(), (128, 128))
+    assert np.array_equal(d[1, :c[1]].cpu().numpy(), np.asarray(wa, np.float32))
+    assert np.array_equal(l[1, :c[1]].cpu().numpy(), np.asarray(wl, np.float32))
+    # variant B + rescale on the dense image with the maximum cap
+    sw, sh = np.float32(736 / 720), np.float32(480 / 478)
+    d, _, c = pkg.decode_threshold(hm[2:3].cuda(), wh[2:3].cuda(), reg[2:3].cuda(), None, pkg.CF_DECODE_B, 0.35, 0.3,
+                                   (640, 640), scale_w=float(sw), scale_h=float(sh), cap=4096)
+    wb = oracle.decode_b(hm[2].numpy(), wh[2].numpy(), reg[2].numpy(), (640, 640), 0.35)
+    wb, _ = oracle.rescale(wb, None, sw, sh)
+    k = int(c.item())
+    assert k == len(wb)
+    assert np.array_equal(d[0, :k].cpu().numpy(), wb)
+
+
+# ---------------------------------------------------------------------------------------------
+# the network
+# ---------------------------------------------------------------------------------------------
+def test_forward_heads_vs_oracle(eng, oracle, sd, f5_640, oracle_heads_640):
+    """EfficientNet.forward on the F5 batch: head maps vs the oracle (fp32 engine bar) and vs the
+    stored reference heat-maps (contract bar)."""
+    x = _x640(oracle, f5_640, IMGS)
+    eng.forward(x)
+    h = {k: v.cpu() for k, v in eng.heads().items()}
+    worst = {}
+    for i, n in enumerate(IMGS):
+        o = oracle_heads_640[n]
+        for k in ("hm", "wh", "lm", "reg"):
+            worst[k] = max(worst.get(k, 0.0), (h[k][i] - o[k][0]).abs().max().item())
+        sig_err = (h["hm_sig"][i] - oracle.sigmoid_clamp(o["hm"])[0]).abs().max().item()
+        worst["hm_sig"] = max(worst.get("hm_sig", 0.0), sig_err)
+    print("max |engine - oracle| per head:", worst)
+    assert worst["hm_sig"] <= HM_SIG_TOL
+    assert worst["hm"] <= HM_LOGIT_TOL_FP32
+    assert worst["wh"] <= 2e-3 and worst["lm"] <= 2e-3 and worst["reg"] <= 2e-4
+
+
+def test_taps_vs_oracle(eng, oracle, sd, f5_640):
+    """Every stage output (NHWC tap) against the oracle's NCHW tap, relative to the stage's scale
+    (the BN-free backbone reaches |x| ~ 1e13)."""
+    x = _x640(oracle, f5_640, ["27"])
+    eng.forward(x)
+    _, taps = oracle.forward(sd, x.cpu(), return_taps=True)
+    for name in ["stem"] + [f"layer{i}" for i in range(7)] + ["conv_last", "fpn"]:
+        got = eng.tap(name).cpu().permute(0, 3, 1, 2)
+        ref = taps[name]
+        assert got.shape == ref.shape, name
+        rel = (got - ref).abs().max().item() / max(ref.abs().max().item(), 1e-30)
+        print(name, "rel err", rel)
+        assert rel < 5e-5, (name, rel)
+
+
+def test_end_to_end_topk_and_boxes(eng, oracle, f5_640, golden):
+    """Network + path C end to end against the reference's stored result: top-k indices bit-exact,
+    every emitted box IoU >= 0.999, scores within 1e-3 (the contract)."""
+    x = _x640(oracle, f5_640, IMGS)
+    eng.forward(x)
+    dets, inds = eng.decode_topk(100)
+    dets, inds = dets.cpu().numpy(), inds.cpu().numpy()
+    for i, n in enumerate(IMGS):
+        gd, gi = golden[f"f5_640/{n}/pathC_dets"], golden[f"f5_640/{n}/pathC_inds"]
+        real = gd[:, 4] > 2e-4  # rows above the clamp floor; below it the order is among ties at 1e-4
+        assert np.array_equal(inds[i][real], gi[real]), n
+        iou = oracle.box_iou(dets[i][real, :4], gd[real, :4])
+        assert iou.min() >= 0.999, (n, iou.min())
+        assert np.abs(dets[i][real, 4] - gd[real, 4]).max() <= 1e-3
+
+
+def test_u8_input_equals_f32_input(eng, oracle, f5_640):
+    """The fused /255, mean/std of the u8 path is bit-identical to feeding the reference's
+    normalised tensor (centerface.py:32-34)."""
+    names = ["27", "8"]
+    eng.forward(_x640(oracle, f5_640, names))
+    a = {k: v.clone() for k, v in eng.heads().items()}
+    u8 = torch.from_numpy(np.stack([f5_640[n] for n in names])).cuda()
+    eng.forward(u8)
+    b = eng.heads()
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_batch_independence_and_idempotence(eng, f5_640):
+    """Size-independent properties: an image's result does not depend on its batch-mates or slot,
+    and re-running the same batch reproduces every bit."""
+    u8 = torch.from_numpy(np.stack([f5_640[n] for n in IMGS + ["27", "1", "8"]])).cuda()  # B=8
+    eng.forward(u8)
+    full = {k: v.clone() for k, v in eng.heads().items()}
+    eng.forward(u8)
+    for k, v in eng.heads().items():
+        assert torch.equal(full[k], v)
+    one = u8[3:4].contiguous()
+    eng.forward(one)
+    for k, v in eng.heads().items():
+        assert torch.equal(full[k][3:4], v), k
+    assert torch.equal(full["hm"][3], full["hm"][5])  # same image (27) in two slots
+
+
+def test_small_and_non_square_inputs(eng, oracle, sd, images):
+    """320-max-side sweep shapes (config 5) incl. the smallest legal 32x32 and non-square maps."""
+    import cv2
+    for (hh, ww) in ((32, 32), (320, 256), (224, 320), (480, 640)):
+        img = cv2.resize(images["27"], (ww, hh))
+        x = torch.from_numpy(oracle.normalize_u8(img))[None]
+        o = oracle.forward(sd, x)
+        eng.forward(x.cuda())
+        h = eng.heads()
+        for k in ("hm", "wh", "lm", "reg"):
+            err = (h[k].cpu() - o[k]).abs().max().item()
+            assert err < (2e-4 if k in ("hm", "reg") else 2e-3), ((hh, ww), k, err)
+
+
+def test_centerface_call_native_sizes(pkg, oracle, sd, images, golden, weights_path):
+    """The drop-in CenterFace(h, w)(img) against the reference's stored __call__ results at each
+    JPEG's own size: same detections, scores within 1e-4, coordinates equal after the reference's
+    floor-division except where a sub-1e-3 wobble crosses an integer."""
+    pkg.CenterFace.print_times = False
+    for n in ("8", "2", "1"):
+        img = images[n]
+        cf = pkg.CenterFace(img.shape[0], img.shape[1], landmarks=True, weights=weights_path)
+        dets, lms = cf(img, threshold=0.35)
+        gd, gl = golden[f"native/{n}/dets"], golden[f"native/{n}/lms"]
+        assert dets.shape == gd.shape and lms.shape == gl.shape, (n, dets.shape, gd.shape)
+        assert dets.dtype == np.float32 and lms.dtype == np.float32
+        assert np.abs(dets[:, 4] - gd[:, 4]).max() < 1e-4
+        assert (np.abs(dets[:, :4] - gd[:, :4]) <= 1.0).all()
+        assert (dets[:, :4] == gd[:, :4]).mean() >= 0.97 and (lms == gl).mean() >= 0.97
+        cf.net.close()
+    # landmarks=False returns only dets (the reference crashes here)
+    img = images["8"]
+    cf = pkg.CenterFace(img.shape[0], img.shape[1], landmarks=False, weights=weights_path)
+    d = cf(img)
+    assert isinstance(d, np.ndarray) and d.shape[1] == 5
+    # an image with no face -> empty (0,5)/(0,10) like centerface.py:60-62
+    cf2 = pkg.CenterFace(64, 64, landmarks=True, weights=weights_path)
+    d, l = cf2(np.zeros((64, 64, 3), np.uint8))
+    assert d.shape == (0, 5) and l.shape == (0, 10)
+
+
+def test_get_detections_vga_letterbox(pkg, oracle, golden, images, weights_path):
+    """Config 4: eval_widerface.get_detections on 640x480 frames letter-boxed into 640x640, path B."""
+    import cv2
+    model = pkg.CenterFaceNet(weights_path, max_batch=5)
+    xs = []
+    for n in IMGS:
+        canvas = np.zeros((640, 640, 3), np.uint8)
+        canvas[80:560] = cv2.resize(images[n], (640, 480))
+        xs.append(oracle.normalize_u8(canvas))
+    out = pkg.get_detections({"input": torch.from_numpy(np.stack(xs))}, model, threshold=0.35)
+    for i, n in enumerate(IMGS):
+        gd = golden[f"c4_vga/{n}/pathB_dets"]
+        assert out[i].shape == gd.shape, (n, out[i].shape, gd.shape)
+        if len(gd):
+            assert oracle.box_iou(out[i][:, :4], gd[:, :4]).min() >= 0.999
+            assert np.abs(out[i][:, 4] - gd[:, 4]).max() <= 1e-3
+    heads = model(torch.from_numpy(np.stack(xs[:2])))[0]
+    assert set(heads) == {"hm", "wh", "lm", "reg"} and heads["lm"].shape == (2, 10, 160, 160)
+    assert np.abs(heads["hm"][0].cpu().numpy() - golden["c4_vga/1/hm"]).max() < 2e-4
+
+
+def test_host_entry_point_matches_device_path(eng, f5_640):
+    """cf_detect_topk_host (H2D + net + decode + D2H) == the device-side calls."""
+    u8 = np.stack([f5_640[n] for n in IMGS])
+    dets, inds = eng.detect_topk_host(u8, K=100)
+    eng.forward(torch.from_numpy(u8).cuda())
+    d2, i2 = eng.decode_topk(100)
+    assert np.array_equal(dets, d2.cpu().numpy()) and np.array_equal(inds, i2.cpu().numpy())
+    assert (np.diff(dets[:, :, 4], axis=1) <= 0).all()  # sortedness
+
+
+def test_errors_are_loud(pkg, eng):
+    with pytest.raises(pkg.CenterFaceError):
+        eng.forward(torch.zeros(9, 3, 64, 64, device="cuda"))       # batch > max_batch
+    with pytest.raises(pkg.CenterFaceError):
+        eng.forward(torch.zeros(1, 3, 100, 64, device="cuda"))      # not a multiple of 32
+    with pytest.raises(pkg.CenterFaceError):
+        pkg.ctdet_decode(torch.zeros(1, 1, 4, 4, device="cuda"), torch.zeros(1, 2, 4, 4, device="cuda"), K=17)

@@ -1,0 +1,124 @@
+"""Host-side logic that needs no GPU: the weight packer's folds, the blob contract, and that the
+C-ABI library loads and exports every symbol declared in include/centerface_b200.h."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import ROOT
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    hdr = open(os.path.join(ROOT, "include", "centerface_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(cf_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 15
+    lib = pkg._lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(pkg._lib.SIGNATURES), declared ^ set(pkg._lib.SIGNATURES)
+    assert lib.cf_abi_version() == 1
+
+
+def test_blob_contract(pkg, weights_path):
+    sd = pkg.load_state_dict(weights_path)
+    blob = pkg.pack_weights(sd)
+    assert len(blob) == pkg._lib.load().cf_weights_blob_bytes()
+    assert blob[:8] == b"CFB200W1"
+
+
+def test_create_rejects_bad_arguments_without_gpu(pkg, weights_path):
+    lib = pkg._lib.load()
+    h = C.c_void_p()
+    assert lib.cf_create(None, 0, 0, 1, 640, 640, 0, C.byref(h)) == -1
+    assert b"NULL" in lib.cf_last_error()
+    blob = pkg.pack_weights(pkg.load_state_dict(weights_path))
+    buf = C.create_string_buffer(blob, len(blob))
+    assert lib.cf_create(C.cast(buf, C.c_void_p), len(blob), 0, 1, 650, 640, 0, C.byref(h)) == -1  # not /32
+    assert lib.cf_create(C.cast(buf, C.c_void_p), len(blob) - 4, 0, 1, 640, 640, 0, C.byref(h)) == -3
+    bad = bytearray(blob)
+    bad[0:8] = b"XXXXXXXX"
+    buf2 = C.create_string_buffer(bytes(bad), len(bad))
+    assert lib.cf_create(C.cast(buf2, C.c_void_p), len(bad), 0, 1, 640, 640, 0, C.byref(h)) == -3
+    if not torch.cuda.is_available():  # the product must fail loudly without a device: no CPU fallback
+        assert lib.cf_create(C.cast(buf, C.c_void_p), len(blob), 0, 1, 640, 640, 0, C.byref(h)) == -4
+        with pytest.raises(pkg.CenterFaceError):
+            pkg.Engine(weights_path)
+
+
+def test_work_model_matches_survey(pkg):
+    by, fl = pkg._lib.work_model(640, 640, pkg.CF_IN_F32_NCHW, 0)
+    assert abs(fl - 4.695e9) / 4.695e9 < 1e-3          # 4.695 GFLOP / image
+    _, fl480 = pkg._lib.work_model(480, 640, pkg.CF_IN_F32_NCHW, 0)
+    assert abs(fl480 - 3.521e9) / 3.521e9 < 1e-3
+    parts = [pkg._lib.work_model(640, 640, pkg.CF_IN_F32_NCHW, c) for c in (1, 2, 3, 4)]
+    assert abs(sum(p[0] for p in parts) - by) < 1 and abs(sum(p[1] for p in parts) - fl) < 1
+
+
+def _entries(pkg, sd_np):
+    from importlib import import_module
+    w = import_module(pkg.__name__ + ".weights")
+    return dict(w.entries(sd_np)), w
+
+
+def test_head_collapse_and_bn_folds_match_oracle(pkg, oracle, sd, weights_path):
+    """The packer's exact folds reproduce the reference graph on random inputs (fp32 tolerance)."""
+    ents, w = _entries(pkg, pkg.load_state_dict(weights_path))
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 24, 12, 10, generator=g)
+    # heads: conv3x3+b -> conv1x1+b for four heads == one 3x3 conv 24->15
+    wc = torch.from_numpy(ents["heads.w"]).reshape(3, 3, 24, 16).permute(3, 2, 0, 1).contiguous()
+    y = F.conv2d(x, wc, torch.from_numpy(ents["heads.b"]), 1, 1)
+    o = 0
+    for head, oc in oracle.HEADS:
+        ref = F.conv2d(F.conv2d(x, sd[head + ".0.weight"], sd[head + ".0.bias"], 1, 1), sd[head + ".1.weight"], sd[head + ".1.bias"])
+        assert (y[:, o:o + oc] - ref).abs().max() < 2e-5 * max(1.0, ref.abs().max().item()), head
+        o += oc
+    # IDAUp (model/centernet.py:186-204)
+    for j, c in ((1, 96), (2, 32), (3, 24)):
+        low = torch.randn(2, 24, 5, 6, generator=g) * 3
+        skip = torch.randn(2, c, 10, 12, generator=g) * 3
+        ref = oracle._idaup(sd, f"up{j}", low, skip)
+        wl = torch.from_numpy(ents[f"up{j}.w"]).reshape(c, 24).t().reshape(24, c, 1, 1)
+        b = F.relu(F.conv2d(skip, wl, torch.from_numpy(ents[f"up{j}.b"])))
+        su = torch.from_numpy(ents[f"up{j}.su"]).reshape(24, 1, 2, 2)
+        a = F.relu(F.conv_transpose2d(low, su, torch.from_numpy(ents[f"up{j}.tu"]), 2, 0, 0, 24))
+        assert (a + b - ref).abs().max() < 1e-4 * max(1.0, ref.abs().max().item()), j
+    # conv_last (conv + BN(1e-5) + Swish) on an input at the magnitude the real network produces
+    x = torch.randn(1, 320, 4, 4, generator=g) * 1e12
+    ref = oracle._swish(oracle._bn(sd, "conv_last.1", F.conv2d(x, sd["conv_last.0.weight"]), 1e-5))
+    wl = torch.from_numpy(ents["clast.w"]).reshape(320, 24).t().reshape(24, 320, 1, 1)
+    got = oracle._swish(F.conv2d(x, wl, torch.from_numpy(ents["clast.b"])))
+    assert (got - ref).abs().max() < 1e-4 * max(1.0, ref.abs().max().item())
+
+
+def test_normalise_lut_is_bit_exact(pkg, oracle):
+    from importlib import import_module
+    w = import_module(pkg.__name__ + ".weights")
+    lut = w.normalise_lut()
+    img = np.arange(256, dtype=np.uint8).reshape(16, 16, 1).repeat(3, axis=2)
+    ref = oracle.normalize_u8(img)  # centerface.py:32-34
+    for c in range(3):
+        assert np.array_equal(lut[c][img[..., c]], ref[c])
+
+
+def test_layouts(pkg, weights_path):
+    sdn = pkg.load_state_dict(weights_path)
+    ents, _ = _entries(pkg, sdn)
+    w = sdn["first_conv.0.1.weight"]
+    assert ents["stem.w"].reshape(3, 3, 3, 32)[1, 2, 0, 5] == w[5, 0, 1, 2]
+    w = sdn["layer1.0.conv.0.1.weight"]  # expand 16->96
+    assert ents["b1.exp"].reshape(16, 96)[3, 40] == w[40, 3, 0, 0]
+    w = sdn["layer2.0.conv.1.1.weight"]  # dw 5x5, 144 ch
+    assert ents["b3.dw"].reshape(25, 144)[7, 100] == w[100, 0, 1, 2]
+    w = sdn["layer6.0.conv.2.weight"]  # project 960->320
+    assert ents["b11.proj"].reshape(960, 320)[900, 300] == w[300, 900, 0, 0]
+
+
+def test_transform_matches_reference_formula(oracle):
+    assert oracle.transform(478, 720) == (480, 736, 480 / 478, 736 / 720)
+    assert oracle.transform(640, 640) == (640, 640, 1.0, 1.0)

@@ -1,0 +1,93 @@
+"""The oracle (oracle/centerface_oracle.py) against the committed golden vectors, which were
+produced by the reference itself (oracle/gen_golden.py asserts bit-equality at generation time).
+Runs on CPU."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import IMGS
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def test_inputs_match_fixture_hashes(golden, f5_640):
+    for n in IMGS:
+        assert sha(f5_640[n]) == str(golden[f"f5_640/{n}/input_sha256"]), n
+
+
+@pytest.mark.parametrize("n", IMGS)
+def test_forward_heads(oracle, golden, oracle_heads_640, n):
+    """EfficientNet.forward restated: hm within the oracle noise floor of the stored reference run
+    (thread count may differ from generation time; SURVEY.md 8c noise floor 3.3e-6 on the logit)."""
+    o = oracle_heads_640[n]
+    assert np.abs(o["hm"][0].numpy() - golden[f"f5_640/{n}/hm"]).max() < 2e-5
+    for k in ("wh", "lm", "reg"):
+        assert abs(o[k].double().sum().item() - float(golden[f"f5_640/{n}/{k}_sum64"])) < 0.5
+        assert abs(o[k].abs().max().item() - float(golden[f"f5_640/{n}/{k}_absmax"])) < 1e-3
+
+
+@pytest.mark.parametrize("n", ["27", "17"])
+def test_decode_paths_on_golden_heads(oracle, golden, n):
+    """Decode restatements on the stored reference head maps: bit-exact."""
+    g = lambda k: golden[f"f5_640/{n}/{k}"]  # noqa: E731
+    hm = oracle.sigmoid_clamp(torch.from_numpy(g("hm"))[None])
+    wh, lm, reg = (torch.from_numpy(g(k))[None] for k in ("wh", "lm", "reg"))
+    da, la = oracle.decode_a(hm.numpy(), wh.numpy(), reg.numpy(), lm.numpy(), (640, 640))
+    assert np.array_equal(np.asarray(da, np.float32), g("pathA_dets"))
+    assert np.array_equal(np.asarray(la, np.float32), g("pathA_lms"))
+    db = oracle.decode_b(hm.numpy()[0], wh.numpy()[0], reg.numpy()[0], (640, 640), 0.35)
+    assert np.array_equal(np.asarray(db, np.float32), g("pathB_dets"))
+    dc, ic = oracle.ctdet_decode(hm, wh, reg, K=100)
+    assert np.array_equal(dc[0].numpy(), g("pathC_dets"))
+    assert np.array_equal(ic[0].numpy().astype(np.int32), g("pathC_inds"))
+
+
+def test_toy_path_b(oracle, golden):
+    hm = np.full((1, 160, 160), 1e-4, np.float32)
+    hm[0, 10, 20] = 0.9
+    wh = np.full((2, 160, 160), 5.0, np.float32)
+    rg = np.zeros((2, 160, 160), np.float32)
+    rg[0], rg[1] = 0.25, 0.75
+    out = oracle.decode_b(hm, wh, rg, (640, 640), 0.35)
+    assert np.array_equal(out, golden["toy/pathB"])
+    assert np.allclose(out, [[75, 33, 95, 53, 0.9]])
+
+
+def test_detect_native_one_image(oracle, sd, golden, images):
+    """CenterFace.__call__ restated end to end (resize, net, decode A, NMS, //scale) on 8.jpg."""
+    n = "8"
+    dets, lms = oracle.detect(sd, images[n])
+    gd, gl = golden[f"native/{n}/dets"], golden[f"native/{n}/lms"]
+    assert dets.shape == gd.shape
+    # scores may wobble at the oracle noise floor between thread counts; coordinates are floor-divided
+    assert np.abs(dets[:, 4] - gd[:, 4]).max() < 1e-5
+    assert (np.abs(dets[:, :4] - gd[:, :4]) <= 1.0).all() and (dets[:, :4] == gd[:, :4]).mean() > 0.98
+    assert (np.abs(lms - gl) <= 1.0).all()
+
+
+def test_post_process(oracle, golden):
+    """ctdet_post_process (utils/post_process.py:83-100) restated."""
+    dets = golden["f5_640/27/pathC_dets"][None].copy()
+    out = oracle.ctdet_post_process(dets, golden["post/27/c"], golden["post/27/s"], 160, 160)
+    assert np.allclose(out[0], golden["post/27/dets"], rtol=0, atol=2e-3)
+
+
+def test_topk_tie_rule(oracle):
+    """(score desc, flat index asc) on ties -- the documented total order."""
+    heat = torch.full((1, 1, 8, 8), 0.5)
+    s, idx, ys, xs = oracle.topk(heat, 5)
+    assert idx[0].tolist() == [0, 1, 2, 3, 4]
+
+
+def test_peak_nms_plateau_and_border(oracle):
+    heat = torch.zeros(1, 1, 4, 4)
+    heat[0, 0, 0, 0] = 0.9   # border pixel competes only with in-bounds neighbours
+    heat[0, 0, 2, 2] = 0.7
+    heat[0, 0, 2, 3] = 0.7   # equal plateau neighbours are both kept
+    out = oracle.peak_nms(heat)
+    assert out[0, 0, 0, 0] == 0.9 and out[0, 0, 2, 2] == 0.7 and out[0, 0, 2, 3] == 0.7
+    assert out[0, 0, 1, 1] == 0
