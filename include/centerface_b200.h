@@ -127,6 +127,12 @@ int cf_detect_threshold_host(cf_engine* e, const uint8_t* images, int batch, int
                              float threshold, float nms_threshold, float scale_w, float scale_h, int cap,
                              float* out_dets, float* out_lms, int32_t* out_counts);
 
+/* Validation hook: one point-wise convolution out[M,N] = epi(A[M,K].W[K,N]) outside any engine, with
+ * the selected GEMM engine (CF_PW_*).  dA/dOut/dRes are DEVICE pointers, hW a HOST [K][N] matrix.
+ * epi: 0 linear (model/centernet.py:118), 1 Swish (:110), 2 + residual dRes (:137).  Synchronous. */
+int cf_debug_pw_gemm(int pw_engine, int epi, const float* dA, const float* hW, float* dOut, int M, int K, int N,
+                     const float* dRes, void* stream);
+
 /* ---- instrumentation -----------------------------------------------------------------
  * Number of kernels this library launched on behalf of the handle since creation.        */
 long long cf_launch_count(cf_engine* e);

@@ -137,9 +137,8 @@ cudaError_t launch_pw_simt(const float* A, const float* Wkn, float* out, int M, 
     return cudaGetLastError();
 }
 
-cudaError_t launch_pw(cf_engine* e, int epi, const float* A, const float* Wkn, float* out, int M, int K, int N,
-                      EpiArgs ea, cudaStream_t s) {
-    if (e->pw_engine != CF_PW_SIMT) return launch_pw_tc(e->tc, e->pw_engine == CF_PW_TCGEN05 ? 3 : 1, epi, A, Wkn, out, M, K, N, ea, s);
+cudaError_t launch_pw_simt_any(int epi, const float* A, const float* Wkn, float* out, int M, int K, int N, EpiArgs ea,
+                               cudaStream_t s) {
     switch (epi) {
         case EPI_LINEAR: return launch_pw_simt<EPI_LINEAR>(A, Wkn, out, M, K, N, ea, s);
         case EPI_SWISH: return launch_pw_simt<EPI_SWISH>(A, Wkn, out, M, K, N, ea, s);
@@ -147,6 +146,21 @@ cudaError_t launch_pw(cf_engine* e, int epi, const float* A, const float* Wkn, f
         case EPI_BIAS_SWISH: return launch_pw_simt<EPI_BIAS_SWISH>(A, Wkn, out, M, K, N, ea, s);
         default: return launch_pw_simt<EPI_IDAUP>(A, Wkn, out, M, K, N, ea, s);
     }
+}
+
+// One point-wise convolution of the plan: fp32 FFMA tiles (validation engine) or the tcgen05 kernel,
+// whose tensor maps and shared-memory plan are resolved here, once per batch shape.
+int make_pw_step(cf_engine* e, std::vector<Step>& P, int epi, const float* A, const float* Wkn, float* out, int M, int K,
+                 int N, EpiArgs ea) {
+    if (e->pw_engine == CF_PW_SIMT) {
+        P.push_back({CLS_PW, [=](cudaStream_t s) { return launch_pw_simt_any(epi, A, Wkn, out, M, K, N, ea, s); }});
+        return CF_OK;
+    }
+    TcLaunch tl;
+    int rc = tc_plan(e->tc, e->pw_engine == CF_PW_TCGEN05 ? 3 : 1, epi, A, Wkn, out, M, K, N, ea, &tl);
+    if (rc) return rc;
+    P.push_back({CLS_PW, [tl](cudaStream_t s) { return tc_launch(tl, s); }});
+    return CF_OK;
 }
 
 template <int KS, int S>
@@ -167,8 +181,10 @@ cudaError_t launch_dw(int ks, int st, const float* in, const float* w, float* ou
 }
 
 // Build the launch list of EfficientNet.forward (model/centernet.py:263-280) for one batch shape.
-void build_plan(cf_engine* e, const void* input, int fmt, int B, int H, int W) {
+int build_plan(cf_engine* e, const void* input, int fmt, int B, int H, int W) {
     e->plan.clear();
+    e->B = 0;
+    int rc = CF_OK;
     auto& P = e->plan;
     const int H2 = H / 2, W2 = W / 2;
     // first_conv, :224
@@ -201,7 +217,7 @@ void build_plan(cf_engine* e, const void* input, int fmt, int B, int H, int W) {
             const float* wexp = e->w[p + ".exp"];
             float* o = e->hidA;
             const int M = B * h * wd, K = b.cin;
-            P.push_back({CLS_PW, [=](cudaStream_t s) { return launch_pw(e, EPI_SWISH, x, wexp, o, M, K, hid, EpiArgs{}, s); }});
+            if ((rc = make_pw_step(e, P, EPI_SWISH, x, wexp, o, M, K, hid, EpiArgs{}))) return rc;
             dw_in = e->hidA;
         }
         const int ho = h / b.s, wo = wd / b.s;
@@ -222,7 +238,7 @@ void build_plan(cf_engine* e, const void* input, int fmt, int B, int H, int W) {
                 epi = EPI_RESIDUAL;
                 ea.res = x;
             }
-            P.push_back({CLS_PW, [=](cudaStream_t s) { return launch_pw(e, epi, a, wpr, o, M, hid, N, ea, s); }});
+            if ((rc = make_pw_step(e, P, epi, a, wpr, o, M, hid, N, ea))) return rc;
         }
         x = e->blk[i];
         h = ho;
@@ -236,7 +252,7 @@ void build_plan(cf_engine* e, const void* input, int fmt, int B, int H, int W) {
         ea.bias = e->w["clast.b"];
         float* o = e->clast;
         const int M = B * h * wd;
-        P.push_back({CLS_PW, [=](cudaStream_t s) { return launch_pw(e, EPI_BIAS_SWISH, a, wl, o, M, 320, 24, ea, s); }});
+        if ((rc = make_pw_step(e, P, EPI_BIAS_SWISH, a, wl, o, M, 320, 24, ea))) return rc;
     }
     // up1..up3, :237-239, :270-272 -> IDAUp.forward :200-204
     const float* low = e->clast;
@@ -257,7 +273,7 @@ void build_plan(cf_engine* e, const void* input, int fmt, int B, int H, int W) {
         const float* wl = e->w[p + ".w"];
         float* o = e->up[j];
         const int M = B * h * wd, K = skip_c[j];
-        P.push_back({CLS_PW, [=](cudaStream_t s) { return launch_pw(e, EPI_IDAUP, a, wl, o, M, K, 24, ea, s); }});
+        if ((rc = make_pw_step(e, P, EPI_IDAUP, a, wl, o, M, K, 24, ea))) return rc;
         low = e->up[j];
     }
     // heads, :240-261, :277-279 (+ sigmoid/clamp of centerface.py:43)
@@ -290,6 +306,7 @@ void build_plan(cf_engine* e, const void* input, int fmt, int B, int H, int W) {
     e->B = B;
     e->H = H;
     e->W = W;
+    return CF_OK;
 }
 
 int dalloc(float** p, size_t floats) {
@@ -416,6 +433,20 @@ int cf_create(const void* weights, size_t weights_bytes, int device, int max_bat
         return bail(fail(CF_ECUDA, "cf_create: cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError())));
     if (pw_engine != CF_PW_SIMT) {
         if ((rc = pw_tc_init(e->tc, device))) return bail(rc);
+        // tf32 hi/lo, K-major, 128B-swizzled images of every point-wise weight matrix
+        auto prep = [&](const std::string& name, int K, int N) {
+            const float* hp = blob.get(name, (uint64_t)K * N, why);
+            return hp ? tc_prepare_layer(e->tc, e->w[name], hp, K, N) : fail(CF_EWEIGHTS, "cf_create: %s", why.c_str());
+        };
+        for (int i = 0; i < 12 && !rc; ++i) {
+            const MBBlock& b = kBlocks[i];
+            if (b.t != 1) rc = prep("b" + std::to_string(i) + ".exp", b.cin, b.hid());
+            if (!rc) rc = prep("b" + std::to_string(i) + ".proj", b.hid(), b.cout);
+        }
+        if (!rc) rc = prep("clast.w", 320, 24);
+        const int skip_c[3] = {96, 32, 24};
+        for (int j = 0; j < 3 && !rc; ++j) rc = prep("up" + std::to_string(j + 1) + ".w", skip_c[j], 24);
+        if (rc) return bail(rc);
     }
     *out = e;
     return CF_OK;
@@ -448,8 +479,13 @@ int cf_forward(cf_engine* e, const void* input, int in_format, int batch, int h,
     CF_CHECK((size_t)h * w <= (size_t)e->max_h * e->max_w, CF_ECAP, "cf_forward: %dx%d exceeds the %dx%d the engine was created for", h, w,
              e->max_h, e->max_w);
     CF_CUDA(cudaSetDevice(e->device));
-    if (e->plan.empty() || e->in != input || e->fmt != in_format || e->B != batch || e->H != h || e->W != w)
-        build_plan(e, input, in_format, batch, h, w);
+    if (e->plan.empty() || e->B == 0 || e->in != input || e->fmt != in_format || e->B != batch || e->H != h || e->W != w) {
+        int rc = build_plan(e, input, in_format, batch, h, w);
+        if (rc) {
+            e->plan.clear();
+            return rc;
+        }
+    }
     return run_steps(e, CLS_ALL, (cudaStream_t)stream);
 }
 
@@ -581,6 +617,41 @@ int cf_detect_threshold_host(cf_engine* e, const uint8_t* images, int batch, int
     if (out_lms) CF_CUDA(cudaMemcpyAsync(out_lms, e->o_lms, (size_t)batch * cap * 10 * 4, cudaMemcpyDeviceToHost, s));
     CF_CUDA(cudaStreamSynchronize(s));
     return CF_OK;
+}
+
+int cf_debug_pw_gemm(int pw_engine, int epi, const float* dA, const float* hW, float* dOut, int M, int K, int N,
+                     const float* dRes, void* stream) {
+    CF_CHECK(dA && hW && dOut && M > 0 && K > 0 && N > 0 && K % 4 == 0 && N % 4 == 0, CF_EINVAL, "cf_debug_pw_gemm: bad arguments");
+    CF_CHECK(epi == EPI_LINEAR || epi == EPI_SWISH || (epi == EPI_RESIDUAL && dRes), CF_EINVAL, "cf_debug_pw_gemm: epi %d unsupported here", epi);
+    EpiArgs ea{};
+    ea.res = dRes;
+    float* dW = nullptr;
+    CF_CUDA(cudaMalloc((void**)&dW, (size_t)K * N * 4));
+    cudaError_t ce = cudaMemcpy(dW, hW, (size_t)K * N * 4, cudaMemcpyHostToDevice);
+    int rc = ce == cudaSuccess ? CF_OK : fail(CF_ECUDA, "cf_debug_pw_gemm: %s", cudaGetErrorString(ce));
+    if (!rc && pw_engine == CF_PW_SIMT) {
+        ce = launch_pw_simt_any(epi, dA, dW, dOut, M, K, N, ea, (cudaStream_t)stream);
+        if (ce != cudaSuccess) rc = fail(CF_ECUDA, "cf_debug_pw_gemm: %s", cudaGetErrorString(ce));
+    } else if (!rc) {
+        PwTcState st;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        rc = pw_tc_init(st, dev);
+        if (!rc) rc = tc_prepare_layer(st, dW, hW, K, N);
+        TcLaunch tl;
+        if (!rc) rc = tc_plan(st, pw_engine == CF_PW_TCGEN05 ? 3 : 1, epi, dA, dW, dOut, M, K, N, ea, &tl);
+        if (!rc) {
+            ce = tc_launch(tl, (cudaStream_t)stream);
+            if (ce != cudaSuccess) rc = fail(CF_ECUDA, "cf_debug_pw_gemm: launch: %s", cudaGetErrorString(ce));
+        }
+        ce = cudaStreamSynchronize((cudaStream_t)stream);
+        if (!rc && ce != cudaSuccess) rc = fail(CF_ECUDA, "cf_debug_pw_gemm: kernel: %s", cudaGetErrorString(ce));
+        pw_tc_destroy(st);
+    }
+    ce = cudaStreamSynchronize((cudaStream_t)stream);
+    if (!rc && ce != cudaSuccess) rc = fail(CF_ECUDA, "cf_debug_pw_gemm: %s", cudaGetErrorString(ce));
+    cudaFree(dW);
+    return rc;
 }
 
 long long cf_launch_count(cf_engine* e) { return e ? e->launches : 0; }

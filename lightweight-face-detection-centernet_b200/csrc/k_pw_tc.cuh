@@ -1,11 +1,540 @@
-// placeholder until the tcgen05 engine lands
+// Point-wise (1x1) convolution on the 5th-generation tensor cores:
+//     out[M,N] = epi( A[M,K] . W[K,N] ),  A = NHWC fp32 activations (pixels are GEMM rows).
+//
+// tcgen05.mma kind::tf32, M=128 per CTA, fp32 accumulators in TMEM, operands staged in shared
+// memory: A by TMA (cp.async.bulk.tensor, SWIZZLE_128B, zero fill past K and past M), W as a
+// pre-swizzled K-major image built once at cf_create (plain cp.async.bulk).
+//
+// Precision.  The reference is fp32 and its back-bone has no normalisation, so an 11-bit operand
+// (one TF32 pass) breaks top-k parity.  kPasses == 3 therefore splits both operands
+// into tf32 hi + tf32 lo parts and issues  A_lo.B_hi + A_hi.B_lo + A_hi.B_hi  into the same
+// accumulator (error ~2^-21 per product, fp32 class).  W is split on the host; A is split in
+// shared memory by four "splitter" warps between the TMA and the MMA stage (element-wise, so the
+// swizzled layout is irrelevant to them).  kPasses == 1 is the throughput mode.
+//
+// Warp roles (512 threads, one persistent CTA per SM):
+//   warp 0      TMA producer          warp 1      MMA issuer (one elected lane)
+//   warp 2      TMEM allocator        warp 3      idle
+//   warps 4-7   A splitters (3-pass)  warps 8-15  two epilogue groups, one per TMEM accumulator stage:
+//                                                 tcgen05.ld -> epilogue math -> swizzled smem -> TMA store
 #pragma once
+#include <cuda.h>
+
+#include <map>
+#include <vector>
+
 #include "common.cuh"
+
 namespace cf {
-struct PwTcState {};
-inline int pw_tc_init(PwTcState&, int) { return fail(CF_EINVAL, "tcgen05 point-wise engine not built yet"); }
-inline void pw_tc_destroy(PwTcState&) {}
-inline cudaError_t launch_pw_tc(PwTcState&, int, int, const float*, const float*, float*, int, int, int, EpiArgs, cudaStream_t) {
-    return cudaErrorNotSupported;
+
+constexpr int TC_THREADS = 512;
+constexpr int TC_BM = 128;           // rows per tile (UMMA M)
+constexpr int TC_BK = 32;            // fp32 K elements per smem block = one 128-byte swizzle row
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
+constexpr int TC_STG_BYTES = 32 * 128;          // one epilogue staging buffer: 32 rows x 32 fp32
+constexpr int TC_STG_BUFS = 2;                  // per epilogue warp
+constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_SMEM_MAX = 232448;             // 227 KB
+
+struct TcLayer {        // per weight matrix, built once
+    float* img = nullptr;   // device: [chunk][kb][hi NC x 128 B | lo NC x 128 B], SW128 K-major
+    int K = 0, N = 0, NC = 0, nchunks = 0, nkb = 0;
+    size_t img_bytes = 0;
+};
+
+struct PwTcState {
+    void* encode = nullptr;  // cuTensorMapEncodeTiled
+    int sms = 148;
+    std::map<const float*, TcLayer> layers;  // keyed by the [K][N] device weight pointer
+};
+
+struct TcParams {
+    const float* bimg;
+    int M, K, N, NC, nchunks, nkb, n_items;
+    int resident;    // 1: the whole B image lives in smem for the kernel's lifetime
+    int stages;
+    uint32_t stage_bytes, a_bytes_stage, b_bytes_block;  // b_bytes_block = NC*128*(passes==3?2:1)
+    uint32_t off_bres, off_stages, off_bars;             // smem offsets from the 1024-aligned base
+    EpiArgs ea;
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded spin: a protocol bug traps (surfacing as a CUDA error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t it = 0; it < (1u << 26); ++it) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0),
+                 "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);  // start address
+    d |= (uint64_t)(1024u >> 4) << 32;         // stride byte offset
+    d |= (uint64_t)1 << 46;                    // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor, kind::tf32: D fp32, A/B tf32 K-major, M=128, N=n
+__host__ __device__ inline uint32_t umma_idesc_tf32(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// round-to-nearest split of an fp32 into tf32 hi (low 13 mantissa bits zero) + exact remainder
+__host__ __device__ inline float tf32_hi(float x) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+#else
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    u = (u + 0x1000u) & 0xFFFFE000u;
+    float r;
+    memcpy(&r, &u, 4);
+    return r;
+#endif
+}
+
+template <int EPI>
+__device__ __forceinline__ float4 tc_epi(float4 acc, int m, int n, int N, const EpiArgs& ea) {
+    return apply_epi<EPI>(acc, m, n, N, ea);
+}
+
+// ---- the kernel -------------------------------------------------------------------------
+template <int kPasses, int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    k_pw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmOut, const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // smem map: [staging 16 x 2 x 4 KB][resident B][stages][barriers]
+    const uint32_t stg_base = base;
+    const uint32_t bres = base + p.off_bres;
+    const uint32_t stages0 = base + p.off_stages;
+    const uint32_t bars = base + p.off_bars;
+    const uint32_t bar_full = bars;                          // [stages]
+    const uint32_t bar_ready = bars + 8 * TC_MAX_STAGES;     // [stages] splitters -> MMA
+    const uint32_t bar_empty = bars + 16 * TC_MAX_STAGES;    // [stages]
+    const uint32_t bar_tfull = bars + 24 * TC_MAX_STAGES;    // [2]
+    const uint32_t bar_tempty = bar_tfull + 16;              // [2]
+    const uint32_t bar_bres = bar_tempty + 16;               // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + p.off_bars + 24 * TC_MAX_STAGES + 48);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmOut) : "memory");
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_ready + 8 * s, 4);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar_tfull + 8 * a, 1);
+            mbar_init(bar_tempty + 8 * a, 4);
+        }
+        mbar_init(bar_bres, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int n_items = p.n_items;  // item = m_tile * nchunks + chunk
+    const int nkb = p.nkb;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            if (p.resident) {
+                const uint32_t total = (uint32_t)p.nchunks * nkb * p.b_bytes_block;
+                mbar_expect_tx(bar_bres, total);
+                for (uint32_t off = 0; off < total; off += 32768u) {
+                    const uint32_t n = total - off < 32768u ? total - off : 32768u;
+                    bulk_load(bres + off, reinterpret_cast<const uint8_t*>(p.bimg) + off, n, bar_bres);
+                }
+            }
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int mt = item / p.nchunks, ch = item - mt * p.nchunks;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    const uint32_t sa = stages0 + stage * p.stage_bytes;
+                    const uint32_t tx = TC_A_BYTES + (p.resident ? 0u : p.b_bytes_block);
+                    mbar_expect_tx(bar_full + 8 * stage, tx);
+                    tma_load_2d(sa, &tmA, kb * TC_BK, mt * TC_BM, bar_full + 8 * stage);
+                    if (!p.resident)
+                        bulk_load(sa + p.a_bytes_stage,
+                                  reinterpret_cast<const uint8_t*>(p.bimg) + (size_t)(ch * nkb + kb) * p.b_bytes_block,
+                                  p.b_bytes_block, bar_full + 8 * stage);
+                    if (++stage == p.stages) stage = 0, phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(p.NC);
+            const uint32_t lo_off = (uint32_t)p.NC * 128u;  // B lo block follows B hi
+            if (p.resident) mbar_wait(bar_bres, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t it = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const int mt = item / p.nchunks, ch = item - mt * p.nchunks;
+                (void)mt;
+                const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
+                mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * 256u;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait((kPasses == 3 ? bar_ready : bar_full) + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t sa = stages0 + stage * p.stage_bytes;
+                    const uint32_t sb = p.resident ? bres + (uint32_t)(ch * nkb + kb) * p.b_bytes_block : sa + p.a_bytes_stage;
+                    const int krem = p.K - kb * TC_BK;
+                    const int nks = krem >= TC_BK ? TC_BK / 8 : (krem + 7) / 8;
+                    const uint64_t a_hi = umma_desc(sa), b_hi = umma_desc(sb);
+                    for (int k = 0; k < nks; ++k) {
+                        const uint64_t ko = (uint64_t)(k * 2);  // +32 bytes along K, in 16-byte units
+                        uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+                        if (kPasses == 3) {
+                            const uint64_t a_lo = umma_desc(sa + TC_A_BYTES), b_lo = umma_desc(sb + lo_off);
+                            umma_tf32(d_tmem, a_lo + ko, b_hi + ko, idesc, acc);
+                            umma_tf32(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+                            acc = 1u;
+                        }
+                        umma_tf32(d_tmem, a_hi + ko, b_hi + ko, idesc, acc);
+                    }
+                    umma_commit(bar_empty + 8 * stage);  // frees the smem slot when these MMAs retire
+                    if (kb == nkb - 1) umma_commit(bar_tfull + 8 * as);
+                    if (++stage == p.stages) stage = 0, phase ^= 1;
+                }
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ================= A splitters (3-pass only) =================
+        if (kPasses == 3) {
+            const int t = threadIdx.x - 128;  // 0..127
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    float4* a = reinterpret_cast<float4*>(base_ptr + p.off_stages + stage * p.stage_bytes);
+                    float4* l = a + TC_A_BYTES / 16;
+#pragma unroll
+                    for (int i = 0; i < TC_A_BYTES / 16 / 128; ++i) {
+                        const float4 v = a[t + i * 128];
+                        const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+                        a[t + i * 128] = h;
+                        l[t + i * 128] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                    }
+                    fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_ready + 8 * stage);
+                    if (++stage == p.stages) stage = 0, phase ^= 1;
+                }
+            }
+        }
+    } else if (warp >= 8) {
+        // ================= epilogue: group g serves accumulator stage g =================
+        const int g = (warp - 8) >> 2;
+        const int q = warp & 3;  // TMEM lane quarter this warp may read
+        const uint32_t stg = stg_base + (uint32_t)(warp - 8) * (TC_STG_BUFS * TC_STG_BYTES);
+        uint8_t* stg_ptr = base_ptr + (size_t)(warp - 8) * (TC_STG_BUFS * TC_STG_BYTES);
+        int buf = 0;
+        uint32_t it = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            if ((int)(it & 1u) != g) continue;
+            const int mt = item / p.nchunks, ch = item - mt * p.nchunks;
+            const uint32_t aphase = (it >> 1) & 1u;
+            mbar_wait(bar_tfull + 8 * g, aphase);
+            tc_fence_after();
+            const int row = mt * TC_BM + q * 32 + lane;
+            const int ncb = p.NC >> 5;
+            for (int cb = 0; cb < ncb; ++cb) {
+                const int col0 = ch * p.NC + cb * 32;
+                if (col0 >= p.N) break;  // padded columns of the last chunk
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 256 + cb * 32), v);
+                if (cb == ncb - 1 || col0 + 32 >= p.N) {
+                    // every TMEM read of this accumulator is done: hand it back to the MMA warp early
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tempty + 8 * g);
+                }
+                if (lane == 0) bulk_wait_read<TC_STG_BUFS - 1>();  // the staging buffer we are about to overwrite
+                __syncwarp();
+                uint8_t* sp = stg_ptr + buf * TC_STG_BYTES + lane * 128;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    const int n = col0 + 4 * j;
+                    if (EPI != EPI_LINEAR && EPI != EPI_SWISH) {
+                        if (row < p.M && n < p.N) o = tc_epi<EPI>(o, row, n, p.N, p.ea);
+                    } else {
+                        o = tc_epi<EPI>(o, row, n, p.N, p.ea);
+                    }
+                    *reinterpret_cast<float4*>(sp + ((j ^ (lane & 7)) << 4)) = o;  // SWIZZLE_128B
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&tmOut, stg + buf * TC_STG_BYTES, col0, mt * TC_BM + q * 32);  // clips rows >= M, cols >= N
+                    bulk_commit();
+                }
+                buf ^= 1;
+            }
+        }
+        if (lane == 0) bulk_wait_all();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---- host side --------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline int pw_tc_init(PwTcState& st, int device) {
+    cudaDriverEntryPointQueryResult qr;
+    void* fn = nullptr;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr);
+    if (e != cudaSuccess || fn == nullptr) return fail(CF_ECUDA, "cuTensorMapEncodeTiled entry point unavailable: %s", cudaGetErrorString(e));
+    st.encode = fn;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) st.sms = prop.multiProcessorCount;
+    return CF_OK;
+}
+
+inline void pw_tc_destroy(PwTcState& st) {
+    for (auto& kv : st.layers)
+        if (kv.second.img) cudaFree(kv.second.img);
+    st.layers.clear();
+}
+
+// fp32 [rows][cols] row-major tensor, box [box_rows][32 floats], SWIZZLE_128B, zero OOB fill
+inline int tc_make_map(PwTcState& st, CUtensorMap* map, const float* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * 4};
+    cuuint32_t box[2] = {32, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = ((PFN_encodeTiled)st.encode)(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box,
+                                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(CF_ECUDA, "cuTensorMapEncodeTiled(rows=%llu, cols=%llu) failed with CUresult %d",
+                                       (unsigned long long)rows, (unsigned long long)cols, (int)r);
+    return CF_OK;
+}
+
+// column-chunk width: a multiple of 32 (epilogue blocks), <= 256 (one TMEM accumulator stage)
+inline void tc_choose_chunks(int N, int* NC, int* nchunks) {
+    const int n32 = (N + 31) / 32;            // 32-column blocks
+    int best_nc = 0, best_pad = 1 << 30, best_chunks = 0;
+    for (int blocks = 1; blocks <= 8; ++blocks) {  // candidate NC = 32*blocks
+        const int chunks = (n32 + blocks - 1) / blocks;
+        const int pad = chunks * blocks - n32;
+        // prefer no padding, then fewer chunks (less re-reading of A); cap the streamed stage at NC<=192
+        if (blocks > 6) continue;
+        if (pad < best_pad || (pad == best_pad && chunks < best_chunks)) best_pad = pad, best_nc = blocks * 32, best_chunks = chunks;
+    }
+    *NC = best_nc;
+    *nchunks = best_chunks;
+}
+
+// Build (once per weight matrix) the tf32 hi/lo, K-major, 128B-swizzled image of W[K][N] (host copy `hw`).
+inline int tc_prepare_layer(PwTcState& st, const float* key, const float* hw, int K, int N) {
+    if (st.layers.count(key)) return CF_OK;
+    TcLayer L;
+    L.K = K;
+    L.N = N;
+    tc_choose_chunks(N, &L.NC, &L.nchunks);
+    L.nkb = (K + TC_BK - 1) / TC_BK;
+    const size_t blk = (size_t)L.NC * 128;  // bytes of one hi (or lo) block
+    L.img_bytes = (size_t)L.nchunks * L.nkb * blk * 2;
+    std::vector<float> img(L.img_bytes / 4, 0.f);
+    for (int ch = 0; ch < L.nchunks; ++ch)
+        for (int kb = 0; kb < L.nkb; ++kb) {
+            float* hi = img.data() + ((size_t)(ch * L.nkb + kb) * 2) * (blk / 4);
+            float* lo = hi + blk / 4;
+            for (int r = 0; r < L.NC; ++r) {
+                const int n = ch * L.NC + r;
+                if (n >= N) continue;
+                for (int kk = 0; kk < TC_BK; ++kk) {
+                    const int k = kb * TC_BK + kk;
+                    if (k >= K) continue;
+                    const float w = hw[(size_t)k * N + n];
+                    const float h = tf32_hi(w);
+                    const int pos = r * 32 + (((kk >> 2) ^ (r & 7)) << 2) + (kk & 3);  // SWIZZLE_128B
+                    hi[pos] = h;
+                    lo[pos] = tf32_hi(w - h);
+                }
+            }
+        }
+    if (cudaMalloc((void**)&L.img, L.img_bytes) != cudaSuccess) return fail(CF_ECUDA, "tc_prepare_layer: cudaMalloc failed");
+    if (cudaMemcpy(L.img, img.data(), L.img_bytes, cudaMemcpyHostToDevice) != cudaSuccess)
+        return fail(CF_ECUDA, "tc_prepare_layer: cudaMemcpy failed");
+    st.layers[key] = L;
+    return CF_OK;
+}
+
+struct TcLaunch {  // everything a launch needs, resolved at plan-build time
+    CUtensorMap tmA, tmOut;
+    TcParams p;
+    int grid = 0;
+    size_t smem = 0;
+    int passes = 3, epi = 0;
+};
+
+inline int tc_plan(PwTcState& st, int passes, int epi, const float* A, const float* Wkn, float* out, int M, int K, int N, EpiArgs ea,
+                   TcLaunch* tl) {
+    auto it = st.layers.find(Wkn);
+    if (it == st.layers.end()) return fail(CF_EINVAL, "tc_plan: weight matrix was not prepared");
+    const TcLayer& L = it->second;
+    int rc;
+    if ((rc = tc_make_map(st, &tl->tmA, A, (uint64_t)M, (uint64_t)K, TC_BM))) return rc;
+    if ((rc = tc_make_map(st, &tl->tmOut, out, (uint64_t)M, (uint64_t)N, 32))) return rc;
+    TcParams& p = tl->p;
+    p.bimg = L.img;
+    p.M = M;
+    p.K = K;
+    p.N = N;
+    p.NC = L.NC;
+    p.nchunks = L.nchunks;
+    p.nkb = L.nkb;
+    p.n_items = ((M + TC_BM - 1) / TC_BM) * L.nchunks;
+    p.ea = ea;
+    const uint32_t hl = passes == 3 ? 2u : 1u;
+    // NOTE: the image always stores hi|lo pairs; one-pass mode addresses only the hi halves, so its
+    // "block" stride is still the pair.
+    p.b_bytes_block = (uint32_t)L.NC * 128u * 2u;
+    p.a_bytes_stage = TC_A_BYTES * hl;
+    const uint32_t stg_bytes = 8u * TC_STG_BUFS * TC_STG_BYTES;  // 8 epilogue warps
+    const uint32_t bar_bytes = 1024;
+    const uint32_t avail = TC_SMEM_MAX - 1024 /*alignment slack*/ - stg_bytes - bar_bytes;
+    const uint32_t b_total = (uint32_t)L.img_bytes;
+    p.resident = (b_total <= 65536u && avail - b_total >= 3u * p.a_bytes_stage) ? 1 : 0;
+    p.stage_bytes = p.a_bytes_stage + (p.resident ? 0u : p.b_bytes_block);
+    const uint32_t room = avail - (p.resident ? b_total : 0u);
+    int stages = (int)(room / p.stage_bytes);
+    if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+    if (stages < 2) return fail(CF_EINVAL, "tc_plan: K=%d N=%d does not fit the shared-memory pipeline", K, N);
+    p.stages = stages;
+    p.off_bres = stg_bytes;
+    p.off_stages = stg_bytes + (p.resident ? b_total : 0u);
+    p.off_bars = p.off_stages + (uint32_t)stages * p.stage_bytes;
+    tl->smem = (size_t)p.off_bars + bar_bytes + 1024;
+    tl->grid = p.n_items < st.sms ? p.n_items : st.sms;
+    tl->passes = passes;
+    tl->epi = epi;
+    return CF_OK;
+}
+
+template <int kPasses, int EPI>
+inline cudaError_t tc_launch_t(const TcLaunch& tl, cudaStream_t s) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(k_pw_tc<kPasses, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    k_pw_tc<kPasses, EPI><<<tl.grid, TC_THREADS, tl.smem, s>>>(tl.tmA, tl.tmOut, tl.p);
+    return cudaGetLastError();
+}
+
+inline cudaError_t tc_launch(const TcLaunch& tl, cudaStream_t s) {
+#define CF_TC_CASE(P, E) \
+    if (tl.passes == P && tl.epi == E) return tc_launch_t<P, E>(tl, s);
+    CF_TC_CASE(3, EPI_LINEAR) CF_TC_CASE(3, EPI_SWISH) CF_TC_CASE(3, EPI_RESIDUAL) CF_TC_CASE(3, EPI_BIAS_SWISH) CF_TC_CASE(3, EPI_IDAUP)
+    CF_TC_CASE(1, EPI_LINEAR) CF_TC_CASE(1, EPI_SWISH) CF_TC_CASE(1, EPI_RESIDUAL) CF_TC_CASE(1, EPI_BIAS_SWISH) CF_TC_CASE(1, EPI_IDAUP)
+#undef CF_TC_CASE
+    return cudaErrorInvalidValue;
+}
+
 }  // namespace cf

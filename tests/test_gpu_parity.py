@@ -13,12 +13,24 @@ from conftest import IMGS
 pytestmark = pytest.mark.gpu
 
 HM_SIG_TOL = 1e-3      # contract
-HM_LOGIT_TOL_FP32 = 2e-4   # what the fp32 engine is held to (oracle noise floor is ~3e-6..1e-5)
+# what each engine is additionally held to on the raw head maps (oracle noise floor: hm 3e-6..1e-5,
+# wh 6e-5).  The tensor-core accumulator truncates (round-toward-zero) once per MMA, measured at
+# -2^-24 per accumulation step (tools/tc_accum_probe.py), which is why 3xTF32 sits above fp32 FFMA.
+HEAD_TOL = {"simt_fp32": {"hm": 5e-5, "wh": 5e-4, "lm": 2e-4, "reg": 2e-5},
+            "tcgen05_3xtf32": {"hm": 5e-4, "wh": 8e-3, "lm": 3e-3, "reg": 1e-4}}
+TAP_TOL = {"simt_fp32": 5e-6, "tcgen05_3xtf32": 1e-4}
 
 
-@pytest.fixture(scope="module")
-def eng(pkg, weights_path):
-    e = pkg.Engine(weights_path, max_batch=8, max_h=640, max_w=640, device=0, pw_engine=pkg.CF_PW_SIMT)
+# Both product engines must meet the contract: the fp32 FFMA validation engine and the tcgen05
+# 3xTF32 engine (hi/lo operand split, fp32-class).  The single-pass TF32 throughput mode is
+# measured and reported by test_single_pass_tf32_report, not gated.
+ENGINES = {"simt_fp32": 0, "tcgen05_3xtf32": 1}
+
+
+@pytest.fixture(scope="module", params=list(ENGINES))
+def eng(request, pkg, weights_path):
+    e = pkg.Engine(weights_path, max_batch=8, max_h=640, max_w=640, device=0, pw_engine=ENGINES[request.param])
+    e.kind = request.param
     yield e
     e.close()
 
@@ -129,10 +141,10 @@ def test_forward_heads_vs_oracle(eng, oracle, sd, f5_640, oracle_heads_640):
             worst[k] = max(worst.get(k, 0.0), (h[k][i] - o[k][0]).abs().max().item())
         sig_err = (h["hm_sig"][i] - oracle.sigmoid_clamp(o["hm"])[0]).abs().max().item()
         worst["hm_sig"] = max(worst.get("hm_sig", 0.0), sig_err)
-    print("max |engine - oracle| per head:", worst)
+    print(eng.kind, "max |engine - oracle| per head:", worst)
     assert worst["hm_sig"] <= HM_SIG_TOL
-    assert worst["hm"] <= HM_LOGIT_TOL_FP32
-    assert worst["wh"] <= 2e-3 and worst["lm"] <= 2e-3 and worst["reg"] <= 2e-4
+    for k, tol in HEAD_TOL[eng.kind].items():
+        assert worst[k] <= tol, (k, worst[k], tol)
 
 
 def test_taps_vs_oracle(eng, oracle, sd, f5_640):
@@ -146,8 +158,8 @@ def test_taps_vs_oracle(eng, oracle, sd, f5_640):
         ref = taps[name]
         assert got.shape == ref.shape, name
         rel = (got - ref).abs().max().item() / max(ref.abs().max().item(), 1e-30)
-        print(name, "rel err", rel)
-        assert rel < 5e-5, (name, rel)
+        print(eng.kind, name, "rel err", rel)
+        assert rel < TAP_TOL[eng.kind], (name, rel)
 
 
 def test_end_to_end_topk_and_boxes(eng, oracle, f5_640, golden):
@@ -162,6 +174,7 @@ def test_end_to_end_topk_and_boxes(eng, oracle, f5_640, golden):
         real = gd[:, 4] > 2e-4  # rows above the clamp floor; below it the order is among ties at 1e-4
         assert np.array_equal(inds[i][real], gi[real]), n
         iou = oracle.box_iou(dets[i][real, :4], gd[real, :4])
+        print(eng.kind, n, "min IoU", iou.min(), "max score err", np.abs(dets[i][real, 4] - gd[real, 4]).max())
         assert iou.min() >= 0.999, (n, iou.min())
         assert np.abs(dets[i][real, 4] - gd[real, 4]).max() <= 1e-3
 
@@ -206,7 +219,7 @@ def test_small_and_non_square_inputs(eng, oracle, sd, images):
         h = eng.heads()
         for k in ("hm", "wh", "lm", "reg"):
             err = (h[k].cpu() - o[k]).abs().max().item()
-            assert err < (2e-4 if k in ("hm", "reg") else 2e-3), ((hh, ww), k, err)
+            assert err < 4 * HEAD_TOL[eng.kind][k], ((hh, ww), k, err)
 
 
 def test_centerface_call_native_sizes(pkg, oracle, sd, images, golden, weights_path):
@@ -274,3 +287,26 @@ def test_errors_are_loud(pkg, eng):
         eng.forward(torch.zeros(1, 3, 100, 64, device="cuda"))      # not a multiple of 32
     with pytest.raises(pkg.CenterFaceError):
         pkg.ctdet_decode(torch.zeros(1, 1, 4, 4, device="cuda"), torch.zeros(1, 2, 4, 4, device="cuda"), K=17)
+
+
+def test_single_pass_tf32_report(pkg, oracle, weights_path, f5_640, golden, oracle_heads_640):
+    """Throughput mode (one TF32 pass, 11-bit operands): NOT parity-gated beyond the heat-map bound;
+    prints how far it is from the contract so the number in bench.py can be read honestly."""
+    e = pkg.Engine(weights_path, max_batch=8, pw_engine=pkg.CF_PW_TCGEN05_1P)
+    e.forward(_x640(oracle, f5_640, IMGS))
+    h = {k: v.cpu() for k, v in e.heads().items()}
+    dets, inds = e.decode_topk(100)
+    dets, inds = dets.cpu().numpy(), inds.cpu().numpy()
+    sig_err, match, ious = 0.0, [], []
+    for i, n in enumerate(IMGS):
+        sig_err = max(sig_err, (h["hm_sig"][i] - oracle.sigmoid_clamp(oracle_heads_640[n]["hm"])[0]).abs().max().item())
+        gd, gi = golden[f"f5_640/{n}/pathC_dets"], golden[f"f5_640/{n}/pathC_inds"]
+        real = gd[:, 4] > 0.3
+        match.append((inds[i][real] == gi[real]).mean() if real.any() else 1.0)
+        same = real & (inds[i] == gi)
+        if same.any():
+            ious.append(oracle.box_iou(dets[i][same, :4], gd[same, :4]).min())
+    print(f"1xTF32: hm_sig max err {sig_err:.2e}; ordered top-k index match (score>0.3) {np.mean(match):.3f}; "
+          f"min IoU on matched boxes {min(ious):.4f}")
+    assert sig_err < 5e-3
+    e.close()
