@@ -182,7 +182,7 @@ def run_b200(a):
     if world > 1:
         dist.barrier()
     B = a.batch
-    pw = a.pw if a.pw >= 0 else L.CF_PW_SIMT
+    pw = a.pw if a.pw >= 0 else L.CF_PW_TCGEN05
     eng = pkg.Engine(WEIGHTS, max_batch=B, max_h=H, max_w=W, device=local, pw_engine=pw)
     dev = torch.device(f"cuda:{local}")
 

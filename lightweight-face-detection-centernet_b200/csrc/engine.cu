@@ -106,6 +106,7 @@ struct cf_engine {
     std::vector<Step> plan;
     long long launches = 0;
     PwTcState tc;  // tensor maps etc. of the tcgen05 engine
+    StemW stem_w;  // host copy: the stem weights are passed to the kernel by value
 };
 
 namespace {
@@ -168,7 +169,10 @@ cudaError_t launch_dw_t(const float* in, const float* w, float* out, int B, int 
                         cudaStream_t s) {
     constexpr int XT = 4;
     const int tiles_x = cdiv(Wo, 4 * XT), tiles_y = cdiv(Ho, 8);
-    k_dw<KS, S, XT><<<B * tiles_x * tiles_y, 256, 0, s>>>(in, w, out, B, Hi, Wi, C, Ho, Wo, tiles_x, tiles_y);
+    const int ctas = B * tiles_x * tiles_y;
+    int csplit = 1;  // aim for >= 8 CTAs per SM; keep >= 8 channel groups (32 channels) per CTA
+    while (ctas * csplit < 148 * 8 && (C / 4) / (csplit * 2) >= 8) csplit *= 2;
+    k_dw<KS, S, XT><<<ctas * csplit, 256, 0, s>>>(in, w, out, B, Hi, Wi, C, Ho, Wo, tiles_x, tiles_y, csplit);
     return cudaGetLastError();
 }
 
@@ -189,19 +193,19 @@ int build_plan(cf_engine* e, const void* input, int fmt, int B, int H, int W) {
     const int H2 = H / 2, W2 = W / 2;
     // first_conv, :224
     {
-        const float* w = e->w["stem.w"];
+        const StemW w = e->stem_w;
         const float* lut = e->w["lut"];
         float* out = e->stem;
-        const long long thr = (long long)B * H2 * W2 * 4;
-        const unsigned grid = (unsigned)((thr + 255) / 256);
+        const long long thr = (long long)B * H2 * W2;
+        const unsigned grid = (unsigned)((thr + 127) / 128);
         if (fmt == CF_IN_U8_HWC)
             P.push_back({CLS_STEM, [=](cudaStream_t s) {
-                             k_stem<1><<<grid, 256, 0, s>>>(input, w, lut, out, B, H, W);
+                             k_stem<1><<<grid, 128, 0, s>>>(input, w, lut, out, B, H, W);
                              return cudaGetLastError();
                          }});
         else
             P.push_back({CLS_STEM, [=](cudaStream_t s) {
-                             k_stem<0><<<grid, 256, 0, s>>>(input, w, lut, out, B, H, W);
+                             k_stem<0><<<grid, 128, 0, s>>>(input, w, lut, out, B, H, W);
                              return cudaGetLastError();
                          }});
     }
@@ -375,6 +379,7 @@ int cf_create(const void* weights, size_t weights_bytes, int device, int max_bat
             const uint64_t off = (uint64_t)(hp - blob.payload);
             if (off % kEntryAlignFloats != 0) return bail(fail(CF_EWEIGHTS, "cf_create: entry %s is not 128-byte aligned", en.name.c_str()));
             e->w[en.name] = e->d_w + off;
+            if (en.name == "stem.w") memcpy(e->stem_w.w, hp, sizeof(e->stem_w.w));
         }
     }
 
@@ -436,7 +441,7 @@ int cf_create(const void* weights, size_t weights_bytes, int device, int max_bat
         // tf32 hi/lo, K-major, 128B-swizzled images of every point-wise weight matrix
         auto prep = [&](const std::string& name, int K, int N) {
             const float* hp = blob.get(name, (uint64_t)K * N, why);
-            return hp ? tc_prepare_layer(e->tc, e->w[name], hp, K, N) : fail(CF_EWEIGHTS, "cf_create: %s", why.c_str());
+            return hp ? tc_prepare_layer(e->tc, e->w[name], hp, K, N, pw_engine == CF_PW_TCGEN05 ? 3 : 1) : fail(CF_EWEIGHTS, "cf_create: %s", why.c_str());
         };
         for (int i = 0; i < 12 && !rc; ++i) {
             const MBBlock& b = kBlocks[i];
@@ -637,7 +642,7 @@ int cf_debug_pw_gemm(int pw_engine, int epi, const float* dA, const float* hW, f
         int dev = 0;
         cudaGetDevice(&dev);
         rc = pw_tc_init(st, dev);
-        if (!rc) rc = tc_prepare_layer(st, dW, hW, K, N);
+        if (!rc) rc = tc_prepare_layer(st, dW, hW, K, N, pw_engine == CF_PW_TCGEN05 ? 3 : 1);
         TcLaunch tl;
         if (!rc) rc = tc_plan(st, pw_engine == CF_PW_TCGEN05 ? 3 : 1, epi, dA, dW, dOut, M, K, N, ea, &tl);
         if (!rc) {

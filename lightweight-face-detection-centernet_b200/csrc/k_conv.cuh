@@ -12,30 +12,33 @@ namespace cf {
 //   FMT 0: fp32 NCHW normalised input (what EfficientNet.forward receives)
 //   FMT 1: u8 HWC BGR input; /255, -mean, /std (centerface.py:32-34) applied through a
 //          768-entry table built on the host with the reference's own fp32 ops (bit-exact).
-// One thread = one output pixel x 8 output channels {4g..4g+3, 16+4g..16+4g+3}, so each
-// quad of threads writes two full 64-byte runs of the 128-byte NHWC pixel.
+// One thread = one output pixel x all 32 output channels.  The 864 weights travel as a by-value
+// kernel parameter, i.e. in the constant bank, so every FFMA takes its weight as a c[][] operand:
+// no shared-memory or register traffic for weights, the kernel is FFMA-issue bound (864 per pixel).
 // ----------------------------------------------------------------------------------------
+struct StemW {
+    float w[27 * 32];  // [(ky*3+kx)*3+ci][co]; passed by value => lives in the constant bank
+};
+
 template <int FMT>
-__global__ void __launch_bounds__(256) k_stem(const void* __restrict__ in, const float* __restrict__ w,
+__global__ void __launch_bounds__(128) k_stem(const void* __restrict__ in, const __grid_constant__ StemW sw,
                                               const float* __restrict__ lut, float* __restrict__ out,
                                               int B, int H, int W) {
-    __shared__ __align__(16) float w_s[27 * 32];
     __shared__ float lut_s[FMT == 1 ? 768 : 1];
-    for (int i = threadIdx.x; i < 27 * 32; i += 256) w_s[i] = w[i];
-    if (FMT == 1)
-        for (int i = threadIdx.x; i < 768; i += 256) lut_s[i] = lut[i];
-    __syncthreads();
-
+    if (FMT == 1) {
+        for (int i = threadIdx.x; i < 768; i += 128) lut_s[i] = lut[i];
+        __syncthreads();
+    }
     const int Ho = H >> 1, Wo = W >> 1;
-    const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
-    const int g = (int)(gid & 3);
-    const long long pix = gid >> 2;
+    const long long pix = (long long)blockIdx.x * 128 + threadIdx.x;
     if (pix >= (long long)B * Ho * Wo) return;
     const int xo = (int)(pix % Wo);
     const int yo = (int)((pix / Wo) % Ho);
     const int b = (int)(pix / ((long long)Wo * Ho));
 
-    float4 a0 = make_float4(0, 0, 0, 0), a1 = a0;
+    float acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
         const int iy = 2 * yo + ky;
@@ -43,12 +46,12 @@ __global__ void __launch_bounds__(256) k_stem(const void* __restrict__ in, const
         for (int kx = 0; kx < 3; ++kx) {
             const int ix = 2 * xo + kx;
             float v[3] = {0.f, 0.f, 0.f};
-            if (iy < H && ix < W) {
+            if (iy < H && ix < W) {  // ZeroPad2d(0,1,0,1): only the bottom/right edge is padded
                 if (FMT == 1) {
                     const uint8_t* p = (const uint8_t*)in + ((size_t)(b * H + iy) * W + ix) * 3;
-                    v[0] = lut_s[p[0]];
-                    v[1] = lut_s[256 + p[1]];
-                    v[2] = lut_s[512 + p[2]];
+                    v[0] = lut_s[__ldg(p)];
+                    v[1] = lut_s[256 + __ldg(p + 1)];
+                    v[2] = lut_s[512 + __ldg(p + 2)];
                 } else {
                     const float* p = (const float*)in + ((size_t)(b * 3) * H + iy) * W + ix;
                     v[0] = __ldg(p);
@@ -57,16 +60,15 @@ __global__ void __launch_bounds__(256) k_stem(const void* __restrict__ in, const
                 }
             }
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float* wr = w_s + ((ky * 3 + kx) * 3 + c) * 32 + 4 * g;
-                fma4(a0, v[c], *reinterpret_cast<const float4*>(wr));
-                fma4(a1, v[c], *reinterpret_cast<const float4*>(wr + 16));
-            }
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int co = 0; co < 32; ++co) acc[co] = fmaf(v[c], sw.w[((ky * 3 + kx) * 3 + c) * 32 + co], acc[co]);
         }
     }
-    float* o = out + (size_t)pix * 32 + 4 * g;
-    st4(o, swish4(a0));
-    st4(o + 16, swish4(a1));
+    float* o = out + (size_t)pix * 32;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+        st4(o + 4 * q, swish4(make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3])));
 }
 
 // ----------------------------------------------------------------------------------------
@@ -80,22 +82,28 @@ __global__ void __launch_bounds__(256) k_stem(const void* __restrict__ in, const
 template <int KS, int S, int XT>
 __global__ void __launch_bounds__(256) k_dw(const float* __restrict__ in, const float* __restrict__ w,
                                             float* __restrict__ out, int B, int Hi, int Wi, int C,
-                                            int Ho, int Wo, int tiles_x, int tiles_y) {
+                                            int Ho, int Wo, int tiles_x, int tiles_y, int csplit) {
     constexpr int LO = (KS - S) / 2;
     constexpr int WIN = (XT - 1) * S + KS;  // input columns feeding XT outputs
     constexpr int TXS = 4;                  // strips per tile row  -> tile width  = 4*XT
     constexpr int TY = 8;                   // tile height
     const int C4 = C >> 2;
     int bid = blockIdx.x;
+    // channel groups [cg0, cg1) of this CTA: small maps (20x20 .. 40x40 with 384-960 channels) have too
+    // few spatial tiles to fill 148 SMs, so the channel axis is split across CTAs as well
+    const int cs = bid % csplit;
+    bid /= csplit;
+    const int cg0 = (int)(((long long)C4 * cs) / csplit), cg1 = (int)(((long long)C4 * (cs + 1)) / csplit);
+    const int CG = cg1 - cg0;
     const int tx0 = (bid % tiles_x) * (TXS * XT);
     bid /= tiles_x;
     const int ty0 = (bid % tiles_y) * TY;
     const int b = bid / tiles_y;
 
-    const int items = TXS * TY * C4;
+    const int items = TXS * TY * CG;
     for (int it = threadIdx.x; it < items; it += 256) {
-        const int c4 = it % C4;
-        const int p = it / C4;
+        const int c4 = cg0 + it % CG;
+        const int p = it / CG;
         const int xo0 = tx0 + (p % TXS) * XT;
         const int yo = ty0 + p / TXS;
         if (yo >= Ho || xo0 >= Wo) continue;

@@ -7,8 +7,8 @@
 //
 // Precision.  The reference is fp32 and its back-bone has no normalisation, so an 11-bit operand
 // (one TF32 pass) breaks top-k parity.  kPasses == 3 therefore splits both operands
-// into tf32 hi + tf32 lo parts and issues  A_lo.B_hi + A_hi.B_lo + A_hi.B_hi  into the same
-// accumulator (error ~2^-21 per product, fp32 class).  W is split on the host; A is split in
+// into tf32 hi + tf32 lo parts and issues  A_lo.B_hi + A_hi.B_lo  into a correction accumulator and
+// A_hi.B_hi into the main one (error ~2^-21 per product, fp32 class; see the MMA warp for why two).  W is split on the host; A is split in
 // shared memory by four "splitter" warps between the TMA and the MMA stage (element-wise, so the
 // swizzled layout is irrelevant to them).  kPasses == 1 is the throughput mode.
 //
@@ -70,10 +70,16 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// Bounded spin: a protocol bug traps (surfacing as a CUDA error) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps after ~4 s (surfacing as a CUDA error) instead of hanging the GPU.
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
-    for (uint32_t it = 0; it < (1u << 26); ++it) {
+    uint64_t t0 = 0;
+    for (uint32_t it = 0;; ++it) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -82,8 +88,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "r"(bar), "r"(parity)
             : "memory");
         if (done) return;
+        if ((it & 1023u) == 1023u) {
+            const uint64_t t = globaltimer_ns();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 4000000000ull) __trap();
+        }
     }
-    __trap();
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -149,8 +159,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // round-to-nearest split of an fp32 into tf32 hi (low 13 mantissa bits zero) + exact remainder
 __host__ __device__ inline float tf32_hi(float x) {
@@ -265,7 +275,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
                 mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
                 tc_fence_after();
+                // 3-pass: the two small cross terms go to their own accumulator (columns +128).  The
+                // tensor core truncates its fp32 accumulator once per MMA (measured -2^-24 per step,
+                // tools/tc_accum_probe.py); keeping the 2K/8 correction steps out of the main sum
+                // leaves it K/8 truncations instead of 3K/8, and the corrections' own truncation
+                // is 2^-11 smaller.  The epilogue adds the two in fp32 (round-to-nearest).
                 const uint32_t d_tmem = tmem_base + as * 256u;
+                const uint32_t d_corr = d_tmem + 128u;
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait((kPasses == 3 ? bar_ready : bar_full) + 8 * stage, phase);
                     tc_fence_after();
@@ -276,12 +292,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     const uint64_t a_hi = umma_desc(sa), b_hi = umma_desc(sb);
                     for (int k = 0; k < nks; ++k) {
                         const uint64_t ko = (uint64_t)(k * 2);  // +32 bytes along K, in 16-byte units
-                        uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+                        const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
                         if (kPasses == 3) {
                             const uint64_t a_lo = umma_desc(sa + TC_A_BYTES), b_lo = umma_desc(sb + lo_off);
-                            umma_tf32(d_tmem, a_lo + ko, b_hi + ko, idesc, acc);
-                            umma_tf32(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
-                            acc = 1u;
+                            umma_tf32(d_corr, a_lo + ko, b_hi + ko, idesc, acc);
+                            umma_tf32(d_corr, a_hi + ko, b_lo + ko, idesc, 1u);
                         }
                         umma_tf32(d_tmem, a_hi + ko, b_hi + ko, idesc, acc);
                     }
@@ -336,7 +351,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 const int col0 = ch * p.NC + cb * 32;
                 if (col0 >= p.N) break;  // padded columns of the last chunk
                 float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 256 + cb * 32), v);
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 256 + cb * 32);
+                tmem_ld32(taddr, v);
+                if (kPasses == 3) {
+                    float c[32];
+                    tmem_ld32(taddr + 128u, c);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] += c[j];
+                } else {
+                    tmem_ld_wait();
+                }
                 if (cb == ncb - 1 || col0 + 32 >= p.N) {
                     // every TMEM read of this accumulator is done: hand it back to the MMA warp early
                     tc_fence_before();
@@ -413,28 +438,27 @@ inline int tc_make_map(PwTcState& st, CUtensorMap* map, const float* ptr, uint64
     return CF_OK;
 }
 
-// column-chunk width: a multiple of 32 (epilogue blocks), <= 256 (one TMEM accumulator stage)
-inline void tc_choose_chunks(int N, int* NC, int* nchunks) {
-    const int n32 = (N + 31) / 32;            // 32-column blocks
-    int best_nc = 0, best_pad = 1 << 30, best_chunks = 0;
-    for (int blocks = 1; blocks <= 8; ++blocks) {  // candidate NC = 32*blocks
+// Column-chunk width NC: a multiple of 32 (epilogue blocks).  One TMEM accumulator stage is 256
+// columns; the 3-pass mode keeps two accumulators per stage (main + correction), so NC <= 128 there.
+// Cost model: MMA/epilogue column work incl. padding + re-reading the A tile once per chunk.
+inline void tc_choose_chunks(int K, int N, int passes, int* NC, int* nchunks) {
+    const int n32 = (N + 31) / 32;
+    const int max_blocks = passes == 3 ? 4 : 6;
+    double best = 1e30;
+    for (int blocks = 1; blocks <= max_blocks; ++blocks) {
         const int chunks = (n32 + blocks - 1) / blocks;
-        const int pad = chunks * blocks - n32;
-        // prefer no padding, then fewer chunks (less re-reading of A); cap the streamed stage at NC<=192
-        if (blocks > 6) continue;
-        if (pad < best_pad || (pad == best_pad && chunks < best_chunks)) best_pad = pad, best_nc = blocks * 32, best_chunks = chunks;
+        const double cost = (double)chunks * blocks + (double)chunks * K / 64.0;
+        if (cost < best - 1e-9) best = cost, *NC = blocks * 32, *nchunks = chunks;
     }
-    *NC = best_nc;
-    *nchunks = best_chunks;
 }
 
 // Build (once per weight matrix) the tf32 hi/lo, K-major, 128B-swizzled image of W[K][N] (host copy `hw`).
-inline int tc_prepare_layer(PwTcState& st, const float* key, const float* hw, int K, int N) {
+inline int tc_prepare_layer(PwTcState& st, const float* key, const float* hw, int K, int N, int passes) {
     if (st.layers.count(key)) return CF_OK;
     TcLayer L;
     L.K = K;
     L.N = N;
-    tc_choose_chunks(N, &L.NC, &L.nchunks);
+    tc_choose_chunks(K, N, passes, &L.NC, &L.nchunks);
     L.nkb = (K + TC_BK - 1) / TC_BK;
     const size_t blk = (size_t)L.NC * 128;  // bytes of one hi (or lo) block
     L.img_bytes = (size_t)L.nchunks * L.nkb * blk * 2;
