@@ -36,7 +36,7 @@ UNIT = "images/s"
 H = W = 640
 PER_GPU_BATCH = 32
 K_TOP = 100
-CLASS_NAMES = {1: "pointwise_gemm", 2: "depthwise", 3: "stem", 4: "heads", 5: "decode_topk"}
+CLASS_NAMES = {1: "pointwise_gemm", 2: "depthwise", 3: "stem", 4: "heads", 5: "decode_topk", 6: "fused_expand_dw"}
 
 
 def parse():
@@ -47,7 +47,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="images per GPU per step")
     ap.add_argument("--pw", type=int, default=int(os.environ.get("CENTERFACE_B200_PW", -1)),
-                    help="point-wise engine: 0 fp32 SIMT, 1 tcgen05 3xTF32, 2 tcgen05 1xTF32 (default: library default)")
+                    help="engine: 0 fp32 SIMT, 1 tcgen05 3xTF32, 2 tcgen05 1xTF32, 3 tcgen05 3xTF32 + fused expand/dw blocks "
+                         "(default: library default)")
     ap.add_argument("--cpu-sample", type=int, default=4, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -250,7 +251,9 @@ def run_b200(a):
     torch.cuda.synchronize()
     for cls, name in CLASS_NAMES.items():
         ms, n = eng.time_class(cls, iters=5)
-        by, fl = L.work_model(H, W, L.CF_IN_U8_HWC, cls)
+        by, fl = L.work_model(H, W, L.CF_IN_U8_HWC, cls, pw)
+        if n == 0:
+            continue
         classes[name] = {"ms_per_step": ms, "launches": n, "alg_bytes": by * B, "alg_flops": fl * B,
                          "gbs": by * B / (ms * 1e-3) / 1e9, "tflops": fl * B / (ms * 1e-3) / 1e12}
     net_ms = sum(c["ms_per_step"] for k, c in classes.items())
@@ -265,7 +268,7 @@ def run_b200(a):
                 "classes": {k: {"ms": round(v["ms_per_step"], 4), "share": round(v["share"], 4), "GBps": round(v["gbs"], 1),
                                 "frac_hbm": round(v["gbs"] / hbm, 4), "TFLOPs": round(v["tflops"], 2), "launches": v["launches"]}
                             for k, v in classes.items()}}
-    by_all, fl_all = L.work_model(H, W, L.CF_IN_U8_HWC, 0)
+    by_all, fl_all = L.work_model(H, W, L.CF_IN_U8_HWC, 0, pw)
     roofline["whole_step"] = {"alg_bytes_per_image": by_all, "alg_flops_per_image": fl_all,
                               "GBps": by_all * B / (ms_per_step * 1e-3) / 1e9,
                               "frac_hbm": by_all * B / (ms_per_step * 1e-3) / 1e9 / hbm,
@@ -278,7 +281,7 @@ def run_b200(a):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": warm,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32" if pw == 0 else ("tf32x3" if pw == 1 else "tf32"), "data": "synthetic",
+                "dtype": {0: "f32", 1: "tf32x3", 2: "tf32", 3: "tf32x3+f32"}[pw], "data": "synthetic",
                 "config": {"workload": f"batch-{B} 640x640 per GPU ({'configs[1]' if world == 1 else 'configs[2] sharding'}), "
                                        f"u8 BGR input, network + sigmoid/clamp + path-C top-{K_TOP} decode"
                                        + (", NCCL all-gather of [B,100,6] boxes" if world > 1 else ""),

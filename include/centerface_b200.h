@@ -47,6 +47,8 @@ extern "C" {
 #define CF_PW_SIMT 0      /* fp32 FFMA tiles (validation engine)                          */
 #define CF_PW_TCGEN05 1   /* tcgen05.mma kind::tf32, 3-pass split (fp32-class accuracy)   */
 #define CF_PW_TCGEN05_1P 2 /* tcgen05.mma kind::tf32 single pass (throughput mode)        */
+#define CF_PW_TCGEN05_FUSED 3 /* CF_PW_TCGEN05 + the shallow MBConv blocks (Cin<=32) run expand+Swish+
+                                 depth-wise+Swish as ONE kernel, hidden tensor kept in shared memory   */
 
 /* decode variants for cf_decode_threshold */
 #define CF_DECODE_A 0 /* centerface.py:73-109   : offsets unused, landmarks, clip to (H,W)   */
@@ -136,13 +138,13 @@ int cf_debug_pw_gemm(int pw_engine, int epi, const float* dA, const float* hW, f
 /* ---- instrumentation -----------------------------------------------------------------
  * Number of kernels this library launched on behalf of the handle since creation.        */
 long long cf_launch_count(cf_engine* e);
-/* Algorithmic bytes / flops of ONE image at (h,w) for kernel class `which`
- * (0 = network = 1+2+3+4, 1 = point-wise GEMMs, 2 = depth-wise, 3 = stem, 4 = heads,
- * 5 = path-C decode).  Bytes: every conv reads its un-padded input once and writes its output
+/* Algorithmic bytes / flops of ONE image at (h,w) for kernel class `which` under engine `pw_engine`
+ * (0 = network = 1+2+3+4+6, 1 = point-wise GEMMs, 2 = depth-wise, 3 = stem, 4 = heads,
+ * 5 = path-C decode, 6 = fused expand+depth-wise blocks).  Bytes: every conv reads its un-padded input once and writes its output
  * once in the engine's fp32 storage (+ residual / low-res re-reads); weights (5 MB per LAUNCH,
  * not per image) are not counted.  Flops: 2*MAC of the REFERENCE graph (model/centernet.py),
  * i.e. the four un-collapsed heads.  in_format selects the stem's input bytes.            */
-int cf_work_model(int h, int w, int in_format, int which, double* bytes, double* flops);
+int cf_work_model(int h, int w, int in_format, int pw_engine, int which, double* bytes, double* flops);
 /* Run only one layer class `iters` times on the current activations (for per-kernel
  * CUDA-event timing in bench.py). which as above.                                        */
 int cf_replay_class(cf_engine* e, int which, int iters, void* stream);

@@ -10,9 +10,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcenterface_b200.so")
 
 CF_IN_F32_NCHW, CF_IN_U8_HWC = 0, 1
-CF_PW_SIMT, CF_PW_TCGEN05, CF_PW_TCGEN05_1P = 0, 1, 2
+CF_PW_SIMT, CF_PW_TCGEN05, CF_PW_TCGEN05_1P, CF_PW_TCGEN05_FUSED = 0, 1, 2, 3
 CF_DECODE_A, CF_DECODE_B = 0, 1
-CLS_ALL, CLS_PW, CLS_DW, CLS_STEM, CLS_HEADS, CLS_DECODE = range(6)
+CLS_ALL, CLS_PW, CLS_DW, CLS_STEM, CLS_HEADS, CLS_DECODE, CLS_FUSED = range(7)
 MAX_CAP = 4096
 
 _f = C.POINTER(C.c_float)
@@ -38,7 +38,7 @@ SIGNATURES = {
                                            C.c_float, C.c_float, C.c_int, _vp, _vp, _vp]),
     "cf_debug_pw_gemm": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "cf_launch_count": (C.c_longlong, [_vp]),
-    "cf_work_model": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "cf_work_model": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "cf_replay_class": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "cf_time_class": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.POINTER(C.c_float), _i]),
 }
@@ -74,8 +74,8 @@ def check(rc, what=""):
         raise CenterFaceError(f"{what or 'centerface_b200'} failed ({rc}): {msg}")
 
 
-def work_model(h, w, in_format=CF_IN_U8_HWC, which=CLS_ALL):
+def work_model(h, w, in_format=CF_IN_U8_HWC, which=CLS_ALL, pw_engine=CF_PW_TCGEN05):
     """(bytes, flops) of one image -- cf_work_model."""
     b, f = C.c_double(), C.c_double()
-    check(load().cf_work_model(h, w, in_format, which, C.byref(b), C.byref(f)), "cf_work_model")
+    check(load().cf_work_model(h, w, in_format, pw_engine, which, C.byref(b), C.byref(f)), "cf_work_model")
     return b.value, f.value

@@ -18,13 +18,18 @@
 #include "k_decode.cuh"
 #include "k_pw_simt.cuh"
 #include "k_pw_tc.cuh"
+#include "k_expdw.cuh"
 #include "net.hpp"
 
 using namespace cf;
 
 namespace {
 
-enum WorkClass { CLS_ALL = 0, CLS_PW = 1, CLS_DW = 2, CLS_STEM = 3, CLS_HEADS = 4, CLS_DECODE = 5 };
+enum WorkClass { CLS_ALL = 0, CLS_PW = 1, CLS_DW = 2, CLS_STEM = 3, CLS_HEADS = 4, CLS_DECODE = 5, CLS_FUSED = 6, CLS_COUNT = 7 };
+
+inline bool engine_is_tc(int pw) { return pw != CF_PW_SIMT; }
+inline int engine_passes(int pw) { return pw == CF_PW_TCGEN05_1P ? 1 : 3; }
+inline bool block_is_fused(int pw, const MBBlock& b) { return pw == CF_PW_TCGEN05_FUSED && b.t != 1 && xd_supported(b.k, b.s, b.cin); }
 
 struct Step {
     int cls;
@@ -158,7 +163,7 @@ int make_pw_step(cf_engine* e, std::vector<Step>& P, int epi, const float* A, co
         return CF_OK;
     }
     TcLaunch tl;
-    int rc = tc_plan(e->tc, e->pw_engine == CF_PW_TCGEN05 ? 3 : 1, epi, A, Wkn, out, M, K, N, ea, &tl);
+    int rc = tc_plan(e->tc, engine_passes(e->pw_engine), epi, A, Wkn, out, M, K, N, ea, &tl);
     if (rc) return rc;
     P.push_back({CLS_PW, [tl](cudaStream_t s) { return tc_launch(tl, s); }});
     return CF_OK;
@@ -217,15 +222,21 @@ int build_plan(cf_engine* e, const void* input, int fmt, int B, int H, int W) {
         const std::string p = "b" + std::to_string(i);
         const int hid = b.hid();
         const float* dw_in = x;
-        if (b.t != 1) {
+        const int ho = h / b.s, wo = wd / b.s;
+        const bool fused = block_is_fused(e->pw_engine, b);
+        if (fused) {
+            // expand + Swish + depth-wise + Swish in one kernel; the hidden tensor stays in shared memory
+            XdLaunch xl;
+            if ((rc = xd_plan(e->tc, b.k, b.s, x, e->w[p + ".exp"], e->w[p + ".dw"], e->hidB, B, h, wd, b.cin, hid, &xl))) return rc;
+            P.push_back({CLS_FUSED, [xl](cudaStream_t s) { return xd_launch(xl, s); }});
+        } else if (b.t != 1) {
             const float* wexp = e->w[p + ".exp"];
             float* o = e->hidA;
             const int M = B * h * wd, K = b.cin;
             if ((rc = make_pw_step(e, P, EPI_SWISH, x, wexp, o, M, K, hid, EpiArgs{}))) return rc;
             dw_in = e->hidA;
         }
-        const int ho = h / b.s, wo = wd / b.s;
-        {
+        if (!fused) {
             const float* wdw = e->w[p + ".dw"];
             float* o = e->hidB;
             const int ks = b.k, st = b.s, hi = h, wi = wd;
@@ -339,7 +350,7 @@ int cf_create(const void* weights, size_t weights_bytes, int device, int max_bat
     CF_CHECK(weights != nullptr, CF_EINVAL, "cf_create: weights is NULL");
     CF_CHECK(max_batch >= 1 && max_h >= 32 && max_w >= 32 && max_h % 32 == 0 && max_w % 32 == 0, CF_EINVAL,
              "cf_create: max_batch=%d max_h=%d max_w=%d (sizes must be positive multiples of 32)", max_batch, max_h, max_w);
-    CF_CHECK(pw_engine >= CF_PW_SIMT && pw_engine <= CF_PW_TCGEN05_1P, CF_EINVAL, "cf_create: unknown pw_engine %d", pw_engine);
+    CF_CHECK(pw_engine >= CF_PW_SIMT && pw_engine <= CF_PW_TCGEN05_FUSED, CF_EINVAL, "cf_create: unknown pw_engine %d", pw_engine);
     CF_CHECK(weights_bytes == blob_bytes(), CF_EWEIGHTS, "cf_create: blob is %zu bytes, expected %zu", weights_bytes, blob_bytes());
     Blob blob;
     std::string why;
@@ -441,11 +452,11 @@ int cf_create(const void* weights, size_t weights_bytes, int device, int max_bat
         // tf32 hi/lo, K-major, 128B-swizzled images of every point-wise weight matrix
         auto prep = [&](const std::string& name, int K, int N) {
             const float* hp = blob.get(name, (uint64_t)K * N, why);
-            return hp ? tc_prepare_layer(e->tc, e->w[name], hp, K, N, pw_engine == CF_PW_TCGEN05 ? 3 : 1) : fail(CF_EWEIGHTS, "cf_create: %s", why.c_str());
+            return hp ? tc_prepare_layer(e->tc, e->w[name], hp, K, N, engine_passes(pw_engine)) : fail(CF_EWEIGHTS, "cf_create: %s", why.c_str());
         };
         for (int i = 0; i < 12 && !rc; ++i) {
             const MBBlock& b = kBlocks[i];
-            if (b.t != 1) rc = prep("b" + std::to_string(i) + ".exp", b.cin, b.hid());
+            if (b.t != 1 && !block_is_fused(pw_engine, b)) rc = prep("b" + std::to_string(i) + ".exp", b.cin, b.hid());
             if (!rc) rc = prep("b" + std::to_string(i) + ".proj", b.hid(), b.cout);
         }
         if (!rc) rc = prep("clast.w", 320, 24);
@@ -642,9 +653,9 @@ int cf_debug_pw_gemm(int pw_engine, int epi, const float* dA, const float* hW, f
         int dev = 0;
         cudaGetDevice(&dev);
         rc = pw_tc_init(st, dev);
-        if (!rc) rc = tc_prepare_layer(st, dW, hW, K, N, pw_engine == CF_PW_TCGEN05 ? 3 : 1);
+        if (!rc) rc = tc_prepare_layer(st, dW, hW, K, N, engine_passes(pw_engine));
         TcLaunch tl;
-        if (!rc) rc = tc_plan(st, pw_engine == CF_PW_TCGEN05 ? 3 : 1, epi, dA, dW, dOut, M, K, N, ea, &tl);
+        if (!rc) rc = tc_plan(st, engine_passes(pw_engine), epi, dA, dW, dOut, M, K, N, ea, &tl);
         if (!rc) {
             ce = tc_launch(tl, (cudaStream_t)stream);
             if (ce != cudaSuccess) rc = fail(CF_ECUDA, "cf_debug_pw_gemm: launch: %s", cudaGetErrorString(ce));
@@ -661,10 +672,10 @@ int cf_debug_pw_gemm(int pw_engine, int epi, const float* dA, const float* hW, f
 
 long long cf_launch_count(cf_engine* e) { return e ? e->launches : 0; }
 
-int cf_work_model(int h, int w, int in_format, int which, double* bytes, double* flops) {
+int cf_work_model(int h, int w, int in_format, int pw_engine, int which, double* bytes, double* flops) {
     CF_CHECK(h >= 32 && w >= 32 && h % 32 == 0 && w % 32 == 0, CF_EINVAL, "cf_work_model: h=%d w=%d must be multiples of 32", h, w);
-    CF_CHECK(which >= CLS_ALL && which <= CLS_DECODE, CF_EINVAL, "cf_work_model: unknown class %d", which);
-    double by[6] = {}, fl[6] = {};
+    CF_CHECK(which >= CLS_ALL && which < CLS_COUNT, CF_EINVAL, "cf_work_model: unknown class %d", which);
+    double by[CLS_COUNT] = {}, fl[CLS_COUNT] = {};
     const double F = 4.0;  // fp32 storage
     double hh = h / 2, ww = w / 2;
     by[CLS_STEM] = (double)h * w * 3 * (in_format == CF_IN_U8_HWC ? 1.0 : F) + hh * ww * 32 * F;
@@ -672,13 +683,18 @@ int cf_work_model(int h, int w, int in_format, int which, double* bytes, double*
     for (int i = 0; i < 12; ++i) {
         const MBBlock& b = kBlocks[i];
         const double hid = b.hid();
-        if (b.t != 1) {
-            by[CLS_PW] += hh * ww * (b.cin + hid) * F;
-            fl[CLS_PW] += 2.0 * hh * ww * b.cin * hid;
-        }
         const double ho = hh / b.s, wo = ww / b.s;
-        by[CLS_DW] += (hh * ww + ho * wo) * hid * F;
-        fl[CLS_DW] += 2.0 * ho * wo * hid * b.k * b.k;
+        if (block_is_fused(pw_engine, b)) {  // X read once, depth-wise output written once; the hidden tensor never reaches HBM
+            by[CLS_FUSED] += (hh * ww * b.cin + ho * wo * hid) * F;
+            fl[CLS_FUSED] += 2.0 * hh * ww * b.cin * hid + 2.0 * ho * wo * hid * b.k * b.k;
+        } else {
+            if (b.t != 1) {
+                by[CLS_PW] += hh * ww * (b.cin + hid) * F;
+                fl[CLS_PW] += 2.0 * hh * ww * b.cin * hid;
+            }
+            by[CLS_DW] += (hh * ww + ho * wo) * hid * F;
+            fl[CLS_DW] += 2.0 * ho * wo * hid * b.k * b.k;
+        }
         by[CLS_PW] += ho * wo * (hid + b.cout + (b.residual() ? b.cout : 0)) * F;
         fl[CLS_PW] += 2.0 * ho * wo * hid * b.cout;
         hh = ho;
@@ -698,7 +714,8 @@ int cf_work_model(int h, int w, int in_format, int which, double* bytes, double*
     fl[CLS_HEADS] = 2.0 * hh * ww * (4 * 24 * 24 * 9 + 24 * 15);   // reference graph: four 3x3 24->24 + 1x1s
     by[CLS_DECODE] = hh * ww * 5 * F + 100 * 6 * F;                // hm, wh, reg in; [K,6] out (centerface_ext.py:52-82)
     fl[CLS_DECODE] = 0;
-    for (int c = CLS_PW; c <= CLS_HEADS; ++c) {
+    for (int c = CLS_PW; c < CLS_COUNT; ++c) {
+        if (c == CLS_DECODE) continue;
         by[CLS_ALL] += by[c];
         fl[CLS_ALL] += fl[c];
     }
@@ -710,7 +727,7 @@ int cf_work_model(int h, int w, int in_format, int which, double* bytes, double*
 int cf_replay_class(cf_engine* e, int which, int iters, void* stream) {
     CF_CHECK(e != nullptr, CF_EINVAL, "cf_replay_class: NULL engine");
     CF_CHECK(!e->plan.empty(), CF_EINVAL, "cf_replay_class: no cf_forward has run on this engine");
-    CF_CHECK(which >= CLS_ALL && which <= CLS_DECODE && iters >= 1, CF_EINVAL, "cf_replay_class: which=%d iters=%d", which, iters);
+    CF_CHECK(which >= CLS_ALL && which < CLS_COUNT && iters >= 1, CF_EINVAL, "cf_replay_class: which=%d iters=%d", which, iters);
     CF_CUDA(cudaSetDevice(e->device));
     for (int i = 0; i < iters; ++i) {
         int rc = run_steps(e, which, (cudaStream_t)stream);

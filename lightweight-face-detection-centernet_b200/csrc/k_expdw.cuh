@@ -1,0 +1,269 @@
+// Fused  expand 1x1 + Swish  ->  depth-wise KSxKS stride S + Swish  for the shallow MBConv blocks
+// (model/centernet.py:109-112 with Cin <= 32: layer1.0, 1.1, 2.0, 2.1, 3.0).
+//
+// Why: the expanded tensor (6 x Cin channels at the block's INPUT resolution) is the largest tensor of
+// the network (layer1.0: 96 x 320 x 320 = 39 MB per image in fp32) and in the layer-wise engine it is
+// written once and read once.  Here it never leaves the SM: a CTA owns a TH x TW output tile, TMA-loads
+// the (TH-1)S+KS x (TW-1)S+KS input halo tile of X (zero fill outside the image = the reference's
+// ZeroPad2d, and swish(0 . W) = 0 because the expand conv has no bias), and for every chunk of 32
+// hidden channels (i) recomputes the expand conv on the halo tile into shared memory, (ii) runs the
+// depth-wise conv from shared memory, (iii) writes the 32 depth-wise output channels (128 B per pixel).
+//
+// The expand conv runs on the fp32 CUDA cores on purpose: K = Cin is 16..32, the phase is bounded by
+// the 2 MUFU ops of each Swish (16/clk/SM) as much as by its FFMAs, and exact fp32 keeps the
+// precision-critical shallow layers at FFMA-engine accuracy.
+//
+//   E-producer mapping: lane = (pg = lane>>3, c4 = lane&7); a thread owns 8 pixels x 4 channels,
+//     a warp 32 consecutive halo pixels x 32 channels; X rows are read as LDS.128 from the TMA's
+//     SWIZZLE_128B image (conflict-free), W rows as LDS.128 (8 distinct addresses = one wavefront).
+//   dw mapping: a thread owns a 2x2 block of outputs for one float4 of channels; the (S+KS)^2 input
+//     window is streamed row by row from the swizzled E tile.
+#pragma once
+#include "k_pw_tc.cuh"
+
+namespace cf {
+
+constexpr int XD_THREADS = 512;
+
+template <int KS, int S>
+struct XdGeom {
+    static constexpr int TH = S == 1 ? 16 : 8, TW = S == 1 ? 16 : 8;
+    static constexpr int IH = (TH - 1) * S + KS, IW = (TW - 1) * S + KS;
+    static constexpr int NPX = IH * IW;                        // halo pixels (<= 512 = one pass)
+    static constexpr int LO = (KS - S) / 2;                    // model/centernet.py:68-70
+    static constexpr int XBYTES = ((NPX * 128 + 1023) / 1024) * 1024;
+};
+
+struct XdParams {
+    const float* We;   // [CIN][hid]
+    const float* Wd;   // [KS*KS][hid]
+    float* D;          // [B][Ho][Wo][hid]
+    int B, Hi, Wi, Ho, Wo, hid;
+    int tiles_x, tiles_y, n_items;
+};
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
+template <int KS, int S, int CIN>
+__global__ void __launch_bounds__(XD_THREADS, 1) k_expdw(const __grid_constant__ CUtensorMap tmX, const XdParams p) {
+    using G = XdGeom<KS, S>;
+    static_assert(G::NPX <= 512, "halo tile must fit one E-producer pass");
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+    // smem map: X[2] | E | We | Wd | barriers
+    uint8_t* Xs = sm;
+    uint8_t* Es = sm + 2 * G::XBYTES;
+    float* We_s = reinterpret_cast<float*>(Es + G::XBYTES);
+    float* Wd_s = We_s + CIN * p.hid;
+    const uint32_t bars = base + 3 * G::XBYTES + (uint32_t)(CIN + KS * KS) * p.hid * 4;  // 16-byte aligned: hid % 4 == 0
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int c4 = lane & 7, pg = lane >> 3;
+
+    if (tid == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+        mbar_init(bars, 1);
+        mbar_init(bars + 8, 1);
+        fence_barrier_init();
+    }
+    for (int i = tid; i < CIN * p.hid / 4; i += XD_THREADS) reinterpret_cast<float4*>(We_s)[i] = ldg4(p.We + 4 * i);
+    for (int i = tid; i < KS * KS * p.hid / 4; i += XD_THREADS) reinterpret_cast<float4*>(Wd_s)[i] = ldg4(p.Wd + 4 * i);
+    __syncthreads();
+
+    auto issue = [&](int item, int buf) {  // thread 0 only
+        const int tx = item % p.tiles_x;
+        const int t2 = item / p.tiles_x;
+        const int ty = t2 % p.tiles_y, b = t2 / p.tiles_y;
+        mbar_expect_tx(bars + 8 * buf, (uint32_t)G::NPX * 128u);
+        tma_load_4d(base + buf * G::XBYTES, &tmX, 0, tx * G::TW * S - G::LO, ty * G::TH * S - G::LO, b, bars + 8 * buf);
+    };
+    if (tid == 0 && (int)blockIdx.x < p.n_items) issue(blockIdx.x, 0);
+
+    const int nch = (p.hid + 31) >> 5;
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+        const int buf = it & 1;
+        // the other X buffer was last read by the previous item's E-producer, which every thread left
+        // through the __syncthreads() below, so it can be refilled while this item computes
+        if (tid == 0 && item + (int)gridDim.x < p.n_items) issue(item + gridDim.x, buf ^ 1);
+        mbar_wait(bars + 8 * buf, (it >> 1) & 1u);
+        const uint8_t* X = Xs + buf * G::XBYTES;
+
+        const int tx = item % p.tiles_x;
+        const int t2 = item / p.tiles_x;
+        const int ty = t2 % p.tiles_y, b = t2 / p.tiles_y;
+
+        for (int ch = 0; ch < nch; ++ch) {
+            const int cbase = ch * 32 + c4 * 4;       // first hidden channel of this thread's float4
+            const bool cvalid = cbase < p.hid;
+            // ---------------- expand + Swish on the halo tile -> E (swizzled rows of 128 B) ----------------
+            {
+                const int p0 = warp * 32 + pg;         // thread's pixels: p0 + 4*i, i = 0..7
+                if (cvalid && warp * 32 < G::NPX) {
+                    float4 acc[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[i] = make_float4(0, 0, 0, 0);
+#pragma unroll
+                    for (int kq = 0; kq < CIN / 4; ++kq) {
+                        const float4 w0 = *reinterpret_cast<const float4*>(We_s + (kq * 4 + 0) * p.hid + cbase);
+                        const float4 w1 = *reinterpret_cast<const float4*>(We_s + (kq * 4 + 1) * p.hid + cbase);
+                        const float4 w2 = *reinterpret_cast<const float4*>(We_s + (kq * 4 + 2) * p.hid + cbase);
+                        const float4 w3 = *reinterpret_cast<const float4*>(We_s + (kq * 4 + 3) * p.hid + cbase);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int px = p0 + 4 * i;
+                            const int pxc = px < G::NPX ? px : G::NPX - 1;  // clamp: rows past the tile are never stored
+                            const float4 x = *reinterpret_cast<const float4*>(X + pxc * 128 + ((kq ^ (pxc & 7)) << 4));
+                            fma4(acc[i], x.x, w0);
+                            fma4(acc[i], x.y, w1);
+                            fma4(acc[i], x.z, w2);
+                            fma4(acc[i], x.w, w3);
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int px = p0 + 4 * i;
+                        if (px < G::NPX) *reinterpret_cast<float4*>(Es + px * 128 + ((c4 ^ (px & 7)) << 4)) = swish4(acc[i]);
+                    }
+                }
+            }
+            __syncthreads();
+            // ---------------- depth-wise KSxKS stride S + Swish from E -> global D ----------------
+            {
+                constexpr int NBX = G::TW / 2, NBLK = (G::TH / 2) * NBX, NWIN = S + KS;
+                const int blk = warp * 4 + pg;
+                if (cvalid && blk < NBLK) {
+                    const int by = blk / NBX, bx = blk - by * NBX;
+                    float4 acc[2][2];
+#pragma unroll
+                    for (int a = 0; a < 2; ++a)
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) acc[a][c] = make_float4(0, 0, 0, 0);
+                    const int r0 = 2 * by * S, q0 = 2 * bx * S;  // window origin inside the halo tile
+#pragma unroll
+                    for (int rr = 0; rr < NWIN; ++rr) {
+                        float4 win[NWIN];
+#pragma unroll
+                        for (int cc = 0; cc < NWIN; ++cc) {
+                            const int px = (r0 + rr) * G::IW + q0 + cc;
+                            win[cc] = *reinterpret_cast<const float4*>(Es + px * 128 + ((c4 ^ (px & 7)) << 4));
+                        }
+#pragma unroll
+                        for (int dy = 0; dy < 2; ++dy) {
+                            const int ky = rr - dy * S;
+                            if (ky < 0 || ky >= KS) continue;
+#pragma unroll
+                            for (int kx = 0; kx < KS; ++kx) {
+                                const float4 wv = *reinterpret_cast<const float4*>(Wd_s + (ky * KS + kx) * p.hid + cbase);
+                                fma44(acc[dy][0], win[kx], wv);
+                                fma44(acc[dy][1], win[S + kx], wv);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                        for (int dx = 0; dx < 2; ++dx) {
+                            const int yo = ty * G::TH + 2 * by + dy, xo = tx * G::TW + 2 * bx + dx;
+                            if (yo < p.Ho && xo < p.Wo)
+                                st4(p.D + ((size_t)(b * p.Ho + yo) * p.Wo + xo) * p.hid + cbase, swish4(acc[dy][dx]));
+                        }
+                }
+            }
+            __syncthreads();  // E is rewritten by the next chunk; X[buf] by the TMA issued two items later
+        }
+    }
+}
+
+// ---- host side --------------------------------------------------------------------------
+// fp32 NHWC tensor [B][H][W][C]: box {32 channels (zero filled past C), IW, IH, 1}, SWIZZLE_128B
+inline int xd_make_map(PwTcState& st, CUtensorMap* map, const float* ptr, int B, int H, int W, int C, int IW, int IH) {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)IW, (cuuint32_t)IH, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = ((PFN_encodeTiled)st.encode)(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box, estr,
+                                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(CF_ECUDA, "cuTensorMapEncodeTiled(4D %dx%dx%dx%d) failed with CUresult %d", B, H, W, C, (int)r);
+    return CF_OK;
+}
+
+struct XdLaunch {
+    CUtensorMap tmX;
+    XdParams p;
+    int ks = 3, s = 1, cin = 16, grid = 0;
+    size_t smem = 0;
+};
+
+template <int KS, int S, int CIN>
+inline cudaError_t xd_launch_t(const XdLaunch& xl, cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(k_expdw<KS, S, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    k_expdw<KS, S, CIN><<<xl.grid, XD_THREADS, xl.smem, st>>>(xl.tmX, xl.p);
+    return cudaGetLastError();
+}
+
+inline bool xd_supported(int ks, int s, int cin) {
+    return (ks == 3 && s == 2 && (cin == 16 || cin == 32)) || (ks == 3 && s == 1 && cin == 24) ||
+           (ks == 5 && s == 2 && cin == 24) || (ks == 5 && s == 1 && cin == 32);
+}
+
+inline cudaError_t xd_launch(const XdLaunch& xl, cudaStream_t st) {
+    if (xl.ks == 3 && xl.s == 2 && xl.cin == 16) return xd_launch_t<3, 2, 16>(xl, st);
+    if (xl.ks == 3 && xl.s == 2 && xl.cin == 32) return xd_launch_t<3, 2, 32>(xl, st);
+    if (xl.ks == 3 && xl.s == 1 && xl.cin == 24) return xd_launch_t<3, 1, 24>(xl, st);
+    if (xl.ks == 5 && xl.s == 2 && xl.cin == 24) return xd_launch_t<5, 2, 24>(xl, st);
+    if (xl.ks == 5 && xl.s == 1 && xl.cin == 32) return xd_launch_t<5, 1, 32>(xl, st);
+    return cudaErrorInvalidValue;
+}
+
+template <int KS, int S>
+inline void xd_geom(int* th, int* tw, int* ih, int* iw, int* xbytes) {
+    using G = XdGeom<KS, S>;
+    *th = G::TH, *tw = G::TW, *ih = G::IH, *iw = G::IW, *xbytes = G::XBYTES;
+}
+
+inline int xd_plan(PwTcState& st, int ks, int s, const float* X, const float* We, const float* Wd, float* D, int B, int Hi, int Wi,
+                   int cin, int hid, XdLaunch* xl) {
+    if (!xd_supported(ks, s, cin)) return fail(CF_EINVAL, "xd_plan: no fused kernel for k=%d s=%d cin=%d", ks, s, cin);
+    int th, tw, ih, iw, xb;
+    if (ks == 3 && s == 1) xd_geom<3, 1>(&th, &tw, &ih, &iw, &xb);
+    else if (ks == 3) xd_geom<3, 2>(&th, &tw, &ih, &iw, &xb);
+    else if (s == 1) xd_geom<5, 1>(&th, &tw, &ih, &iw, &xb);
+    else xd_geom<5, 2>(&th, &tw, &ih, &iw, &xb);
+    int rc = xd_make_map(st, &xl->tmX, X, B, Hi, Wi, cin, iw, ih);
+    if (rc) return rc;
+    XdParams& p = xl->p;
+    p.We = We;
+    p.Wd = Wd;
+    p.D = D;
+    p.B = B;
+    p.Hi = Hi;
+    p.Wi = Wi;
+    p.Ho = Hi / s;
+    p.Wo = Wi / s;
+    p.hid = hid;
+    p.tiles_x = (p.Wo + tw - 1) / tw;
+    p.tiles_y = (p.Ho + th - 1) / th;
+    p.n_items = B * p.tiles_x * p.tiles_y;
+    xl->ks = ks;
+    xl->s = s;
+    xl->cin = cin;
+    xl->grid = p.n_items < st.sms ? p.n_items : st.sms;
+    xl->smem = (size_t)3 * xb + (size_t)(cin + ks * ks) * hid * 4 + 64 + 1024;
+    if (xl->smem > (size_t)TC_SMEM_MAX) return fail(CF_EINVAL, "xd_plan: tile does not fit shared memory (%zu B)", xl->smem);
+    return CF_OK;
+}
+
+}  // namespace cf

@@ -57,6 +57,11 @@ def test_work_model_matches_survey(pkg):
     assert abs(fl480 - 3.521e9) / 3.521e9 < 1e-3
     parts = [pkg._lib.work_model(640, 640, pkg.CF_IN_F32_NCHW, c) for c in (1, 2, 3, 4)]
     assert abs(sum(p[0] for p in parts) - by) < 1 and abs(sum(p[1] for p in parts) - fl) < 1
+    # fusing expand+dw of the shallow blocks removes the hidden-tensor traffic, not the flops
+    byf, flf = pkg._lib.work_model(640, 640, pkg.CF_IN_F32_NCHW, 0, pkg.CF_PW_TCGEN05_FUSED)
+    assert abs(flf - fl) < 1 and byf < 0.65 * by
+    partsf = [pkg._lib.work_model(640, 640, pkg.CF_IN_F32_NCHW, c, pkg.CF_PW_TCGEN05_FUSED) for c in (1, 2, 3, 4, 6)]
+    assert abs(sum(p[0] for p in partsf) - byf) < 1
 
 
 def _entries(pkg, sd_np):
