@@ -122,6 +122,15 @@ int cf_decode_threshold(const float* hm_sig, const float* wh, const float* reg, 
 int cf_detect_topk_host(cf_engine* e, const uint8_t* images, int batch, int h, int w, int K,
                         float* out_dets, int32_t* out_inds);
 
+/* Pipelined form of cf_detect_topk_host for streams of batches: cf_submit_topk_host enqueues one batch
+ * (H2D on a copy stream, overlapping the previous batch's kernels; network, decode and D2H on the compute
+ * stream) and returns; at most two submissions are in flight (a third blocks on the oldest).
+ * cf_wait_host blocks until the OLDEST in-flight submission has delivered its host outputs.  The host
+ * buffers of a submission must stay valid (and should be pinned) until its wait returns.          */
+int cf_submit_topk_host(cf_engine* e, const uint8_t* images, int batch, int h, int w, int K,
+                        float* out_dets, int32_t* out_inds);
+int cf_wait_host(cf_engine* e);
+
 /* Same for the threshold paths: the body of CenterFace.__call__ after cv2.resize
  * (centerface.py:32-62) for variant A, or of get_detections (eval_widerface.py:83-89) for
  * variant B, on a HOST u8 BGR batch [B,h,w,3].  Host outputs as in cf_decode_threshold.    */

@@ -34,6 +34,8 @@ SIGNATURES = {
     "cf_decode_threshold": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                       C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, _vp, _vp, _vp, _vp]),
     "cf_detect_topk_host": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "cf_submit_topk_host": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "cf_wait_host": (C.c_int, [_vp]),
     "cf_detect_threshold_host": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                            C.c_float, C.c_float, C.c_int, _vp, _vp, _vp]),
     "cf_debug_pw_gemm": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),

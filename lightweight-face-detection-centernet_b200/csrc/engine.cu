@@ -108,7 +108,19 @@ struct cf_engine {
     // last forward
     int B = 0, H = 0, W = 0, fmt = -1;
     const void* in = nullptr;
-    std::vector<Step> plan;
+    std::vector<Step> plan;          // launch list of the current (input, format, shape)
+    struct CachedPlan {
+        const void* in;
+        int fmt, B, H, W;
+        std::vector<Step> steps;
+    };
+    std::vector<CachedPlan> plan_cache;  // the pipelined host path alternates between two input buffers
+    // pipelined host entry points: two input slots, copy stream, events
+    uint8_t* in_slot[2] = {nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    bool slot_used[2] = {false, false};
+    long long submitted = 0, waited = 0;
     long long launches = 0;
     PwTcState tc;  // tensor maps etc. of the tcgen05 engine
     StemW stem_w;  // host copy: the stem weights are passed to the kernel by value
@@ -432,6 +444,7 @@ int cf_create(const void* weights, size_t weights_bytes, int device, int max_bat
         if ((rc = dalloc(&e->hm_sig, Bm * px4))) return bail(rc);
         if ((rc = dalloc(&e->peak, Bm * px4))) return bail(rc);
     }
+    e->in_u8 = nullptr;
     e->o_dets_floats = Bm * (size_t)THRESH_MAX_CAP * 6;  // covers [B,K<=1024,6] and [B,cap<=4096,5]
     e->o_lms_floats = Bm * (size_t)THRESH_MAX_CAP * 10;
     e->o_inds_n = Bm * 1024;
@@ -439,8 +452,14 @@ int cf_create(const void* weights, size_t weights_bytes, int device, int max_bat
     if ((rc = dalloc(&e->o_lms, e->o_lms_floats))) return bail(rc);
     if (cudaMalloc((void**)&e->o_inds, e->o_inds_n * 4) != cudaSuccess ||
         cudaMalloc((void**)&e->o_counts, Bm * 4) != cudaSuccess ||
-        cudaMalloc((void**)&e->in_u8, Bm * (size_t)max_h * max_w * 3) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess)
+        cudaMalloc((void**)&e->in_slot[0], Bm * (size_t)max_h * max_w * 3) != cudaSuccess ||
+        cudaMalloc((void**)&e->in_slot[1], Bm * (size_t)max_h * max_w * 3) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_copied[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_copied[1], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_done[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_done[1], cudaEventDisableTiming) != cudaSuccess)
         return bail(fail(CF_ECUDA, "cf_create: staging allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
 
     if (cudaFuncSetAttribute(k_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, HEADS_SMEM) != cudaSuccess ||
@@ -480,7 +499,12 @@ int cf_destroy(cf_engine* e) {
         if (p) cudaFree(p);
     if (e->o_inds) cudaFree(e->o_inds);
     if (e->o_counts) cudaFree(e->o_counts);
-    if (e->in_u8) cudaFree(e->in_u8);
+    for (int i = 0; i < 2; ++i) {
+        if (e->in_slot[i]) cudaFree(e->in_slot[i]);
+        if (e->ev_copied[i]) cudaEventDestroy(e->ev_copied[i]);
+        if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]);
+    }
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
     return CF_OK;
@@ -496,10 +520,29 @@ int cf_forward(cf_engine* e, const void* input, int in_format, int batch, int h,
              e->max_h, e->max_w);
     CF_CUDA(cudaSetDevice(e->device));
     if (e->plan.empty() || e->B == 0 || e->in != input || e->fmt != in_format || e->B != batch || e->H != h || e->W != w) {
-        int rc = build_plan(e, input, in_format, batch, h, w);
-        if (rc) {
-            e->plan.clear();
-            return rc;
+        // stash the current plan, then reuse a cached one or build a new one
+        if (!e->plan.empty() && e->B != 0) {
+            if (e->plan_cache.size() >= 4) e->plan_cache.erase(e->plan_cache.begin());
+            e->plan_cache.push_back({e->in, e->fmt, e->B, e->H, e->W, std::move(e->plan)});
+        }
+        e->plan.clear();
+        bool hit = false;
+        for (size_t i = 0; i < e->plan_cache.size(); ++i) {
+            auto& c = e->plan_cache[i];
+            if (c.in == input && c.fmt == in_format && c.B == batch && c.H == h && c.W == w) {
+                e->plan = std::move(c.steps);
+                e->in = c.in, e->fmt = c.fmt, e->B = c.B, e->H = c.H, e->W = c.W;
+                e->plan_cache.erase(e->plan_cache.begin() + i);
+                hit = true;
+                break;
+            }
+        }
+        if (!hit) {
+            int rc = build_plan(e, input, in_format, batch, h, w);
+            if (rc) {
+                e->plan.clear();
+                return rc;
+            }
         }
     }
     return run_steps(e, CLS_ALL, (cudaStream_t)stream);
@@ -595,20 +638,66 @@ int cf_decode_threshold(const float* hm_sig, const float* wh, const float* reg, 
     return CF_OK;
 }
 
-int cf_detect_topk_host(cf_engine* e, const uint8_t* images, int batch, int h, int w, int K, float* out_dets,
-                        int32_t* out_inds) {
-    CF_CHECK(e && images && out_dets, CF_EINVAL, "cf_detect_topk_host: NULL argument");
-    CF_CHECK(batch >= 1 && batch <= e->max_batch, CF_ECAP, "cf_detect_topk_host: batch %d outside [1,%d]", batch, e->max_batch);
-    CF_CHECK(K >= 1 && K <= 1024, CF_EINVAL, "cf_detect_topk_host: K=%d outside [1,1024]", K);
+// Enqueue one batch on the engine's own streams: H2D of the u8 images into input slot (n mod 2) on the
+// copy stream (overlapping the previous batch's kernels), then network + decode + D2H on the compute
+// stream.  At most two submissions are in flight; a third waits for the oldest.
+namespace {
+int host_wait_oldest(cf_engine* e) {
+    if (e->waited >= e->submitted) return fail(CF_EINVAL, "cf_wait_host: nothing in flight");
+    CF_CUDA(cudaEventSynchronize(e->ev_done[e->waited & 1]));
+    ++e->waited;
+    return CF_OK;
+}
+int host_stage_input(cf_engine* e, const uint8_t* images, size_t bytes, int* slot_out) {
     CF_CUDA(cudaSetDevice(e->device));
-    cudaStream_t s = e->stream;
-    CF_CUDA(cudaMemcpyAsync(e->in_u8, images, (size_t)batch * h * w * 3, cudaMemcpyHostToDevice, s));
-    int rc = cf_forward(e, e->in_u8, CF_IN_U8_HWC, batch, h, w, s);
+    if (e->submitted - e->waited >= 2) {
+        int rc = host_wait_oldest(e);
+        if (rc) return rc;
+    }
+    const int slot = (int)(e->submitted & 1);
+    // the slot's previous contents were last read by the stem kernel of submission n-2
+    if (e->slot_used[slot]) CF_CUDA(cudaStreamWaitEvent(e->copy_stream, e->ev_done[slot], 0));
+    CF_CUDA(cudaMemcpyAsync(e->in_slot[slot], images, bytes, cudaMemcpyHostToDevice, e->copy_stream));
+    CF_CUDA(cudaEventRecord(e->ev_copied[slot], e->copy_stream));
+    CF_CUDA(cudaStreamWaitEvent(e->stream, e->ev_copied[slot], 0));
+    e->slot_used[slot] = true;
+    *slot_out = slot;
+    return CF_OK;
+}
+}  // namespace
+
+int cf_submit_topk_host(cf_engine* e, const uint8_t* images, int batch, int h, int w, int K, float* out_dets,
+                        int32_t* out_inds) {
+    CF_CHECK(e && images && out_dets, CF_EINVAL, "cf_submit_topk_host: NULL argument");
+    CF_CHECK(batch >= 1 && batch <= e->max_batch, CF_ECAP, "cf_submit_topk_host: batch %d outside [1,%d]", batch, e->max_batch);
+    CF_CHECK(K >= 1 && K <= 1024, CF_EINVAL, "cf_submit_topk_host: K=%d outside [1,1024]", K);
+    CF_CHECK(h >= 32 && w >= 32 && h % 32 == 0 && w % 32 == 0 && (size_t)h * w <= (size_t)e->max_h * e->max_w, CF_EINVAL,
+             "cf_submit_topk_host: bad size %dx%d", h, w);
+    int slot = 0;
+    int rc = host_stage_input(e, images, (size_t)batch * h * w * 3, &slot);
     if (rc) return rc;
+    cudaStream_t s = e->stream;
+    if ((rc = cf_forward(e, e->in_slot[slot], CF_IN_U8_HWC, batch, h, w, s))) return rc;
     if ((rc = cf_decode_topk(e, K, e->o_dets, e->o_inds, s))) return rc;
     CF_CUDA(cudaMemcpyAsync(out_dets, e->o_dets, (size_t)batch * K * 6 * 4, cudaMemcpyDeviceToHost, s));
     if (out_inds) CF_CUDA(cudaMemcpyAsync(out_inds, e->o_inds, (size_t)batch * K * 4, cudaMemcpyDeviceToHost, s));
-    CF_CUDA(cudaStreamSynchronize(s));
+    CF_CUDA(cudaEventRecord(e->ev_done[slot], s));
+    ++e->submitted;
+    return CF_OK;
+}
+
+int cf_wait_host(cf_engine* e) {
+    CF_CHECK(e != nullptr, CF_EINVAL, "cf_wait_host: NULL engine");
+    CF_CUDA(cudaSetDevice(e->device));
+    return host_wait_oldest(e);
+}
+
+int cf_detect_topk_host(cf_engine* e, const uint8_t* images, int batch, int h, int w, int K, float* out_dets,
+                        int32_t* out_inds) {
+    int rc = cf_submit_topk_host(e, images, batch, h, w, K, out_dets, out_inds);
+    if (rc) return rc;
+    while (e->waited < e->submitted)
+        if ((rc = host_wait_oldest(e))) return rc;
     return CF_OK;
 }
 
@@ -617,11 +706,13 @@ int cf_detect_threshold_host(cf_engine* e, const uint8_t* images, int batch, int
                              float* out_dets, float* out_lms, int32_t* out_counts) {
     CF_CHECK(e && images && out_dets && out_counts, CF_EINVAL, "cf_detect_threshold_host: NULL argument");
     CF_CHECK(batch >= 1 && batch <= e->max_batch, CF_ECAP, "cf_detect_threshold_host: batch %d outside [1,%d]", batch, e->max_batch);
-    CF_CUDA(cudaSetDevice(e->device));
-    cudaStream_t s = e->stream;
-    CF_CUDA(cudaMemcpyAsync(e->in_u8, images, (size_t)batch * h * w * 3, cudaMemcpyHostToDevice, s));
-    int rc = cf_forward(e, e->in_u8, CF_IN_U8_HWC, batch, h, w, s);
+    CF_CHECK(h >= 32 && w >= 32 && h % 32 == 0 && w % 32 == 0 && (size_t)h * w <= (size_t)e->max_h * e->max_w, CF_EINVAL,
+             "cf_detect_threshold_host: bad size %dx%d", h, w);
+    int slot = 0;
+    int rc = host_stage_input(e, images, (size_t)batch * h * w * 3, &slot);
     if (rc) return rc;
+    cudaStream_t s = e->stream;
+    if ((rc = cf_forward(e, e->in_slot[slot], CF_IN_U8_HWC, batch, h, w, s))) return rc;
     // `size` as the reference passes it: (H',W') in centerface.py:51, fixed (640,640) in eval_widerface.py:88
     const int size_h = variant == CF_DECODE_B ? 640 : h, size_w = variant == CF_DECODE_B ? 640 : w;
     rc = cf_decode_threshold(e->hm_sig, e->wh, e->reg, e->lm, batch, h / 4, w / 4, variant, threshold, nms_threshold, size_h,
@@ -631,7 +722,10 @@ int cf_detect_threshold_host(cf_engine* e, const uint8_t* images, int batch, int
     CF_CUDA(cudaMemcpyAsync(out_counts, e->o_counts, (size_t)batch * 4, cudaMemcpyDeviceToHost, s));
     CF_CUDA(cudaMemcpyAsync(out_dets, e->o_dets, (size_t)batch * cap * 5 * 4, cudaMemcpyDeviceToHost, s));
     if (out_lms) CF_CUDA(cudaMemcpyAsync(out_lms, e->o_lms, (size_t)batch * cap * 10 * 4, cudaMemcpyDeviceToHost, s));
-    CF_CUDA(cudaStreamSynchronize(s));
+    CF_CUDA(cudaEventRecord(e->ev_done[slot], s));
+    ++e->submitted;
+    while (e->waited < e->submitted)
+        if ((rc = host_wait_oldest(e))) return rc;
     return CF_OK;
 }
 

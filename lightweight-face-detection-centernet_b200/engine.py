@@ -141,6 +141,25 @@ class Engine:
         self.shape = (B, H, W)
         return out_dets, out_inds
 
+    def submit_topk_host(self, images, K, out_dets, out_inds=None):
+        """Pipelined form: enqueue one host batch (pinned buffers; they must outlive the matching wait_host)."""
+        B, H, W, c = images.shape
+        assert c == 3
+        ip, k0 = _host_ptr(images)
+        dp, k1 = _host_ptr(out_dets)
+        np_, k2 = _host_ptr(out_inds) if out_inds is not None else (None, None)
+        L.check(self.lib.cf_submit_topk_host(self.h, C.c_void_p(ip), B, H, W, K, C.c_void_p(dp),
+                                             C.c_void_p(np_) if np_ else None), "cf_submit_topk_host")
+        self.shape = (B, H, W)
+        self._inflight = getattr(self, "_inflight", [])
+        self._inflight.append((k0, k1, k2))
+
+    def wait_host(self):
+        """Block until the oldest submit_topk_host has delivered its outputs."""
+        L.check(self.lib.cf_wait_host(self.h), "cf_wait_host")
+        if getattr(self, "_inflight", None):
+            self._inflight.pop(0)
+
     def detect_threshold_host(self, images, variant, threshold, nms_threshold=0.3, scale_w=0.0, scale_h=0.0,
                               cap=1024, landmarks=True):
         """u8 BGR [B,H,W,3] host batch -> list of (dets [n,5], lms [n,10] | None) per image.

@@ -281,6 +281,26 @@ def test_host_entry_point_matches_device_path(eng, f5_640):
     assert (np.diff(dets[:, :, 4], axis=1) <= 0).all()  # sortedness
 
 
+def test_pipelined_host_api(eng, f5_640):
+    """cf_submit_topk_host / cf_wait_host (double-buffered H2D) deliver the same results, in order."""
+    batches = [np.stack([f5_640[n] for n in names]) for names in (["1", "17"], ["2", "27"], ["8", "1"], ["27", "27"])]
+    want = [eng.detect_topk_host(b, K=50) for b in batches]
+    outs = [(torch.empty((2, 50, 6)).pin_memory(), torch.empty((2, 50), dtype=torch.int32).pin_memory()) for _ in range(2)]
+    pinned = [torch.from_numpy(b).pin_memory() for b in batches]
+    got = []
+    for i, b in enumerate(pinned):
+        eng.submit_topk_host(b, 50, outs[i % 2][0], outs[i % 2][1])
+        if i >= 1:
+            eng.wait_host()
+            got.append((outs[(i - 1) % 2][0].numpy().copy(), outs[(i - 1) % 2][1].numpy().copy()))
+    eng.wait_host()
+    got.append((outs[(len(pinned) - 1) % 2][0].numpy().copy(), outs[(len(pinned) - 1) % 2][1].numpy().copy()))
+    for (wd, wi), (gd, gi) in zip(want, got):
+        assert np.array_equal(wd, gd) and np.array_equal(wi, gi)
+    with pytest.raises(Exception):
+        eng.wait_host()  # nothing in flight
+
+
 def test_errors_are_loud(pkg, eng):
     with pytest.raises(pkg.CenterFaceError):
         eng.forward(torch.zeros(9, 3, 64, 64, device="cuda"))       # batch > max_batch
