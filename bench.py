@@ -183,7 +183,7 @@ def run_b200(a):
     if world > 1:
         dist.barrier()
     B = a.batch
-    pw = a.pw if a.pw >= 0 else L.CF_PW_TCGEN05
+    pw = a.pw if a.pw >= 0 else L.CF_PW_TCGEN05_FUSED_TC
     eng = pkg.Engine(WEIGHTS, max_batch=B, max_h=H, max_w=W, device=local, pw_engine=pw)
     dev = torch.device(f"cuda:{local}")
 
@@ -277,8 +277,15 @@ def run_b200(a):
         by, fl = L.work_model(H, W, L.CF_IN_U8_HWC, cls, pw)
         if n == 0:
             continue
-        classes[name] = {"ms_per_step": ms, "launches": n, "alg_bytes": by * B, "alg_flops": fl * B,
-                         "gbs": by * B / (ms * 1e-3) / 1e9, "tflops": fl * B / (ms * 1e-3) / 1e12}
+        # Algorithmic bytes = SURVEY.md 8(d)'s LAYER-WISE figure (every conv reads its input once and writes its
+        # output once).  A fused kernel is credited with the layer-wise bytes of the layers it replaces; the bytes
+        # it actually has to move (`min_bytes`) are what fusion saved and are reported beside it.
+        by_lw = by
+        if cls == L.CLS_FUSED:
+            lw = lambda c: L.work_model(H, W, L.CF_IN_U8_HWC, c, L.CF_PW_TCGEN05)[0] - L.work_model(H, W, L.CF_IN_U8_HWC, c, pw)[0]  # noqa: E731
+            by_lw = lw(L.CLS_PW) + lw(L.CLS_DW)
+        classes[name] = {"ms_per_step": ms, "launches": n, "alg_bytes": by_lw * B, "min_bytes": by * B, "alg_flops": fl * B,
+                         "gbs": by_lw * B / (ms * 1e-3) / 1e9, "tflops": fl * B / (ms * 1e-3) / 1e12}
     net_ms = sum(c["ms_per_step"] for k, c in classes.items())
     for c in classes.values():
         c["share"] = c["ms_per_step"] / net_ms
@@ -286,13 +293,14 @@ def run_b200(a):
     tc = classes[top]
     roofline = {"kernel": top, "bound": "hbm", "achieved": tc["gbs"], "peak": hbm, "unit": "GB/s", "frac": tc["gbs"] / hbm,
                 "traffic": None, "peak_source": peak_src, "launches": tc["launches"], "ms": tc["ms_per_step"],
-                "alg_bytes_per_step": tc["alg_bytes"], "share_of_step": tc["share"],
+                "alg_bytes_per_step": tc["alg_bytes"], "min_bytes_per_step": tc["min_bytes"], "share_of_step": tc["share"],
                 "tensor_frac_of_sustained_bf16": tc["tflops"] / tf,
                 "classes": {k: {"ms": round(v["ms_per_step"], 4), "share": round(v["share"], 4), "GBps": round(v["gbs"], 1),
                                 "frac_hbm": round(v["gbs"] / hbm, 4), "TFLOPs": round(v["tflops"], 2), "launches": v["launches"]}
                             for k, v in classes.items()}}
-    by_all, fl_all = L.work_model(H, W, L.CF_IN_U8_HWC, 0, pw)
-    roofline["whole_step"] = {"alg_bytes_per_image": by_all, "alg_flops_per_image": fl_all,
+    by_min, _ = L.work_model(H, W, L.CF_IN_U8_HWC, 0, pw)
+    by_all, fl_all = L.work_model(H, W, L.CF_IN_U8_HWC, 0, L.CF_PW_TCGEN05)  # layer-wise algorithmic bytes
+    roofline["whole_step"] = {"alg_bytes_per_image": by_all, "min_bytes_per_image": by_min, "alg_flops_per_image": fl_all,
                               "GBps": by_all * B / (ms_per_step * 1e-3) / 1e9,
                               "frac_hbm": by_all * B / (ms_per_step * 1e-3) / 1e9 / hbm,
                               "TFLOPs": fl_all * B / (ms_per_step * 1e-3) / 1e12}
@@ -304,7 +312,7 @@ def run_b200(a):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": warm,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": {0: "f32", 1: "tf32x3", 2: "tf32", 3: "tf32x3+f32"}[pw], "data": "synthetic",
+                "dtype": {0: "f32", 1: "tf32x3", 2: "tf32", 3: "tf32x3+f32", 4: "tf32x3"}[pw], "data": "synthetic",
                 "config": {"workload": f"batch-{B} 640x640 per GPU ({'configs[1]' if world == 1 else 'configs[2] sharding'}), "
                                        f"u8 BGR input, network + sigmoid/clamp + path-C top-{K_TOP} decode"
                                        + (", NCCL all-gather of [B,100,6] boxes" if world > 1 else ""),

@@ -48,7 +48,10 @@ extern "C" {
 #define CF_PW_TCGEN05 1   /* tcgen05.mma kind::tf32, 3-pass split (fp32-class accuracy)   */
 #define CF_PW_TCGEN05_1P 2 /* tcgen05.mma kind::tf32 single pass (throughput mode)        */
 #define CF_PW_TCGEN05_FUSED 3 /* CF_PW_TCGEN05 + the shallow MBConv blocks (Cin<=32) run expand+Swish+
-                                 depth-wise+Swish as ONE kernel, hidden tensor kept in shared memory   */
+                                 depth-wise+Swish as ONE kernel, hidden tensor kept in shared memory;
+                                 expand on the fp32 CUDA cores                                        */
+#define CF_PW_TCGEN05_FUSED_TC 4 /* same fusion, the expand conv of the fused blocks on tcgen05 (3xTF32),
+                                    accumulators drained from TMEM straight into the shared-memory tile */
 
 /* decode variants for cf_decode_threshold */
 #define CF_DECODE_A 0 /* centerface.py:73-109   : offsets unused, landmarks, clip to (H,W)   */

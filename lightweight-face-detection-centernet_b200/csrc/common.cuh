@@ -42,9 +42,16 @@ inline int fail(int code, const char* fmt, ...) {
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 // ---- device math -----------------------------------------------------------------------
-// Swish (model/centernet.py:39-40) x*sigmoid(x) = x/(1+e^-x): MUFU.EX2 + MUFU.RCP, ~4 ulp.
+// Swish (model/centernet.py:39-40) x*sigmoid(x) = x * rcp(1 + 2^(-x*log2 e)): MUFU.EX2 + MUFU.RCP (~2 ulp each) and
+// three FP32 ops.  The .ftz forms drop the denormal pre/post-scaling code the default intrinsics emit (4 extra
+// instructions per element); denormal intermediates only occur for |x| > 87, where the result is x or -0 anyway.
 // x -> -inf gives -0, x -> +inf gives x; no NaN is produced for finite x.
-__device__ __forceinline__ float swishf(float x) { return __fdividef(x, 1.f + __expf(-x)); }
+__device__ __forceinline__ float swishf(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+    return x * r;
+}
 
 __device__ __forceinline__ float4 swish4(float4 v) {
     return make_float4(swishf(v.x), swishf(v.y), swishf(v.z), swishf(v.w));

@@ -19,6 +19,8 @@
 #include "k_pw_simt.cuh"
 #include "k_pw_tc.cuh"
 #include "k_expdw.cuh"
+#include "k_mbx.cuh"
+#include "k_dwt.cuh"
 #include "net.hpp"
 
 using namespace cf;
@@ -29,7 +31,11 @@ enum WorkClass { CLS_ALL = 0, CLS_PW = 1, CLS_DW = 2, CLS_STEM = 3, CLS_HEADS = 
 
 inline bool engine_is_tc(int pw) { return pw != CF_PW_SIMT; }
 inline int engine_passes(int pw) { return pw == CF_PW_TCGEN05_1P ? 1 : 3; }
-inline bool block_is_fused(int pw, const MBBlock& b) { return pw == CF_PW_TCGEN05_FUSED && b.t != 1 && xd_supported(b.k, b.s, b.cin); }
+inline bool block_is_fused(int pw, const MBBlock& b) {
+    if (b.t == 1 || !xd_supported(b.k, b.s, b.cin)) return false;
+    if (pw == CF_PW_TCGEN05_FUSED) return true;
+    return pw == CF_PW_TCGEN05_FUSED_TC;
+}
 
 struct Step {
     int cls;
@@ -193,8 +199,32 @@ cudaError_t launch_dw_t(const float* in, const float* w, float* out, int B, int 
     return cudaGetLastError();
 }
 
+template <int KS, int S, int VEC, int XT, int TY>
+cudaError_t launch_dw3_t(const float* in, const float* w, float* out, int B, int Hi, int Wi, int C, int Ho, int Wo, int cvl,
+                         cudaStream_t s) {
+    const int cv = C / VEC;
+    const int nstrip = cdiv(Wo, XT), ncvh = cv / cvl, ntile_y = cdiv(Ho, TY);
+    const long long ntasks = (long long)B * ntile_y * ncvh * nstrip * cvl;
+    k_dw3<KS, S, VEC, XT, TY><<<(unsigned)((ntasks + 255) / 256), 256, 0, s>>>(in, w, out, B, Hi, Wi, C, Ho, Wo, cvl, nstrip, ncvh,
+                                                                                ntile_y, ntasks);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_dw(int ks, int st, const float* in, const float* w, float* out, int B, int Hi, int Wi, int C,
                       int Ho, int Wo, cudaStream_t s) {
+    // register-tiled kernel when the channel vectors split into lane groups of >= 128 contiguous bytes
+    const int vec = ks == 5 ? 2 : 4;
+    if (C % vec == 0) {
+        const int cv = C / vec;
+        int cvl = 32;
+        while (cvl > 1 && cv % cvl != 0) cvl >>= 1;
+        if (cvl * vec * 4 >= 128) {
+            if (ks == 3 && st == 1) return launch_dw3_t<3, 1, 4, 2, 4>(in, w, out, B, Hi, Wi, C, Ho, Wo, cvl, s);
+            if (ks == 3 && st == 2) return launch_dw3_t<3, 2, 4, 2, 4>(in, w, out, B, Hi, Wi, C, Ho, Wo, cvl, s);
+            if (ks == 5 && st == 1) return launch_dw3_t<5, 1, 2, 4, 4>(in, w, out, B, Hi, Wi, C, Ho, Wo, cvl, s);
+            return launch_dw3_t<5, 2, 2, 4, 4>(in, w, out, B, Hi, Wi, C, Ho, Wo, cvl, s);
+        }
+    }
     if (ks == 3 && st == 1) return launch_dw_t<3, 1>(in, w, out, B, Hi, Wi, C, Ho, Wo, s);
     if (ks == 3 && st == 2) return launch_dw_t<3, 2>(in, w, out, B, Hi, Wi, C, Ho, Wo, s);
     if (ks == 5 && st == 1) return launch_dw_t<5, 1>(in, w, out, B, Hi, Wi, C, Ho, Wo, s);
@@ -238,9 +268,15 @@ int build_plan(cf_engine* e, const void* input, int fmt, int B, int H, int W) {
         const bool fused = block_is_fused(e->pw_engine, b);
         if (fused) {
             // expand + Swish + depth-wise + Swish in one kernel; the hidden tensor stays in shared memory
-            XdLaunch xl;
-            if ((rc = xd_plan(e->tc, b.k, b.s, x, e->w[p + ".exp"], e->w[p + ".dw"], e->hidB, B, h, wd, b.cin, hid, &xl))) return rc;
-            P.push_back({CLS_FUSED, [xl](cudaStream_t s) { return xd_launch(xl, s); }});
+            if (e->pw_engine == CF_PW_TCGEN05_FUSED_TC) {
+                MbxLaunch ml;
+                if ((rc = mbx_plan(e->tc, b.k, b.s, x, e->w[p + ".exp"], e->w[p + ".dw"], e->hidB, B, h, wd, b.cin, hid, &ml))) return rc;
+                P.push_back({CLS_FUSED, [ml](cudaStream_t s) { return mbx_launch(ml, s); }});
+            } else {
+                XdLaunch xl;
+                if ((rc = xd_plan(e->tc, b.k, b.s, x, e->w[p + ".exp"], e->w[p + ".dw"], e->hidB, B, h, wd, b.cin, hid, &xl))) return rc;
+                P.push_back({CLS_FUSED, [xl](cudaStream_t s) { return xd_launch(xl, s); }});
+            }
         } else if (b.t != 1) {
             const float* wexp = e->w[p + ".exp"];
             float* o = e->hidA;
@@ -252,7 +288,13 @@ int build_plan(cf_engine* e, const void* input, int fmt, int B, int H, int W) {
             const float* wdw = e->w[p + ".dw"];
             float* o = e->hidB;
             const int ks = b.k, st = b.s, hi = h, wi = wd;
-            P.push_back({CLS_DW, [=](cudaStream_t s) { return launch_dw(ks, st, dw_in, wdw, o, B, hi, wi, hid, ho, wo, s); }});
+            if (engine_is_tc(e->pw_engine) && dwt_supported(hid)) {  // TMA-fed depth-wise kernel
+                DwtLaunch dl;
+                if ((rc = dwt_plan(e->tc, ks, st, dw_in, wdw, o, B, hi, wi, hid, &dl))) return rc;
+                P.push_back({CLS_DW, [dl](cudaStream_t s) { return dwt_launch(dl, s); }});
+            } else {
+                P.push_back({CLS_DW, [=](cudaStream_t s) { return launch_dw(ks, st, dw_in, wdw, o, B, hi, wi, hid, ho, wo, s); }});
+            }
         }
         {
             const float* wpr = e->w[p + ".proj"];
@@ -362,7 +404,7 @@ int cf_create(const void* weights, size_t weights_bytes, int device, int max_bat
     CF_CHECK(weights != nullptr, CF_EINVAL, "cf_create: weights is NULL");
     CF_CHECK(max_batch >= 1 && max_h >= 32 && max_w >= 32 && max_h % 32 == 0 && max_w % 32 == 0, CF_EINVAL,
              "cf_create: max_batch=%d max_h=%d max_w=%d (sizes must be positive multiples of 32)", max_batch, max_h, max_w);
-    CF_CHECK(pw_engine >= CF_PW_SIMT && pw_engine <= CF_PW_TCGEN05_FUSED, CF_EINVAL, "cf_create: unknown pw_engine %d", pw_engine);
+    CF_CHECK(pw_engine >= CF_PW_SIMT && pw_engine <= CF_PW_TCGEN05_FUSED_TC, CF_EINVAL, "cf_create: unknown pw_engine %d", pw_engine);
     CF_CHECK(weights_bytes == blob_bytes(), CF_EWEIGHTS, "cf_create: blob is %zu bytes, expected %zu", weights_bytes, blob_bytes());
     Blob blob;
     std::string why;
@@ -476,6 +518,11 @@ int cf_create(const void* weights, size_t weights_bytes, int device, int max_bat
         for (int i = 0; i < 12 && !rc; ++i) {
             const MBBlock& b = kBlocks[i];
             if (b.t != 1 && !block_is_fused(pw_engine, b)) rc = prep("b" + std::to_string(i) + ".exp", b.cin, b.hid());
+            if (b.t != 1 && block_is_fused(pw_engine, b) && pw_engine == CF_PW_TCGEN05_FUSED_TC) {  // 32-column chunk images
+                const std::string nm = "b" + std::to_string(i) + ".exp";
+                const float* hp = blob.get(nm, (uint64_t)b.cin * b.hid(), why);
+                rc = hp ? tc_prepare_layer(e->tc, e->w[nm], hp, b.cin, b.hid(), 3, 32) : fail(CF_EWEIGHTS, "cf_create: %s", why.c_str());
+            }
             if (!rc) rc = prep("b" + std::to_string(i) + ".proj", b.hid(), b.cout);
         }
         if (!rc) rc = prep("clast.w", 320, 24);

@@ -138,6 +138,97 @@ __global__ void __launch_bounds__(256) k_dw(const float* __restrict__ in, const 
 }
 
 // ----------------------------------------------------------------------------------------
+// K3b depth-wise, register-tiled (second generation; profiles/r1_summary.md: the first kernel issues 4.5 (3x3)
+// to 16 (5x5) L1 loads per output vector and is LSU-bound, 1.6-2.8 TB/s).  A thread owns XT x TY outputs of
+// VEC channels; all KS*KS taps of its channels sit in registers (VEC = 2 for 5x5 so that 25 taps fit), input rows
+// are streamed once through a WIN-wide register window and every loaded value feeds up to KS x KS FMAs:
+// 3 (3x3) to 4 (5x5 s1) loads per output vector.  Lanes run along the channel axis (CVL consecutive channel
+// vectors, >= 128 contiguous bytes per pixel), then along x strips.
+// ----------------------------------------------------------------------------------------
+template <int VEC>
+struct VecT;
+template <>
+struct VecT<2> {
+    typedef float2 T;
+};
+template <>
+struct VecT<4> {
+    typedef float4 T;
+};
+__device__ __forceinline__ float2 vzero(float2*) { return make_float2(0, 0); }
+__device__ __forceinline__ float4 vzero(float4*) { return make_float4(0, 0, 0, 0); }
+__device__ __forceinline__ void vfma(float2& a, float2 x, float2 w) {
+    a.x = fmaf(x.x, w.x, a.x);
+    a.y = fmaf(x.y, w.y, a.y);
+}
+__device__ __forceinline__ void vfma(float4& a, float4 x, float4 w) { fma44(a, x, w); }
+__device__ __forceinline__ float2 vswish(float2 v) { return make_float2(swishf(v.x), swishf(v.y)); }
+__device__ __forceinline__ float4 vswish(float4 v) { return swish4(v); }
+
+template <int KS, int S, int VEC, int XT, int TY>
+__global__ void __launch_bounds__(256) k_dw3(const float* __restrict__ in, const float* __restrict__ w,
+                                             float* __restrict__ out, int B, int Hi, int Wi, int C, int Ho, int Wo,
+                                             int cvl, int nstrip, int ncvh, int ntile_y, long long ntasks) {
+    typedef typename VecT<VEC>::T V;
+    constexpr int LO = (KS - S) / 2;
+    constexpr int WIN = (XT - 1) * S + KS, ROWS = (TY - 1) * S + KS;
+    long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (t >= ntasks) return;
+    const int cv_lo = (int)(t % cvl);
+    t /= cvl;
+    const int strip = (int)(t % nstrip);
+    t /= nstrip;
+    const int cv_hi = (int)(t % ncvh);
+    t /= ncvh;
+    const int ty = (int)(t % ntile_y);
+    const int b = (int)(t / ntile_y);
+    const int c0 = (cv_hi * cvl + cv_lo) * VEC;
+    const int xo0 = strip * XT, yo0 = ty * TY;
+
+    V wt[KS * KS];
+#pragma unroll
+    for (int i = 0; i < KS * KS; ++i) wt[i] = __ldg(reinterpret_cast<const V*>(w + (size_t)i * C + c0));
+    V acc[TY][XT];
+#pragma unroll
+    for (int y = 0; y < TY; ++y)
+#pragma unroll
+        for (int x = 0; x < XT; ++x) acc[y][x] = vzero((V*)nullptr);
+
+    const int ix0 = xo0 * S - LO, iy0 = yo0 * S - LO;
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        const int iy = iy0 + r;
+        if (iy < 0 || iy >= Hi) continue;  // zero padding rows contribute nothing
+        const float* row = in + ((size_t)(b * Hi + iy) * Wi) * C + c0;
+        V win[WIN];
+#pragma unroll
+        for (int i = 0; i < WIN; ++i) {
+            const int ix = ix0 + i;
+            win[i] = (ix >= 0 && ix < Wi) ? __ldg(reinterpret_cast<const V*>(row + (size_t)ix * C)) : vzero((V*)nullptr);
+        }
+#pragma unroll
+        for (int y = 0; y < TY; ++y) {
+            const int ky = r - y * S;
+            if (ky < 0 || ky >= KS) continue;
+#pragma unroll
+            for (int kx = 0; kx < KS; ++kx)
+#pragma unroll
+                for (int x = 0; x < XT; ++x) vfma(acc[y][x], win[x * S + kx], wt[ky * KS + kx]);
+        }
+    }
+#pragma unroll
+    for (int y = 0; y < TY; ++y) {
+        const int yo = yo0 + y;
+        if (yo >= Ho) continue;
+#pragma unroll
+        for (int x = 0; x < XT; ++x) {
+            const int xo = xo0 + x;
+            if (xo < Wo) *reinterpret_cast<V*>(out + ((size_t)(b * Ho + yo) * Wo + xo) * C + c0) = vswish(acc[y][x]);
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------
 // K5 heads.  The reference runs, per head, conv3x3(24->24)+b0 then conv1x1(24->c)+b1 with no
 // non-linearity between (model/centernet.py:249-256), so all four heads collapse exactly
 // (up to fp rounding) into ONE 3x3 conv 24->15: W' = W1.W0, b' = W1.b0 + b1,

@@ -1,0 +1,159 @@
+// k_dwt: depth-wise KSxKS stride S + Swish fed by TMA (third-generation depth-wise kernel).
+//
+// The register/L1 kernels (k_dw, k_dw3 in k_conv.cuh) are latency-bound: ncu shows 48 % of their warp stalls on
+// the long scoreboard at 36 % of DRAM peak -- a thread can keep only a handful of 16-byte loads in flight.  Here the
+// loads are bulk tensor copies: a CTA walks over (image, 10x10 output tile, 32-channel chunk) items, one elected
+// thread keeps NST halo tiles in flight with cp.async.bulk.tensor.4d (box = 32 channels x IW x IH, SWIZZLE_128B,
+// zero fill outside the image = the reference's ZeroPad2d, model/centernet.py:63-70), and all 256 threads compute
+// from shared memory with the same 2x2-output register blocking as the fused kernel (xd_dw_phase_g).  Bytes in flight
+// per SM = NST x tile (up to ~190 KB) instead of a few KB of registers.
+#pragma once
+#include "k_expdw.cuh"
+
+namespace cf {
+
+constexpr int DWT_THREADS = 256;
+
+template <int KS, int S>
+struct DwtGeom {
+    static constexpr int TH = 10, TW = 10;  // divides every map of the network (320, 160, 80, 40, 20)
+    static constexpr int IH = (TH - 1) * S + KS, IW = (TW - 1) * S + KS;
+    static constexpr int NPX = IH * IW;
+    static constexpr int LO = (KS - S) / 2;
+    static constexpr int XBYTES = ((NPX * 128 + 1023) / 1024) * 1024;
+};
+
+struct DwtParams {
+    XdParams x;  // We unused; hid = C
+    int nchunk;  // ceil(C / 32); TMA zero-fills the channels past C in the last chunk
+    int nst;     // pipeline stages
+};
+
+template <int KS, int S>
+__global__ void __launch_bounds__(DWT_THREADS, 2) k_dwt(const __grid_constant__ CUtensorMap tmX, const DwtParams P) {
+    using G = DwtGeom<KS, S>;
+    const XdParams& p = P.x;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+    const int nst = P.nst;
+    const uint32_t bars = base + (uint32_t)nst * G::XBYTES;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int c4 = lane & 7, pg = lane >> 3;
+    if (tid == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+        for (int i = 0; i < nst; ++i) mbar_init(bars + 8 * i, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    // item = ((b * tiles_y + ty) * tiles_x + tx) * nchunk + chunk : chunks of one tile are adjacent
+    auto issue = [&](int item, int stage) {  // thread 0 only
+        const int ch = item % P.nchunk;
+        int t = item / P.nchunk;
+        const int tx = t % p.tiles_x;
+        t /= p.tiles_x;
+        const int ty = t % p.tiles_y, b = t / p.tiles_y;
+        mbar_expect_tx(bars + 8 * stage, (uint32_t)G::NPX * 128u);
+        tma_load_4d(base + stage * G::XBYTES, &tmX, ch * 32, tx * G::TW * S - G::LO, ty * G::TH * S - G::LO, b, bars + 8 * stage);
+    };
+    if (tid == 0)
+        for (int i = 0; i < nst; ++i) {
+            const long long item = (long long)blockIdx.x + (long long)i * gridDim.x;
+            if (item < p.n_items) issue((int)item, i);
+        }
+    uint32_t it = 0;
+    for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+        const int stage = (int)(it % (uint32_t)nst);
+        mbar_wait(bars + 8 * stage, (it / (uint32_t)nst) & 1u);
+        const int ch = (int)(item % P.nchunk);
+        int t = (int)(item / P.nchunk);
+        const int tx = t % p.tiles_x;
+        t /= p.tiles_x;
+        const int ty = t % p.tiles_y, b = t / p.tiles_y;
+        const int cbase = ch * 32 + c4 * 4;
+        xd_dw_phase_g<G, KS, S, 2, 2, true, DWT_THREADS / 32>(sm + stage * G::XBYTES, p.Wd, p, warp, pg, c4, cbase, cbase < p.hid, b, ty, tx);
+        __syncthreads();  // every thread is done with this stage: refill it
+        if (tid == 0) {
+            const long long nxt = item + (long long)nst * gridDim.x;
+            if (nxt < p.n_items) issue((int)nxt, stage);
+        }
+    }
+}
+
+struct DwtLaunch {
+    CUtensorMap tmX;
+    DwtParams p;
+    int ks = 3, s = 1, grid = 0;
+    size_t smem = 0;
+};
+
+template <int KS, int S>
+inline cudaError_t dwt_launch_t(const DwtLaunch& dl, cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(k_dwt<KS, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    k_dwt<KS, S><<<dl.grid, DWT_THREADS, dl.smem, st>>>(dl.tmX, dl.p);
+    return cudaGetLastError();
+}
+
+inline cudaError_t dwt_launch(const DwtLaunch& dl, cudaStream_t st) {
+    if (dl.ks == 3 && dl.s == 1) return dwt_launch_t<3, 1>(dl, st);
+    if (dl.ks == 3 && dl.s == 2) return dwt_launch_t<3, 2>(dl, st);
+    if (dl.ks == 5 && dl.s == 1) return dwt_launch_t<5, 1>(dl, st);
+    return dwt_launch_t<5, 2>(dl, st);
+}
+
+template <int KS, int S>
+inline void dwt_geom(int* ih, int* iw, int* xb) {
+    using G = DwtGeom<KS, S>;
+    *ih = G::IH, *iw = G::IW, *xb = G::XBYTES;
+}
+
+inline bool dwt_supported(int C) { return C % 4 == 0 && C >= 16; }
+
+inline int dwt_plan(PwTcState& st, int ks, int s, const float* X, const float* Wd, float* D, int B, int Hi, int Wi, int C, DwtLaunch* dl) {
+    if (!dwt_supported(C)) return fail(CF_EINVAL, "dwt_plan: C=%d is not a multiple of 4", C);
+    int ih, iw, xb;
+    if (ks == 3 && s == 1) dwt_geom<3, 1>(&ih, &iw, &xb);
+    else if (ks == 3) dwt_geom<3, 2>(&ih, &iw, &xb);
+    else if (s == 1) dwt_geom<5, 1>(&ih, &iw, &xb);
+    else dwt_geom<5, 2>(&ih, &iw, &xb);
+    int rc = xd_make_map(st, &dl->tmX, X, B, Hi, Wi, C, iw, ih);
+    if (rc) return rc;
+    XdParams& p = dl->p.x;
+    p.We = nullptr;
+    p.Wd = Wd;
+    p.D = D;
+    p.B = B;
+    p.Hi = Hi;
+    p.Wi = Wi;
+    p.Ho = Hi / s;
+    p.Wo = Wi / s;
+    p.hid = C;
+    p.tiles_x = (p.Wo + 9) / 10;
+    p.tiles_y = (p.Ho + 9) / 10;
+    dl->p.nchunk = (C + 31) / 32;
+    const long long items = (long long)B * p.tiles_x * p.tiles_y * dl->p.nchunk;
+    if (items > 0x7fffffffLL) return fail(CF_EINVAL, "dwt_plan: too many tiles");
+    p.n_items = (int)items;
+    // two CTAs per SM when at least three stages fit in half of the shared memory, else one CTA with all of it
+    const int per_cta2 = (TC_SMEM_MAX / 2 - 2048) / xb;
+    int ctas_per_sm = 2, nst = per_cta2;
+    if (nst < 3) ctas_per_sm = 1, nst = (TC_SMEM_MAX - 2048) / xb;
+    if (nst > 8) nst = 8;
+    if (nst < 1) return fail(CF_EINVAL, "dwt_plan: tile does not fit shared memory");
+    dl->p.nst = nst;
+    dl->smem = (size_t)nst * xb + 64 + 1024;
+    dl->ks = ks;
+    dl->s = s;
+    const int want = ctas_per_sm * st.sms;
+    dl->grid = p.n_items < want ? p.n_items : want;
+    return CF_OK;
+}
+
+}  // namespace cf

@@ -49,6 +49,70 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
         : "memory");
 }
 
+// depth-wise KSxKS stride S + Swish from the swizzled E tile -> global D.  A thread owns an XT x YT block of
+// outputs for one float4 of channels; the ((YT-1)S+KS) x ((XT-1)S+KS) input window is streamed row by row.
+// Block shapes are chosen so that the phase spreads over as many of the 16 warps as the tile allows:
+// 16x16 tiles (S=1): 2x2 blocks on 16 warps; 8x8 tiles (S=2): 1x1 on 16 warps (3x3) or 2x1 on 8 warps (5x5).
+template <int KS, int S>
+struct XdDwShape {
+    static constexpr int XT = (S == 1) ? 2 : (KS == 3 ? 1 : 2);
+    static constexpr int YT = (S == 1) ? 2 : 1;
+};
+
+template <typename G, int KS, int S, int XT, int YT, bool WD_GLOBAL, int NWARPS>
+__device__ __forceinline__ void xd_dw_phase_g(const uint8_t* Es, const float* Wd_s, const XdParams& p, int warp, int pg, int c4,
+                                              int cbase, bool cvalid, int b, int ty, int tx) {
+    constexpr int NBX = G::TW / XT, NBLK = (G::TH / YT) * NBX;
+    static_assert(G::TW % XT == 0 && G::TH % YT == 0, "output blocks must tile the output tile");
+    constexpr int NROW = (YT - 1) * S + KS, NCOL = (XT - 1) * S + KS;
+    if (!cvalid) return;
+    for (int blk = warp * 4 + pg; blk < NBLK; blk += NWARPS * 4) {
+        const int by = blk / NBX, bx = blk - by * NBX;
+        float4 acc[YT][XT];
+#pragma unroll
+        for (int a = 0; a < YT; ++a)
+#pragma unroll
+            for (int c = 0; c < XT; ++c) acc[a][c] = make_float4(0, 0, 0, 0);
+        const int r0 = YT * by * S, q0 = XT * bx * S;  // window origin inside the halo tile
+#pragma unroll
+        for (int rr = 0; rr < NROW; ++rr) {
+            float4 win[NCOL];
+#pragma unroll
+            for (int cc = 0; cc < NCOL; ++cc) {
+                const int px = (r0 + rr) * G::IW + q0 + cc;
+                win[cc] = *reinterpret_cast<const float4*>(Es + px * 128 + ((c4 ^ (px & 7)) << 4));
+            }
+#pragma unroll
+            for (int dy = 0; dy < YT; ++dy) {
+                const int ky = rr - dy * S;
+                if (ky < 0 || ky >= KS) continue;
+#pragma unroll
+                for (int kx = 0; kx < KS; ++kx) {
+                    const float4 wv = WD_GLOBAL ? ldg4(Wd_s + (ky * KS + kx) * p.hid + cbase)
+                                                : *reinterpret_cast<const float4*>(Wd_s + (ky * KS + kx) * p.hid + cbase);
+#pragma unroll
+                    for (int dx = 0; dx < XT; ++dx) fma44(acc[dy][dx], win[dx * S + kx], wv);
+                }
+            }
+        }
+#pragma unroll
+        for (int dy = 0; dy < YT; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < XT; ++dx) {
+                const int yo = ty * G::TH + YT * by + dy, xo = tx * G::TW + XT * bx + dx;
+                if (yo < p.Ho && xo < p.Wo)
+                    st4(p.D + ((size_t)(b * p.Ho + yo) * p.Wo + xo) * p.hid + cbase, swish4(acc[dy][dx]));
+            }
+    }
+}
+
+template <int KS, int S>
+__device__ __forceinline__ void xd_dw_phase(const uint8_t* Es, const float* Wd_s, const XdParams& p, int warp, int pg, int c4,
+                                            int cbase, bool cvalid, int b, int ty, int tx) {
+    xd_dw_phase_g<XdGeom<KS, S>, KS, S, XdDwShape<KS, S>::XT, XdDwShape<KS, S>::YT, false, XD_THREADS / 32>(
+        Es, Wd_s, p, warp, pg, c4, cbase, cvalid, b, ty, tx);
+}
+
 template <int KS, int S, int CIN>
 __global__ void __launch_bounds__(XD_THREADS, 1) k_expdw(const __grid_constant__ CUtensorMap tmX, const XdParams p) {
     using G = XdGeom<KS, S>;
@@ -134,50 +198,172 @@ __global__ void __launch_bounds__(XD_THREADS, 1) k_expdw(const __grid_constant__
                 }
             }
             __syncthreads();
-            // ---------------- depth-wise KSxKS stride S + Swish from E -> global D ----------------
-            {
-                constexpr int NBX = G::TW / 2, NBLK = (G::TH / 2) * NBX, NWIN = S + KS;
-                const int blk = warp * 4 + pg;
-                if (cvalid && blk < NBLK) {
-                    const int by = blk / NBX, bx = blk - by * NBX;
-                    float4 acc[2][2];
-#pragma unroll
-                    for (int a = 0; a < 2; ++a)
-#pragma unroll
-                        for (int c = 0; c < 2; ++c) acc[a][c] = make_float4(0, 0, 0, 0);
-                    const int r0 = 2 * by * S, q0 = 2 * bx * S;  // window origin inside the halo tile
-#pragma unroll
-                    for (int rr = 0; rr < NWIN; ++rr) {
-                        float4 win[NWIN];
-#pragma unroll
-                        for (int cc = 0; cc < NWIN; ++cc) {
-                            const int px = (r0 + rr) * G::IW + q0 + cc;
-                            win[cc] = *reinterpret_cast<const float4*>(Es + px * 128 + ((c4 ^ (px & 7)) << 4));
-                        }
-#pragma unroll
-                        for (int dy = 0; dy < 2; ++dy) {
-                            const int ky = rr - dy * S;
-                            if (ky < 0 || ky >= KS) continue;
-#pragma unroll
-                            for (int kx = 0; kx < KS; ++kx) {
-                                const float4 wv = *reinterpret_cast<const float4*>(Wd_s + (ky * KS + kx) * p.hid + cbase);
-                                fma44(acc[dy][0], win[kx], wv);
-                                fma44(acc[dy][1], win[S + kx], wv);
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-                        for (int dx = 0; dx < 2; ++dx) {
-                            const int yo = ty * G::TH + 2 * by + dy, xo = tx * G::TW + 2 * bx + dx;
-                            if (yo < p.Ho && xo < p.Wo)
-                                st4(p.D + ((size_t)(b * p.Ho + yo) * p.Wo + xo) * p.hid + cbase, swish4(acc[dy][dx]));
-                        }
-                }
-            }
+            xd_dw_phase<KS, S>(Es, Wd_s, p, warp, pg, c4, cbase, cvalid, b, ty, tx);
             __syncthreads();  // E is rewritten by the next chunk; X[buf] by the TMA issued two items later
         }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// Tensor-core variant: the expand conv of a 32-channel chunk is  E[NPX x 32] = X[NPX x Cin] . We[Cin x 32]
+// on tcgen05 (kind::tf32, 3-pass hi/lo split like k_pw_tc).  The TMA's SWIZZLE_128B halo tile IS the
+// K-major A operand (row = halo pixel, 128 B = 32 K-floats), so M-blocks of 128 halo pixels are issued
+// straight from it; accumulators (main + correction per M-block) live in TMEM; warp w drains TMEM lane
+// quarter (w & 3) of M-block (w >> 2), applies Swish and writes the swizzled E rows the depth-wise phase
+// reads.  The MMAs of chunk c+1 are issued before the depth-wise phase of chunk c and overlap it.
+// This removes the ~512..1024 FFMAs per thread and chunk of the CUDA-core variant; what remains is bounded
+// by the two MUFU ops of each Swish.
+// ---------------------------------------------------------------------------------------------------
+struct XdTcParams {
+    XdParams x;
+    const float* we_img;   // [chunk][hi 32 x 128 B | lo 32 x 128 B], K-major SWIZZLE_128B (tc_prepare_layer, NC = 32)
+    uint32_t off_xlo, off_e, off_we, off_wd, off_bars;  // smem offsets from the 1024-aligned base
+    int prefetch;          // 1: two X buffers, the next tile is loaded while this one computes
+};
+
+template <int KS, int S, int CIN>
+__global__ void __launch_bounds__(XD_THREADS, 1) k_expdw_tc(const __grid_constant__ CUtensorMap tmX, const XdTcParams P) {
+    using G = XdGeom<KS, S>;
+    constexpr int NMB = (G::NPX + 127) / 128;  // M-blocks of 128 halo pixels (<= 4)
+    static_assert(NMB <= 4, "TMEM: 64 columns per M-block, 256 allocated");
+    const XdParams& p = P.x;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+    uint8_t* Xlo = sm + P.off_xlo;
+    uint8_t* Es = sm + P.off_e;
+    float* Wd_s = reinterpret_cast<float*>(sm + P.off_wd);
+    const uint32_t we_s = base + P.off_we;
+    const uint32_t bars = base + P.off_bars;  // [0],[1]: X full; [2]: MMA done
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + P.off_bars + 32);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int c4 = lane & 7, pg = lane >> 3;
+    const int nch = (p.hid + 31) >> 5;
+
+    if (tid == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+        mbar_init(bars, 1);
+        mbar_init(bars + 8, 1);
+        mbar_init(bars + 16, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = tid; i < KS * KS * p.hid / 4; i += XD_THREADS) reinterpret_cast<float4*>(Wd_s)[i] = ldg4(p.Wd + 4 * i);
+    for (int i = tid; i < nch * 512; i += XD_THREADS)  // 8 KB of hi|lo image per chunk
+        reinterpret_cast<float4*>(sm + P.off_we)[i] = ldg4(P.we_img + 4 * i);
+    fence_proxy_async();  // the weight image is read by the tensor core (async proxy)
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto issue_tma = [&](int item, int buf) {  // thread 0 only
+        fence_proxy_async();  // the buffer was last written in place by generic-proxy stores (tf32 rounding)
+        const int tx = item % p.tiles_x;
+        const int t2 = item / p.tiles_x;
+        const int ty = t2 % p.tiles_y, b = t2 / p.tiles_y;
+        mbar_expect_tx(bars + 8 * buf, (uint32_t)G::NPX * 128u);
+        tma_load_4d(base + buf * G::XBYTES, &tmX, 0, tx * G::TW * S - G::LO, ty * G::TH * S - G::LO, b, bars + 8 * buf);
+    };
+    const uint32_t idesc = umma_idesc_tf32(32);
+    auto issue_mma = [&](int ch, uint32_t xa) {  // thread 0 only: all M-blocks of one 32-channel chunk
+        const uint64_t b_hi = umma_desc(we_s + ch * 8192), b_lo = umma_desc(we_s + ch * 8192 + 4096);
+#pragma unroll
+        for (int mb = 0; mb < NMB; ++mb) {
+            const uint64_t a_hi = umma_desc(xa + mb * 16384), a_lo = umma_desc(base + P.off_xlo + mb * 16384);
+            const uint32_t d_main = tmem_base + mb * 64, d_corr = d_main + 32;
+#pragma unroll
+            for (int k = 0; k < (CIN + 7) / 8; ++k) {
+                const uint64_t ko = (uint64_t)(k * 2);
+                umma_tf32(d_corr, a_lo + ko, b_hi + ko, idesc, k > 0);
+                umma_tf32(d_corr, a_hi + ko, b_lo + ko, idesc, 1u);
+                umma_tf32(d_main, a_hi + ko, b_hi + ko, idesc, k > 0);
+            }
+        }
+        umma_commit(bars + 16);
+    };
+
+    if (tid == 0 && (int)blockIdx.x < p.n_items) issue_tma(blockIdx.x, 0);
+    uint32_t it = 0, mma_phase = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+        const int buf = P.prefetch ? (int)(it & 1) : 0;
+        if (P.prefetch) {
+            if (tid == 0 && item + (int)gridDim.x < p.n_items) issue_tma(item + gridDim.x, buf ^ 1);
+            mbar_wait(bars + 8 * buf, (it >> 1) & 1u);
+        } else {
+            mbar_wait(bars, it & 1u);
+        }
+        uint8_t* X = sm + buf * G::XBYTES;
+        const int tx = item % p.tiles_x;
+        const int t2 = item / p.tiles_x;
+        const int ty = t2 % p.tiles_y, b = t2 / p.tiles_y;
+
+        // split the halo tile once: X <- rn_tf32(X) in place, Xlo <- the exact remainder
+        for (int i = tid; i < G::NPX * 8; i += XD_THREADS) {
+            float4* a = reinterpret_cast<float4*>(X) + i;
+            const float4 v = *a;
+            const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+            *a = h;
+            reinterpret_cast<float4*>(Xlo)[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            issue_mma(0, base + buf * G::XBYTES);
+        }
+        for (int ch = 0; ch < nch; ++ch) {
+            const int cbase = ch * 32 + c4 * 4;
+            const bool cvalid = cbase < p.hid;
+            // ---- drain the accumulators: + correction, Swish, swizzled E rows ----
+            mbar_wait(bars + 16, mma_phase);
+            mma_phase ^= 1u;
+            tc_fence_after();
+            {
+                // warp w drains columns [8*(w>>2), +8) of TMEM lane quarter (w&3) for every M-block, so all 16
+                // warps share the Swish (MUFU) work of the chunk
+                const int q = warp & 3, cg = warp >> 2;
+#pragma unroll
+                for (int mb = 0; mb < NMB; ++mb) {
+                    if (mb * 128 + q * 32 >= G::NPX) break;  // warp-uniform: no valid halo pixel in these 32 rows
+                    const int px = mb * 128 + q * 32 + lane;
+                    float v[8], c[8];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * 64 + cg * 8);
+                    tmem_ld8(taddr, v);
+                    tmem_ld8(taddr + 32u, c);
+                    tmem_ld_wait();
+                    if (px < G::NPX) {
+                        uint8_t* er = Es + px * 128;
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const float4 o = swish4(make_float4(v[4 * j] + c[4 * j], v[4 * j + 1] + c[4 * j + 1],
+                                                                v[4 * j + 2] + c[4 * j + 2], v[4 * j + 3] + c[4 * j + 3]));
+                            *reinterpret_cast<float4*>(er + (((2 * cg + j) ^ (px & 7)) << 4)) = o;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncthreads();  // E complete; every TMEM read of this chunk is done
+            if (tid == 0 && ch + 1 < nch) {
+                tc_fence_after();
+                issue_mma(ch + 1, base + buf * G::XBYTES);  // overlaps the depth-wise phase below
+            }
+            xd_dw_phase<KS, S>(Es, Wd_s, p, warp, pg, c4, cbase, cvalid, b, ty, tx);
+            __syncthreads();  // E is rewritten by the next chunk
+        }
+        if (!P.prefetch && tid == 0 && item + (int)gridDim.x < p.n_items) issue_tma(item + gridDim.x, 0);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
     }
 }
 
@@ -198,6 +384,8 @@ inline int xd_make_map(PwTcState& st, CUtensorMap* map, const float* ptr, int B,
 struct XdLaunch {
     CUtensorMap tmX;
     XdParams p;
+    XdTcParams tp;
+    bool tc = false;  // tensor-core expand
     int ks = 3, s = 1, cin = 16, grid = 0;
     size_t smem = 0;
 };
@@ -210,7 +398,17 @@ inline cudaError_t xd_launch_t(const XdLaunch& xl, cudaStream_t st) {
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    k_expdw<KS, S, CIN><<<xl.grid, XD_THREADS, xl.smem, st>>>(xl.tmX, xl.p);
+    if (xl.tc) {
+        static bool attr_tc = false;
+        if (!attr_tc) {
+            cudaError_t e = cudaFuncSetAttribute(k_expdw_tc<KS, S, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
+            if (e != cudaSuccess) return e;
+            attr_tc = true;
+        }
+        k_expdw_tc<KS, S, CIN><<<xl.grid, XD_THREADS, xl.smem, st>>>(xl.tmX, xl.tp);
+    } else {
+        k_expdw<KS, S, CIN><<<xl.grid, XD_THREADS, xl.smem, st>>>(xl.tmX, xl.p);
+    }
     return cudaGetLastError();
 }
 
@@ -234,8 +432,41 @@ inline void xd_geom(int* th, int* tw, int* ih, int* iw, int* xbytes) {
     *th = G::TH, *tw = G::TW, *ih = G::IH, *iw = G::IW, *xbytes = G::XBYTES;
 }
 
+// shared-memory map of k_expdw_tc: X[1 or 2] | Xlo | E | We images | Wd | barriers.  Returns the dynamic smem size
+// (> TC_SMEM_MAX if even the single-buffered variant does not fit).
+inline size_t xd_tc_layout(int ks, int hid, int npx, int xb, XdTcParams* tp) {
+    const uint32_t nch = (uint32_t)(hid + 31) / 32;
+    const uint32_t nmb = (uint32_t)(npx + 127) / 128;
+    const uint32_t we_bytes = nch * 8192u, wd_bytes = (((uint32_t)(ks * ks * hid * 4) + 1023u) / 1024u) * 1024u;
+    // the A operand of the last M-block reads up to nmb*16 KB past a tile's start: keep every tile region that large
+    const uint32_t xreg = nmb * 16384u > (uint32_t)xb ? nmb * 16384u : (uint32_t)xb;
+    size_t smem = 0;
+    for (int pf = 1; pf >= 0; --pf) {
+        const uint32_t nx = pf ? 2u : 1u;
+        // X buffers are XBYTES apart (the kernel's indexing); the region after the last one absorbs the over-read
+        const uint32_t off_xlo = (nx - 1) * (uint32_t)xb + xreg;
+        const uint32_t off_e = off_xlo + xreg;
+        const uint32_t off_we = off_e + (uint32_t)xb;
+        const uint32_t off_wd = off_we + we_bytes;
+        const uint32_t off_bars = off_wd + wd_bytes;
+        smem = (size_t)off_bars + 64 + 1024;
+        if (tp) tp->prefetch = pf, tp->off_xlo = off_xlo, tp->off_e = off_e, tp->off_we = off_we, tp->off_wd = off_wd, tp->off_bars = off_bars;
+        if (smem <= (size_t)TC_SMEM_MAX) break;
+    }
+    return smem;
+}
+
+inline bool xd_tc_fits(int ks, int s, int hid) {
+    int th, tw, ih, iw, xb;
+    if (ks == 3 && s == 1) xd_geom<3, 1>(&th, &tw, &ih, &iw, &xb);
+    else if (ks == 3) xd_geom<3, 2>(&th, &tw, &ih, &iw, &xb);
+    else if (s == 1) xd_geom<5, 1>(&th, &tw, &ih, &iw, &xb);
+    else xd_geom<5, 2>(&th, &tw, &ih, &iw, &xb);
+    return xd_tc_layout(ks, hid, ih * iw, xb, nullptr) <= (size_t)TC_SMEM_MAX;
+}
+
 inline int xd_plan(PwTcState& st, int ks, int s, const float* X, const float* We, const float* Wd, float* D, int B, int Hi, int Wi,
-                   int cin, int hid, XdLaunch* xl) {
+                   int cin, int hid, XdLaunch* xl, bool tc = false) {
     if (!xd_supported(ks, s, cin)) return fail(CF_EINVAL, "xd_plan: no fused kernel for k=%d s=%d cin=%d", ks, s, cin);
     int th, tw, ih, iw, xb;
     if (ks == 3 && s == 1) xd_geom<3, 1>(&th, &tw, &ih, &iw, &xb);
@@ -262,6 +493,16 @@ inline int xd_plan(PwTcState& st, int ks, int s, const float* X, const float* We
     xl->cin = cin;
     xl->grid = p.n_items < st.sms ? p.n_items : st.sms;
     xl->smem = (size_t)3 * xb + (size_t)(cin + ks * ks) * hid * 4 + 64 + 1024;
+    xl->tc = tc;
+    if (tc) {
+        auto it = st.layers.find(We);
+        if (it == st.layers.end() || it->second.NC != 32 || it->second.nkb != 1)
+            return fail(CF_EINVAL, "xd_plan: expand weights were not prepared as 32-column tensor-core images");
+        XdTcParams& tp = xl->tp;
+        tp.x = p;
+        tp.we_img = it->second.img;
+        xl->smem = xd_tc_layout(ks, hid, ih * iw, xb, &tp);
+    }
     if (xl->smem > (size_t)TC_SMEM_MAX) return fail(CF_EINVAL, "xd_plan: tile does not fit shared memory (%zu B)", xl->smem);
     return CF_OK;
 }

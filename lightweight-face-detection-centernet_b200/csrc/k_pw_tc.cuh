@@ -160,6 +160,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // round-to-nearest split of an fp32 into tf32 hi (low 13 mantissa bits zero) + exact remainder
@@ -453,12 +460,13 @@ inline void tc_choose_chunks(int K, int N, int passes, int* NC, int* nchunks) {
 }
 
 // Build (once per weight matrix) the tf32 hi/lo, K-major, 128B-swizzled image of W[K][N] (host copy `hw`).
-inline int tc_prepare_layer(PwTcState& st, const float* key, const float* hw, int K, int N, int passes) {
+inline int tc_prepare_layer(PwTcState& st, const float* key, const float* hw, int K, int N, int passes, int force_nc = 0) {
     if (st.layers.count(key)) return CF_OK;
     TcLayer L;
     L.K = K;
     L.N = N;
     tc_choose_chunks(K, N, passes, &L.NC, &L.nchunks);
+    if (force_nc) L.NC = force_nc, L.nchunks = (N + force_nc - 1) / force_nc;
     L.nkb = (K + TC_BK - 1) / TC_BK;
     const size_t blk = (size_t)L.NC * 128;  // bytes of one hi (or lo) block
     L.img_bytes = (size_t)L.nchunks * L.nkb * blk * 2;
