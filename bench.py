@@ -36,7 +36,7 @@ UNIT = "images/s"
 H = W = 640
 PER_GPU_BATCH = 32
 K_TOP = 100
-CLASS_NAMES = {1: "pointwise_gemm", 2: "depthwise", 3: "stem", 4: "heads", 5: "decode_topk", 6: "fused_expand_dw"}
+CLASS_NAMES = {1: "pointwise_gemm", 2: "depthwise", 3: "stem", 4: "heads", 5: "decode_topk", 6: "fused_blocks"}
 
 
 def parse():
@@ -183,7 +183,7 @@ def run_b200(a):
     if world > 1:
         dist.barrier()
     B = a.batch
-    pw = a.pw if a.pw >= 0 else L.CF_PW_TCGEN05_FUSED_TC
+    pw = a.pw if a.pw >= 0 else L.CF_PW_TCGEN05
     eng = pkg.Engine(WEIGHTS, max_batch=B, max_h=H, max_w=W, device=local, pw_engine=pw)
     dev = torch.device(f"cuda:{local}")
 
@@ -312,7 +312,7 @@ def run_b200(a):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": warm,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": {0: "f32", 1: "tf32x3", 2: "tf32", 3: "tf32x3+f32", 4: "tf32x3"}[pw], "data": "synthetic",
+                "dtype": {0: "f32", 1: "tf32x3", 2: "tf32", 3: "tf32x3+f32", 4: "tf32x3", 5: "tf32x3"}[pw], "data": "synthetic",
                 "config": {"workload": f"batch-{B} 640x640 per GPU ({'configs[1]' if world == 1 else 'configs[2] sharding'}), "
                                        f"u8 BGR input, network + sigmoid/clamp + path-C top-{K_TOP} decode"
                                        + (", NCCL all-gather of [B,100,6] boxes" if world > 1 else ""),

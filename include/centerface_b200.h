@@ -52,6 +52,8 @@ extern "C" {
                                  expand on the fp32 CUDA cores                                        */
 #define CF_PW_TCGEN05_FUSED_TC 4 /* same fusion, the expand conv of the fused blocks on tcgen05 (3xTF32),
                                     accumulators drained from TMEM straight into the shared-memory tile */
+#define CF_PW_TCGEN05_DWP 5 /* CF_PW_TCGEN05 + the shallow blocks run depth-wise+Swish+projection(+residual) as ONE
+                               kernel: the depth-wise output is written as the tcgen05 A operand in shared memory */
 
 /* decode variants for cf_decode_threshold */
 #define CF_DECODE_A 0 /* centerface.py:73-109   : offsets unused, landmarks, clip to (H,W)   */

@@ -46,7 +46,7 @@ class CenterFace(object):
         self.img_h_new, self.img_w_new, self.scale_h, self.scale_w = self.transform(height, width)
         if engine is None:
             if pw_engine is None:
-                pw_engine = int(os.environ.get("CENTERFACE_B200_PW", L.CF_PW_TCGEN05_FUSED_TC))
+                pw_engine = int(os.environ.get("CENTERFACE_B200_PW", L.CF_PW_TCGEN05))
             engine = Engine(_resolve_weights(weights), max_batch=1, max_h=self.img_h_new, max_w=self.img_w_new,
                             device=device, pw_engine=pw_engine)
         self.net = engine
@@ -100,7 +100,7 @@ class CenterFaceNet(object):
     """Model-level drop-in for ``efficientnet_b0()`` as eval_widerface.get_detections uses it
     (eval_widerface.py:76-90): ``model(x)[0]`` is a dict of cuda tensors 'hm','wh','lm','reg'."""
 
-    def __init__(self, weights=None, max_batch=32, max_h=640, max_w=640, device=0, pw_engine=L.CF_PW_TCGEN05_FUSED_TC):
+    def __init__(self, weights=None, max_batch=32, max_h=640, max_w=640, device=0, pw_engine=L.CF_PW_TCGEN05):
         self.engine = Engine(_resolve_weights(weights), max_batch, max_h, max_w, device, pw_engine)
 
     def eval(self):

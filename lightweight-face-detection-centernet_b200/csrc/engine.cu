@@ -21,6 +21,7 @@
 #include "k_expdw.cuh"
 #include "k_mbx.cuh"
 #include "k_dwt.cuh"
+#include "k_dwp.cuh"
 #include "net.hpp"
 
 using namespace cf;
@@ -31,6 +32,9 @@ enum WorkClass { CLS_ALL = 0, CLS_PW = 1, CLS_DW = 2, CLS_STEM = 3, CLS_HEADS = 
 
 inline bool engine_is_tc(int pw) { return pw != CF_PW_SIMT; }
 inline int engine_passes(int pw) { return pw == CF_PW_TCGEN05_1P ? 1 : 3; }
+// depth-wise + projection fused (k_dwp): the shallow blocks, where the depth-wise output is large and tiles are plentiful
+inline bool block_is_dwp(int pw, int i) { return pw == CF_PW_TCGEN05_DWP && i <= 5 && dwp_supported(kBlocks[i].hid(), kBlocks[i].cout); }
+
 inline bool block_is_fused(int pw, const MBBlock& b) {
     if (b.t == 1 || !xd_supported(b.k, b.s, b.cin)) return false;
     if (pw == CF_PW_TCGEN05_FUSED) return true;
@@ -284,19 +288,26 @@ int build_plan(cf_engine* e, const void* input, int fmt, int B, int H, int W) {
             if ((rc = make_pw_step(e, P, EPI_SWISH, x, wexp, o, M, K, hid, EpiArgs{}))) return rc;
             dw_in = e->hidA;
         }
-        if (!fused) {
-            const float* wdw = e->w[p + ".dw"];
-            float* o = e->hidB;
-            const int ks = b.k, st = b.s, hi = h, wi = wd;
-            if (engine_is_tc(e->pw_engine) && dwt_supported(hid)) {  // TMA-fed depth-wise kernel
-                DwtLaunch dl;
-                if ((rc = dwt_plan(e->tc, ks, st, dw_in, wdw, o, B, hi, wi, hid, &dl))) return rc;
-                P.push_back({CLS_DW, [dl](cudaStream_t s) { return dwt_launch(dl, s); }});
-            } else {
-                P.push_back({CLS_DW, [=](cudaStream_t s) { return launch_dw(ks, st, dw_in, wdw, o, B, hi, wi, hid, ho, wo, s); }});
+        if (block_is_dwp(e->pw_engine, i)) {
+            // depth-wise + Swish + projection (+ residual) in one kernel; the depth-wise output stays in shared memory
+            DwpLaunch dl;
+            if ((rc = dwp_plan(e->tc, b.k, b.s, dw_in, e->w[p + ".dw"], e->w[p + ".proj"], e->blk[i], b.residual() ? x : nullptr, B, h, wd,
+                               hid, b.cout, &dl)))
+                return rc;
+            P.push_back({CLS_FUSED, [dl](cudaStream_t s) { return dwp_launch(dl, s); }});
+        } else {
+            if (!fused) {
+                const float* wdw = e->w[p + ".dw"];
+                float* o = e->hidB;
+                const int ks = b.k, st = b.s, hi = h, wi = wd;
+                if (engine_is_tc(e->pw_engine) && dwt_supported(hid)) {  // TMA-fed depth-wise kernel
+                    DwtLaunch dl;
+                    if ((rc = dwt_plan(e->tc, ks, st, dw_in, wdw, o, B, hi, wi, hid, &dl))) return rc;
+                    P.push_back({CLS_DW, [dl](cudaStream_t s) { return dwt_launch(dl, s); }});
+                } else {
+                    P.push_back({CLS_DW, [=](cudaStream_t s) { return launch_dw(ks, st, dw_in, wdw, o, B, hi, wi, hid, ho, wo, s); }});
+                }
             }
-        }
-        {
             const float* wpr = e->w[p + ".proj"];
             const float* a = e->hidB;
             float* o = e->blk[i];
@@ -404,7 +415,7 @@ int cf_create(const void* weights, size_t weights_bytes, int device, int max_bat
     CF_CHECK(weights != nullptr, CF_EINVAL, "cf_create: weights is NULL");
     CF_CHECK(max_batch >= 1 && max_h >= 32 && max_w >= 32 && max_h % 32 == 0 && max_w % 32 == 0, CF_EINVAL,
              "cf_create: max_batch=%d max_h=%d max_w=%d (sizes must be positive multiples of 32)", max_batch, max_h, max_w);
-    CF_CHECK(pw_engine >= CF_PW_SIMT && pw_engine <= CF_PW_TCGEN05_FUSED_TC, CF_EINVAL, "cf_create: unknown pw_engine %d", pw_engine);
+    CF_CHECK(pw_engine >= CF_PW_SIMT && pw_engine <= CF_PW_TCGEN05_DWP, CF_EINVAL, "cf_create: unknown pw_engine %d", pw_engine);
     CF_CHECK(weights_bytes == blob_bytes(), CF_EWEIGHTS, "cf_create: blob is %zu bytes, expected %zu", weights_bytes, blob_bytes());
     Blob blob;
     std::string why;
@@ -523,7 +534,13 @@ int cf_create(const void* weights, size_t weights_bytes, int device, int max_bat
                 const float* hp = blob.get(nm, (uint64_t)b.cin * b.hid(), why);
                 rc = hp ? tc_prepare_layer(e->tc, e->w[nm], hp, b.cin, b.hid(), 3, 32) : fail(CF_EWEIGHTS, "cf_create: %s", why.c_str());
             }
-            if (!rc) rc = prep("b" + std::to_string(i) + ".proj", b.hid(), b.cout);
+            if (!rc && block_is_dwp(pw_engine, i)) {  // one padded-N image per 32-channel K block
+                const std::string nm = "b" + std::to_string(i) + ".proj";
+                const float* hp = blob.get(nm, (uint64_t)b.hid() * b.cout, why);
+                rc = hp ? tc_prepare_layer(e->tc, e->w[nm], hp, b.hid(), b.cout, 3, dwp_ncp(b.cout)) : fail(CF_EWEIGHTS, "cf_create: %s", why.c_str());
+            } else if (!rc) {
+                rc = prep("b" + std::to_string(i) + ".proj", b.hid(), b.cout);
+            }
         }
         if (!rc) rc = prep("clast.w", 320, 24);
         const int skip_c[3] = {96, 32, 24};
@@ -836,8 +853,15 @@ int cf_work_model(int h, int w, int in_format, int pw_engine, int which, double*
             by[CLS_DW] += (hh * ww + ho * wo) * hid * F;
             fl[CLS_DW] += 2.0 * ho * wo * hid * b.k * b.k;
         }
-        by[CLS_PW] += ho * wo * (hid + b.cout + (b.residual() ? b.cout : 0)) * F;
-        fl[CLS_PW] += 2.0 * ho * wo * hid * b.cout;
+        if (block_is_dwp(pw_engine, i)) {  // expanded tensor in, block output out; the depth-wise output never reaches HBM
+            by[CLS_DW] -= (hh * ww + ho * wo) * hid * F;
+            fl[CLS_DW] -= 2.0 * ho * wo * hid * b.k * b.k;
+            by[CLS_FUSED] += (hh * ww * hid + ho * wo * (b.cout + (b.residual() ? b.cout : 0))) * F;
+            fl[CLS_FUSED] += 2.0 * ho * wo * hid * b.k * b.k + 2.0 * ho * wo * hid * b.cout;
+        } else {
+            by[CLS_PW] += ho * wo * (hid + b.cout + (b.residual() ? b.cout : 0)) * F;
+            fl[CLS_PW] += 2.0 * ho * wo * hid * b.cout;
+        }
         hh = ho;
         ww = wo;
     }

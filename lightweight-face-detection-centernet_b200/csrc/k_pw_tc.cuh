@@ -52,6 +52,10 @@ struct TcParams {
     const float* bimg;
     int M, K, N, NC, nchunks, nkb, n_items;
     int resident;    // 1: the whole B image lives in smem for the kernel's lifetime
+    int direct;      // 1: narrow outputs (N <= 64): the epilogue stores rows straight from registers, the staging
+                     //    buffers' 64 KB go to two more pipeline stages
+    float* out;      // [M][N] (direct stores)
+    int dbg;         // development only (env CF_TC_DEBUG): 1 skip the A split, 2 skip the stores, 4 skip the MMAs
     int stages;
     uint32_t stage_bytes, a_bytes_stage, b_bytes_block;  // b_bytes_block = NC*128*(passes==3?2:1)
     uint32_t off_bres, off_stages, off_bars;             // smem offsets from the 1024-aligned base
@@ -287,8 +291,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 // tools/tc_accum_probe.py); keeping the 2K/8 correction steps out of the main sum
                 // leaves it K/8 truncations instead of 3K/8, and the corrections' own truncation
                 // is 2^-11 smaller.  The epilogue adds the two in fp32 (round-to-nearest).
+                // The correction accumulator sits right behind the main one (columns [NC, 2NC)) and the weight image
+                // stores the hi block right before the lo block, so  A_hi . [B_hi | B_lo]  is ONE MMA of width 2NC
+                // filling both accumulators; only  A_lo . B_hi  needs a second one.  For the narrow layers (N <= 64)
+                // an MMA is bound by streaming its 128 x 32 B A operand out of shared memory (measured ~60 cycles
+                // per instruction whatever N is, tools/tc_shape_probe.py), so two MMAs per K step instead of three
+                // is a third off the tensor-pipe time.
                 const uint32_t d_tmem = tmem_base + as * 256u;
-                const uint32_t d_corr = d_tmem + 128u;
+                const uint32_t d_corr = d_tmem + (uint32_t)p.NC;
+                const uint32_t idesc2 = umma_idesc_tf32(2 * p.NC);
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait((kPasses == 3 ? bar_ready : bar_full) + 8 * stage, phase);
                     tc_fence_after();
@@ -298,14 +309,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     const int nks = krem >= TC_BK ? TC_BK / 8 : (krem + 7) / 8;
                     const uint64_t a_hi = umma_desc(sa), b_hi = umma_desc(sb);
                     for (int k = 0; k < nks; ++k) {
+                        if ((p.dbg & 4) && !(kb == 0 && k == 0)) break;
                         const uint64_t ko = (uint64_t)(k * 2);  // +32 bytes along K, in 16-byte units
                         const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
                         if (kPasses == 3) {
-                            const uint64_t a_lo = umma_desc(sa + TC_A_BYTES), b_lo = umma_desc(sb + lo_off);
-                            umma_tf32(d_corr, a_lo + ko, b_hi + ko, idesc, acc);
-                            umma_tf32(d_corr, a_hi + ko, b_lo + ko, idesc, 1u);
+                            const uint64_t a_lo = umma_desc(sa + TC_A_BYTES);
+                            umma_tf32(d_tmem, a_hi + ko, b_hi + ko, idesc2, acc);  // main += hi.hi ; corr += hi.lo
+                            umma_tf32(d_corr, a_lo + ko, b_hi + ko, idesc, 1u);    // corr += lo.hi
+                        } else {
+                            umma_tf32(d_tmem, a_hi + ko, b_hi + ko, idesc, acc);
                         }
-                        umma_tf32(d_tmem, a_hi + ko, b_hi + ko, idesc, acc);
                     }
                     umma_commit(bar_empty + 8 * stage);  // frees the smem slot when these MMAs retire
                     if (kb == nkb - 1) umma_commit(bar_tfull + 8 * as);
@@ -326,6 +339,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     float4* l = a + TC_A_BYTES / 16;
 #pragma unroll
                     for (int i = 0; i < TC_A_BYTES / 16 / 128; ++i) {
+                        if (p.dbg & 1) break;
                         const float4 v = a[t + i * 128];
                         const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
                         a[t + i * 128] = h;
@@ -362,7 +376,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 tmem_ld32(taddr, v);
                 if (kPasses == 3) {
                     float c[32];
-                    tmem_ld32(taddr + 128u, c);
+                    tmem_ld32(taddr + (uint32_t)p.NC, c);
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] += c[j];
@@ -374,6 +388,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_tempty + 8 * g);
+                }
+                if (p.dbg & 2) continue;
+                if (p.direct) {
+                    // one thread = one output row: up to 128 contiguous bytes per 32-column block
+                    if (row < p.M) {
+                        float* orow = p.out + (size_t)row * p.N + col0;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int n = col0 + 4 * j;
+                            if (n < p.N) {
+                                float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                                o = tc_epi<EPI>(o, row, n, p.N, p.ea);
+                                st4(orow + 4 * j, o);
+                            }
+                        }
+                    }
+                    continue;
                 }
                 if (lane == 0) bulk_wait_read<TC_STG_BUFS - 1>();  // the staging buffer we are about to overwrite
                 __syncwarp();
@@ -527,7 +558,12 @@ inline int tc_plan(PwTcState& st, int passes, int epi, const float* A, const flo
     // "block" stride is still the pair.
     p.b_bytes_block = (uint32_t)L.NC * 128u * 2u;
     p.a_bytes_stage = TC_A_BYTES * hl;
-    const uint32_t stg_bytes = 8u * TC_STG_BUFS * TC_STG_BYTES;  // 8 epilogue warps
+    p.direct = (N <= 64) ? 1 : 0;
+    if (const char* ev = getenv("CF_TC_DIRECT")) p.direct = atoi(ev);
+    p.out = out;
+    p.dbg = 0;
+    if (const char* ev = getenv("CF_TC_DEBUG")) p.dbg = atoi(ev);
+    const uint32_t stg_bytes = p.direct ? 0u : 8u * TC_STG_BUFS * TC_STG_BYTES;  // 8 epilogue warps
     const uint32_t bar_bytes = 1024;
     const uint32_t avail = TC_SMEM_MAX - 1024 /*alignment slack*/ - stg_bytes - bar_bytes;
     const uint32_t b_total = (uint32_t)L.img_bytes;

@@ -32,7 +32,7 @@ class Engine:
     ``max_h x max_w``.  Replaces efficientnet_b0() + load_state_dict + .cuda()
     (centerface.py:19-24)."""
 
-    def __init__(self, weights, max_batch=1, max_h=640, max_w=640, device=0, pw_engine=L.CF_PW_TCGEN05_FUSED_TC):
+    def __init__(self, weights, max_batch=1, max_h=640, max_w=640, device=0, pw_engine=L.CF_PW_TCGEN05):
         self.lib = L.load()
         if isinstance(weights, (str, bytes)) and not isinstance(weights, bytes):
             weights = load_state_dict(weights)
