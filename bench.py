@@ -114,40 +114,51 @@ def run_reference(a):
 # clocks sampler (B200_PROFILING.md)
 # ---------------------------------------------------------------------------------------------
 class Clocks:
+    """Samples SM clock, power and throttle reasons every 100 ms from ONE streaming nvidia-smi process while the
+    timed regions run (B200_PROFILING.md recipe)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.index, self.rows, self.stop = index, [], False
+        self.index, self.rows, self.proc = index, [], None
         self.t = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
-        while not self.stop:
-            try:
-                r = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                   capture_output=True, text=True, timeout=5)
-                if r.returncode == 0 and r.stdout.strip():
-                    self.rows.append([c.strip() for c in r.stdout.strip().split(",")])
-            except Exception:
-                pass
-            time.sleep(0.1)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                c = [x.strip() for x in line.strip().split(",")]
+                if len(c) >= 7:
+                    self.rows.append(c)
+        except Exception:
+            pass
 
     def __enter__(self):
         self.t.start()
+        time.sleep(0.3)
         return self
 
     def __exit__(self, *exc):
-        self.stop = True
-        self.t.join(timeout=6)
+        time.sleep(0.15)
+        if self.proc is not None:
+            self.proc.terminate()
+        self.t.join(timeout=5)
 
     def summary(self):
-        if not self.rows:
+        rows = []
+        for r in self.rows:
+            try:
+                rows.append((float(r[0]), float(r[1]), float(r[2]), r[3:7]))
+            except ValueError:
+                continue
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows)
+        sm = sorted(r[0] for r in rows)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows)}
+        reasons = [n for i, n in enumerate(names) if any(r[3][i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": rows[0][1], "reasons": reasons,
+                "power_w_max": max(r[2] for r in rows), "samples": len(rows)}
 
 
 def peaks():
@@ -298,6 +309,13 @@ def run_b200(a):
                 "classes": {k: {"ms": round(v["ms_per_step"], 4), "share": round(v["share"], 4), "GBps": round(v["gbs"], 1),
                                 "frac_hbm": round(v["gbs"] / hbm, 4), "TFLOPs": round(v["tflops"], 2), "launches": v["launches"]}
                             for k, v in classes.items()}}
+    try:  # measured DRAM bytes of the dominant class (ncu, committed under profiles/), if it matches this run
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))
+        if (tj.get("engine"), tj.get("batch"), tj.get("h"), tj.get("w")) == (pw, B, H, W):
+            roofline["traffic"] = tj["dram_bytes_per_step"].get(top)
+            roofline["traffic_source"] = "profiles/traffic_r1.json"
+    except Exception:
+        pass
     by_min, _ = L.work_model(H, W, L.CF_IN_U8_HWC, 0, pw)
     by_all, fl_all = L.work_model(H, W, L.CF_IN_U8_HWC, 0, L.CF_PW_TCGEN05)  # layer-wise algorithmic bytes
     roofline["whole_step"] = {"alg_bytes_per_image": by_all, "min_bytes_per_image": by_min, "alg_flops_per_image": fl_all,
