@@ -74,6 +74,7 @@ __device__ __forceinline__ void xd_dw_phase_g(const uint8_t* Es, const float* Wd
 #pragma unroll
             for (int c = 0; c < XT; ++c) acc[a][c] = make_float4(0, 0, 0, 0);
         const int r0 = YT * by * S, q0 = XT * bx * S;  // window origin inside the halo tile
+        float4 wt[KS][KS];  // tap rows are loaded once, when the first input row needs them, and stay live for YT rows
 #pragma unroll
         for (int rr = 0; rr < NROW; ++rr) {
             float4 win[NCOL];
@@ -82,16 +83,20 @@ __device__ __forceinline__ void xd_dw_phase_g(const uint8_t* Es, const float* Wd
                 const int px = (r0 + rr) * G::IW + q0 + cc;
                 win[cc] = *reinterpret_cast<const float4*>(Es + px * 128 + ((c4 ^ (px & 7)) << 4));
             }
+            if (rr < KS) {
+#pragma unroll
+                for (int kx = 0; kx < KS; ++kx)
+                    wt[rr][kx] = WD_GLOBAL ? ldg4(Wd_s + (rr * KS + kx) * p.hid + cbase)
+                                           : *reinterpret_cast<const float4*>(Wd_s + (rr * KS + kx) * p.hid + cbase);
+            }
 #pragma unroll
             for (int dy = 0; dy < YT; ++dy) {
                 const int ky = rr - dy * S;
                 if (ky < 0 || ky >= KS) continue;
 #pragma unroll
                 for (int kx = 0; kx < KS; ++kx) {
-                    const float4 wv = WD_GLOBAL ? ldg4(Wd_s + (ky * KS + kx) * p.hid + cbase)
-                                                : *reinterpret_cast<const float4*>(Wd_s + (ky * KS + kx) * p.hid + cbase);
 #pragma unroll
-                    for (int dx = 0; dx < XT; ++dx) fma44(acc[dy][dx], win[dx * S + kx], wv);
+                    for (int dx = 0; dx < XT; ++dx) fma44(acc[dy][dx], win[dx * S + kx], wt[ky][kx]);
                 }
             }
         }

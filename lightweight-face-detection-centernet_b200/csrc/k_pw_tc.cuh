@@ -12,6 +12,13 @@
 // shared memory by four "splitter" warps between the TMA and the MMA stage (element-wise, so the
 // swizzled layout is irrelevant to them).  kPasses == 1 is the throughput mode.
 //
+// Narrow layers (column chunk NC <= 64, i.e. the projection convs): an MMA there costs the time to stream its 128 x 32 B
+// A operand out of shared memory, three times per K step in the naive 3-pass form.  For them the splitter warps
+// hand the split operand to the tensor core through TENSOR MEMORY instead: each splitter thread owns one row of the
+// 128 x 32 block, reads it once from the TMA's swizzled image, and tcgen05.st's hi and lo halves into a four-slot
+// TMEM ring (lane = row, column = k); the MMAs take A from TMEM ([a_tmem] operand form) and only the small weight
+// tile from shared memory, the smem stage (16 KB, no lo copy) is released as soon as the splitters have read it.
+//
 // Warp roles (512 threads, one persistent CTA per SM):
 //   warp 0      TMA producer          warp 1      MMA issuer (one elected lane)
 //   warp 2      TMEM allocator        warp 3      idle
@@ -33,7 +40,7 @@ constexpr int TC_BK = 32;            // fp32 K elements per smem block = one 128
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
 constexpr int TC_STG_BYTES = 32 * 128;          // one epilogue staging buffer: 32 rows x 32 fp32
 constexpr int TC_STG_BUFS = 2;                  // per epilogue warp
-constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_MAX_STAGES = 12;
 constexpr int TC_SMEM_MAX = 232448;             // 227 KB
 
 struct TcLayer {        // per weight matrix, built once
@@ -55,6 +62,8 @@ struct TcParams {
     int direct;      // 1: narrow outputs (N <= 64): the epilogue stores rows straight from registers, the staging
                      //    buffers' 64 KB go to two more pipeline stages
     float* out;      // [M][N] (direct stores)
+    int atmem;       // 1: narrow layers (NC <= 64): the split A operand is handed to the tensor core in TMEM
+                     //    (tcgen05.st by the splitter warps) instead of shared memory
     int dbg;         // development only (env CF_TC_DEBUG): 1 skip the A split, 2 skip the stores, 4 skip the MMAs
     int stages;
     uint32_t stage_bytes, a_bytes_stage, b_bytes_block;  // b_bytes_block = NC*128*(passes==3?2:1)
@@ -148,6 +157,28 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// A operand in tensor memory (lane = row, one tf32 per 32-bit column), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
+    const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+        "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+        "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -213,6 +244,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const uint32_t bar_tempty = bar_tfull + 16;              // [2]
     const uint32_t bar_bres = bar_tempty + 16;               // [1]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + p.off_bars + 24 * TC_MAX_STAGES + 48);
+    const uint32_t bar_aready = bars + 24 * TC_MAX_STAGES + 64, bar_aempty = bar_aready + 32;  // [4] each: TMEM A ring (atmem)
+    constexpr uint32_t kATmemCol = 256;  // accumulators use columns [0,256), the A ring 4 x (32 hi + 32 lo) above
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -220,7 +253,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_ready + 8 * s, 4);
-            mbar_init(bar_empty + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, (p.atmem && p.resident) ? 4 : 1);  // atmem: the splitters free the smem stage
+        }
+        for (int a = 0; a < 4; ++a) {
+            mbar_init(bar_aready + 8 * a, 4);
+            mbar_init(bar_aempty + 8 * a, 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(bar_tfull + 8 * a, 1);
@@ -279,7 +316,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             if (p.resident) mbar_wait(bar_bres, 0);
             int stage = 0;
             uint32_t phase = 0;
-            uint32_t it = 0;
+            uint32_t it = 0, acnt = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
                 const int mt = item / p.nchunks, ch = item - mt * p.nchunks;
                 (void)mt;
@@ -297,10 +334,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 // an MMA is bound by streaming its 128 x 32 B A operand out of shared memory (measured ~60 cycles
                 // per instruction whatever N is, tools/tc_shape_probe.py), so two MMAs per K step instead of three
                 // is a third off the tensor-pipe time.
-                const uint32_t d_tmem = tmem_base + as * 256u;
+                const uint32_t d_tmem = tmem_base + as * (p.atmem ? 128u : 256u);  // atmem: accumulators in [0,256), A ring above
                 const uint32_t d_corr = d_tmem + (uint32_t)p.NC;
                 const uint32_t idesc2 = umma_idesc_tf32(2 * p.NC);
                 for (int kb = 0; kb < nkb; ++kb) {
+                    if (kPasses == 3 && p.atmem) {
+                        const uint32_t aslot = acnt & 3u;
+                        mbar_wait(bar_aready + 8 * aslot, (acnt >> 2) & 1u);
+                        tc_fence_after();
+                        const uint32_t sb = p.resident ? bres + (uint32_t)(ch * nkb + kb) * p.b_bytes_block
+                                                       : stages0 + stage * p.stage_bytes + p.a_bytes_stage;
+                        const int krem = p.K - kb * TC_BK;
+                        const int nks = krem >= TC_BK ? TC_BK / 8 : (krem + 7) / 8;
+                        const uint64_t b_hi = umma_desc(sb);
+                        const uint32_t a_hi = tmem_base + kATmemCol + aslot * 64u, a_lo = a_hi + 32u;
+                        for (int k = 0; k < nks; ++k) {
+                            const uint64_t ko = (uint64_t)(k * 2);
+                            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+                            umma_tf32_ts(d_tmem, a_hi + 8u * k, b_hi + ko, idesc2, acc);
+                            umma_tf32_ts(d_corr, a_lo + 8u * k, b_hi + ko, idesc, 1u);
+                        }
+                        umma_commit(bar_aempty + 8 * aslot);
+                        if (!p.resident) umma_commit(bar_empty + 8 * stage);
+                        if (kb == nkb - 1) umma_commit(bar_tfull + 8 * as);
+                        ++acnt;
+                        if (++stage == p.stages) stage = 0, phase ^= 1;
+                        continue;
+                    }
                     mbar_wait((kPasses == 3 ? bar_ready : bar_full) + 8 * stage, phase);
                     tc_fence_after();
                     const uint32_t sa = stages0 + stage * p.stage_bytes;
@@ -331,9 +391,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         if (kPasses == 3) {
             const int t = threadIdx.x - 128;  // 0..127
             int stage = 0;
-            uint32_t phase = 0;
+            uint32_t phase = 0, acnt = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 for (int kb = 0; kb < nkb; ++kb) {
+                    if (p.atmem) {
+                        // thread = one row of the 128 x 32 A block: read it from the TMA's swizzled image, split it and
+                        // store both halves into this warp's TMEM lane quarter
+                        const uint32_t aslot = acnt & 3u;
+                        mbar_wait(bar_full + 8 * stage, phase);
+                        const int q = warp & 3, row = q * 32 + lane;
+                        const uint8_t* ar = base_ptr + p.off_stages + stage * p.stage_bytes + row * 128;
+                        float hi[32], lo[32];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 v = *reinterpret_cast<const float4*>(ar + ((j ^ (row & 7)) << 4));
+                            hi[4 * j] = tf32_hi(v.x), hi[4 * j + 1] = tf32_hi(v.y), hi[4 * j + 2] = tf32_hi(v.z), hi[4 * j + 3] = tf32_hi(v.w);
+                            lo[4 * j] = v.x - hi[4 * j], lo[4 * j + 1] = v.y - hi[4 * j + 1], lo[4 * j + 2] = v.z - hi[4 * j + 2],
+                                   lo[4 * j + 3] = v.w - hi[4 * j + 3];
+                        }
+                        mbar_wait(bar_aempty + 8 * aslot, ((acnt >> 2) & 1u) ^ 1u);
+                        tc_fence_after();
+                        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + kATmemCol + aslot * 64u;
+                        tmem_st32(ta, hi);
+                        tmem_st32(ta + 32u, lo);
+                        tmem_st_wait();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {
+                            mbar_arrive(bar_aready + 8 * aslot);
+                            if (p.resident) mbar_arrive(bar_empty + 8 * stage);  // the smem stage can be refilled already
+                        }
+                        ++acnt;
+                        if (++stage == p.stages) stage = 0, phase ^= 1;
+                        continue;
+                    }
                     mbar_wait(bar_full + 8 * stage, phase);
                     float4* a = reinterpret_cast<float4*>(base_ptr + p.off_stages + stage * p.stage_bytes);
                     float4* l = a + TC_A_BYTES / 16;
@@ -372,7 +463,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 const int col0 = ch * p.NC + cb * 32;
                 if (col0 >= p.N) break;  // padded columns of the last chunk
                 float v[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 256 + cb * 32);
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * (p.atmem ? 128 : 256) + cb * 32);
                 tmem_ld32(taddr, v);
                 if (kPasses == 3) {
                     float c[32];
@@ -557,7 +648,10 @@ inline int tc_plan(PwTcState& st, int passes, int epi, const float* A, const flo
     // NOTE: the image always stores hi|lo pairs; one-pass mode addresses only the hi halves, so its
     // "block" stride is still the pair.
     p.b_bytes_block = (uint32_t)L.NC * 128u * 2u;
-    p.a_bytes_stage = TC_A_BYTES * hl;
+    // narrow layers: A operand through TMEM (both accumulator pairs fit columns [0,256), the A ring sits above them)
+    p.atmem = (passes == 3 && L.NC <= 64) ? 1 : 0;
+    if (const char* ev = getenv("CF_TC_ATMEM")) p.atmem = (atoi(ev) != 0 && passes == 3 && L.NC <= 64) ? 1 : 0;
+    p.a_bytes_stage = p.atmem ? TC_A_BYTES : TC_A_BYTES * hl;
     p.direct = (N <= 64) ? 1 : 0;
     if (const char* ev = getenv("CF_TC_DIRECT")) p.direct = atoi(ev);
     p.out = out;
