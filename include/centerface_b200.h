@@ -149,6 +149,10 @@ int cf_detect_threshold_host(cf_engine* e, const uint8_t* images, int batch, int
 int cf_debug_pw_gemm(int pw_engine, int epi, const float* dA, const float* hW, float* dOut, int M, int K, int N,
                      const float* dRes, void* stream);
 
+/* Development probe: stream a device [M][K] fp32 matrix through a `stages`-deep TMA ring of box_rows x 32-float boxes
+ * with one thread per CTA and no consumer work; *ms = mean kernel time.  (tools/tma_probe.py)            */
+int cf_debug_tma_stream(const float* dA, int M, int K, int stages, int box_rows, int ctas_per_sm, float* ms);
+
 /* ---- instrumentation -----------------------------------------------------------------
  * Number of kernels this library launched on behalf of the handle since creation.        */
 long long cf_launch_count(cf_engine* e);

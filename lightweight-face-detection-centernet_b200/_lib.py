@@ -39,6 +39,7 @@ SIGNATURES = {
     "cf_detect_threshold_host": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                            C.c_float, C.c_float, C.c_int, _vp, _vp, _vp]),
     "cf_debug_pw_gemm": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "cf_debug_tma_stream": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "cf_launch_count": (C.c_longlong, [_vp]),
     "cf_work_model": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "cf_replay_class": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),

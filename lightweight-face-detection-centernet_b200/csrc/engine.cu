@@ -828,6 +828,38 @@ int cf_debug_pw_gemm(int pw_engine, int epi, const float* dA, const float* hW, f
     return rc;
 }
 
+int cf_debug_tma_stream(const float* dA, int M, int K, int stages, int box_rows, int ctas_per_sm, float* ms) {
+    CF_CHECK(dA && M > 0 && K >= 4 && K % 4 == 0 && stages >= 1 && box_rows >= 8 && box_rows <= 256 && ms, CF_EINVAL, "cf_debug_tma_stream: bad arguments");
+    PwTcState st;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int rc = pw_tc_init(st, dev);
+    if (rc) return rc;
+    CUtensorMap tm;
+    if ((rc = tc_make_map(st, &tm, dA, (uint64_t)M, (uint64_t)K, (uint32_t)box_rows))) return rc;
+    const uint32_t box_bytes = (uint32_t)box_rows * 128u;
+    const size_t smem = (size_t)stages * box_bytes + 1024 + 1024;
+    CF_CHECK(smem <= (size_t)TC_SMEM_MAX / (size_t)ctas_per_sm, CF_EINVAL, "cf_debug_tma_stream: %zu B of smem do not fit", smem);
+    CF_CUDA(cudaFuncSetAttribute(k_tma_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int n_tiles = (M + box_rows - 1) / box_rows, nkb = (K + TC_BK - 1) / TC_BK;
+    const int grid = std::min(n_tiles, st.sms * ctas_per_sm);
+    cudaEvent_t a, b;
+    CF_CUDA(cudaEventCreate(&a));
+    CF_CUDA(cudaEventCreate(&b));
+    k_tma_probe<<<grid, 32, smem>>>(tm, n_tiles, nkb, stages, box_rows, box_bytes);  // warm
+    cudaEventRecord(a);
+    for (int i = 0; i < 5; ++i) k_tma_probe<<<grid, 32, smem>>>(tm, n_tiles, nkb, stages, box_rows, box_bytes);
+    cudaEventRecord(b);
+    cudaError_t ce = cudaEventSynchronize(b);
+    float t = 0.f;
+    cudaEventElapsedTime(&t, a, b);
+    *ms = t / 5.f;
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    if (ce != cudaSuccess) return fail(CF_ECUDA, "cf_debug_tma_stream: %s", cudaGetErrorString(ce));
+    return CF_OK;
+}
+
 long long cf_launch_count(cf_engine* e) { return e ? e->launches : 0; }
 
 int cf_work_model(int h, int w, int in_format, int pw_engine, int which, double* bytes, double* flops) {

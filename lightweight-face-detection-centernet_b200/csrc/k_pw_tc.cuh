@@ -62,6 +62,8 @@ struct TcParams {
     int direct;      // 1: narrow outputs (N <= 64): the epilogue stores rows straight from registers, the staging
                      //    buffers' 64 KB go to two more pipeline stages
     float* out;      // [M][N] (direct stores)
+    int nacc;        // TMEM accumulator stages (2 or 4); stage stride = acc_stride columns
+    uint32_t acc_stride;
     int atmem;       // 1: narrow layers (NC <= 64): the split A operand is handed to the tensor core in TMEM
                      //    (tcgen05.st by the splitter warps) instead of shared memory
     int dbg;         // development only (env CF_TC_DEBUG): 1 skip the A split, 2 skip the stores, 4 skip the MMAs
@@ -240,11 +242,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const uint32_t bar_full = bars;                          // [stages]
     const uint32_t bar_ready = bars + 8 * TC_MAX_STAGES;     // [stages] splitters -> MMA
     const uint32_t bar_empty = bars + 16 * TC_MAX_STAGES;    // [stages]
-    const uint32_t bar_tfull = bars + 24 * TC_MAX_STAGES;    // [2]
-    const uint32_t bar_tempty = bar_tfull + 16;              // [2]
-    const uint32_t bar_bres = bar_tempty + 16;               // [1]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + p.off_bars + 24 * TC_MAX_STAGES + 48);
-    const uint32_t bar_aready = bars + 24 * TC_MAX_STAGES + 64, bar_aempty = bar_aready + 32;  // [4] each: TMEM A ring (atmem)
+    const uint32_t bar_tfull = bars + 24 * TC_MAX_STAGES;    // [4]
+    const uint32_t bar_tempty = bar_tfull + 32;              // [4]
+    const uint32_t bar_bres = bar_tempty + 32;               // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + p.off_bars + 24 * TC_MAX_STAGES + 80);
+    const uint32_t bar_aready = bars + 24 * TC_MAX_STAGES + 96, bar_aempty = bar_aready + 32;  // [4] each: TMEM A ring (atmem)
     constexpr uint32_t kATmemCol = 256;  // accumulators use columns [0,256), the A ring 4 x (32 hi + 32 lo) above
 
     if (warp == 0 && lane == 0) {
@@ -259,7 +261,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             mbar_init(bar_aready + 8 * a, 4);
             mbar_init(bar_aempty + 8 * a, 1);
         }
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < 4; ++a) {
             mbar_init(bar_tfull + 8 * a, 1);
             mbar_init(bar_tempty + 8 * a, 4);
         }
@@ -320,7 +322,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
                 const int mt = item / p.nchunks, ch = item - mt * p.nchunks;
                 (void)mt;
-                const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
+                const uint32_t as = it % (uint32_t)p.nacc, aphase = (it / (uint32_t)p.nacc) & 1u;
                 mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
                 tc_fence_after();
                 // 3-pass: the two small cross terms go to their own accumulator (columns +128).  The
@@ -334,7 +336,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 // an MMA is bound by streaming its 128 x 32 B A operand out of shared memory (measured ~60 cycles
                 // per instruction whatever N is, tools/tc_shape_probe.py), so two MMAs per K step instead of three
                 // is a third off the tensor-pipe time.
-                const uint32_t d_tmem = tmem_base + as * (p.atmem ? 128u : 256u);  // atmem: accumulators in [0,256), A ring above
+                const uint32_t d_tmem = tmem_base + as * p.acc_stride;  // atmem: accumulators in [0,256), A ring above
                 const uint32_t d_corr = d_tmem + (uint32_t)p.NC;
                 const uint32_t idesc2 = umma_idesc_tf32(2 * p.NC);
                 for (int kb = 0; kb < nkb; ++kb) {
@@ -452,10 +454,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         int buf = 0;
         uint32_t it = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-            if ((int)(it & 1u) != g) continue;
+            if ((int)(it & 1u) != g) continue;  // group g serves accumulator stages g, g+2 (nacc is even)
+            const uint32_t as = it % (uint32_t)p.nacc;
             const int mt = item / p.nchunks, ch = item - mt * p.nchunks;
-            const uint32_t aphase = (it >> 1) & 1u;
-            mbar_wait(bar_tfull + 8 * g, aphase);
+            const uint32_t aphase = (it / (uint32_t)p.nacc) & 1u;
+            mbar_wait(bar_tfull + 8 * as, aphase);
             tc_fence_after();
             const int row = mt * TC_BM + q * 32 + lane;
             const int ncb = p.NC >> 5;
@@ -463,7 +466,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 const int col0 = ch * p.NC + cb * 32;
                 if (col0 >= p.N) break;  // padded columns of the last chunk
                 float v[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * (p.atmem ? 128 : 256) + cb * 32);
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (as * p.acc_stride + (uint32_t)(cb * 32));
                 tmem_ld32(taddr, v);
                 if (kPasses == 3) {
                     float c[32];
@@ -478,7 +481,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     // every TMEM read of this accumulator is done: hand it back to the MMA warp early
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_tempty + 8 * g);
+                    if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
                 }
                 if (p.dbg & 2) continue;
                 if (p.direct) {
@@ -528,6 +531,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+
+// ---- development probe: how fast can ONE thread per SM stream a [M][K] fp32 matrix through a TMA ring? ------------
+// (tools/tma_probe.py; no consumer work at all: wait for a box, re-arm the slot, issue the next box)
+__global__ void __launch_bounds__(32, 1) k_tma_probe(const __grid_constant__ CUtensorMap tmA, int n_tiles, int nkb, int stages,
+                                                     int box_rows, uint32_t box_bytes) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + (uint32_t)stages * box_bytes;
+    if (threadIdx.x != 0) return;
+    for (int s = 0; s < stages; ++s) mbar_init(bars + 8 * s, 1);
+    fence_barrier_init();
+    const long long my = ((long long)n_tiles - 1 - blockIdx.x) / gridDim.x + 1;  // tiles of this CTA (grid <= n_tiles)
+    const long long total = my * nkb;
+    auto issue = [&](long long j) {
+        const int s = (int)(j % stages);
+        const long long tile = blockIdx.x + (j / nkb) * (long long)gridDim.x;
+        mbar_expect_tx(bars + 8 * s, box_bytes);
+        tma_load_2d(base + s * box_bytes, &tmA, (int)(j % nkb) * TC_BK, (int)tile * box_rows, bars + 8 * s);
+    };
+    for (long long j = 0; j < stages && j < total; ++j) issue(j);
+    for (long long j = 0; j < total; ++j) {
+        mbar_wait(bars + 8 * (int)(j % stages), (uint32_t)(j / stages) & 1u);
+        if (j + stages < total) issue(j + stages);
     }
 }
 
@@ -652,6 +681,12 @@ inline int tc_plan(PwTcState& st, int passes, int epi, const float* A, const flo
     p.atmem = (passes == 3 && L.NC <= 64) ? 1 : 0;
     if (const char* ev = getenv("CF_TC_ATMEM")) p.atmem = (atoi(ev) != 0 && passes == 3 && L.NC <= 64) ? 1 : 0;
     p.a_bytes_stage = p.atmem ? TC_A_BYTES : TC_A_BYTES * hl;
+    {   // accumulator ring: as many (main+correction) pairs as fit the accumulator columns, 2 or 4
+        const uint32_t acc_cols = p.atmem ? 256u : 512u, pair = (passes == 3 ? 2u : 1u) * (uint32_t)L.NC;
+        p.nacc = (4u * pair <= acc_cols) ? 4 : 2;
+        if (const char* ev = getenv("CF_TC_NACC")) p.nacc = atoi(ev) == 4 && 4u * pair <= acc_cols ? 4 : 2;
+        p.acc_stride = acc_cols / (uint32_t)p.nacc;
+    }
     p.direct = (N <= 64) ? 1 : 0;
     if (const char* ev = getenv("CF_TC_DIRECT")) p.direct = atoi(ev);
     p.out = out;
