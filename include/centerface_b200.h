@@ -106,6 +106,12 @@ int cf_ctdet_decode(const float* heat, const float* wh, const float* reg, int ba
 /* same, on the heads of the last cf_forward */
 int cf_decode_topk(cf_engine* e, int K, float* out_dets, int32_t* out_inds, void* stream);
 
+/* Replaces ctdet_post_process (utils/post_process.py:83-100) for the single face class: maps both corners of every
+ * row of dets [B,K,6] (DEVICE, output-map units) through the per-image inverse affine trans [B,6] (DEVICE, fp64,
+ * row-major 2x3 = get_affine_transform(c, s, 0, (w,h), inv=1), utils/image.py:27-61, built by the caller) and
+ * writes out [B,K,5] = x1,y1,x2,y2,score (DEVICE fp32).                                                        */
+int cf_ctdet_post_process(const float* dets, const double* trans, int batch, int K, float* out, void* stream);
+
 /* ---- decode, paths A and B -----------------------------------------------------------
  * Replaces CenterFace.decode + nms (centerface.py:73-151) / eval_widerface.decode + nms
  * (eval_widerface.py:92-152) and, when scale_w/scale_h are non-zero, the float32 floor
@@ -152,6 +158,21 @@ int cf_debug_pw_gemm(int pw_engine, int epi, const float* dA, const float* hW, f
 /* Development probe: stream a device [M][K] fp32 matrix through a `stages`-deep TMA ring of box_rows x 32-float boxes
  * with one thread per CTA and no consumer work; *ms = mean kernel time.  (tools/tma_probe.py)            */
 int cf_debug_tma_stream(const float* dA, int M, int K, int stages, int box_rows, int ctas_per_sm, float* ms);
+
+/* ---- pre-processing ---------------------------------------------------------
+ * cv2.resize(img, (W',H')) of centerface.py:30 (default INTER_LINEAR, 8UC3) on the device, bit-exact with OpenCV
+ * 4.x (fixed-point bilinear; exact 2x decimation = INTER_AREA).  cf_resize_tables builds the per-column/per-row
+ * index + weight table on the HOST (3*dw + 4*dh int32) with OpenCV's own arithmetic; cf_resize_u8 resizes a DEVICE
+ * batch [B,sh,sw,3] -> [B,dh,dw,3] with a DEVICE copy of that table.                                    */
+int cf_resize_tables(int sh, int sw, int dh, int dw, int32_t* tab, size_t tab_ints, int* area2);
+int cf_resize_u8(const uint8_t* src, int batch, int sh, int sw, uint8_t* dst, int dh, int dw, const int32_t* tab, int area2,
+                 void* stream);
+/* The whole body of CenterFace.__call__ (centerface.py:29-62) for one HOST u8 BGR image [h,w,3] at its own size:
+ * H2D, resize to (net_h,net_w), normalise, network, sigmoid/clamp, threshold decode (variant A/B), NMS, //scale,
+ * D2H of out_dets [cap,5], out_lms [cap,10] (may be NULL) and out_count (negative = more than cap candidates).  */
+int cf_detect_image_host(cf_engine* e, const uint8_t* image, int h, int w, int net_h, int net_w, int variant, float threshold,
+                         float nms_threshold, float scale_w, float scale_h, int cap, float* out_dets, float* out_lms,
+                         int32_t* out_count);
 
 /* ---- instrumentation -----------------------------------------------------------------
  * Number of kernels this library launched on behalf of the handle since creation.        */

@@ -31,6 +31,7 @@ SIGNATURES = {
     "cf_tap": (C.c_int, [_vp, C.c_char_p, C.POINTER(_vp), _i, _i, _i]),
     "cf_ctdet_decode": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "cf_decode_topk": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp]),
+    "cf_ctdet_post_process": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp]),
     "cf_decode_threshold": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                       C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, _vp, _vp, _vp, _vp]),
     "cf_detect_topk_host": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
@@ -40,6 +41,10 @@ SIGNATURES = {
                                            C.c_float, C.c_float, C.c_int, _vp, _vp, _vp]),
     "cf_debug_pw_gemm": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "cf_debug_tma_stream": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "cf_resize_tables": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, _i]),
+    "cf_resize_u8": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp]),
+    "cf_detect_image_host": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
+                                       C.c_float, C.c_int, _vp, _vp, _vp]),
     "cf_launch_count": (C.c_longlong, [_vp]),
     "cf_work_model": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "cf_replay_class": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),

@@ -39,6 +39,7 @@ class CenterFace(object):
     mean = np.array([0.408, 0.447, 0.470], dtype=np.float32).reshape(1, 1, 3)
     std = np.array([0.289, 0.274, 0.278], dtype=np.float32).reshape(1, 1, 3)
     print_times = True  # the reference prints "cpu times = ..." on every call (centerface.py:49)
+    gpu_resize = True   # cv2.resize on the device (bit-exact with OpenCV's INTER_LINEAR); False = cv2 on the host
 
     def __init__(self, height, width, landmarks=True, weights=None, device=0, pw_engine=None, engine=None):
         self.landmarks = landmarks
@@ -52,15 +53,19 @@ class CenterFace(object):
         self.net = engine
 
     def __call__(self, img, threshold=0.2):
-        import cv2
-        img = cv2.resize(img, (self.img_w_new, self.img_h_new))  # centerface.py:30
         begin = datetime.datetime.now()
-        # centerface.py:32-51 + :55-58 in one library call: normalise, net, sigmoid/clamp, decode A
-        # (0.3 hard-coded at :77 -- the `threshold` argument is ignored by the reference), NMS 0.3,
-        # float32 floor-division by the scales.
-        img = np.ascontiguousarray(img, dtype=np.uint8)[None]
-        (dets, lms), = self.net.detect_threshold_host(
-            img, L.CF_DECODE_A, 0.3, 0.3, np.float32(self.scale_w), np.float32(self.scale_h), landmarks=self.landmarks)
+        # centerface.py:30-51 + :55-58 in one library call: resize, normalise, net, sigmoid/clamp, decode A (0.3 hard-coded at
+        # :77 -- the `threshold` argument is ignored by the reference), NMS 0.3, float32 floor-division by the scales.
+        if self.gpu_resize:
+            dets, lms = self.net.detect_image_host(np.ascontiguousarray(img, dtype=np.uint8), self.img_h_new, self.img_w_new,
+                                                   L.CF_DECODE_A, 0.3, 0.3, np.float32(self.scale_w), np.float32(self.scale_h),
+                                                   landmarks=self.landmarks)
+        else:
+            import cv2
+            img = cv2.resize(img, (self.img_w_new, self.img_h_new))  # centerface.py:30
+            img = np.ascontiguousarray(img, dtype=np.uint8)[None]
+            (dets, lms), = self.net.detect_threshold_host(
+                img, L.CF_DECODE_A, 0.3, 0.3, np.float32(self.scale_w), np.float32(self.scale_h), landmarks=self.landmarks)
         end = datetime.datetime.now()
         if self.print_times:
             print("cpu times = ", end - begin)

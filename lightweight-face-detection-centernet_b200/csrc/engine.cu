@@ -130,6 +130,12 @@ struct cf_engine {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     bool slot_used[2] = {false, false};
+    // device-side cv2.resize: source staging + coefficient tables of the last (source, network) size pair
+    uint8_t* src_u8 = nullptr;
+    size_t src_u8_bytes = 0;
+    int32_t* rs_tab = nullptr;
+    size_t rs_tab_ints = 0;
+    ResizeTables rs;
     long long submitted = 0, waited = 0;
     long long launches = 0;
     PwTcState tc;  // tensor maps etc. of the tcgen05 engine
@@ -568,6 +574,8 @@ int cf_destroy(cf_engine* e) {
         if (e->ev_copied[i]) cudaEventDestroy(e->ev_copied[i]);
         if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]);
     }
+    if (e->src_u8) cudaFree(e->src_u8);
+    if (e->rs_tab) cudaFree(e->rs_tab);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -674,6 +682,13 @@ int cf_decode_topk(cf_engine* e, int K, float* out_dets, int32_t* out_inds, void
     int rc = cf_ctdet_decode(e->hm_sig, e->wh, e->reg, e->B, e->H / 4, e->W / 4, K, out_dets, out_inds, e->peak, stream);
     if (rc == CF_OK) e->launches += 2;
     return rc;
+}
+
+int cf_ctdet_post_process(const float* dets, const double* trans, int batch, int K, float* out, void* stream) {
+    CF_CHECK(dets && trans && out && batch > 0 && K > 0, CF_EINVAL, "cf_ctdet_post_process: bad arguments");
+    k_affine_boxes<<<cdiv(batch * K, 256), 256, 0, (cudaStream_t)stream>>>(dets, trans, out, batch, K);
+    CF_CUDA(cudaGetLastError());
+    return CF_OK;
 }
 
 int cf_decode_threshold(const float* hm_sig, const float* wh, const float* reg, const float* lm, int batch, int h,
@@ -786,6 +801,79 @@ int cf_detect_threshold_host(cf_engine* e, const uint8_t* images, int batch, int
     CF_CUDA(cudaMemcpyAsync(out_counts, e->o_counts, (size_t)batch * 4, cudaMemcpyDeviceToHost, s));
     CF_CUDA(cudaMemcpyAsync(out_dets, e->o_dets, (size_t)batch * cap * 5 * 4, cudaMemcpyDeviceToHost, s));
     if (out_lms) CF_CUDA(cudaMemcpyAsync(out_lms, e->o_lms, (size_t)batch * cap * 10 * 4, cudaMemcpyDeviceToHost, s));
+    CF_CUDA(cudaEventRecord(e->ev_done[slot], s));
+    ++e->submitted;
+    while (e->waited < e->submitted)
+        if ((rc = host_wait_oldest(e))) return rc;
+    return CF_OK;
+}
+
+int cf_resize_u8(const uint8_t* src, int batch, int sh, int sw, uint8_t* dst, int dh, int dw, const int32_t* tab, int area2,
+                 void* stream) {
+    CF_CHECK(src && dst && (tab || area2) && batch > 0 && sh > 0 && sw > 0 && dh > 0 && dw > 0, CF_EINVAL, "cf_resize_u8: bad arguments");
+    const long long n = (long long)batch * dh * dw;
+    k_resize_u8<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, dst, tab, batch, sh, sw, dh, dw, area2);
+    CF_CUDA(cudaGetLastError());
+    return CF_OK;
+}
+
+int cf_resize_tables(int sh, int sw, int dh, int dw, int32_t* tab, size_t tab_ints, int* area2) {
+    CF_CHECK(sh > 0 && sw > 0 && dh > 0 && dw > 0 && tab && area2, CF_EINVAL, "cf_resize_tables: bad arguments");
+    CF_CHECK(tab_ints >= (size_t)3 * dw + (size_t)4 * dh, CF_ECAP, "cf_resize_tables: table needs %zu ints", (size_t)3 * dw + (size_t)4 * dh);
+    ResizeTables t;
+    t.build(sh, sw, dh, dw);
+    memcpy(tab, t.tab.data(), t.tab.size() * sizeof(int32_t));
+    *area2 = t.area2;
+    return CF_OK;
+}
+
+int cf_detect_image_host(cf_engine* e, const uint8_t* image, int h, int w, int net_h, int net_w, int variant, float threshold,
+                         float nms_threshold, float scale_w, float scale_h, int cap, float* out_dets, float* out_lms,
+                         int32_t* out_count) {
+    CF_CHECK(e && image && out_dets && out_count, CF_EINVAL, "cf_detect_image_host: NULL argument");
+    CF_CHECK(h > 0 && w > 0, CF_EINVAL, "cf_detect_image_host: bad source size %dx%d", h, w);
+    CF_CHECK(net_h >= 32 && net_w >= 32 && net_h % 32 == 0 && net_w % 32 == 0 && (size_t)net_h * net_w <= (size_t)e->max_h * e->max_w,
+             CF_EINVAL, "cf_detect_image_host: bad network size %dx%d", net_h, net_w);
+    CF_CUDA(cudaSetDevice(e->device));
+    if (e->submitted - e->waited >= 2) {
+        int rc0 = host_wait_oldest(e);
+        if (rc0) return rc0;
+    }
+    cudaStream_t s = e->stream;
+    const size_t src_bytes = (size_t)h * w * 3;
+    if (src_bytes > e->src_u8_bytes) {
+        CF_CUDA(cudaStreamSynchronize(s));
+        if (e->src_u8) cudaFree(e->src_u8);
+        e->src_u8 = nullptr, e->src_u8_bytes = 0;
+        CF_CUDA(cudaMalloc((void**)&e->src_u8, src_bytes));
+        e->src_u8_bytes = src_bytes;
+    }
+    if (e->rs.sh != h || e->rs.sw != w || e->rs.dh != net_h || e->rs.dw != net_w) {
+        e->rs.build(h, w, net_h, net_w);
+        if (e->rs.tab.size() > e->rs_tab_ints) {
+            CF_CUDA(cudaStreamSynchronize(s));
+            if (e->rs_tab) cudaFree(e->rs_tab);
+            e->rs_tab = nullptr, e->rs_tab_ints = 0;
+            CF_CUDA(cudaMalloc((void**)&e->rs_tab, e->rs.tab.size() * sizeof(int32_t)));
+            e->rs_tab_ints = e->rs.tab.size();
+        }
+        CF_CUDA(cudaMemcpyAsync(e->rs_tab, e->rs.tab.data(), e->rs.tab.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    }
+    const int slot = (int)(e->submitted & 1);
+    CF_CUDA(cudaMemcpyAsync(e->src_u8, image, src_bytes, cudaMemcpyHostToDevice, s));
+    int rc = cf_resize_u8(e->src_u8, 1, h, w, e->in_slot[slot], net_h, net_w, e->rs_tab, e->rs.area2, s);  // centerface.py:30
+    if (rc) return rc;
+    ++e->launches;
+    e->slot_used[slot] = true;
+    if ((rc = cf_forward(e, e->in_slot[slot], CF_IN_U8_HWC, 1, net_h, net_w, s))) return rc;
+    const int size_h = variant == CF_DECODE_B ? 640 : net_h, size_w = variant == CF_DECODE_B ? 640 : net_w;
+    rc = cf_decode_threshold(e->hm_sig, e->wh, e->reg, e->lm, 1, net_h / 4, net_w / 4, variant, threshold, nms_threshold, size_h, size_w,
+                             scale_w, scale_h, cap, e->o_dets, out_lms ? e->o_lms : nullptr, e->o_counts, s);
+    if (rc) return rc;
+    ++e->launches;
+    CF_CUDA(cudaMemcpyAsync(out_count, e->o_counts, 4, cudaMemcpyDeviceToHost, s));
+    CF_CUDA(cudaMemcpyAsync(out_dets, e->o_dets, (size_t)cap * 5 * 4, cudaMemcpyDeviceToHost, s));
+    if (out_lms) CF_CUDA(cudaMemcpyAsync(out_lms, e->o_lms, (size_t)cap * 10 * 4, cudaMemcpyDeviceToHost, s));
     CF_CUDA(cudaEventRecord(e->ev_done[slot], s));
     ++e->submitted;
     while (e->waited < e->submitted)

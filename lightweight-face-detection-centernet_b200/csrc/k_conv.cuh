@@ -8,6 +8,45 @@
 namespace cf {
 
 // ----------------------------------------------------------------------------------------
+// K0 pre-processing: cv2.resize(img, (W', H')) of centerface.py:30, default INTER_LINEAR on 8UC3, on the device
+// and bit-exact (OpenCV modules/imgproc/src/resize.cpp; restated and pinned in oracle/centerface_oracle.py::
+// resize_linear_u8).  The per-column / per-row source index and the two 11-bit fixed-point weights are built on the
+// host with OpenCV's own float arithmetic (ResizeTables) and read here; one thread = one output pixel x 3 channels.
+//   tab layout (int32): xofs[dw] | xa0[dw] | xa1[dw] | y0[dh] | y1[dh] | yb0[dh] | yb1[dh]
+// area2 = 1: the exact 2x decimation that OpenCV silently switches to INTER_AREA.
+// ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_resize_u8(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                                   const int32_t* __restrict__ tab, int B, int sh, int sw, int dh, int dw,
+                                                   int area2) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= (long long)B * dh * dw) return;
+    const int dx = (int)(i % dw);
+    const int dy = (int)((i / dw) % dh);
+    const int b = (int)(i / ((long long)dw * dh));
+    const uint8_t* s = src + (size_t)b * sh * sw * 3;
+    uint8_t* o = dst + (size_t)i * 3;
+    if (area2) {
+        const uint8_t* p0 = s + ((size_t)(2 * dy) * sw + 2 * dx) * 3;
+        const uint8_t* p1 = p0 + (size_t)sw * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) o[c] = (uint8_t)((p0[c] + p0[3 + c] + p1[c] + p1[3 + c] + 2) >> 2);
+        return;
+    }
+    const int sx = tab[dx], a0 = tab[dw + dx], a1 = tab[2 * dw + dx];
+    const int sx1 = min(sx + 1, sw - 1);
+    const int32_t* ty = tab + 3 * dw;
+    const int y0 = ty[dy], y1 = ty[dh + dy], b0 = ty[2 * dh + dy], b1 = ty[3 * dh + dy];
+    const uint8_t* r0 = s + (size_t)y0 * sw * 3;
+    const uint8_t* r1 = s + (size_t)y1 * sw * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int h0 = r0[sx * 3 + c] * a0 + r0[sx1 * 3 + c] * a1;  // HResizeLinear, int32
+        const int h1 = r1[sx * 3 + c] * a0 + r1[sx1 * 3 + c] * a1;
+        o[c] = (uint8_t)((((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2);  // VResizeLinear<uchar>
+    }
+}
+
+// ----------------------------------------------------------------------------------------
 // K1 stem: ZeroPad2d(0,1,0,1) + conv3x3 s2 3->32 (no bias) + Swish   (model/centernet.py:224)
 //   FMT 0: fp32 NCHW normalised input (what EfficientNet.forward receives)
 //   FMT 1: u8 HWC BGR input; /255, -mean, /std (centerface.py:32-34) applied through a

@@ -319,4 +319,23 @@ __global__ void __launch_bounds__(1024) k_thresh_nms(const float* __restrict__ h
     if (tid == 0) out_counts[b] = nk;
 }
 
+// ---- ctdet_post_process (utils/post_process.py:83-100): map the two corners of every [x1,y1,x2,y2,score,cls] row
+//      through the per-image inverse affine `trans` (2x3, fp64, built on the host exactly like
+//      utils/image.py:27-61 does) in fp64 like np.dot, round once to fp32, keep the score -------------------------
+__global__ void __launch_bounds__(256) k_affine_boxes(const float* __restrict__ dets, const double* __restrict__ trans,
+                                                      float* __restrict__ out, int B, int K) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= B * K) return;
+    const double* t = trans + (size_t)(i / K) * 6;
+    const float* d = dets + (size_t)i * 6;
+    float* o = out + (size_t)i * 5;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {  // affine_transform(pt, t): t . [x, y, 1] with pt as float32 (utils/image.py:64-67)
+        const double x = (double)d[2 * c], y = (double)d[2 * c + 1];
+        o[2 * c] = __double2float_rn(__dadd_rn(__dadd_rn(__dmul_rn(t[0], x), __dmul_rn(t[1], y)), t[2]));
+        o[2 * c + 1] = __double2float_rn(__dadd_rn(__dadd_rn(__dmul_rn(t[3], x), __dmul_rn(t[4], y)), t[5]));
+    }
+    o[4] = d[4];
+}
+
 }  // namespace cf

@@ -1,6 +1,7 @@
 // Static description of the reference network (model/centernet.py:207-261) and of the packed
 // weight blob produced by weights.py.  Host-only.
 #pragma once
+#include <math.h>
 #include <stdint.h>
 #include <string.h>
 
@@ -73,6 +74,41 @@ struct Blob {
                          std::to_string(count),
                    nullptr;
         return payload + it->second.first;
+    }
+};
+
+// ---- cv2.resize INTER_LINEAR tables (OpenCV resize.cpp: the xofs/ialpha and yofs/ibeta loops of cv::resize) -----------
+// Same IEEE operations as OpenCV: scale = 1 / (dst / src) in double, f = float((d + 0.5) * scale - 0.5), floor,
+// weights rounded half-to-even to 11-bit fixed point.  x clamps (index, fraction) at the borders; y keeps the
+// fraction and clips the two row indices.
+struct ResizeTables {
+    int sh = 0, sw = 0, dh = 0, dw = 0, area2 = 0;
+    std::vector<int32_t> tab;  // xofs[dw] | xa0[dw] | xa1[dw] | y0[dh] | y1[dh] | yb0[dh] | yb1[dh]
+    void build(int sh_, int sw_, int dh_, int dw_) {
+        sh = sh_, sw = sw_, dh = dh_, dw = dw_;
+        area2 = (sh == 2 * dh && sw == 2 * dw) ? 1 : 0;
+        tab.assign((size_t)3 * dw + (size_t)4 * dh, 0);
+        const double scale_x = 1.0 / ((double)dw / sw), scale_y = 1.0 / ((double)dh / sh);
+        for (int dx = 0; dx < dw; ++dx) {
+            float fx = (float)((dx + 0.5) * scale_x - 0.5);
+            int sx = (int)floorf(fx);
+            fx -= sx;
+            if (sx < 0) fx = 0.f, sx = 0;
+            if (sx >= sw - 1) fx = 0.f, sx = sw - 1;
+            tab[dx] = sx;
+            tab[dw + dx] = (int32_t)lrintf((1.f - fx) * 2048.f);
+            tab[2 * dw + dx] = (int32_t)lrintf(fx * 2048.f);
+        }
+        int32_t* ty = tab.data() + 3 * dw;
+        for (int dy = 0; dy < dh; ++dy) {
+            float fy = (float)((dy + 0.5) * scale_y - 0.5);
+            const int sy = (int)floorf(fy);
+            fy -= sy;
+            ty[dy] = sy < 0 ? 0 : (sy > sh - 1 ? sh - 1 : sy);
+            ty[dh + dy] = sy + 1 < 0 ? 0 : (sy + 1 > sh - 1 ? sh - 1 : sy + 1);
+            ty[2 * dh + dy] = (int32_t)lrintf((1.f - fy) * 2048.f);
+            ty[3 * dh + dy] = (int32_t)lrintf(fy * 2048.f);
+        }
     }
 };
 

@@ -160,6 +160,30 @@ class Engine:
         if getattr(self, "_inflight", None):
             self._inflight.pop(0)
 
+    def detect_image_host(self, image, net_h, net_w, variant, threshold, nms_threshold=0.3, scale_w=0.0, scale_h=0.0, cap=1024,
+                          landmarks=True):
+        """One host u8 BGR image [h,w,3] at its own size -> (dets [n,5], lms [n,10] | None): resize on the device (bit-exact
+        cv2.resize), network, decode, NMS, //scale -- the body of CenterFace.__call__ (centerface.py:29-62)."""
+        h, w, c = image.shape
+        assert c == 3 and image.dtype == np.uint8
+        image = np.ascontiguousarray(image)
+        want_lms = landmarks and variant == L.CF_DECODE_A
+        while True:
+            dets = np.empty((cap, 5), np.float32)
+            lms = np.empty((cap, 10), np.float32) if want_lms else None
+            count = np.empty((1,), np.int32)
+            L.check(self.lib.cf_detect_image_host(
+                self.h, C.c_void_p(image.ctypes.data), h, w, net_h, net_w, variant, threshold, nms_threshold, scale_w, scale_h, cap,
+                C.c_void_p(dets.ctypes.data), C.c_void_p(lms.ctypes.data) if want_lms else None, C.c_void_p(count.ctypes.data)),
+                "cf_detect_image_host")
+            self.shape = (1, net_h, net_w)
+            n = int(count[0])
+            if n >= 0:
+                return dets[:n].copy(), (lms[:n].copy() if want_lms else None)
+            if -n > L.MAX_CAP or cap == L.MAX_CAP:
+                raise L.CenterFaceError(f"{-n} pixels above the threshold; the decode kernel caps at {L.MAX_CAP}")
+            cap = L.MAX_CAP
+
     def detect_threshold_host(self, images, variant, threshold, nms_threshold=0.3, scale_w=0.0, scale_h=0.0,
                               cap=1024, landmarks=True):
         """u8 BGR [B,H,W,3] host batch -> list of (dets [n,5], lms [n,10] | None) per image.
@@ -184,6 +208,23 @@ class Engine:
                 raise L.CenterFaceError(f"{need} pixels above the threshold in one image; the decode kernel caps at {L.MAX_CAP}")
             cap = L.MAX_CAP
         return [(dets[i, :counts[i]].copy(), lms[i, :counts[i]].copy() if want_lms else None) for i in range(B)]
+
+
+def resize_u8(images, dh, dw):
+    """cv2.resize(img, (dw, dh)) (INTER_LINEAR) for a cuda uint8 batch [B,h,w,3] -> [B,dh,dw,3], bit-exact with OpenCV."""
+    import torch
+    lib = L.load()
+    assert images.is_cuda and images.dtype == torch.uint8 and images.is_contiguous() and images.shape[3] == 3
+    B, sh, sw, _ = images.shape
+    tab = np.empty((3 * dw + 4 * dh,), np.int32)
+    area2 = C.c_int32()
+    L.check(lib.cf_resize_tables(sh, sw, dh, dw, C.c_void_p(tab.ctypes.data), tab.size, C.byref(area2)), "cf_resize_tables")
+    t_dev = torch.from_numpy(tab).to(images.device)
+    out = torch.empty((B, dh, dw, 3), dtype=torch.uint8, device=images.device)
+    with torch.cuda.device(images.device):
+        L.check(lib.cf_resize_u8(C.c_void_p(images.data_ptr()), B, sh, sw, C.c_void_p(out.data_ptr()), dh, dw, C.c_void_p(t_dev.data_ptr()),
+                                 area2.value, C.c_void_p(torch.cuda.current_stream(images.device).cuda_stream)), "cf_resize_u8")
+    return out
 
 
 def ctdet_decode(heat, wh, reg=None, cat_spec_wh=False, K=100, return_inds=False):
@@ -227,3 +268,48 @@ def decode_threshold(hm_sig, wh, reg, lm, variant, threshold, nms_threshold=0.3,
                                         size[0], size[1], scale_w, scale_h, cap, p(dets), p(lms), p(counts),
                                         C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "cf_decode_threshold")
     return dets, lms, counts
+
+
+def inverse_affine(center, scale, output_size):
+    """get_affine_transform(center, scale, 0, output_size, inv=1), utils/image.py:27-61, for rot = 0 and no shift:
+    the same three float32 point pairs handed to the same cv2.getAffineTransform (host-side geometry, fp64 2x3)."""
+    import cv2
+    if not isinstance(scale, (np.ndarray, list)):
+        scale = np.array([scale, scale], dtype=np.float32)
+    center = np.asarray(center, dtype=np.float32)
+    src_w, dst_w, dst_h = scale[0], output_size[0], output_size[1]
+    src_dir = [0.0, src_w * -0.5]                      # get_dir([0, src_w * -0.5], 0)
+    dst_dir = np.array([0, dst_w * -0.5], np.float32)
+    src = np.zeros((3, 2), dtype=np.float32)
+    dst = np.zeros((3, 2), dtype=np.float32)
+    src[0, :] = center
+    src[1, :] = center + src_dir
+    dst[0, :] = [dst_w * 0.5, dst_h * 0.5]
+    dst[1, :] = np.array([dst_w * 0.5, dst_h * 0.5], np.float32) + dst_dir
+
+    def third(a, b):                                   # get_3rd_point, utils/image.py:70-72
+        direct = a - b
+        return b + np.array([-direct[1], direct[0]], dtype=np.float32)
+
+    src[2:, :] = third(src[0, :], src[1, :])
+    dst[2:, :] = third(dst[0, :], dst[1, :])
+    return cv2.getAffineTransform(np.float32(dst), np.float32(src))
+
+
+def ctdet_post_process(dets, c, s, h, w, num_classes=1):
+    """Drop-in for utils.post_process.ctdet_post_process (utils/post_process.py:83-100), single face class: dets is a
+    cuda fp32 tensor [B,K,6] (the output of ctdet_decode); returns the reference's 1-based class dict per image."""
+    import torch
+    assert num_classes == 1, "the face detector has one class"
+    lib = L.load()
+    assert dets.is_cuda and dets.dtype == torch.float32 and dets.is_contiguous() and dets.shape[2] == 6
+    B, K, _ = dets.shape
+    trans = np.stack([inverse_affine(c[i], s[i], (w, h)) for i in range(B)]).reshape(B, 6).astype(np.float64)
+    t_dev = torch.from_numpy(trans).to(dets.device)
+    out = torch.empty((B, K, 5), dtype=torch.float32, device=dets.device)
+    with torch.cuda.device(dets.device):
+        L.check(lib.cf_ctdet_post_process(C.c_void_p(dets.data_ptr()), C.c_void_p(t_dev.data_ptr()), B, K, C.c_void_p(out.data_ptr()),
+                                          C.c_void_p(torch.cuda.current_stream(dets.device).cuda_stream)), "cf_ctdet_post_process")
+    out = out.cpu().numpy()
+    cls = dets[:, :, 5].cpu().numpy()
+    return [{1: out[i][cls[i] == 0].tolist()} for i in range(B)]

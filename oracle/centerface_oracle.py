@@ -207,6 +207,49 @@ def normalize_u8(img_u8_hwc):
     return np.ascontiguousarray(img.transpose(2, 0, 1))
 
 
+def resize_linear_u8(src, dh, dw):
+    """cv2.resize(src, (dw, dh)) with the default INTER_LINEAR for 8-bit images, restated.
+
+    The arithmetic lives in a third-party dependency the reference calls (centerface.py:30): OpenCV, not
+    pinned by the reference (no requirements file); this image has opencv-python 4.13.0.  Algorithm
+    (modules/imgproc/src/resize.cpp, resizeGeneric_ with HResizeLinear / VResizeLinear for uchar):
+      * scale = 1 / (dst / src) in double;  f = float((d + 0.5) * scale - 0.5);  s = floor(f);  f -= s
+      * x: s < 0 -> (s, f) = (0, 0);  s >= w-1 -> (w-1, 0).   y: f is kept, the two rows are clipped into the image
+      * coefficients are rounded to 11-bit fixed point: cvRound(w * 2048) (round half to even)
+      * horizontal pass in int32, vertical pass  (((b0 * (H0 >> 4)) >> 16) + ((b1 * (H1 >> 4)) >> 16) + 2) >> 2
+      * an exact 2x decimation in both axes is silently switched to INTER_AREA: (a + b + c + d + 2) >> 2
+    tests/test_oracle_golden.py pins this against cv2 itself on the bundled JPEGs (bit-exact)."""
+    sh, sw, _ = src.shape
+    if sh == 2 * dh and sw == 2 * dw:
+        s = src.astype(np.int32)
+        return ((s[0::2, 0::2] + s[0::2, 1::2] + s[1::2, 0::2] + s[1::2, 1::2] + 2) >> 2).astype(np.uint8)
+
+    def frac(dn, sn):
+        scale = 1.0 / (dn / sn)
+        f = ((np.arange(dn) + 0.5) * scale - 0.5).astype(np.float32)
+        s0 = np.floor(f).astype(np.int32)
+        return s0, (f - s0).astype(np.float32)
+
+    def fix(f):
+        return np.rint((np.float32(1.0) - f) * np.float32(2048)).astype(np.int32), np.rint(f * np.float32(2048)).astype(np.int32)
+
+    sx, fx = frac(dw, sw)
+    lo, hi = sx < 0, sx >= sw - 1
+    fx[lo | hi] = 0
+    sx[lo] = 0
+    sx[hi] = sw - 1
+    ax0, ax1 = fix(fx)
+    sx1 = np.minimum(sx + 1, sw - 1)
+    sy0, fy = frac(dh, sh)
+    by0, by1 = fix(fy)
+    sy, sy1 = np.clip(sy0, 0, sh - 1), np.clip(sy0 + 1, 0, sh - 1)
+    S = src.astype(np.int32)
+    h0 = S[sy][:, sx] * ax0[None, :, None] + S[sy][:, sx1] * ax1[None, :, None]
+    h1 = S[sy1][:, sx] * ax0[None, :, None] + S[sy1][:, sx1] * ax1[None, :, None]
+    out = (((by0[:, None, None] * (h0 >> 4)) >> 16) + ((by1[:, None, None] * (h1 >> 4)) >> 16) + 2) >> 2
+    return out.astype(np.uint8)
+
+
 def preprocess(img_u8_hwc, h_new, w_new):
     """centerface.py:30-37: cv2 bilinear stretch to (w_new,h_new) then normalise -> [1,3,H,W]."""
     import cv2

@@ -303,6 +303,47 @@ def test_pipelined_host_api(eng, f5_640):
         eng.wait_host()  # nothing in flight
 
 
+def test_device_resize_is_bit_exact_with_cv2(pkg, images):
+    """Row f1: cv2.resize (INTER_LINEAR, 8UC3) on the device, incl. the exact-2x INTER_AREA special case and a batch."""
+    import cv2
+    for n in ("8", "1", "17"):
+        img = images[n]
+        h, w = img.shape[:2]
+        sizes = [(640, 640), (int(np.ceil(h / 32) * 32), int(np.ceil(w / 32) * 32)), (320, 256), (h + 7, w + 13)]
+        if h % 2 == 0 and w % 2 == 0:
+            sizes.append((h // 2, w // 2))
+        for dh, dw in sizes:
+            got = pkg.resize_u8(torch.from_numpy(img[None].copy()).cuda(), dh, dw)[0].cpu().numpy()
+            assert np.array_equal(got, cv2.resize(img, (dw, dh))), (n, (h, w), (dh, dw))
+    a, b = images["27"][:600, :1000], images["17"][:600, :1000]
+    got = pkg.resize_u8(torch.from_numpy(np.stack([a, b])).cuda(), 640, 640).cpu().numpy()
+    assert np.array_equal(got[0], cv2.resize(a, (640, 640))) and np.array_equal(got[1], cv2.resize(b, (640, 640)))
+
+
+def test_centerface_device_resize_equals_host_resize(pkg, images, weights_path):
+    """CenterFace.__call__ with the resize on the device returns exactly what it returns with cv2.resize on the host."""
+    pkg.CenterFace.print_times = False
+    for n in ("8", "27"):
+        img = images[n]
+        cf = pkg.CenterFace(img.shape[0], img.shape[1], landmarks=True, weights=weights_path)
+        cf.gpu_resize = True
+        d1, l1 = cf(img)
+        cf.gpu_resize = False
+        d2, l2 = cf(img)
+        assert len(d1) > 0 and np.array_equal(d1, d2) and np.array_equal(l1, l2), n
+        cf.net.close()
+
+
+def test_ctdet_post_process_matches_reference(pkg, golden):
+    """utils.post_process.ctdet_post_process on the GPU against the reference's stored output (same cv2 affine on the
+    host, fp64 dot per point on the device): bit-exact."""
+    dets = torch.from_numpy(golden["f5_640/27/pathC_dets"][None].copy()).cuda()
+    out = pkg.ctdet_post_process(dets, golden["post/27/c"], golden["post/27/s"], 160, 160, 1)
+    got = np.asarray(out[0][1], np.float32)
+    assert got.shape == golden["post/27/dets"].shape
+    assert np.array_equal(got, golden["post/27/dets"]), np.abs(got - golden["post/27/dets"]).max()
+
+
 def test_errors_are_loud(pkg, eng):
     with pytest.raises(pkg.CenterFaceError):
         eng.forward(torch.zeros(9, 3, 64, 64, device="cuda"))       # batch > max_batch

@@ -127,3 +127,38 @@ def test_layouts(pkg, weights_path):
 def test_transform_matches_reference_formula(oracle):
     assert oracle.transform(478, 720) == (480, 736, 480 / 478, 736 / 720)
     assert oracle.transform(640, 640) == (640, 640, 1.0, 1.0)
+
+
+def test_inverse_affine_matches_oracle_closed_form(pkg, oracle):
+    """The host-side affine of ctdet_post_process (cv2.getAffineTransform on the reference's three point pairs)
+    against the oracle's closed form."""
+    from importlib import import_module
+    eng = import_module(pkg.__name__ + ".engine")
+    for c, s, wh in (((512.0, 304.5), 1024.0, (160, 160)), ((320.0, 240.0), 640.0, (160, 120))):
+        t = eng.inverse_affine(np.array(c, np.float32), s, wh)
+        assert np.allclose(t, oracle.inverse_affine(c, s, wh[0], wh[1]), rtol=0, atol=1e-4)
+
+
+def test_resize_tables_reproduce_cv2(pkg, images):
+    """cf_resize_tables (the C++ restatement of OpenCV's index/weight loops) drives a numpy version of the device
+    kernel's arithmetic; the result must equal cv2.resize bit for bit."""
+    import cv2
+    lib = pkg._lib.load()
+    img = images["8"]
+    sh, sw = img.shape[:2]
+    for dh, dw in ((384, 512), (640, 640), (320, 320), (sh + 7, sw + 13)):
+        tab = np.empty((3 * dw + 4 * dh,), np.int32)
+        area2 = C.c_int32()
+        assert lib.cf_resize_tables(sh, sw, dh, dw, C.c_void_p(tab.ctypes.data), tab.size, C.byref(area2)) == 0
+        assert area2.value == 0
+        sx, a0, a1 = tab[:dw], tab[dw:2 * dw], tab[2 * dw:3 * dw]
+        y0, y1, b0, b1 = (tab[3 * dw + k * dh:3 * dw + (k + 1) * dh] for k in range(4))
+        sx1 = np.minimum(sx + 1, sw - 1)
+        S = img.astype(np.int32)
+        h0 = S[y0][:, sx] * a0[None, :, None] + S[y0][:, sx1] * a1[None, :, None]
+        h1 = S[y1][:, sx] * a0[None, :, None] + S[y1][:, sx1] * a1[None, :, None]
+        out = ((((b0[:, None, None] * (h0 >> 4)) >> 16) + ((b1[:, None, None] * (h1 >> 4)) >> 16) + 2) >> 2).astype(np.uint8)
+        assert np.array_equal(out, cv2.resize(img, (dw, dh))), (dh, dw)
+    tab = np.empty((3 * 245 + 4 * 176,), np.int32)
+    assert lib.cf_resize_tables(352, 490, 176, 245, C.c_void_p(tab.ctypes.data), tab.size, C.byref(area2)) == 0 and area2.value == 1
+    assert lib.cf_resize_tables(352, 490, 176, 245, C.c_void_p(tab.ctypes.data), 10, C.byref(area2)) == -5

@@ -91,3 +91,16 @@ def test_peak_nms_plateau_and_border(oracle):
     out = oracle.peak_nms(heat)
     assert out[0, 0, 0, 0] == 0.9 and out[0, 0, 2, 2] == 0.7 and out[0, 0, 2, 3] == 0.7
     assert out[0, 0, 1, 1] == 0
+
+
+def test_resize_restatement_is_bit_exact_against_cv2(oracle, images):
+    """cv2.resize (INTER_LINEAR, 8UC3) restated: up-, down-, mixed scaling, the /32 sizes CenterFace.__call__ uses and
+    the exact-2x case that OpenCV routes to INTER_AREA."""
+    import cv2
+    for n, img in images.items():
+        h, w = img.shape[:2]
+        sizes = [(640, 640), (480, 640), (int(np.ceil(h / 32) * 32), int(np.ceil(w / 32) * 32)), (320, 320), (h + 7, w + 13)]
+        if h % 2 == 0 and w % 2 == 0:
+            sizes.append((h // 2, w // 2))
+        for dh, dw in sizes:
+            assert np.array_equal(oracle.resize_linear_u8(img, dh, dw), cv2.resize(img, (dw, dh))), (n, (h, w), (dh, dw))
