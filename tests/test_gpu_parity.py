@@ -211,6 +211,25 @@ def test_batch_independence_and_idempotence(eng, f5_640):
     assert torch.equal(full["hm"][3], full["hm"][5])  # same image (27) in two slots
 
 
+def test_full_size_batch32_properties(pkg, weights_path, f5_640):
+    """BASELINE.json configs[1] size (batch 32 @ 640x640): size-independent properties on the full-size run -- every image's
+    heads and top-k list equal its batch-1 result bit for bit wherever it sits in the batch, scores are sorted, indices are
+    unique and in range, replay is idempotent."""
+    e = pkg.Engine(weights_path, max_batch=32)
+    rng = np.random.RandomState(1234)
+    order = [IMGS[i % 5] for i in rng.permutation(32)]
+    u8 = np.stack([np.roll(f5_640[n], int(rng.randint(0, 32)), axis=1) if k % 2 else f5_640[n] for k, n in enumerate(order)])
+    dets, inds = e.detect_topk_host(u8, K=100)
+    d2, i2 = e.detect_topk_host(u8, K=100)
+    assert np.array_equal(dets, d2) and np.array_equal(inds, i2)
+    assert (np.diff(dets[:, :, 4], axis=1) <= 0).all()
+    assert inds.min() >= 0 and inds.max() < 160 * 160 and all(len(set(r)) == 100 for r in inds.tolist())
+    for slot in (0, 13, 31):
+        d1, i1 = e.detect_topk_host(u8[slot:slot + 1], K=100)
+        assert np.array_equal(d1[0], dets[slot]) and np.array_equal(i1[0], inds[slot]), slot
+    e.close()
+
+
 def test_small_and_non_square_inputs(eng, oracle, sd, images):
     """320-max-side sweep shapes (config 5) incl. the smallest legal 32x32 and non-square maps."""
     import cv2
