@@ -22,6 +22,7 @@
 #include "k_mbx.cuh"
 #include "k_dwt.cuh"
 #include "k_dwp.cuh"
+#include "k_pwn.cuh"
 #include "net.hpp"
 
 using namespace cf;
@@ -189,6 +190,17 @@ int make_pw_step(cf_engine* e, std::vector<Step>& P, int epi, const float* A, co
     if (e->pw_engine == CF_PW_SIMT) {
         P.push_back({CLS_PW, [=](cudaStream_t s) { return launch_pw_simt_any(epi, A, Wkn, out, M, K, N, ea, s); }});
         return CF_OK;
+    }
+    if (engine_passes(e->pw_engine) == 3) {  // narrow layers: the role-free kernel
+        auto it = e->tc.layers.find(Wkn);
+        const char* ev = getenv("CF_PWN");
+        if (it != e->tc.layers.end() && pwn_eligible(it->second) && !(ev && atoi(ev) == 0)) {
+            PwnLaunch pl;
+            int rc = pwn_plan(e->tc, epi, A, Wkn, out, M, K, N, ea, &pl);
+            if (rc) return rc;
+            P.push_back({CLS_PW, [pl](cudaStream_t s) { return pwn_launch(pl, s); }});
+            return CF_OK;
+        }
     }
     TcLaunch tl;
     int rc = tc_plan(e->tc, engine_passes(e->pw_engine), epi, A, Wkn, out, M, K, N, ea, &tl);
@@ -901,6 +913,20 @@ int cf_debug_pw_gemm(int pw_engine, int epi, const float* dA, const float* hW, f
         rc = pw_tc_init(st, dev);
         if (!rc) rc = tc_prepare_layer(st, dW, hW, K, N, engine_passes(pw_engine));
         TcLaunch tl;
+        const char* ev = getenv("CF_PWN");
+        if (!rc && engine_passes(pw_engine) == 3 && pwn_eligible(st.layers[dW]) && !(ev && atoi(ev) == 0)) {
+            PwnLaunch pl;
+            rc = pwn_plan(st, epi, dA, dW, dOut, M, K, N, ea, &pl);
+            if (!rc) {
+                ce = pwn_launch(pl, (cudaStream_t)stream);
+                if (ce != cudaSuccess) rc = fail(CF_ECUDA, "cf_debug_pw_gemm: launch: %s", cudaGetErrorString(ce));
+            }
+            ce = cudaStreamSynchronize((cudaStream_t)stream);
+            if (!rc && ce != cudaSuccess) rc = fail(CF_ECUDA, "cf_debug_pw_gemm: kernel: %s", cudaGetErrorString(ce));
+            pw_tc_destroy(st);
+            cudaFree(dW);
+            return rc;
+        }
         if (!rc) rc = tc_plan(st, engine_passes(pw_engine), epi, dA, dW, dOut, M, K, N, ea, &tl);
         if (!rc) {
             ce = tc_launch(tl, (cudaStream_t)stream);

@@ -1,0 +1,244 @@
+// k_pwn: point-wise convolution for the NARROW layers (column chunk NC <= 64, weight image <= 48 KB: the projection
+// convs of the shallow blocks and the FPN laterals).
+//
+// k_pw_tc's warp-specialised pipeline hands a 16 KB tile through five mbarrier hops (producer thread -> 4 splitter
+// warps -> MMA thread -> epilogue group -> ...); on these layers every stage has too little work per tile and the
+// per-tile hand-off chain, not HBM or the tensor pipe, sets the pace (profiles/r1_fused_kernels.md, section 4:
+// the same matrix streams at 6.2 TB/s through a bare TMA ring, the full GEMM runs at 3.8 TB/s).  Here there are no
+// roles: a 256-thread CTA walks over its 128-row tiles and ALL threads take part in every phase --
+//   wait for the TMA box (K block of 32)  ->  every thread splits 16 elements of its row into tf32 hi + lo and
+//   tcgen05.st's them into a two-slot TMEM ring (lane = row)  ->  one thread issues  A_hi.[B_hi|B_lo]  and  A_lo.B_hi
+//   with A from TMEM and the resident weight image from shared memory  ->  after the last K block all threads drain
+//   the accumulator pair, apply the epilogue and store their rows --
+// with CTA-wide barriers in between, and two such CTAs share an SM so one CTA's TMA / MMA latency is the other's
+// compute phase.
+#pragma once
+#include "k_pw_tc.cuh"
+
+namespace cf {
+
+constexpr int PWN_THREADS = 256;
+
+struct PwnParams {
+    const float* bimg;  // [kb][hi NC x 128 B | lo NC x 128 B]
+    float* out;
+    int M, K, N, NC, nkb, n_tiles, nst;
+    uint32_t off_b, off_bars, b_bytes;
+    EpiArgs ea;
+};
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+    const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(PWN_THREADS, 2) k_pwn(const __grid_constant__ CUtensorMap tmA, const PwnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+    const int nst = p.nst, nkb = p.nkb;
+    const uint32_t bsm = base + p.off_b;
+    const uint32_t bars = base + p.off_bars;  // [0..nst) A full | B full | A-slot free x2 | accumulator ready
+    const uint32_t bar_b = bars + 8 * nst, bar_afree = bar_b + 8, bar_acc = bar_afree + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + p.off_bars + 8 * nst + 40);
+    constexpr uint32_t kACol = 128;  // TMEM: accumulator pair in columns [0, 2NC <= 128), A ring 2 x (32 hi + 32 lo) above
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, half = warp >> 2;  // TMEM lane quarter; which 16 of a K block's 32 elements / which column half
+
+    if (tid == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        for (int i = 0; i < nst + 4; ++i) mbar_init(bars + 8 * i, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int my_tiles = ((int)blockIdx.x < p.n_tiles) ? (p.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const long long total = (long long)my_tiles * nkb;  // job j = (my tile j / nkb, K block j % nkb)
+    auto issue_a = [&](long long j) {  // thread 0 only
+        const int stage = (int)(j % nst);
+        const int tile = (int)blockIdx.x + (int)(j / nkb) * (int)gridDim.x;
+        mbar_expect_tx(bars + 8 * stage, TC_A_BYTES);
+        tma_load_2d(base + stage * TC_A_BYTES, &tmA, (int)(j % nkb) * TC_BK, tile * TC_BM, bars + 8 * stage);
+    };
+    if (tid == 0 && total > 0) {
+        mbar_expect_tx(bar_b, p.b_bytes);
+        for (uint32_t off = 0; off < p.b_bytes; off += 32768u) {
+            const uint32_t n = p.b_bytes - off < 32768u ? p.b_bytes - off : 32768u;
+            bulk_load(bsm + off, reinterpret_cast<const uint8_t*>(p.bimg) + off, n, bar_b);
+        }
+        for (long long j = 0; j < nst && j < total; ++j) issue_a(j);
+    }
+    const uint32_t idesc = umma_idesc_tf32(p.NC), idesc2 = umma_idesc_tf32(2 * p.NC);
+    const uint32_t d_main = tmem_base, d_corr = tmem_base + (uint32_t)p.NC;
+    const uint32_t blk_bytes = (uint32_t)p.NC * 256u;  // one K block of the weight image (hi | lo)
+
+    for (long long j = 0; j < total; ++j) {
+        const int kb = (int)(j % nkb);
+        const int tile = (int)blockIdx.x + (int)(j / nkb) * (int)gridDim.x;
+        const int stage = (int)(j % nst);
+        const uint32_t aslot = (uint32_t)(j & 1);
+        // ---- split: this thread's 16 elements of row (32q + lane) -> tf32 hi / lo -> TMEM ----
+        mbar_wait(bars + 8 * stage, (uint32_t)(j / nst) & 1u);
+        const int row = q * 32 + lane;
+        const uint8_t* ar = sm + stage * TC_A_BYTES + row * 128;
+        float hi[16], lo[16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float4 v = *reinterpret_cast<const float4*>(ar + (((half * 4 + c) ^ (row & 7)) << 4));
+            hi[4 * c] = tf32_hi(v.x), hi[4 * c + 1] = tf32_hi(v.y), hi[4 * c + 2] = tf32_hi(v.z), hi[4 * c + 3] = tf32_hi(v.w);
+            lo[4 * c] = v.x - hi[4 * c], lo[4 * c + 1] = v.y - hi[4 * c + 1], lo[4 * c + 2] = v.z - hi[4 * c + 2], lo[4 * c + 3] = v.w - hi[4 * c + 3];
+        }
+        if (j >= 2) mbar_wait(bar_afree + 8 * aslot, (uint32_t)((j >> 1) - 1) & 1u);  // MMAs of job j-2 have read this slot
+        tc_fence_after();
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + kACol + aslot * 64u + (uint32_t)half * 16u;
+        tmem_st16(ta, hi);
+        tmem_st16(ta + 32u, lo);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncthreads();  // the A block is in TMEM, the smem stage is drained
+        if (tid == 0) {
+            if (j + nst < total) issue_a(j + nst);
+            if (j == 0) mbar_wait(bar_b, 0);
+            tc_fence_after();
+            const uint64_t b_hi = umma_desc(bsm + (uint32_t)kb * blk_bytes);
+            const uint32_t a_hi = tmem_base + kACol + aslot * 64u, a_lo = a_hi + 32u;
+            const int krem = p.K - kb * TC_BK;
+            const int nks = krem >= TC_BK ? TC_BK / 8 : (krem + 7) / 8;
+            for (int k = 0; k < nks; ++k) {
+                const uint64_t ko = (uint64_t)(k * 2);
+                umma_tf32_ts(d_main, a_hi + 8u * k, b_hi + ko, idesc2, (kb > 0 || k > 0) ? 1u : 0u);  // main += hi.hi ; corr += hi.lo
+                umma_tf32_ts(d_corr, a_lo + 8u * k, b_hi + ko, idesc, 1u);                              // corr += lo.hi
+            }
+            umma_commit(bar_afree + 8 * aslot);
+            if (kb == nkb - 1) umma_commit(bar_acc);
+        }
+        if (kb == nkb - 1) {
+            // ---- tile done: drain main + correction, epilogue, store this thread's half of the row ----
+            mbar_wait(bar_acc, (uint32_t)(j / nkb) & 1u);
+            tc_fence_after();
+            const int grow = tile * TC_BM + row;
+            const int ncols = p.NC >> 1;  // 16 or 32 columns per thread
+            for (int c0 = half * ncols; c0 < (half + 1) * ncols; c0 += 16) {
+                float v[16], c[16];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+                tmem_ld16(taddr, v);
+                tmem_ld16(taddr + (uint32_t)p.NC, c);
+                tmem_ld_wait();
+                if (grow < p.M) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const int n = c0 + 4 * g;
+                        if (n < p.N) {
+                            float4 o = make_float4(v[4 * g] + c[4 * g], v[4 * g + 1] + c[4 * g + 1], v[4 * g + 2] + c[4 * g + 2],
+                                                   v[4 * g + 3] + c[4 * g + 3]);
+                            o = apply_epi<EPI>(o, grow, n, p.N, p.ea);
+                            st4(p.out + (size_t)grow * p.N + n, o);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncthreads();  // every accumulator read is done before the next tile's first MMA overwrites it
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    }
+}
+
+// ---- host side --------------------------------------------------------------------------
+struct PwnLaunch {
+    CUtensorMap tmA;
+    PwnParams p;
+    int epi = 0, grid = 0;
+    size_t smem = 0;
+};
+
+// eligible: 3-pass, one column chunk of <= 64 columns, weight image small enough to sit beside a >= 3 stage A ring
+// in half an SM's shared memory
+// Measured (tools/tc_shape_probe.py, same call): K=32,N=16: 179 -> 157 us; K=144,N=24: 159 -> 172 us; K=192,N=32: 53 -> 61 us --
+// the CTA-wide barrier per K block costs more than the hand-off chain it removes once a tile has several K blocks, so
+// only single-K-block layers (K <= 32: layer0 projection, FPN laterals up2/up3) take this kernel.
+inline bool pwn_eligible(const TcLayer& L) { return L.nchunks == 1 && L.NC <= 64 && L.nkb == 1 && L.img_bytes <= 49152; }
+
+inline int pwn_plan(PwTcState& st, int epi, const float* A, const float* Wkn, float* out, int M, int K, int N, EpiArgs ea, PwnLaunch* pl) {
+    auto it = st.layers.find(Wkn);
+    if (it == st.layers.end()) return fail(CF_EINVAL, "pwn_plan: weight matrix was not prepared");
+    const TcLayer& L = it->second;
+    if (!pwn_eligible(L)) return fail(CF_EINVAL, "pwn_plan: layer K=%d N=%d is not a narrow layer", K, N);
+    int rc = tc_make_map(st, &pl->tmA, A, (uint64_t)M, (uint64_t)K, TC_BM);
+    if (rc) return rc;
+    PwnParams& p = pl->p;
+    p.bimg = L.img;
+    p.out = out;
+    p.M = M;
+    p.K = K;
+    p.N = N;
+    p.NC = L.NC;
+    p.nkb = L.nkb;
+    p.n_tiles = (M + TC_BM - 1) / TC_BM;
+    p.b_bytes = (uint32_t)L.img_bytes;
+    p.ea = ea;
+    const uint32_t b_al = (p.b_bytes + 1023u) & ~1023u;
+    const int ctas = 2;  // 256 TMEM columns per CTA (accumulator pair + two-slot A ring): two CTAs fill the SM's 512
+    int nst = ((int)(TC_SMEM_MAX / 2) - 1024 - 2048 - (int)b_al) / TC_A_BYTES;
+    if (nst > 6) nst = 6;
+    if (nst < 2) return fail(CF_EINVAL, "pwn_plan: does not fit shared memory");
+    p.nst = nst;
+    p.off_b = (uint32_t)nst * TC_A_BYTES;
+    p.off_bars = p.off_b + b_al;
+    pl->smem = (size_t)p.off_bars + 1024 + 1024;
+    pl->epi = epi;
+    const int want = ctas * st.sms;
+    pl->grid = p.n_tiles < want ? p.n_tiles : want;
+    return CF_OK;
+}
+
+template <int EPI>
+inline cudaError_t pwn_launch_t(const PwnLaunch& pl, cudaStream_t s) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(k_pwn<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX / 2);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    k_pwn<EPI><<<pl.grid, PWN_THREADS, pl.smem, s>>>(pl.tmA, pl.p);
+    return cudaGetLastError();
+}
+
+inline cudaError_t pwn_launch(const PwnLaunch& pl, cudaStream_t s) {
+    switch (pl.epi) {
+        case EPI_LINEAR: return pwn_launch_t<EPI_LINEAR>(pl, s);
+        case EPI_SWISH: return pwn_launch_t<EPI_SWISH>(pl, s);
+        case EPI_RESIDUAL: return pwn_launch_t<EPI_RESIDUAL>(pl, s);
+        case EPI_BIAS_SWISH: return pwn_launch_t<EPI_BIAS_SWISH>(pl, s);
+        default: return pwn_launch_t<EPI_IDAUP>(pl, s);
+    }
+}
+
+}  // namespace cf
