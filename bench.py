@@ -330,7 +330,7 @@ def run_b200(a):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": warm,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": {0: "f32", 1: "tf32x3", 2: "tf32", 3: "tf32x3+f32", 4: "tf32x3", 5: "tf32x3"}[pw], "data": "synthetic",
+                "dtype": {0: "f32", 1: "tf32x3", 2: "tf32", 3: "tf32x3+f32", 4: "tf32x3", 5: "tf32x3", 6: "tf32x3/tf32"}[pw], "data": "synthetic",
                 "config": {"workload": f"batch-{B} 640x640 per GPU ({'configs[1]' if world == 1 else 'configs[2] sharding'}), "
                                        f"u8 BGR input, network + sigmoid/clamp + path-C top-{K_TOP} decode"
                                        + (", NCCL all-gather of [B,100,6] boxes" if world > 1 else ""),

@@ -52,6 +52,7 @@ extern "C" {
                                  expand on the fp32 CUDA cores                                        */
 #define CF_PW_TCGEN05_FUSED_TC 4 /* same fusion, the expand conv of the fused blocks on tcgen05 (3xTF32),
                                     accumulators drained from TMEM straight into the shared-memory tile */
+#define CF_PW_TCGEN05_MIXED 6 /* CF_PW_TCGEN05 with a single TF32 pass on the stride-16/32 stages (K or N >= 384) only */
 #define CF_PW_TCGEN05_DWP 5 /* CF_PW_TCGEN05 + the shallow blocks run depth-wise+Swish+projection(+residual) as ONE
                                kernel: the depth-wise output is written as the tcgen05 A operand in shared memory */
 

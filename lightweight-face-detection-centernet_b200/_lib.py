@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcenterface_b200.so")
 
 CF_IN_F32_NCHW, CF_IN_U8_HWC = 0, 1
-CF_PW_SIMT, CF_PW_TCGEN05, CF_PW_TCGEN05_1P, CF_PW_TCGEN05_FUSED, CF_PW_TCGEN05_FUSED_TC, CF_PW_TCGEN05_DWP = 0, 1, 2, 3, 4, 5
+CF_PW_SIMT, CF_PW_TCGEN05, CF_PW_TCGEN05_1P, CF_PW_TCGEN05_FUSED, CF_PW_TCGEN05_FUSED_TC, CF_PW_TCGEN05_DWP, CF_PW_TCGEN05_MIXED = 0, 1, 2, 3, 4, 5, 6
 CF_DECODE_A, CF_DECODE_B = 0, 1
 CLS_ALL, CLS_PW, CLS_DW, CLS_STEM, CLS_HEADS, CLS_DECODE, CLS_FUSED = range(7)
 MAX_CAP = 4096

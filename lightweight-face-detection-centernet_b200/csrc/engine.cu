@@ -33,6 +33,13 @@ enum WorkClass { CLS_ALL = 0, CLS_PW = 1, CLS_DW = 2, CLS_STEM = 3, CLS_HEADS = 
 
 inline bool engine_is_tc(int pw) { return pw != CF_PW_SIMT; }
 inline int engine_passes(int pw) { return pw == CF_PW_TCGEN05_1P ? 1 : 3; }
+// CF_PW_TCGEN05_MIXED: single TF32 pass for the point-wise convs of the stride-16/32 stages (layer3.1 .. layer6.0, i.e.
+// every GEMM with K or N >= 384), 3xTF32 everywhere else.  Those stages are the precision-insensitive ones (SURVEY.md
+// 7.3-2: quantising them to 11 bits moves the heat-map by 1e-4 .. 8e-6) and the tensor-bound ones.
+inline int layer_passes(int pw, int K, int N) {
+    if (pw == CF_PW_TCGEN05_MIXED) return (K >= 384 || N >= 384) ? 1 : 3;
+    return engine_passes(pw);
+}
 // depth-wise + projection fused (k_dwp): the shallow blocks, where the depth-wise output is large and tiles are plentiful
 inline bool block_is_dwp(int pw, int i) { return pw == CF_PW_TCGEN05_DWP && i <= 5 && dwp_supported(kBlocks[i].hid(), kBlocks[i].cout); }
 
@@ -191,7 +198,8 @@ int make_pw_step(cf_engine* e, std::vector<Step>& P, int epi, const float* A, co
         P.push_back({CLS_PW, [=](cudaStream_t s) { return launch_pw_simt_any(epi, A, Wkn, out, M, K, N, ea, s); }});
         return CF_OK;
     }
-    if (engine_passes(e->pw_engine) == 3) {  // narrow layers: the role-free kernel
+    const int passes = layer_passes(e->pw_engine, K, N);
+    if (passes == 3) {  // narrow layers: the role-free kernel
         auto it = e->tc.layers.find(Wkn);
         const char* ev = getenv("CF_PWN");
         if (it != e->tc.layers.end() && pwn_eligible(it->second) && !(ev && atoi(ev) == 0)) {
@@ -203,7 +211,7 @@ int make_pw_step(cf_engine* e, std::vector<Step>& P, int epi, const float* A, co
         }
     }
     TcLaunch tl;
-    int rc = tc_plan(e->tc, engine_passes(e->pw_engine), epi, A, Wkn, out, M, K, N, ea, &tl);
+    int rc = tc_plan(e->tc, passes, epi, A, Wkn, out, M, K, N, ea, &tl);
     if (rc) return rc;
     P.push_back({CLS_PW, [tl](cudaStream_t s) { return tc_launch(tl, s); }});
     return CF_OK;
@@ -433,7 +441,7 @@ int cf_create(const void* weights, size_t weights_bytes, int device, int max_bat
     CF_CHECK(weights != nullptr, CF_EINVAL, "cf_create: weights is NULL");
     CF_CHECK(max_batch >= 1 && max_h >= 32 && max_w >= 32 && max_h % 32 == 0 && max_w % 32 == 0, CF_EINVAL,
              "cf_create: max_batch=%d max_h=%d max_w=%d (sizes must be positive multiples of 32)", max_batch, max_h, max_w);
-    CF_CHECK(pw_engine >= CF_PW_SIMT && pw_engine <= CF_PW_TCGEN05_DWP, CF_EINVAL, "cf_create: unknown pw_engine %d", pw_engine);
+    CF_CHECK(pw_engine >= CF_PW_SIMT && pw_engine <= CF_PW_TCGEN05_MIXED, CF_EINVAL, "cf_create: unknown pw_engine %d", pw_engine);
     CF_CHECK(weights_bytes == blob_bytes(), CF_EWEIGHTS, "cf_create: blob is %zu bytes, expected %zu", weights_bytes, blob_bytes());
     Blob blob;
     std::string why;
@@ -542,7 +550,7 @@ int cf_create(const void* weights, size_t weights_bytes, int device, int max_bat
         // tf32 hi/lo, K-major, 128B-swizzled images of every point-wise weight matrix
         auto prep = [&](const std::string& name, int K, int N) {
             const float* hp = blob.get(name, (uint64_t)K * N, why);
-            return hp ? tc_prepare_layer(e->tc, e->w[name], hp, K, N, engine_passes(pw_engine)) : fail(CF_EWEIGHTS, "cf_create: %s", why.c_str());
+            return hp ? tc_prepare_layer(e->tc, e->w[name], hp, K, N, layer_passes(pw_engine, K, N)) : fail(CF_EWEIGHTS, "cf_create: %s", why.c_str());
         };
         for (int i = 0; i < 12 && !rc; ++i) {
             const MBBlock& b = kBlocks[i];
