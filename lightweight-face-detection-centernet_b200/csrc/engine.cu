@@ -148,6 +148,7 @@ struct cf_engine {
     long long launches = 0;
     PwTcState tc;  // tensor maps etc. of the tcgen05 engine
     StemW stem_w;  // host copy: the stem weights are passed to the kernel by value
+    HeadsW heads_w;  // likewise the collapsed head conv
 };
 
 namespace {
@@ -385,12 +386,10 @@ int build_plan(cf_engine* e, const void* input, int fmt, int B, int H, int W) {
     // heads, :240-261, :277-279 (+ sigmoid/clamp of centerface.py:43)
     {
         const float* a = e->up[2];
-        const float* wh_ = e->w["heads.w"];
-        const float* bh = e->w["heads.b"];
         const int hh = h, ww = wd;
         P.push_back({CLS_HEADS, [=](cudaStream_t s) {
                          dim3 g(cdiv(ww, 32), cdiv(hh, 16), B);
-                         k_heads<<<g, 128, HEADS_SMEM, s>>>(a, wh_, bh, e->hm, e->wh, e->lm, e->reg, e->hm_sig, B, hh, ww);
+                         k_heads<<<g, 128, HEADS_SMEM, s>>>(a, e->heads_w, e->hm, e->wh, e->lm, e->reg, e->hm_sig, B, hh, ww);
                          return cudaGetLastError();
                      }});
     }
@@ -482,6 +481,8 @@ int cf_create(const void* weights, size_t weights_bytes, int device, int max_bat
             if (off % kEntryAlignFloats != 0) return bail(fail(CF_EWEIGHTS, "cf_create: entry %s is not 128-byte aligned", en.name.c_str()));
             e->w[en.name] = e->d_w + off;
             if (en.name == "stem.w") memcpy(e->stem_w.w, hp, sizeof(e->stem_w.w));
+            if (en.name == "heads.w") memcpy(e->heads_w.w, hp, sizeof(e->heads_w.w));
+            if (en.name == "heads.b") memcpy(e->heads_w.b, hp, sizeof(e->heads_w.b));
         }
     }
 

@@ -277,23 +277,23 @@ __global__ void __launch_bounds__(256) k_dw3(const float* __restrict__ in, const
 // CTA = 128 threads, 32x16 output pixels; thread = 4 pixels (x = sx + 8p) x 16 outputs.
 // smem: input tile [18][34][28] (pixel stride 28 floats -> conflict-free LDS.128) + weights.
 // ----------------------------------------------------------------------------------------
+struct HeadsW {
+    float w[216 * 16];  // [(ky*3+kx)*24+ci][16], passed by value => constant bank (13.8 KB of the 32 KB parameter space)
+    float b[16];
+};
 constexpr int HEADS_PS = 28;  // padded pixel stride in floats
-constexpr int HEADS_SMEM = (18 * 34 * HEADS_PS + 216 * 16 + 16) * 4;
+constexpr int HEADS_SMEM = (18 * 34 * HEADS_PS) * 4;
 
-__global__ void __launch_bounds__(128) k_heads(const float* __restrict__ in, const float* __restrict__ w,
-                                               const float* __restrict__ bias, float* __restrict__ hm,
+__global__ void __launch_bounds__(128) k_heads(const float* __restrict__ in, const __grid_constant__ HeadsW hw,
+                                               float* __restrict__ hm,
                                                float* __restrict__ wh, float* __restrict__ lm,
                                                float* __restrict__ reg, float* __restrict__ hm_sig,
                                                int B, int H, int W) {
     extern __shared__ __align__(16) float sm[];
     float* tile = sm;                        // [18][34][28]
-    float* ws = sm + 18 * 34 * HEADS_PS;     // [9][24][16]
-    float* bs = ws + 216 * 16;               // [16]
     const int tid = threadIdx.x;
     const int x00 = blockIdx.x * 32, y00 = blockIdx.y * 16, b = blockIdx.z;
 
-    for (int i = tid; i < 216 * 16 / 4; i += 128) st4(ws + i * 4, ldg4(w + i * 4));
-    if (tid < 16) bs[tid] = bias[tid];
     for (int i = tid; i < 18 * 34 * 6; i += 128) {
         const int c4 = i % 6;
         const int px = (i / 6) % 34;
@@ -312,26 +312,28 @@ __global__ void __launch_bounds__(128) k_heads(const float* __restrict__ in, con
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[p][q] = make_float4(0, 0, 0, 0);
 
-    for (int ky = 0; ky < 3; ++ky) {
+    // weights come from the constant bank: the tap loop is rolled (code size), its 24 x 16 weights are addressed with a
+    // uniform offset, so the inner loop is 4 LDS.128 of inputs per 256 FFMAs instead of 20
+#pragma unroll 1
+    for (int t = 0; t < 9; ++t) {
+        const int ky = t / 3, kx = t - ky * 3;
+        const float* trow = tile + ((sy + ky) * 34 + sx + kx) * HEADS_PS;
+        const float* wt = hw.w + t * 24 * 16;
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-            const float* trow = tile + ((sy + ky) * 34 + sx + kx) * HEADS_PS;
-            const float* wt = ws + (ky * 3 + kx) * 24 * 16;
+        for (int c4 = 0; c4 < 6; ++c4) {
+            float4 a[4];
 #pragma unroll
-            for (int c4 = 0; c4 < 6; ++c4) {
-                float4 a[4];
+            for (int p = 0; p < 4; ++p) a[p] = *reinterpret_cast<const float4*>(trow + p * 8 * HEADS_PS + c4 * 4);
 #pragma unroll
-                for (int p = 0; p < 4; ++p) a[p] = *reinterpret_cast<const float4*>(trow + p * 8 * HEADS_PS + c4 * 4);
+            for (int ci = 0; ci < 4; ++ci) {
 #pragma unroll
-                for (int ci = 0; ci < 4; ++ci) {
+                for (int q = 0; q < 4; ++q) {
+                    const float* wq = wt + (c4 * 4 + ci) * 16 + q * 4;
+                    const float4 wv = make_float4(wq[0], wq[1], wq[2], wq[3]);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 wv = *reinterpret_cast<const float4*>(wt + (c4 * 4 + ci) * 16 + q * 4);
-#pragma unroll
-                        for (int p = 0; p < 4; ++p) {
-                            const float av = ci == 0 ? a[p].x : ci == 1 ? a[p].y : ci == 2 ? a[p].z : a[p].w;
-                            fma4(acc[p][q], av, wv);
-                        }
+                    for (int p = 0; p < 4; ++p) {
+                        const float av = ci == 0 ? a[p].x : ci == 1 ? a[p].y : ci == 2 ? a[p].z : a[p].w;
+                        fma4(acc[p][q], av, wv);
                     }
                 }
             }
@@ -348,10 +350,10 @@ __global__ void __launch_bounds__(128) k_heads(const float* __restrict__ in, con
         float o[16];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            o[q * 4 + 0] = acc[p][q].x + bs[q * 4 + 0];
-            o[q * 4 + 1] = acc[p][q].y + bs[q * 4 + 1];
-            o[q * 4 + 2] = acc[p][q].z + bs[q * 4 + 2];
-            o[q * 4 + 3] = acc[p][q].w + bs[q * 4 + 3];
+            o[q * 4 + 0] = acc[p][q].x + hw.b[q * 4 + 0];
+            o[q * 4 + 1] = acc[p][q].y + hw.b[q * 4 + 1];
+            o[q * 4 + 2] = acc[p][q].z + hw.b[q * 4 + 2];
+            o[q * 4 + 3] = acc[p][q].w + hw.b[q * 4 + 3];
         }
         const size_t pix = (size_t)y * W + x;
         hm[(size_t)b * plane + pix] = o[0];
