@@ -156,6 +156,12 @@ int cf_detect_threshold_host(cf_engine* e, const uint8_t* images, int batch, int
 int cf_debug_pw_gemm(int pw_engine, int epi, const float* dA, const float* hW, float* dOut, int M, int K, int N,
                      const float* dRes, void* stream);
 
+/* Same call, then `iters` more launches bracketed by CUDA events on `stream`: *ms = mean kernel time; `desc` (may be
+ * NULL) receives the resolved launch plan (kernel, column chunk, stages ...).  The CF_TC_* environment variables read at
+ * plan time select plan variants.  (tools/tc_tune.py)                                                                 */
+int cf_debug_pw_gemm_time(int pw_engine, int epi, const float* dA, const float* hW, float* dOut, int M, int K, int N,
+                          const float* dRes, void* stream, int iters, float* ms, char* desc, int desc_cap);
+
 /* Development probe: stream a device [M][K] fp32 matrix through a `stages`-deep TMA ring of box_rows x 32-float boxes
  * with one thread per CTA and no consumer work; *ms = mean kernel time.  (tools/tma_probe.py)            */
 int cf_debug_tma_stream(const float* dA, int M, int K, int stages, int box_rows, int ctas_per_sm, float* ms);
@@ -191,6 +197,9 @@ int cf_replay_class(cf_engine* e, int which, int iters, void* stream);
 /* cf_replay_class bracketed by CUDA events on `stream`; *ms = mean device time of ONE replay of
  * the class, *launches = kernels per replay.  Synchronises the stream.                    */
 int cf_time_class(cf_engine* e, int which, int iters, void* stream, float* ms, int* launches);
+/* Every launch of the current plan (network + path-C decode, in order) timed separately with CUDA events on `stream`,
+ * mean over `iters` passes after one warm-up pass: ms[i], cls[i] (class as above, may be NULL) for i < *n_steps <= cap. */
+int cf_time_steps(cf_engine* e, int iters, void* stream, float* ms, int* cls, int cap, int* n_steps);
 
 #ifdef __cplusplus
 }

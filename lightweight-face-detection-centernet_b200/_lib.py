@@ -40,6 +40,8 @@ SIGNATURES = {
     "cf_detect_threshold_host": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                            C.c_float, C.c_float, C.c_int, _vp, _vp, _vp]),
     "cf_debug_pw_gemm": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "cf_debug_pw_gemm_time": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int,
+                                        C.POINTER(C.c_float), C.c_char_p, C.c_int]),
     "cf_debug_tma_stream": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "cf_resize_tables": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, _i]),
     "cf_resize_u8": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp]),
@@ -49,6 +51,7 @@ SIGNATURES = {
     "cf_work_model": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "cf_replay_class": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "cf_time_class": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.POINTER(C.c_float), _i]),
+    "cf_time_steps": (C.c_int, [_vp, C.c_int, _vp, C.POINTER(C.c_float), _i, C.c_int, _i]),
 }
 
 _lib = None

@@ -202,8 +202,7 @@ int make_pw_step(cf_engine* e, std::vector<Step>& P, int epi, const float* A, co
     const int passes = layer_passes(e->pw_engine, K, N);
     if (passes == 3) {  // narrow layers: the role-free kernel
         auto it = e->tc.layers.find(Wkn);
-        const char* ev = getenv("CF_PWN");
-        if (it != e->tc.layers.end() && pwn_eligible(it->second) && !(ev && atoi(ev) == 0)) {
+        if (it != e->tc.layers.end() && pwn_eligible(it->second) && tc_tune_for(K, N, passes).pwn != 0) {
             PwnLaunch pl;
             int rc = pwn_plan(e->tc, epi, A, Wkn, out, M, K, N, ea, &pl);
             if (rc) return rc;
@@ -902,53 +901,74 @@ int cf_detect_image_host(cf_engine* e, const uint8_t* image, int h, int w, int n
     return CF_OK;
 }
 
-int cf_debug_pw_gemm(int pw_engine, int epi, const float* dA, const float* hW, float* dOut, int M, int K, int N,
-                     const float* dRes, void* stream) {
+int cf_debug_pw_gemm_time(int pw_engine, int epi, const float* dA, const float* hW, float* dOut, int M, int K, int N,
+                          const float* dRes, void* stream, int iters, float* ms, char* desc, int desc_cap) {
     CF_CHECK(dA && hW && dOut && M > 0 && K > 0 && N > 0 && K % 4 == 0 && N % 4 == 0, CF_EINVAL, "cf_debug_pw_gemm: bad arguments");
     CF_CHECK(epi == EPI_LINEAR || epi == EPI_SWISH || (epi == EPI_RESIDUAL && dRes), CF_EINVAL, "cf_debug_pw_gemm: epi %d unsupported here", epi);
+    CF_CHECK(iters >= 0 && (iters == 0 || ms != nullptr), CF_EINVAL, "cf_debug_pw_gemm: iters=%d needs ms", iters);
+    cudaStream_t s = (cudaStream_t)stream;
     EpiArgs ea{};
     ea.res = dRes;
     float* dW = nullptr;
     CF_CUDA(cudaMalloc((void**)&dW, (size_t)K * N * 4));
     cudaError_t ce = cudaMemcpy(dW, hW, (size_t)K * N * 4, cudaMemcpyHostToDevice);
     int rc = ce == cudaSuccess ? CF_OK : fail(CF_ECUDA, "cf_debug_pw_gemm: %s", cudaGetErrorString(ce));
+    PwTcState st;
+    std::function<cudaError_t()> launch;
+    char d[256] = "";
+    TcLaunch tl;
+    PwnLaunch pl;
     if (!rc && pw_engine == CF_PW_SIMT) {
-        ce = launch_pw_simt_any(epi, dA, dW, dOut, M, K, N, ea, (cudaStream_t)stream);
-        if (ce != cudaSuccess) rc = fail(CF_ECUDA, "cf_debug_pw_gemm: %s", cudaGetErrorString(ce));
+        launch = [&]() { return launch_pw_simt_any(epi, dA, dW, dOut, M, K, N, ea, s); };
+        snprintf(d, sizeof d, "simt");
     } else if (!rc) {
-        PwTcState st;
         int dev = 0;
         cudaGetDevice(&dev);
+        const int passes = engine_passes(pw_engine);
         rc = pw_tc_init(st, dev);
-        if (!rc) rc = tc_prepare_layer(st, dW, hW, K, N, engine_passes(pw_engine));
-        TcLaunch tl;
-        const char* ev = getenv("CF_PWN");
-        if (!rc && engine_passes(pw_engine) == 3 && pwn_eligible(st.layers[dW]) && !(ev && atoi(ev) == 0)) {
-            PwnLaunch pl;
+        if (!rc) rc = tc_prepare_layer(st, dW, hW, K, N, passes);
+        if (!rc && passes == 3 && pwn_eligible(st.layers[dW]) && tc_tune_for(K, N, passes).pwn != 0) {
             rc = pwn_plan(st, epi, dA, dW, dOut, M, K, N, ea, &pl);
-            if (!rc) {
-                ce = pwn_launch(pl, (cudaStream_t)stream);
-                if (ce != cudaSuccess) rc = fail(CF_ECUDA, "cf_debug_pw_gemm: launch: %s", cudaGetErrorString(ce));
-            }
-            ce = cudaStreamSynchronize((cudaStream_t)stream);
-            if (!rc && ce != cudaSuccess) rc = fail(CF_ECUDA, "cf_debug_pw_gemm: kernel: %s", cudaGetErrorString(ce));
-            pw_tc_destroy(st);
-            cudaFree(dW);
-            return rc;
+            launch = [&]() { return pwn_launch(pl, s); };
+            snprintf(d, sizeof d, "pwn NC=%d nst=%d grid=%d smem=%zu", pl.p.NC, pl.p.nst, pl.grid, pl.smem);
+        } else if (!rc) {
+            rc = tc_plan(st, passes, epi, dA, dW, dOut, M, K, N, ea, &tl);
+            launch = [&]() { return tc_launch(tl, s); };
+            snprintf(d, sizeof d, "tc NC=%d chunks=%d stages=%d atmem=%d direct=%d resident=%d nacc=%d grid=%d smem=%zu", tl.p.NC,
+                     tl.p.nchunks, tl.p.stages, tl.p.atmem, tl.p.direct, tl.p.resident, tl.p.nacc, tl.grid, tl.smem);
         }
-        if (!rc) rc = tc_plan(st, engine_passes(pw_engine), epi, dA, dW, dOut, M, K, N, ea, &tl);
-        if (!rc) {
-            ce = tc_launch(tl, (cudaStream_t)stream);
-            if (ce != cudaSuccess) rc = fail(CF_ECUDA, "cf_debug_pw_gemm: launch: %s", cudaGetErrorString(ce));
-        }
-        ce = cudaStreamSynchronize((cudaStream_t)stream);
-        if (!rc && ce != cudaSuccess) rc = fail(CF_ECUDA, "cf_debug_pw_gemm: kernel: %s", cudaGetErrorString(ce));
-        pw_tc_destroy(st);
     }
-    ce = cudaStreamSynchronize((cudaStream_t)stream);
-    if (!rc && ce != cudaSuccess) rc = fail(CF_ECUDA, "cf_debug_pw_gemm: %s", cudaGetErrorString(ce));
+    if (desc && desc_cap > 0) snprintf(desc, (size_t)desc_cap, "%s", d);
+    if (!rc) {
+        ce = launch();
+        if (ce != cudaSuccess) rc = fail(CF_ECUDA, "cf_debug_pw_gemm: launch: %s", cudaGetErrorString(ce));
+        ce = cudaStreamSynchronize(s);
+        if (!rc && ce != cudaSuccess) rc = fail(CF_ECUDA, "cf_debug_pw_gemm: kernel: %s", cudaGetErrorString(ce));
+    }
+    if (!rc && iters > 0) {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaEventRecord(a, s);
+        for (int i = 0; i < iters && ce == cudaSuccess; ++i) ce = launch();
+        cudaEventRecord(b, s);
+        cudaError_t ce2 = cudaEventSynchronize(b);
+        if (ce != cudaSuccess || ce2 != cudaSuccess)
+            rc = fail(CF_ECUDA, "cf_debug_pw_gemm: timed loop: %s", cudaGetErrorString(ce != cudaSuccess ? ce : ce2));
+        float t = 0.f;
+        cudaEventElapsedTime(&t, a, b);
+        *ms = t / (float)iters;
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+    }
+    pw_tc_destroy(st);
     cudaFree(dW);
     return rc;
+}
+
+int cf_debug_pw_gemm(int pw_engine, int epi, const float* dA, const float* hW, float* dOut, int M, int K, int N,
+                     const float* dRes, void* stream) {
+    return cf_debug_pw_gemm_time(pw_engine, epi, dA, hW, dOut, M, K, N, dRes, stream, 0, nullptr, nullptr, 0);
 }
 
 int cf_debug_tma_stream(const float* dA, int M, int K, int stages, int box_rows, int ctas_per_sm, float* ms) {
@@ -1080,6 +1100,39 @@ int cf_time_class(cf_engine* e, int which, int iters, void* stream, float* ms, i
     }
     cudaEventDestroy(a);
     cudaEventDestroy(b);
+    return rc;
+}
+
+int cf_time_steps(cf_engine* e, int iters, void* stream, float* ms, int* cls, int cap, int* n_steps) {
+    CF_CHECK(e != nullptr && ms != nullptr && n_steps != nullptr && iters >= 1, CF_EINVAL, "cf_time_steps: bad arguments");
+    CF_CHECK(!e->plan.empty(), CF_EINVAL, "cf_time_steps: no cf_forward has run on this engine");
+    const int n = (int)e->plan.size();
+    *n_steps = n;
+    CF_CHECK(cap >= n, CF_ECAP, "cf_time_steps: the plan has %d steps, room for %d", n, cap);
+    CF_CUDA(cudaSetDevice(e->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    std::vector<cudaEvent_t> ev((size_t)n + 1);
+    for (auto& x : ev) CF_CUDA(cudaEventCreate(&x));
+    for (int i = 0; i < n; ++i) ms[i] = 0.f, cls ? cls[i] = e->plan[i].cls : 0;
+    int rc = CF_OK;
+    for (int it = 0; it <= iters && rc == CF_OK; ++it) {  // pass 0 warms up
+        cudaEventRecord(ev[0], s);
+        for (int i = 0; i < n; ++i) {
+            cudaError_t err = e->plan[i].run(s);
+            if (err != cudaSuccess) rc = fail(CF_ECUDA, "cf_time_steps: launch %d failed: %s", i, cudaGetErrorString(err));
+            ++e->launches;
+            cudaEventRecord(ev[i + 1], s);
+        }
+        cudaError_t ce = cudaEventSynchronize(ev[n]);
+        if (rc == CF_OK && ce != cudaSuccess) rc = fail(CF_ECUDA, "cf_time_steps: %s", cudaGetErrorString(ce));
+        if (it == 0 || rc != CF_OK) continue;
+        for (int i = 0; i < n; ++i) {
+            float t = 0.f;
+            cudaEventElapsedTime(&t, ev[i], ev[i + 1]);
+            ms[i] += t / (float)iters;
+        }
+    }
+    for (auto& x : ev) cudaEventDestroy(x);
     return rc;
 }
 

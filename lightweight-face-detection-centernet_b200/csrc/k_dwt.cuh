@@ -145,7 +145,13 @@ inline int dwt_plan(PwTcState& st, int ks, int s, const float* X, const float* W
     const int per_cta2 = (TC_SMEM_MAX / 2 - 2048) / xb;
     int ctas_per_sm = 2, nst = per_cta2;
     if (nst < 3) ctas_per_sm = 1, nst = (TC_SMEM_MAX - 2048) / xb;
+    if (const char* ev = getenv("CF_DWT_CTAS")) {  // development probe (tools/step_times.py)
+        if (atoi(ev) == 1) ctas_per_sm = 1, nst = (TC_SMEM_MAX - 2048) / xb;
+    }
     if (nst > 8) nst = 8;
+    if (const char* ev = getenv("CF_DWT_NST")) {
+        if (atoi(ev) >= 1 && atoi(ev) < nst) nst = atoi(ev);
+    }
     if (nst < 1) return fail(CF_EINVAL, "dwt_plan: tile does not fit shared memory");
     dl->p.nst = nst;
     dl->smem = (size_t)nst * xb + 64 + 1024;

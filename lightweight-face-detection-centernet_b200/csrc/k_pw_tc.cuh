@@ -596,6 +596,45 @@ inline int tc_make_map(PwTcState& st, CUtensorMap* map, const float* ptr, uint64
     return CF_OK;
 }
 
+// Per-layer plan overrides.  Defaults come from the cost model below; `tc_tuned_table` holds the (K, N) entries that a
+// sweep on the device (tools/tc_tune.py, batch 32 @ 640x640) found faster than the model's choice; the CF_TC_* environment
+// variables override both and exist only for that sweep.
+struct TcTune {
+    int nc = 0;       // column chunk width (0: cost model)
+    int atmem = -1;   // A operand through TMEM (-1: NC <= 64)
+    int direct = -1;  // epilogue stores rows straight from registers (-1: N <= 64)
+    int nacc = 0;     // accumulator stages (0: as many as fit, 2 or 4)
+    int pwn = -1;     // role-free kernel for eligible layers (-1: yes)
+    int grid = 0;     // CTA count cap (0: one per SM)
+};
+struct TcTuneEntry {
+    int K, N;
+    TcTune t;
+};
+inline const TcTuneEntry* tc_tuned_table(int* n);  // defined at the end of this file
+
+inline TcTune tc_tune_for(int K, int N, int passes) {
+    TcTune t;
+    if (passes == 3) {
+        int n = 0;
+        const TcTuneEntry* tab = tc_tuned_table(&n);
+        for (int i = 0; i < n; ++i)
+            if (tab[i].K == K && tab[i].N == N) t = tab[i].t;
+    }
+    if (const char* ev = getenv("CF_TC_TABLE")) {
+        if (atoi(ev) == 0) t = TcTune();
+    }
+    if (const char* ev = getenv("CF_TC_NC")) t.nc = atoi(ev);
+    if (const char* ev = getenv("CF_TC_ATMEM")) t.atmem = atoi(ev);
+    if (const char* ev = getenv("CF_TC_DIRECT")) t.direct = atoi(ev);
+    if (const char* ev = getenv("CF_TC_NACC")) t.nacc = atoi(ev);
+    if (const char* ev = getenv("CF_PWN")) t.pwn = atoi(ev);
+    if (const char* ev = getenv("CF_TC_GRID")) t.grid = atoi(ev);
+    const int nc_max = passes == 3 ? 128 : 192;
+    if (t.nc < 0 || t.nc % 32 != 0 || t.nc > nc_max) t.nc = 0;
+    return t;
+}
+
 // Column-chunk width NC: a multiple of 32 (epilogue blocks).  One TMEM accumulator stage is 256
 // columns; the 3-pass mode keeps two accumulators per stage (main + correction), so NC <= 128 there.
 // Cost model: MMA/epilogue column work incl. padding + re-reading the A tile once per chunk.
@@ -617,6 +656,7 @@ inline int tc_prepare_layer(PwTcState& st, const float* key, const float* hw, in
     L.K = K;
     L.N = N;
     tc_choose_chunks(K, N, passes, &L.NC, &L.nchunks);
+    if (!force_nc) force_nc = tc_tune_for(K, N, passes).nc;
     if (force_nc) L.NC = force_nc, L.nchunks = (N + force_nc - 1) / force_nc;
     L.nkb = (K + TC_BK - 1) / TC_BK;
     const size_t blk = (size_t)L.NC * 128;  // bytes of one hi (or lo) block
@@ -678,17 +718,18 @@ inline int tc_plan(PwTcState& st, int passes, int epi, const float* A, const flo
     // "block" stride is still the pair.
     p.b_bytes_block = (uint32_t)L.NC * 128u * 2u;
     // narrow layers: A operand through TMEM (both accumulator pairs fit columns [0,256), the A ring sits above them)
+    const TcTune tune = tc_tune_for(K, N, passes);
     p.atmem = (passes == 3 && L.NC <= 64) ? 1 : 0;
-    if (const char* ev = getenv("CF_TC_ATMEM")) p.atmem = (atoi(ev) != 0 && passes == 3 && L.NC <= 64) ? 1 : 0;
+    if (tune.atmem >= 0) p.atmem = (tune.atmem != 0 && passes == 3 && L.NC <= 64) ? 1 : 0;
     p.a_bytes_stage = p.atmem ? TC_A_BYTES : TC_A_BYTES * hl;
     {   // accumulator ring: as many (main+correction) pairs as fit the accumulator columns, 2 or 4
         const uint32_t acc_cols = p.atmem ? 256u : 512u, pair = (passes == 3 ? 2u : 1u) * (uint32_t)L.NC;
         p.nacc = (4u * pair <= acc_cols) ? 4 : 2;
-        if (const char* ev = getenv("CF_TC_NACC")) p.nacc = atoi(ev) == 4 && 4u * pair <= acc_cols ? 4 : 2;
+        if (tune.nacc) p.nacc = tune.nacc == 4 && 4u * pair <= acc_cols ? 4 : 2;
         p.acc_stride = acc_cols / (uint32_t)p.nacc;
     }
     p.direct = (N <= 64) ? 1 : 0;
-    if (const char* ev = getenv("CF_TC_DIRECT")) p.direct = atoi(ev);
+    if (tune.direct >= 0) p.direct = tune.direct ? 1 : 0;
     p.out = out;
     p.dbg = 0;
     if (const char* ev = getenv("CF_TC_DEBUG")) p.dbg = atoi(ev);
@@ -708,6 +749,7 @@ inline int tc_plan(PwTcState& st, int passes, int epi, const float* A, const flo
     p.off_bars = p.off_stages + (uint32_t)stages * p.stage_bytes;
     tl->smem = (size_t)p.off_bars + bar_bytes + 1024;
     tl->grid = p.n_items < st.sms ? p.n_items : st.sms;
+    if (tune.grid > 0 && tune.grid < tl->grid) tl->grid = tune.grid;
     tl->passes = passes;
     tl->epi = epi;
     return CF_OK;
@@ -732,6 +774,15 @@ inline cudaError_t tc_launch(const TcLaunch& tl, cudaStream_t s) {
     CF_TC_CASE(1, EPI_LINEAR) CF_TC_CASE(1, EPI_SWISH) CF_TC_CASE(1, EPI_RESIDUAL) CF_TC_CASE(1, EPI_BIAS_SWISH) CF_TC_CASE(1, EPI_IDAUP)
 #undef CF_TC_CASE
     return cudaErrorInvalidValue;
+}
+
+// (K, N) -> plan, from tools/tc_tune.py on a B200 at batch 32 @ 640x640 (profiles/r2_tc_tune.md).
+inline const TcTuneEntry* tc_tuned_table(int* n) {
+    static const TcTuneEntry tab[] = {
+        {0, 0, TcTune()},
+    };
+    *n = (int)(sizeof(tab) / sizeof(tab[0]));
+    return tab;
 }
 
 }  // namespace cf

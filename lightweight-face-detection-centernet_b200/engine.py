@@ -120,6 +120,13 @@ class Engine:
         L.check(self.lib.cf_time_class(self.h, which, iters, self._stream(), C.byref(ms), C.byref(n)), "cf_time_class")
         return ms.value, n.value
 
+    def time_steps(self, iters=5):
+        """Per-launch device ms of the current plan (network + path-C decode, in launch order) -> (ms[], cls[])."""
+        cap = 128
+        ms, cls, n = (C.c_float * cap)(), (C.c_int32 * cap)(), C.c_int32()
+        L.check(self.lib.cf_time_steps(self.h, iters, self._stream(), ms, cls, cap, C.byref(n)), "cf_time_steps")
+        return list(ms[:n.value]), list(cls[:n.value])
+
     @property
     def launches(self):
         return int(self.lib.cf_launch_count(self.h))

@@ -1,0 +1,58 @@
+#!/usr/bin/env python
+"""Per-launch CUDA-event times of one forward + path-C decode (cf_time_steps), batch 32 @ 640x640 by default."""
+import argparse
+import importlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+pkg = importlib.import_module("lightweight-face-detection-centernet_b200")
+
+BLOCKS = [(32, 16, 1, 3, 1), (16, 24, 6, 3, 2), (24, 24, 6, 3, 1), (24, 32, 6, 5, 2), (32, 32, 6, 5, 1), (32, 64, 6, 3, 2),
+          (64, 64, 6, 3, 1), (64, 96, 6, 5, 1), (96, 96, 6, 5, 1), (96, 160, 6, 5, 2), (160, 160, 6, 5, 1), (160, 320, 6, 3, 1)]
+
+
+def names():
+    out = ["stem 3->32 s2"]
+    for i, (cin, cout, t, k, s) in enumerate(BLOCKS):
+        if t != 1:
+            out.append(f"b{i} expand {cin}->{cin * t}")
+        out.append(f"b{i} dw{k} s{s} {cin * t}ch")
+        out.append(f"b{i} project {cin * t}->{cout}" + (" +res" if cin == cout and s == 1 else ""))
+    out += ["conv_last 320->24", "up1 96->24", "up2 32->24", "up3 24->24", "heads 3x3 24->15", "peak mask", "top-k"]
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--size", type=int, default=640)
+    ap.add_argument("--pw", type=int, default=1)
+    ap.add_argument("--iters", type=int, default=10)
+    a = ap.parse_args()
+    w = os.path.join(ROOT, "tests", "golden", "weights_e100.npz")
+    eng = pkg.Engine(w, max_batch=a.batch, max_h=a.size, max_w=a.size, device=0, pw_engine=a.pw)
+    x = torch.from_numpy(np.random.RandomState(0).randint(0, 256, size=(a.batch, a.size, a.size, 3), dtype=np.uint8)).cuda()
+    eng.forward(x)
+    eng.decode_topk(100)
+    torch.cuda.synchronize()
+    ms, cls = eng.time_steps(a.iters)
+    nm = names()
+    if len(nm) != len(ms):
+        nm = [f"step {i}" for i in range(len(ms))]
+    cname = {1: "pw", 2: "dw", 3: "stem", 4: "heads", 5: "decode", 6: "fused"}
+    print(f"| # | launch | class | us |\n|---|---|---|---|")
+    for i, (n, t, c) in enumerate(zip(nm, ms, cls)):
+        print(f"| {i} | {n} | {cname.get(c, c)} | {t * 1e3:.1f} |")
+    tot = {}
+    for t, c in zip(ms, cls):
+        tot[c] = tot.get(c, 0.0) + t
+    print("total us:", round(sum(ms) * 1e3, 1), {cname.get(c, c): round(v * 1e3, 1) for c, v in tot.items()})
+
+
+if __name__ == "__main__":
+    main()
