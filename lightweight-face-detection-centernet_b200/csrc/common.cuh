@@ -41,6 +41,32 @@ inline int fail(int code, const char* fmt, ...) {
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// Kernel launch with the programmatic-stream-serialization attribute (CF_PDL=0 turns it off: plain stream order).
+// Only kernels that call pdl_wait() before touching activation memory may be launched through this.
+inline bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("CF_PDL");
+        v = e ? (atoi(e) != 0) : 1;
+    }
+    return v != 0;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 // ---- device math -----------------------------------------------------------------------
 // Swish (model/centernet.py:39-40) x*sigmoid(x) = x * rcp(1 + 2^(-x*log2 e)): MUFU.EX2 + MUFU.RCP (~2 ulp each) and
 // three FP32 ops.  The .ftz forms drop the denormal pre/post-scaling code the default intrinsics emit (4 extra
@@ -58,6 +84,17 @@ __device__ __forceinline__ float4 swish4(float4 v) {
 }
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// L2-only load for activations the PREVIOUS kernel of the stream wrote: under programmatic dependent launch this kernel
+// may already be resident while they are produced, so they are never read through the non-coherent (.nc) path.
+__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+
+// ---- programmatic dependent launch ------------------------------------------------------
+// Every kernel of the forward chain calls pdl_trigger() first (the next kernel of the stream may be scheduled as soon as
+// all CTAs of this one have started) and pdl_wait() before its first access to activation memory (blocks until the
+// previous kernel has completed and its writes are visible).  In between sits the prologue that depends on nothing:
+// barrier init, TMEM allocation, tensor-map prefetch, weight staging.  Without the launch attribute both are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
 __device__ __forceinline__ void fma4(float4& acc, float a, float4 w) {
@@ -95,7 +132,7 @@ template <int EPI>
 __device__ __forceinline__ float4 apply_epi(float4 acc, int m, int n, int N, const EpiArgs& ea) {
     if (EPI == EPI_SWISH) return swish4(acc);
     if (EPI == EPI_RESIDUAL) {
-        float4 r = ldg4(ea.res + (size_t)m * N + n);
+        float4 r = ldcg4(ea.res + (size_t)m * N + n);
         return make_float4(acc.x + r.x, acc.y + r.y, acc.z + r.z, acc.w + r.w);
     }
     if (EPI == EPI_BIAS_SWISH) {
@@ -108,7 +145,7 @@ __device__ __forceinline__ float4 apply_epi(float4 acc, int m, int n, int N, con
         int y = t % ea.Ho;
         int b = t / ea.Ho;
         int Hl = ea.Ho >> 1, Wl = ea.Wo >> 1;
-        float4 lo = ldg4(ea.low + ((size_t)(b * Hl + (y >> 1)) * Wl + (x >> 1)) * N + n);
+        float4 lo = ldcg4(ea.low + ((size_t)(b * Hl + (y >> 1)) * Wl + (x >> 1)) * N + n);
         int q = (y & 1) * 2 + (x & 1);
         float4 bb = ldg4(ea.bias + n), tt = ldg4(ea.tu + n);
         float s0 = __ldg(ea.su + (n + 0) * 4 + q), s1 = __ldg(ea.su + (n + 1) * 4 + q);

@@ -23,6 +23,7 @@
 #include "k_dwt.cuh"
 #include "k_dwp.cuh"
 #include "k_pwn.cuh"
+#include "k_stem_tc.cuh"
 #include "net.hpp"
 
 using namespace cf;
@@ -275,15 +276,24 @@ int build_plan(cf_engine* e, const void* input, int fmt, int B, int H, int W) {
         float* out = e->stem;
         const long long thr = (long long)B * H2 * W2;
         const unsigned grid = (unsigned)((thr + 127) / 128);
-        if (fmt == CF_IN_U8_HWC)
+        // CF_STEM_TC=1: the role-free tcgen05 stem (k_stem_tc.cuh).  Parity-green but slower than the FFMA stem
+        // (255 vs 222 us per 32-image batch: its per-tile split -> MMA -> drain chain is serial), so it is opt-in.
+        const char* ev = getenv("CF_STEM_TC");
+        if (engine_is_tc(e->pw_engine) && ev && atoi(ev) == 1) {
+            StcParams sp;
+            int sgrid = 0;
+            if ((rc = stc_plan(e->tc, e->w["stem.w"], input, lut, out, B, H, W, &sp, &sgrid))) return rc;
+            if (fmt == CF_IN_U8_HWC)
+                P.push_back({CLS_STEM, [=](cudaStream_t s) { return stc_launch_t<1>(sp, sgrid, s); }});
+            else
+                P.push_back({CLS_STEM, [=](cudaStream_t s) { return stc_launch_t<0>(sp, sgrid, s); }});
+        } else if (fmt == CF_IN_U8_HWC)
             P.push_back({CLS_STEM, [=](cudaStream_t s) {
-                             k_stem<1><<<grid, 128, 0, s>>>(input, w, lut, out, B, H, W);
-                             return cudaGetLastError();
+                             return launch_pdl(k_stem<1>, dim3(grid), dim3(128), 0, s, input, w, lut, out, B, H, W);
                          }});
         else
             P.push_back({CLS_STEM, [=](cudaStream_t s) {
-                             k_stem<0><<<grid, 128, 0, s>>>(input, w, lut, out, B, H, W);
-                             return cudaGetLastError();
+                             return launch_pdl(k_stem<0>, dim3(grid), dim3(128), 0, s, input, w, lut, out, B, H, W);
                          }});
     }
     // layer0..layer6, :225-235 -> MBConvBlock.forward :128-140
@@ -388,8 +398,8 @@ int build_plan(cf_engine* e, const void* input, int fmt, int B, int H, int W) {
         const int hh = h, ww = wd;
         P.push_back({CLS_HEADS, [=](cudaStream_t s) {
                          dim3 g(cdiv(ww, 32), cdiv(hh, 16), B);
-                         k_heads<<<g, 128, HEADS_SMEM, s>>>(a, e->heads_w, e->hm, e->wh, e->lm, e->reg, e->hm_sig, B, hh, ww);
-                         return cudaGetLastError();
+                         return launch_pdl(k_heads, g, dim3(128), (size_t)HEADS_SMEM, s, a, e->heads_w, e->hm, e->wh, e->lm, e->reg, e->hm_sig,
+                                           B, hh, ww);
                      }});
     }
     // path-C decode on the heads (entered through cf_decode_topk; listed for cf_replay_class)
@@ -397,12 +407,12 @@ int build_plan(cf_engine* e, const void* input, int fmt, int B, int H, int W) {
         const int hh = h, ww = wd;
         P.push_back({CLS_DECODE, [=](cudaStream_t s) {
                          const long long n = (long long)B * hh * ww;
-                         k_peak_mask<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(e->hm_sig, e->peak, B, hh, ww);
-                         return cudaGetLastError();
+                         return launch_pdl(k_peak_mask, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, (const float*)e->hm_sig, e->peak, B,
+                                           hh, ww);
                      }});
         P.push_back({CLS_DECODE, [=](cudaStream_t s) {
-                         k_topk<<<B, 1024, 0, s>>>(e->peak, e->wh, e->reg, hh, ww, 100, e->o_dets, e->o_inds);
-                         return cudaGetLastError();
+                         return launch_pdl(k_topk, dim3(B), dim3(1024), 0, s, (const float*)e->peak, (const float*)e->wh,
+                                           (const float*)e->reg, hh, ww, 100, e->o_dets, e->o_inds);
                      }});
     }
     e->in = input;
@@ -569,6 +579,10 @@ int cf_create(const void* weights, size_t weights_bytes, int device, int max_bat
             }
         }
         if (!rc) rc = prep("clast.w", 320, 24);
+        if (!rc) {  // the stem as a K = 27 (one K block), N = 32 GEMM: k_stem_tc
+            const float* hp = blob.get("stem.w", 27 * 32, why);
+            rc = hp ? tc_prepare_layer(e->tc, e->w["stem.w"], hp, 27, 32, 3, STC_NC) : fail(CF_EWEIGHTS, "cf_create: %s", why.c_str());
+        }
         const int skip_c[3] = {96, 32, 24};
         for (int j = 0; j < 3 && !rc; ++j) rc = prep("up" + std::to_string(j + 1) + ".w", skip_c[j], 24);
         if (rc) return bail(rc);
@@ -690,9 +704,8 @@ int cf_ctdet_decode(const float* heat, const float* wh, const float* reg, int ba
     CF_CHECK(K >= 1 && K <= 1024 && K <= h * w, CF_EINVAL, "cf_ctdet_decode: K=%d outside [1,min(1024,h*w)]", K);
     cudaStream_t s = (cudaStream_t)stream;
     const long long n = (long long)batch * h * w;
-    k_peak_mask<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(heat, scratch, batch, h, w);
-    k_topk<<<batch, 1024, 0, s>>>(scratch, wh, reg, h, w, K, out_dets, out_inds);
-    CF_CUDA(cudaGetLastError());
+    CF_CUDA(launch_pdl(k_peak_mask, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, heat, scratch, batch, h, w));
+    CF_CUDA(launch_pdl(k_topk, dim3(batch), dim3(1024), 0, s, (const float*)scratch, wh, reg, h, w, K, out_dets, out_inds));
     return CF_OK;
 }
 

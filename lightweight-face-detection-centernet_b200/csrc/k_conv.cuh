@@ -64,10 +64,12 @@ __global__ void __launch_bounds__(128) k_stem(const void* __restrict__ in, const
                                               const float* __restrict__ lut, float* __restrict__ out,
                                               int B, int H, int W) {
     __shared__ float lut_s[FMT == 1 ? 768 : 1];
+    pdl_trigger();
     if (FMT == 1) {
         for (int i = threadIdx.x; i < 768; i += 128) lut_s[i] = lut[i];
         __syncthreads();
     }
+    pdl_wait();  // `out` may still be read by the previous forward's kernels
     const int Ho = H >> 1, Wo = W >> 1;
     const long long pix = (long long)blockIdx.x * 128 + threadIdx.x;
     if (pix >= (long long)B * Ho * Wo) return;
@@ -293,6 +295,8 @@ __global__ void __launch_bounds__(128) k_heads(const float* __restrict__ in, con
     float* tile = sm;                        // [18][34][28]
     const int tid = threadIdx.x;
     const int x00 = blockIdx.x * 32, y00 = blockIdx.y * 16, b = blockIdx.z;
+    pdl_trigger();
+    pdl_wait();
 
     for (int i = tid; i < 18 * 34 * 6; i += 128) {
         const int c4 = i % 6;
@@ -300,7 +304,7 @@ __global__ void __launch_bounds__(128) k_heads(const float* __restrict__ in, con
         const int py = i / (6 * 34);
         const int gy = y00 + py - 1, gx = x00 + px - 1;
         float4 v = make_float4(0, 0, 0, 0);
-        if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = ldg4(in + ((size_t)(b * H + gy) * W + gx) * 24 + c4 * 4);
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = ldcg4(in + ((size_t)(b * H + gy) * W + gx) * 24 + c4 * 4);
         st4(tile + (py * 34 + px) * HEADS_PS + c4 * 4, v);
     }
     __syncthreads();

@@ -24,12 +24,14 @@ __device__ __forceinline__ float fkey_inv(uint32_t k) {
 //      neighbours; equal plateau neighbours are all kept), centerface_ext.py:44-50 -----
 __global__ void __launch_bounds__(256) k_peak_mask(const float* __restrict__ heat, float* __restrict__ pk,
                                                    int B, int H, int W) {
+    pdl_trigger();
+    pdl_wait();
     const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
     if (i >= (long long)B * H * W) return;
     const int x = (int)(i % W);
     const int y = (int)((i / W) % H);
     const float* img = heat + (i - (long long)y * W - x);
-    const float v = __ldg(img + y * W + x);
+    const float v = __ldcg(img + y * W + x);
     bool keep = true;
 #pragma unroll
     for (int dy = -1; dy <= 1; ++dy) {
@@ -39,7 +41,7 @@ __global__ void __launch_bounds__(256) k_peak_mask(const float* __restrict__ hea
         for (int dx = -1; dx <= 1; ++dx) {
             const int xx = x + dx;
             if (xx < 0 || xx >= W) continue;
-            keep = keep && !(__ldg(img + yy * W + xx) > v);
+            keep = keep && !(__ldcg(img + yy * W + xx) > v);
         }
     }
     pk[i] = keep ? v : v * 0.f;  // heat * keep.float()
@@ -79,13 +81,15 @@ __global__ void __launch_bounds__(1024) k_topk(const float* __restrict__ pk, con
     const int HW = H * W;
     const int b = blockIdx.x;
     const float* p = pk + (size_t)b * HW;
+    pdl_trigger();
+    pdl_wait();
 
     unsigned prefix = 0, mask = 0, krem = K;
     for (int pass = 3; pass >= 0; --pass) {
         if (tid < 256) hist[tid] = 0;
         __syncthreads();
         for (int i = tid; i < HW; i += 1024) {
-            const uint32_t key = fkey(__ldg(p + i));
+            const uint32_t key = fkey(__ldcg(p + i));
             if ((key & mask) == prefix) atomicAdd(&hist[(key >> (8 * pass)) & 255u], 1u);
         }
         __syncthreads();
@@ -117,7 +121,7 @@ __global__ void __launch_bounds__(1024) k_topk(const float* __restrict__ pk, con
     for (int base = 0; base < HW; base += 1024) {
         const int i = base + tid;
         const bool valid = i < HW;
-        const uint32_t key = valid ? fkey(__ldg(p + i)) : 0u;
+        const uint32_t key = valid ? fkey(__ldcg(p + i)) : 0u;
         const bool gt = valid && key > T;
         const bool eq = valid && key == T;
         if (gt) {
@@ -149,14 +153,14 @@ __global__ void __launch_bounds__(1024) k_topk(const float* __restrict__ pk, con
         const float score = fkey_inv((uint32_t)(c >> 32));
         float xs = (float)(idx % W), ys = (float)(idx / W);  // centerface_ext.py:18-19
         if (reg) {
-            xs = __fadd_rn(xs, __ldg(reg + ((size_t)b * 2 + 0) * HW + idx));  // :62
-            ys = __fadd_rn(ys, __ldg(reg + ((size_t)b * 2 + 1) * HW + idx));  // :63
+            xs = __fadd_rn(xs, __ldcg(reg + ((size_t)b * 2 + 0) * HW + idx));  // :62
+            ys = __fadd_rn(ys, __ldcg(reg + ((size_t)b * 2 + 1) * HW + idx));  // :63
         } else {
             xs += 0.5f;
             ys += 0.5f;
         }
-        const float hw = __ldg(wh + ((size_t)b * 2 + 0) * HW + idx) / 2.f;
-        const float hh = __ldg(wh + ((size_t)b * 2 + 1) * HW + idx) / 2.f;
+        const float hw = __ldcg(wh + ((size_t)b * 2 + 0) * HW + idx) / 2.f;
+        const float hh = __ldcg(wh + ((size_t)b * 2 + 1) * HW + idx) / 2.f;
         float* d = dets + ((size_t)b * K + r) * 6;
         d[0] = __fsub_rn(xs, hw);
         d[1] = __fsub_rn(ys, hh);

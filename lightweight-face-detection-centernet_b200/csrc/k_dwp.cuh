@@ -26,7 +26,7 @@ struct DwpParams {
 
 template <int KS, int S>
 __global__ void __launch_bounds__(DWT_THREADS, 2) k_dwp(const __grid_constant__ CUtensorMap tmX, const DwpParams P) {
-    using G = DwtGeom<KS, S>;
+    using G = DwtGeom<KS, S, 0>;
     constexpr int XT = 2, YT = 2, NBX = G::TW / XT, NBLK = (G::TH / YT) * NBX;  // 25 blocks of 2x2 outputs
     constexpr int NROW = (YT - 1) * S + KS, NCOL = (XT - 1) * S + KS;
     static_assert(NBLK <= (DWT_THREADS / 32) * 4, "one output block per (warp, lane group)");
@@ -259,10 +259,11 @@ inline int dwp_plan(PwTcState& st, int ks, int s, const float* E, const float* W
     if (it == st.layers.end() || it->second.NC != ncp || it->second.nchunks != 1)
         return fail(CF_EINVAL, "dwp_plan: projection weights were not prepared as one %d-column image per K block", ncp);
     int ih, iw, xb;
-    if (ks == 3 && s == 1) dwt_geom<3, 1>(&ih, &iw, &xb);
-    else if (ks == 3) dwt_geom<3, 2>(&ih, &iw, &xb);
-    else if (s == 1) dwt_geom<5, 1>(&ih, &iw, &xb);
-    else dwt_geom<5, 2>(&ih, &iw, &xb);
+    int th_, tw_;
+    if (ks == 3 && s == 1) dwt_geom<3, 1, 0>(&th_, &tw_, &ih, &iw, &xb);
+    else if (ks == 3) dwt_geom<3, 2, 0>(&th_, &tw_, &ih, &iw, &xb);
+    else if (s == 1) dwt_geom<5, 1, 0>(&th_, &tw_, &ih, &iw, &xb);
+    else dwt_geom<5, 2, 0>(&th_, &tw_, &ih, &iw, &xb);
     int rc = xd_make_map(st, &dl->tmX, E, B, Hi, Wi, C, iw, ih);
     if (rc) return rc;
     DwpParams& P = dl->p;

@@ -14,9 +14,14 @@ namespace cf {
 
 constexpr int DWT_THREADS = 256;
 
-template <int KS, int S>
+// Output tile per item.  GEOM 0: 10 x 10, divides every map of the network (320, 160, 80, 40, 20) but fills only 25 of the
+// CTA's 32 block slots (8 warps x 4 pixel groups, one 2x2 output block each); GEOM 1: 8 rows x 16 columns = 32 blocks, every
+// thread busy, for the maps it divides (stride-2/4/8 stages).  Tiles that overhang the map are legal either way: TMA zero-fills
+// the reads (= the reference's zero padding) and the stores are clipped.
+template <int KS, int S, int GEOM>
 struct DwtGeom {
-    static constexpr int TH = 10, TW = 10;  // divides every map of the network (320, 160, 80, 40, 20)
+    static constexpr int TH = GEOM == 0 ? 10 : (GEOM == 1 || GEOM == 3) ? 8 : 16;
+    static constexpr int TW = GEOM == 0 ? 10 : (GEOM == 1 || GEOM == 2) ? 16 : 32;
     static constexpr int IH = (TH - 1) * S + KS, IW = (TW - 1) * S + KS;
     static constexpr int NPX = IH * IW;
     static constexpr int LO = (KS - S) / 2;
@@ -29,9 +34,9 @@ struct DwtParams {
     int nst;     // pipeline stages
 };
 
-template <int KS, int S>
+template <int KS, int S, int GEOM>
 __global__ void __launch_bounds__(DWT_THREADS, 2) k_dwt(const __grid_constant__ CUtensorMap tmX, const DwtParams P) {
-    using G = DwtGeom<KS, S>;
+    using G = DwtGeom<KS, S, GEOM>;
     const XdParams& p = P.x;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -41,12 +46,14 @@ __global__ void __launch_bounds__(DWT_THREADS, 2) k_dwt(const __grid_constant__ 
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int c4 = lane & 7, pg = lane >> 3;
+    pdl_trigger();
     if (tid == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
         for (int i = 0; i < nst; ++i) mbar_init(bars + 8 * i, 1);
         fence_barrier_init();
     }
     __syncthreads();
+    pdl_wait();
 
     // item = ((b * tiles_y + ty) * tiles_x + tx) * nchunk + chunk : chunks of one tile are adjacent
     auto issue = [&](int item, int stage) {  // thread 0 only
@@ -85,44 +92,80 @@ __global__ void __launch_bounds__(DWT_THREADS, 2) k_dwt(const __grid_constant__ 
 struct DwtLaunch {
     CUtensorMap tmX;
     DwtParams p;
-    int ks = 3, s = 1, grid = 0;
+    int ks = 3, s = 1, geom = 0, grid = 0;
     size_t smem = 0;
 };
 
-template <int KS, int S>
+template <int KS, int S, int GEOM>
 inline cudaError_t dwt_launch_t(const DwtLaunch& dl, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k_dwt<KS, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
+        cudaError_t e = cudaFuncSetAttribute(k_dwt<KS, S, GEOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    k_dwt<KS, S><<<dl.grid, DWT_THREADS, dl.smem, st>>>(dl.tmX, dl.p);
-    return cudaGetLastError();
+    return launch_pdl(k_dwt<KS, S, GEOM>, dim3(dl.grid), dim3(DWT_THREADS), dl.smem, st, dl.tmX, dl.p);
 }
 
 inline cudaError_t dwt_launch(const DwtLaunch& dl, cudaStream_t st) {
-    if (dl.ks == 3 && dl.s == 1) return dwt_launch_t<3, 1>(dl, st);
-    if (dl.ks == 3 && dl.s == 2) return dwt_launch_t<3, 2>(dl, st);
-    if (dl.ks == 5 && dl.s == 1) return dwt_launch_t<5, 1>(dl, st);
-    return dwt_launch_t<5, 2>(dl, st);
+#define CF_DWT_CASE(K_, S_)                                                   \
+    if (dl.ks == K_ && dl.s == S_) {                                          \
+        switch (dl.geom) {                                                    \
+            case 1: return dwt_launch_t<K_, S_, 1>(dl, st);                   \
+            case 2: return dwt_launch_t<K_, S_, 2>(dl, st);                   \
+            case 3: return dwt_launch_t<K_, S_, 3>(dl, st);                   \
+            case 4: return dwt_launch_t<K_, S_, 4>(dl, st);                   \
+            default: return dwt_launch_t<K_, S_, 0>(dl, st);                  \
+        }                                                                     \
+    }
+    CF_DWT_CASE(3, 1) CF_DWT_CASE(3, 2) CF_DWT_CASE(5, 1) CF_DWT_CASE(5, 2)
+#undef CF_DWT_CASE
+    return cudaErrorInvalidValue;
 }
 
-template <int KS, int S>
-inline void dwt_geom(int* ih, int* iw, int* xb) {
-    using G = DwtGeom<KS, S>;
-    *ih = G::IH, *iw = G::IW, *xb = G::XBYTES;
+template <int KS, int S, int GEOM>
+inline void dwt_geom(int* th, int* tw, int* ih, int* iw, int* xb) {
+    using G = DwtGeom<KS, S, GEOM>;
+    *th = G::TH, *tw = G::TW, *ih = G::IH, *iw = G::IW, *xb = G::XBYTES;
 }
 
 inline bool dwt_supported(int C) { return C % 4 == 0 && C >= 16; }
 
 inline int dwt_plan(PwTcState& st, int ks, int s, const float* X, const float* Wd, float* D, int B, int Hi, int Wi, int C, DwtLaunch* dl) {
     if (!dwt_supported(C)) return fail(CF_EINVAL, "dwt_plan: C=%d is not a multiple of 4", C);
-    int ih, iw, xb;
-    if (ks == 3 && s == 1) dwt_geom<3, 1>(&ih, &iw, &xb);
-    else if (ks == 3) dwt_geom<3, 2>(&ih, &iw, &xb);
-    else if (s == 1) dwt_geom<5, 1>(&ih, &iw, &xb);
-    else dwt_geom<5, 2>(&ih, &iw, &xb);
+    const int Ho = Hi / s, Wo = Wi / s;
+    // Tile geometry per layer, from a sweep on the device at batch 32 @ 640x640 (profiles/r2_tuning.md; us per launch,
+    // 10x10 -> chosen): stride-1 layers take 16x16 tiles with two CTAs x two stages per SM (3x3/32ch 207 -> 150,
+    // 3x3/144ch 258 -> 185, 5x5/192ch 131 -> 113), the 5x5 stride-2 layer 8x16 (207 -> 141); the 3x3 stride-2 layer is
+    // HBM-bound at 6.2 TB/s with any tile and the stride-16/32 maps (40x40, 20x20) are not divisible: both keep 10x10.
+    const int gth[5] = {10, 8, 16, 8, 16}, gtw[5] = {10, 16, 16, 32, 32};
+    auto divides = [&](int g) {  // ... and one halo tile fits shared memory
+        const int hh = (gth[g] - 1) * s + ks, hw = (gtw[g] - 1) * s + ks;
+        return Ho % gth[g] == 0 && Wo % gtw[g] == 0 && (size_t)((hh * hw * 128 + 1023) / 1024 * 1024) + 2048 <= (size_t)TC_SMEM_MAX;
+    };
+    int geom = (s == 1 && divides(2)) ? 2 : (ks == 5 && divides(1)) ? 1 : 0;
+    if (const char* ev = getenv("CF_DWT_GEOM")) {  // development probe: geometry index wherever it divides the map
+        const int g = atoi(ev);
+        if (g == 0) geom = 0;
+        else if (g >= 1 && g <= 4) geom = divides(g) ? g : geom;
+    }
+    int th = 0, tw = 0, ih = 0, iw = 0, xb = 0;
+#define CF_DWT_GEOM_CASE(K_, S_)                                              \
+    if (ks == K_ && s == S_) {                                                \
+        switch (geom) {                                                       \
+            case 1: dwt_geom<K_, S_, 1>(&th, &tw, &ih, &iw, &xb); break;      \
+            case 2: dwt_geom<K_, S_, 2>(&th, &tw, &ih, &iw, &xb); break;      \
+            case 3: dwt_geom<K_, S_, 3>(&th, &tw, &ih, &iw, &xb); break;      \
+            case 4: dwt_geom<K_, S_, 4>(&th, &tw, &ih, &iw, &xb); break;      \
+            default: dwt_geom<K_, S_, 0>(&th, &tw, &ih, &iw, &xb); break;     \
+        }                                                                     \
+    }
+    CF_DWT_GEOM_CASE(3, 1) CF_DWT_GEOM_CASE(3, 2) CF_DWT_GEOM_CASE(5, 1) CF_DWT_GEOM_CASE(5, 2)
+#undef CF_DWT_GEOM_CASE
+    if (th == 0) return fail(CF_EINVAL, "dwt_plan: unsupported kernel %dx%d stride %d", ks, ks, s);
+    if (iw > 256 || ih > 256 || xb + 2048 > TC_SMEM_MAX) {  // TMA box limit / one stage must fit
+        return fail(CF_EINVAL, "dwt_plan: tile geometry %d does not fit (halo %dx%d)", geom, ih, iw);
+    }
     int rc = xd_make_map(st, &dl->tmX, X, B, Hi, Wi, C, iw, ih);
     if (rc) return rc;
     XdParams& p = dl->p.x;
@@ -135,8 +178,8 @@ inline int dwt_plan(PwTcState& st, int ks, int s, const float* X, const float* W
     p.Ho = Hi / s;
     p.Wo = Wi / s;
     p.hid = C;
-    p.tiles_x = (p.Wo + 9) / 10;
-    p.tiles_y = (p.Ho + 9) / 10;
+    p.tiles_x = (p.Wo + tw - 1) / tw;
+    p.tiles_y = (p.Ho + th - 1) / th;
     dl->p.nchunk = (C + 31) / 32;
     const long long items = (long long)B * p.tiles_x * p.tiles_y * dl->p.nchunk;
     if (items > 0x7fffffffLL) return fail(CF_EINVAL, "dwt_plan: too many tiles");
@@ -144,7 +187,9 @@ inline int dwt_plan(PwTcState& st, int ks, int s, const float* X, const float* W
     // two CTAs per SM when at least three stages fit in half of the shared memory, else one CTA with all of it
     const int per_cta2 = (TC_SMEM_MAX / 2 - 2048) / xb;
     int ctas_per_sm = 2, nst = per_cta2;
-    if (nst < 3) ctas_per_sm = 1, nst = (TC_SMEM_MAX - 2048) / xb;
+    int min2 = geom == 2 ? 2 : 3;
+    if (const char* ev = getenv("CF_DWT_MIN2")) min2 = atoi(ev);  // development probe: fewest stages worth two CTAs per SM
+    if (nst < min2) ctas_per_sm = 1, nst = (TC_SMEM_MAX - 2048) / xb;
     if (const char* ev = getenv("CF_DWT_CTAS")) {  // development probe (tools/step_times.py)
         if (atoi(ev) == 1) ctas_per_sm = 1, nst = (TC_SMEM_MAX - 2048) / xb;
     }
@@ -157,6 +202,7 @@ inline int dwt_plan(PwTcState& st, int ks, int s, const float* X, const float* W
     dl->smem = (size_t)nst * xb + 64 + 1024;
     dl->ks = ks;
     dl->s = s;
+    dl->geom = geom;
     const int want = ctas_per_sm * st.sms;
     dl->grid = p.n_items < want ? p.n_items : want;
     return CF_OK;

@@ -58,7 +58,8 @@ struct PwTcState {
 struct TcParams {
     const float* bimg;
     int M, K, N, NC, nchunks, nkb, n_items;
-    int resident;    // 1: the whole B image lives in smem for the kernel's lifetime
+    int resident;    // 1: the whole B image lives in smem for the kernel's lifetime; 2: the image of ONE column chunk does --
+                     //    the grid is a multiple of nchunks, so a CTA's items all share the chunk blockIdx.x % nchunks
     int direct;      // 1: narrow outputs (N <= 64): the epilogue stores rows straight from registers, the staging
                      //    buffers' 64 KB go to two more pipeline stages
     float* out;      // [M][N] (direct stores)
@@ -233,6 +234,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_trigger();
 
     // smem map: [staging 16 x 2 x 4 KB][resident B][stages][barriers]
     const uint32_t stg_base = base;
@@ -285,13 +287,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         // ================= TMA producer =================
         if (lane == 0) {
             if (p.resident) {
-                const uint32_t total = (uint32_t)p.nchunks * nkb * p.b_bytes_block;
+                const uint32_t chunk_bytes = (uint32_t)nkb * p.b_bytes_block;
+                const uint32_t total = p.resident == 2 ? chunk_bytes : (uint32_t)p.nchunks * chunk_bytes;
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(p.bimg) +
+                                     (p.resident == 2 ? (size_t)(blockIdx.x % (unsigned)p.nchunks) * chunk_bytes : (size_t)0);
                 mbar_expect_tx(bar_bres, total);
                 for (uint32_t off = 0; off < total; off += 32768u) {
                     const uint32_t n = total - off < 32768u ? total - off : 32768u;
-                    bulk_load(bres + off, reinterpret_cast<const uint8_t*>(p.bimg) + off, n, bar_bres);
+                    bulk_load(bres + off, src + off, n, bar_bres);
                 }
             }
+            pdl_wait();  // the weights above depend on nothing; A is the previous kernel's output
             int stage = 0;
             uint32_t phase = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -344,7 +350,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                         const uint32_t aslot = acnt & 3u;
                         mbar_wait(bar_aready + 8 * aslot, (acnt >> 2) & 1u);
                         tc_fence_after();
-                        const uint32_t sb = p.resident ? bres + (uint32_t)(ch * nkb + kb) * p.b_bytes_block
+                        const uint32_t sb = p.resident ? bres + (uint32_t)((p.resident == 2 ? 0 : ch * nkb) + kb) * p.b_bytes_block
                                                        : stages0 + stage * p.stage_bytes + p.a_bytes_stage;
                         const int krem = p.K - kb * TC_BK;
                         const int nks = krem >= TC_BK ? TC_BK / 8 : (krem + 7) / 8;
@@ -366,7 +372,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     mbar_wait((kPasses == 3 ? bar_ready : bar_full) + 8 * stage, phase);
                     tc_fence_after();
                     const uint32_t sa = stages0 + stage * p.stage_bytes;
-                    const uint32_t sb = p.resident ? bres + (uint32_t)(ch * nkb + kb) * p.b_bytes_block : sa + p.a_bytes_stage;
+                    const uint32_t sb = p.resident ? bres + (uint32_t)((p.resident == 2 ? 0 : ch * nkb) + kb) * p.b_bytes_block
+                                                   : sa + p.a_bytes_stage;
                     const int krem = p.K - kb * TC_BK;
                     const int nks = krem >= TC_BK ? TC_BK / 8 : (krem + 7) / 8;
                     const uint64_t a_hi = umma_desc(sa), b_hi = umma_desc(sb);
@@ -447,6 +454,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
     } else if (warp >= 8) {
         // ================= epilogue: group g serves accumulator stage g =================
+        pdl_wait();  // residual / low-res reads and the output stores touch activation memory
         const int g = (warp - 8) >> 2;
         const int q = warp & 3;  // TMEM lane quarter this warp may read
         const uint32_t stg = stg_base + (uint32_t)(warp - 8) * (TC_STG_BUFS * TC_STG_BYTES);
@@ -606,6 +614,7 @@ struct TcTune {
     int nacc = 0;     // accumulator stages (0: as many as fit, 2 or 4)
     int pwn = -1;     // role-free kernel for eligible layers (-1: yes)
     int grid = 0;     // CTA count cap (0: one per SM)
+    int rchunk = -1;  // per-CTA resident column chunk when the whole weight image does not fit (-1: yes)
 };
 struct TcTuneEntry {
     int K, N;
@@ -630,6 +639,7 @@ inline TcTune tc_tune_for(int K, int N, int passes) {
     if (const char* ev = getenv("CF_TC_NACC")) t.nacc = atoi(ev);
     if (const char* ev = getenv("CF_PWN")) t.pwn = atoi(ev);
     if (const char* ev = getenv("CF_TC_GRID")) t.grid = atoi(ev);
+    if (const char* ev = getenv("CF_TC_RCHUNK")) t.rchunk = atoi(ev);
     const int nc_max = passes == 3 ? 128 : 192;
     if (t.nc < 0 || t.nc % 32 != 0 || t.nc > nc_max) t.nc = 0;
     return t;
@@ -738,17 +748,27 @@ inline int tc_plan(PwTcState& st, int passes, int epi, const float* A, const flo
     const uint32_t avail = TC_SMEM_MAX - 1024 /*alignment slack*/ - stg_bytes - bar_bytes;
     const uint32_t b_total = (uint32_t)L.img_bytes;
     p.resident = (b_total <= 65536u && avail - b_total >= 3u * p.a_bytes_stage) ? 1 : 0;
+    // Wide layers whose image does not fit: streaming the chunk's weights again for every 128-row tile makes them
+    // L2-bandwidth bound (the weight stream is NC/64 times the A stream).  If one chunk's image fits beside two A stages,
+    // pin each CTA to one chunk instead (grid = a multiple of nchunks) and keep that chunk resident.
+    const uint32_t chunk_total = (uint32_t)L.nkb * p.b_bytes_block;
+    uint32_t b_res = p.resident ? b_total : 0u;
+    if (!p.resident && tune.rchunk != 0 && L.nchunks > 1 && L.nchunks <= st.sms && chunk_total + 2u * p.a_bytes_stage <= avail) {
+        p.resident = 2;
+        b_res = chunk_total;
+    }
     p.stage_bytes = p.a_bytes_stage + (p.resident ? 0u : p.b_bytes_block);
-    const uint32_t room = avail - (p.resident ? b_total : 0u);
+    const uint32_t room = avail - b_res;
     int stages = (int)(room / p.stage_bytes);
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
     if (stages < 2) return fail(CF_EINVAL, "tc_plan: K=%d N=%d does not fit the shared-memory pipeline", K, N);
     p.stages = stages;
     p.off_bres = stg_bytes;
-    p.off_stages = stg_bytes + (p.resident ? b_total : 0u);
+    p.off_stages = stg_bytes + b_res;
     p.off_bars = p.off_stages + (uint32_t)stages * p.stage_bytes;
     tl->smem = (size_t)p.off_bars + bar_bytes + 1024;
     tl->grid = p.n_items < st.sms ? p.n_items : st.sms;
+    if (p.resident == 2) tl->grid = tl->grid / L.nchunks * L.nchunks;  // n_items is a multiple of nchunks
     if (tune.grid > 0 && tune.grid < tl->grid) tl->grid = tune.grid;
     tl->passes = passes;
     tl->epi = epi;
@@ -763,8 +783,7 @@ inline cudaError_t tc_launch_t(const TcLaunch& tl, cudaStream_t s) {
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    k_pw_tc<kPasses, EPI><<<tl.grid, TC_THREADS, tl.smem, s>>>(tl.tmA, tl.tmOut, tl.p);
-    return cudaGetLastError();
+    return launch_pdl(k_pw_tc<kPasses, EPI>, dim3(tl.grid), dim3(TC_THREADS), tl.smem, s, tl.tmA, tl.tmOut, tl.p);
 }
 
 inline cudaError_t tc_launch(const TcLaunch& tl, cudaStream_t s) {

@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(PWN_THREADS, 2) k_pwn(const __grid_constant__ 
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = warp & 3, half = warp >> 2;  // TMEM lane quarter; which 16 of a K block's 32 elements / which column half
+    pdl_trigger();
 
     if (tid == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -88,8 +89,10 @@ __global__ void __launch_bounds__(PWN_THREADS, 2) k_pwn(const __grid_constant__ 
             const uint32_t n = p.b_bytes - off < 32768u ? p.b_bytes - off : 32768u;
             bulk_load(bsm + off, reinterpret_cast<const uint8_t*>(p.bimg) + off, n, bar_b);
         }
-        for (long long j = 0; j < nst && j < total; ++j) issue_a(j);
     }
+    pdl_wait();  // everything above (barriers, TMEM, weights) depends on nothing; A is the previous kernel's output
+    if (tid == 0 && total > 0)
+        for (long long j = 0; j < nst && j < total; ++j) issue_a(j);
     const uint32_t idesc = umma_idesc_tf32(p.NC), idesc2 = umma_idesc_tf32(2 * p.NC);
     const uint32_t d_main = tmem_base, d_corr = tmem_base + (uint32_t)p.NC;
     const uint32_t blk_bytes = (uint32_t)p.NC * 256u;  // one K block of the weight image (hi | lo)
@@ -227,8 +230,7 @@ inline cudaError_t pwn_launch_t(const PwnLaunch& pl, cudaStream_t s) {
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    k_pwn<EPI><<<pl.grid, PWN_THREADS, pl.smem, s>>>(pl.tmA, pl.p);
-    return cudaGetLastError();
+    return launch_pdl(k_pwn<EPI>, dim3(pl.grid), dim3(PWN_THREADS), pl.smem, s, pl.tmA, pl.p);
 }
 
 inline cudaError_t pwn_launch(const PwnLaunch& pl, cudaStream_t s) {

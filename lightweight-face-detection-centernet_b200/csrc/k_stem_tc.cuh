@@ -1,0 +1,219 @@
+// k_stem_tc: the stem convolution on the tensor cores.
+//
+//     ZeroPad2d(0,1,0,1) + conv3x3 s2 3->32 + Swish   (model/centernet.py:224, :58-70), fused u8 normalisation
+//     (centerface.py:32-34) through the same 3 x 256 table as k_stem.
+//
+// The FFMA stem (k_stem, k_conv.cuh) is instruction-issue bound: 864 FFMAs + ~900 other instructions per output
+// pixel (SASS), 222 us per 32-image batch against an HBM floor of 70 us.  But the stem IS a dense contraction,
+//     out[pixel][32] = sum_{k = (ky*3+kx)*3+c < 27}  x[pixel, k] . w[k][32],
+// i.e. a GEMM with K = 27 (padded to one 32-wide K block) and N = 32, so it takes the role-free tcgen05 kernel of the
+// narrow point-wise layers (k_pwn) with a different A producer: instead of splitting a TMA box, every thread gathers 16 of
+// its pixel's 27 inputs straight from the image (u8 -> table, or fp32 NCHW), splits them into tf32 hi + lo and stores
+// them into TMEM (lane = pixel row of the 128-pixel tile, column = k); one thread issues
+//     A_hi.[W_hi|W_lo] -> main | correction,   A_lo.W_hi -> correction
+// with the weight image (8 KB, built by tc_prepare_layer) resident in shared memory; all threads drain the
+// accumulator pair, apply Swish and store their half row.  The next tile's bytes are fetched before the current
+// tile's MMA/drain phase so that the global-load latency overlaps it; three CTAs (128 TMEM columns each) share an SM.
+//
+// Arithmetic: 3xTF32 (error ~2^-21 per product, fp32 accumulation in TMEM), the same as every point-wise convolution
+// of this engine; the fp32-FFMA validation engine (CF_PW_SIMT) keeps k_stem.
+#pragma once
+#include "k_pwn.cuh"
+
+namespace cf {
+
+constexpr int STC_THREADS = 256;
+constexpr int STC_NC = 32;                      // output channels = one column chunk
+constexpr uint32_t STC_B_BYTES = STC_NC * 256;  // [hi 32 x 128 B | lo 32 x 128 B]
+constexpr uint32_t STC_OFF_LUT = STC_B_BYTES;   // 768 floats
+constexpr uint32_t STC_OFF_BARS = STC_OFF_LUT + 768 * 4;
+constexpr size_t STC_SMEM = STC_OFF_BARS + 64 + 1024;  // + alignment slack
+
+struct StcParams {
+    const void* in;     // FMT 1: u8 [B,H,W,3]; FMT 0: fp32 [B,3,H,W]
+    const float* bimg;  // tf32 hi|lo image of stem.w [27][32] (K padded to 32)
+    const float* lut;   // [3][256]
+    float* out;         // [B,H/2,W/2,32]
+    int B, H, W, n_tiles;
+    long long n_pix;
+};
+
+// raw[i] for k = K0 + i: the byte (FMT 1) or the fp32 bit pattern (FMT 0) of input element k of pixel (b, yo, xo);
+// bit i of the returned mask is set where the element exists (k < 27 and inside the image; the pad is bottom/right only).
+template <int FMT, int K0>
+__device__ __forceinline__ uint32_t stc_gather(const StcParams& p, bool valid, int b, int yo, int xo, uint32_t (&raw)[16]) {
+    uint32_t mask = 0;
+    const bool last_y = (2 * yo + 2 >= p.H), last_x = (2 * xo + 2 >= p.W);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int k = K0 + i;
+        raw[i] = 0;
+        if (k >= 27) continue;
+        const int ky = k / 9, r = k - ky * 9, kx = r / 3, c = r - kx * 3;
+        const bool ok = valid && !(ky == 2 && last_y) && !(kx == 2 && last_x);
+        if (ok) {
+            if (FMT == 1) {
+                const uint8_t* q = (const uint8_t*)p.in + ((size_t)(b * p.H + 2 * yo + ky) * p.W + 2 * xo + kx) * 3 + c;
+                raw[i] = __ldg(q);
+            } else {
+                const float* q = (const float*)p.in + ((size_t)(b * 3 + c) * p.H + 2 * yo + ky) * p.W + 2 * xo + kx;
+                raw[i] = __float_as_uint(__ldg(q));
+            }
+            mask |= 1u << i;
+        }
+    }
+    return mask;
+}
+
+// raw -> normalised fp32 -> tf32 hi + exact remainder
+template <int FMT, int K0>
+__device__ __forceinline__ void stc_split(const uint32_t (&raw)[16], uint32_t mask, const float* lut_s, float (&hi)[16], float (&lo)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        constexpr int c0 = K0 % 3;
+        const int c = (c0 + i) % 3;  // k = (ky*3+kx)*3 + c
+        float v = 0.f;
+        if (mask & (1u << i)) v = FMT == 1 ? lut_s[c * 256 + raw[i]] : __uint_as_float(raw[i]);
+        hi[i] = tf32_hi(v);
+        lo[i] = v - hi[i];
+    }
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(STC_THREADS, 3) k_stem_tc(const StcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bsm = base;
+    float* lut_s = reinterpret_cast<float*>(sm + STC_OFF_LUT);
+    const uint32_t bars = base + STC_OFF_BARS;  // B full | accumulator ready
+    const uint32_t bar_b = bars, bar_acc = bars + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + STC_OFF_BARS + 40);
+    constexpr uint32_t kACol = 64;  // TMEM (128 columns, three CTAs per SM): accumulator pair in [0, 64), A hi | lo in [64, 128)
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, half = warp >> 2;  // TMEM lane quarter; K elements [16 half, 16 half + 16) / output columns likewise
+    pdl_trigger();
+
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) mbar_init(bars + 8 * i, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (FMT == 1)
+        for (int i = tid; i < 768; i += STC_THREADS) lut_s[i] = __ldg(p.lut + i);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int my_tiles = ((int)blockIdx.x < p.n_tiles) ? (p.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    if (tid == 0 && my_tiles > 0) {
+        mbar_expect_tx(bar_b, STC_B_BYTES);
+        bulk_load(bsm, p.bimg, STC_B_BYTES, bar_b);
+    }
+    pdl_wait();  // the image may come from the resize kernel; `out` may still be read by the previous forward
+
+    const uint32_t idesc = umma_idesc_tf32(STC_NC), idesc2 = umma_idesc_tf32(2 * STC_NC);
+    const uint32_t d_main = tmem_base, d_corr = tmem_base + (uint32_t)STC_NC;
+    const int row = q * 32 + lane;
+    const int Ho = p.H >> 1, Wo = p.W >> 1;
+
+    uint32_t raw[16];
+    uint32_t mask = 0;
+    auto gather = [&](int tile) {
+        const long long pix = (long long)tile * TC_BM + row;
+        const bool valid = pix < p.n_pix;
+        const int xo = (int)(pix % Wo);
+        const int yo = (int)((pix / Wo) % Ho);
+        const int b = (int)(pix / ((long long)Wo * Ho));
+        mask = half == 0 ? stc_gather<FMT, 0>(p, valid, b, yo, xo, raw) : stc_gather<FMT, 16>(p, valid, b, yo, xo, raw);
+    };
+    if (my_tiles > 0) gather((int)blockIdx.x);
+
+    for (int j = 0; j < my_tiles; ++j) {
+        const int tile = (int)blockIdx.x + j * (int)gridDim.x;
+        // ---- this thread's 16 inputs -> normalised fp32 -> tf32 hi / lo -> TMEM ----
+        float hi[16], lo[16];
+        if (half == 0) stc_split<FMT, 0>(raw, mask, lut_s, hi, lo);
+        else stc_split<FMT, 16>(raw, mask, lut_s, hi, lo);
+        if (j + 1 < my_tiles) gather(tile + (int)gridDim.x);  // in flight during this tile's MMA + drain
+        // the previous tile's MMAs have read the A block: every thread saw its accumulator barrier before the tile-end sync
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + kACol + (uint32_t)half * 16u;
+        tc_fence_after();
+        tmem_st16(ta, hi);
+        tmem_st16(ta + 32u, lo);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncthreads();  // the A block is in TMEM
+        if (tid == 0) {
+            if (j == 0) mbar_wait(bar_b, 0);
+            tc_fence_after();
+            const uint64_t b_hi = umma_desc(bsm);
+            const uint32_t a_hi = tmem_base + kACol, a_lo = a_hi + 32u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {  // K = 27 -> four 8-wide steps (elements 27..31 are zero on both sides)
+                const uint64_t ko = (uint64_t)(k * 2);
+                umma_tf32_ts(d_main, a_hi + 8u * k, b_hi + ko, idesc2, k > 0 ? 1u : 0u);  // main += hi.hi ; corr += hi.lo
+                umma_tf32_ts(d_corr, a_lo + 8u * k, b_hi + ko, idesc, 1u);                 // corr += lo.hi
+            }
+            umma_commit(bar_acc);
+        }
+        // ---- drain main + correction, Swish, store this thread's 16 channels of its pixel ----
+        mbar_wait(bar_acc, (uint32_t)j & 1u);
+        tc_fence_after();
+        const long long pix = (long long)tile * TC_BM + row;
+        {
+            float v[16], c[16];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 16);
+            tmem_ld16(taddr, v);
+            tmem_ld16(taddr + (uint32_t)STC_NC, c);
+            tmem_ld_wait();
+            if (pix < p.n_pix) {
+                float* o = p.out + (size_t)pix * 32 + half * 16;
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    st4(o + 4 * g, swish4(make_float4(v[4 * g] + c[4 * g], v[4 * g + 1] + c[4 * g + 1], v[4 * g + 2] + c[4 * g + 2],
+                                                      v[4 * g + 3] + c[4 * g + 3])));
+            }
+        }
+        tc_fence_before();
+        __syncthreads();  // every accumulator read is done before the next tile's first MMA overwrites it
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+    }
+}
+
+template <int FMT>
+inline cudaError_t stc_launch_t(const StcParams& p, int grid, cudaStream_t s) {
+    return launch_pdl(k_stem_tc<FMT>, dim3(grid), dim3(STC_THREADS), STC_SMEM, s, p);
+}
+
+inline int stc_plan(PwTcState& st, const float* key_w, const void* in, const float* lut, float* out, int B, int H, int W, StcParams* p,
+                    int* grid) {
+    auto it = st.layers.find(key_w);
+    if (it == st.layers.end()) return fail(CF_EINVAL, "stc_plan: the stem weight image was not prepared");
+    const TcLayer& L = it->second;
+    if (L.NC != STC_NC || L.nchunks != 1 || L.nkb != 1) return fail(CF_EINVAL, "stc_plan: unexpected stem image NC=%d chunks=%d nkb=%d", L.NC, L.nchunks, L.nkb);
+    p->in = in;
+    p->bimg = L.img;
+    p->lut = lut;
+    p->out = out;
+    p->B = B;
+    p->H = H;
+    p->W = W;
+    p->n_pix = (long long)B * (H / 2) * (W / 2);
+    p->n_tiles = (int)((p->n_pix + TC_BM - 1) / TC_BM);
+    const int want = 3 * st.sms;
+    *grid = p->n_tiles < want ? p->n_tiles : want;
+    return CF_OK;
+}
+
+}  // namespace cf

@@ -50,7 +50,8 @@ def variants(K, N):
     for nc in range(32, min(128, n32) + 1, 32):
         for direct in (0, 1):
             for atmem in ((1, 0) if nc <= 64 else (0,)):
-                v.append({"CF_TC_NC": nc, "CF_TC_DIRECT": direct, "CF_TC_ATMEM": atmem, "CF_PWN": 0})
+                for rchunk in (1, 0):
+                    v.append({"CF_TC_NC": nc, "CF_TC_DIRECT": direct, "CF_TC_ATMEM": atmem, "CF_PWN": 0, "CF_TC_RCHUNK": rchunk})
         if nc <= 64 and K <= 32 and n32 <= nc:
             v.append({"CF_TC_NC": nc, "CF_PWN": 1})
     return v
@@ -83,7 +84,7 @@ def main():
             continue
         g = torch.Generator(device="cuda").manual_seed(K * 1000 + N)
         A = torch.randn(M, K, device="cuda", generator=g)
-        Wm = np.random.RandomState(K + N).randn(K, N).astype(np.float32) / np.sqrt(K)
+        Wm = np.ascontiguousarray((np.random.RandomState(K + N).randn(K, N) / np.sqrt(K)).astype(np.float32))
         R = torch.randn(M, N, device="cuda", generator=g) if epi == RES else None
         out = torch.empty(M, N, device="cuda")
         idx = torch.cat([torch.randint(M, (4096,), device="cuda", generator=g), torch.arange(M - 300, M, device="cuda"),
@@ -102,7 +103,7 @@ def main():
             f.write(json.dumps({"key": key, "status": "started"}) + "\n")
             f.flush()
             os.fsync(f.fileno())
-            for k in ("CF_TC_NC", "CF_TC_DIRECT", "CF_TC_ATMEM", "CF_PWN"):
+            for k in ("CF_TC_NC", "CF_TC_DIRECT", "CF_TC_ATMEM", "CF_PWN", "CF_TC_RCHUNK"):
                 os.environ.pop(k, None)
             for k, val in v.items():
                 os.environ[k] = str(val)
