@@ -10,7 +10,8 @@ from ._lib import (CF_DECODE_A, CF_DECODE_B, CF_IN_F32_NCHW, CF_IN_U8_HWC, CF_PW
 from .build import build
 from .weights import load_state_dict, pack_weights
 
-__all__ = ["CenterFace", "CenterFaceNet", "Engine", "ctdet_decode", "decode_threshold", "get_detections", "ctdet_post_process", "resize_u8", "build",
+__all__ = ["CenterFace", "CenterFaceNet", "Engine", "ctdet_decode", "decode_threshold", "get_detections", "ctdet_post_process", "resize_u8", "evaluate", "bbox_overlap",
+           "write_detections_txt", "build",
            "pack_weights", "load_state_dict", "CenterFaceError", "CF_DECODE_A", "CF_DECODE_B", "CF_IN_F32_NCHW",
            "CF_IN_U8_HWC", "CF_PW_SIMT", "CF_PW_TCGEN05", "CF_PW_TCGEN05_1P", "CF_PW_TCGEN05_FUSED", "CF_PW_TCGEN05_FUSED_TC", "CF_PW_TCGEN05_DWP", "CF_PW_TCGEN05_MIXED"]
 
@@ -18,6 +19,9 @@ __all__ = ["CenterFace", "CenterFaceNet", "Engine", "ctdet_decode", "decode_thre
 def __getattr__(name):  # engine/centerface import torch lazily; keep `import pkg` light
     if name in ("CenterFace", "CenterFaceNet", "get_detections"):
         from . import centerface as m
+        return getattr(m, name)
+    if name in ("evaluate", "bbox_overlap", "write_detections_txt"):
+        from . import widerface as m
         return getattr(m, name)
     if name in ("Engine", "ctdet_decode", "decode_threshold", "ctdet_post_process", "inverse_affine", "resize_u8"):
         from . import engine as m

@@ -411,8 +411,7 @@ int build_plan(cf_engine* e, const void* input, int fmt, int B, int H, int W) {
                                            hh, ww);
                      }});
         P.push_back({CLS_DECODE, [=](cudaStream_t s) {
-                         return launch_pdl(k_topk, dim3(B), dim3(1024), 0, s, (const float*)e->peak, (const float*)e->wh,
-                                           (const float*)e->reg, hh, ww, 100, e->o_dets, e->o_inds);
+                         return launch_topk(e->peak, e->wh, e->reg, B, hh, ww, 100, e->o_dets, e->o_inds, s);
                      }});
     }
     e->in = input;
@@ -705,7 +704,7 @@ int cf_ctdet_decode(const float* heat, const float* wh, const float* reg, int ba
     cudaStream_t s = (cudaStream_t)stream;
     const long long n = (long long)batch * h * w;
     CF_CUDA(launch_pdl(k_peak_mask, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, heat, scratch, batch, h, w));
-    CF_CUDA(launch_pdl(k_topk, dim3(batch), dim3(1024), 0, s, (const float*)scratch, wh, reg, h, w, K, out_dets, out_inds));
+    CF_CUDA(launch_topk(scratch, wh, reg, batch, h, w, K, out_dets, out_inds, s));
     return CF_OK;
 }
 

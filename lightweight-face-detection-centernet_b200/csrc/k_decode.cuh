@@ -70,9 +70,16 @@ __device__ __forceinline__ void bitonic_desc(unsigned long long* keys, int n) {
 // ---- K7+K8: per-image top-K of the peak map + gather + box assembly ------------------
 // grid = B, block = 1024.  4-pass MSB radix select of the K-th largest score, ordered
 // (lowest index first) admission of ties at the threshold, bitonic sort of the K winners.
+// SM: the image's H*W keys are read ONCE (all loads in flight together) into dynamic shared memory (4 B each, H*W <= 51 200)
+// and the four radix passes and the collection pass run on that copy; otherwise every pass re-reads the map from L2.
+// The histogram increments are warp-aggregated (__match_any_sync): after the peak mask ~95 % of a map is +0.0, i.e. ONE
+// radix bin, and 25 600 shared-memory atomics on one address were most of this kernel's 68 us.
+constexpr int TOPK_SMEM_MAX_HW = 51200;
+template <bool SM>
 __global__ void __launch_bounds__(1024) k_topk(const float* __restrict__ pk, const float* __restrict__ wh,
                                                const float* __restrict__ reg, int H, int W, int K,
                                                float* __restrict__ dets, int32_t* __restrict__ inds) {
+    extern __shared__ uint32_t skeys[];
     __shared__ unsigned hist[256];
     __shared__ unsigned long long buf[1024];
     __shared__ unsigned wcnt[32];
@@ -84,13 +91,28 @@ __global__ void __launch_bounds__(1024) k_topk(const float* __restrict__ pk, con
     pdl_trigger();
     pdl_wait();
 
+    if (SM) {
+#pragma unroll 8
+        for (int i = tid; i < HW; i += 1024) skeys[i] = fkey(__ldcg(p + i));
+        __syncthreads();
+    }
+    auto key_at = [&](int i) -> uint32_t { return SM ? skeys[i] : fkey(__ldcg(p + i)); };
+    const int HWp = (HW + 1023) & ~1023;  // whole warps walk the tail together (ballots below)
+
     unsigned prefix = 0, mask = 0, krem = K;
     for (int pass = 3; pass >= 0; --pass) {
         if (tid < 256) hist[tid] = 0;
         __syncthreads();
-        for (int i = tid; i < HW; i += 1024) {
-            const uint32_t key = fkey(__ldcg(p + i));
-            if ((key & mask) == prefix) atomicAdd(&hist[(key >> (8 * pass)) & 255u], 1u);
+        for (int i = tid; i < HWp; i += 1024) {
+            const bool in = i < HW;
+            const uint32_t key = in ? key_at(i) : 0u;
+            const bool hit = in && (key & mask) == prefix;
+            const unsigned bin = (key >> (8 * pass)) & 255u;
+            const unsigned act = __ballot_sync(0xffffffffu, hit);
+            if (hit) {
+                const unsigned same = __match_any_sync(act, bin);
+                if (lane == __ffs(same) - 1) atomicAdd(&hist[bin], (unsigned)__popc(same));
+            }
         }
         __syncthreads();
         if (tid == 0) {
@@ -121,7 +143,7 @@ __global__ void __launch_bounds__(1024) k_topk(const float* __restrict__ pk, con
     for (int base = 0; base < HW; base += 1024) {
         const int i = base + tid;
         const bool valid = i < HW;
-        const uint32_t key = valid ? fkey(__ldcg(p + i)) : 0u;
+        const uint32_t key = valid ? key_at(i) : 0u;
         const bool gt = valid && key > T;
         const bool eq = valid && key == T;
         if (gt) {
@@ -170,6 +192,21 @@ __global__ void __launch_bounds__(1024) k_topk(const float* __restrict__ pk, con
         d[5] = 0.f;
         if (inds) inds[(size_t)b * K + r] = idx;
     }
+}
+
+inline cudaError_t launch_topk(const float* pk, const float* wh, const float* reg, int B, int H, int W, int K, float* dets,
+                               int32_t* inds, cudaStream_t s) {
+    const int HW = H * W;
+    if (HW <= TOPK_SMEM_MAX_HW) {
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaError_t e = cudaFuncSetAttribute(k_topk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOPK_SMEM_MAX_HW * 4);
+            if (e != cudaSuccess) return e;
+            attr_done = true;
+        }
+        return launch_pdl(k_topk<true>, dim3(B), dim3(1024), (size_t)HW * 4, s, pk, wh, reg, H, W, K, dets, inds);
+    }
+    return launch_pdl(k_topk<false>, dim3(B), dim3(1024), 0, s, pk, wh, reg, H, W, K, dets, inds);
 }
 
 // numpy float32 floor_divide (npy_floor_dividef -> npy_divmodf), used by centerface.py:56-58

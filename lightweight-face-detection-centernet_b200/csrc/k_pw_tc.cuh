@@ -797,8 +797,20 @@ inline cudaError_t tc_launch(const TcLaunch& tl, cudaStream_t s) {
 
 // (K, N) -> plan, from tools/tc_tune.py on a B200 at batch 32 @ 640x640 (profiles/r2_tc_tune.md).
 inline const TcTuneEntry* tc_tuned_table(int* n) {
+    auto mk = [](int nc, int atmem, int direct, int rchunk) {
+        TcTune t;
+        t.nc = nc, t.atmem = atmem, t.direct = direct, t.rchunk = rchunk;
+        return t;
+    };
+    // us per launch, cost-model plan -> this plan (gpurun_out/r2e_tc_tune.jsonl)
     static const TcTuneEntry tab[] = {
-        {0, 0, TcTune()},
+        {24, 144, mk(64, 1, 0, -1)},    // layer1.1 / layer2.0 expand   145.1 -> 139.5
+        {384, 64, mk(0, -1, 0, -1)},    // layer3.1 project              34.2 -> 32.3
+        {384, 96, mk(96, -1, 1, -1)},   // layer4.0 project              40.1 -> 37.5
+        {96, 576, mk(128, -1, 0, 0)},   // layer4.1 / layer5.0 expand    60.8 -> 53.1
+        {576, 96, mk(96, -1, 1, -1)},   // layer4.1 project              64.1 -> 55.3
+        {960, 160, mk(96, -1, 1, -1)},  // layer5.1 project              57.2 -> 55.4
+        {960, 320, mk(128, -1, 1, 0)},  // layer6.0 project              77.1 -> 73.3
     };
     *n = (int)(sizeof(tab) / sizeof(tab[0]));
     return tab;
