@@ -128,6 +128,30 @@ struct EpiArgs {
     int Ho, Wo;         // output map size (IDAUP: m -> (b,y,x))
 };
 
+// IDAUp epilogue in two halves, so that a kernel can fetch the low-resolution operand (an L2 read that does not depend on
+// the GEMM) before it waits for its accumulator: idaup_low() -> the float4 of `low` under output row m, columns n..n+3,
+// and the 2x2 sub-pixel q of that row; idaup_apply() -> relu(BN(convT(low))) + relu(BN(lateral)).
+__device__ __forceinline__ const float* idaup_low_ptr(int m, int n, int N, const EpiArgs& ea, int* q) {
+    const int x = m % ea.Wo;
+    const int t = m / ea.Wo;
+    const int y = t % ea.Ho;
+    const int b = t / ea.Ho;
+    const int Hl = ea.Ho >> 1, Wl = ea.Wo >> 1;
+    *q = (y & 1) * 2 + (x & 1);
+    return ea.low + ((size_t)(b * Hl + (y >> 1)) * Wl + (x >> 1)) * N + n;
+}
+__device__ __forceinline__ float4 idaup_apply(float4 acc, float4 lo, int n, int q, const EpiArgs& ea) {
+    const float4 bb = ldg4(ea.bias + n), tt = ldg4(ea.tu + n);
+    const float s0 = __ldg(ea.su + (n + 0) * 4 + q), s1 = __ldg(ea.su + (n + 1) * 4 + q);
+    const float s2 = __ldg(ea.su + (n + 2) * 4 + q), s3 = __ldg(ea.su + (n + 3) * 4 + q);
+    float4 o;
+    o.x = fmaxf(fmaf(lo.x, s0, tt.x), 0.f) + fmaxf(acc.x + bb.x, 0.f);
+    o.y = fmaxf(fmaf(lo.y, s1, tt.y), 0.f) + fmaxf(acc.y + bb.y, 0.f);
+    o.z = fmaxf(fmaf(lo.z, s2, tt.z), 0.f) + fmaxf(acc.z + bb.z, 0.f);
+    o.w = fmaxf(fmaf(lo.w, s3, tt.w), 0.f) + fmaxf(acc.w + bb.w, 0.f);
+    return o;
+}
+
 template <int EPI>
 __device__ __forceinline__ float4 apply_epi(float4 acc, int m, int n, int N, const EpiArgs& ea) {
     if (EPI == EPI_SWISH) return swish4(acc);
@@ -140,22 +164,9 @@ __device__ __forceinline__ float4 apply_epi(float4 acc, int m, int n, int N, con
         return swish4(make_float4(acc.x + b.x, acc.y + b.y, acc.z + b.z, acc.w + b.w));
     }
     if (EPI == EPI_IDAUP) {
-        int x = m % ea.Wo;
-        int t = m / ea.Wo;
-        int y = t % ea.Ho;
-        int b = t / ea.Ho;
-        int Hl = ea.Ho >> 1, Wl = ea.Wo >> 1;
-        float4 lo = ldcg4(ea.low + ((size_t)(b * Hl + (y >> 1)) * Wl + (x >> 1)) * N + n);
-        int q = (y & 1) * 2 + (x & 1);
-        float4 bb = ldg4(ea.bias + n), tt = ldg4(ea.tu + n);
-        float s0 = __ldg(ea.su + (n + 0) * 4 + q), s1 = __ldg(ea.su + (n + 1) * 4 + q);
-        float s2 = __ldg(ea.su + (n + 2) * 4 + q), s3 = __ldg(ea.su + (n + 3) * 4 + q);
-        float4 o;
-        o.x = fmaxf(fmaf(lo.x, s0, tt.x), 0.f) + fmaxf(acc.x + bb.x, 0.f);
-        o.y = fmaxf(fmaf(lo.y, s1, tt.y), 0.f) + fmaxf(acc.y + bb.y, 0.f);
-        o.z = fmaxf(fmaf(lo.z, s2, tt.z), 0.f) + fmaxf(acc.z + bb.z, 0.f);
-        o.w = fmaxf(fmaf(lo.w, s3, tt.w), 0.f) + fmaxf(acc.w + bb.w, 0.f);
-        return o;
+        int q;
+        const float4 lo = ldcg4(idaup_low_ptr(m, n, N, ea, &q));
+        return idaup_apply(acc, lo, n, q, ea);
     }
     return acc;
 }

@@ -115,18 +115,25 @@ __global__ void __launch_bounds__(1024) k_topk(const float* __restrict__ pk, con
             }
         }
         __syncthreads();
-        if (tid == 0) {
-            unsigned cum = 0;
-            int sel = 0;
-            for (int bin = 255; bin >= 0; --bin) {
-                if (cum + hist[bin] >= krem) {
-                    sel = bin;
-                    break;
-                }
-                cum += hist[bin];
+        // the bin holding the krem-th largest key: S(bin) = #keys in bins >= bin; pick the one with S >= krem > S - hist[bin]
+        unsigned hbin = 0, suf = 0;
+        if (tid < 256) {
+            hbin = hist[tid];
+            suf = hbin;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const unsigned t = __shfl_down_sync(0xffffffffu, suf, off);
+                if (lane + off < 32) suf += t;
             }
-            s_krem = krem - cum;
-            s_prefix = prefix | ((unsigned)sel << (8 * pass));
+            if (lane == 0) wcnt[warp] = suf;  // this warp's 32 bins
+        }
+        __syncthreads();
+        if (tid < 256) {
+            for (int w2 = warp + 1; w2 < 8; ++w2) suf += wcnt[w2];
+            if (suf >= krem && suf - hbin < krem) {  // exactly one bin (at least krem keys match the prefix)
+                s_krem = krem - (suf - hbin);
+                s_prefix = prefix | ((unsigned)tid << (8 * pass));
+            }
         }
         __syncthreads();
         krem = s_krem;
@@ -139,31 +146,82 @@ __global__ void __launch_bounds__(1024) k_topk(const float* __restrict__ pk, con
     if (tid == 0) s_cnt = 0;
     for (int i = tid; i < 1024; i += 1024) buf[i] = 0ull;
     __syncthreads();
-    unsigned eq_run = 0;
-    for (int base = 0; base < HW; base += 1024) {
-        const int i = base + tid;
-        const bool valid = i < HW;
-        const uint32_t key = valid ? key_at(i) : 0u;
-        const bool gt = valid && key > T;
-        const bool eq = valid && key == T;
-        if (gt) {
-            const unsigned slot = atomicAdd(&s_cnt, 1u);
-            buf[slot] = ((unsigned long long)key << 32) | (0xFFFFFFFFu - (unsigned)i);
+    if (SM) {
+        // winners above the threshold take slots in any order (they are sorted below); ties AT the threshold are admitted
+        // lowest index first: per (row of 1024, warp) tie counts -> block-wide exclusive scan -> rank = base + lane rank
+        unsigned* ecnt = skeys + HWp;  // [rows * 32], rows = HWp / 1024 <= 50
+        const int rows = HWp >> 10;
+        for (int v = 0; v < rows; ++v) {
+            const int i = v * 1024 + tid;
+            const bool valid = i < HW;
+            const uint32_t key = valid ? skeys[i] : 0u;
+            const bool gt = valid && key > T;
+            const unsigned mg = __ballot_sync(0xffffffffu, gt);
+            if (mg) {
+                unsigned basee = 0;
+                if (lane == 0) basee = atomicAdd(&s_cnt, (unsigned)__popc(mg));
+                basee = __shfl_sync(0xffffffffu, basee, 0);
+                if (gt) buf[basee + __popc(mg & ((1u << lane) - 1u))] = ((unsigned long long)key << 32) | (0xFFFFFFFFu - (unsigned)i);
+            }
+            const unsigned me = __ballot_sync(0xffffffffu, valid && key == T);
+            if (lane == 0) ecnt[v * 32 + warp] = __popc(me);
         }
-        const unsigned m = __ballot_sync(0xffffffffu, eq);
-        if (lane == 0) wcnt[warp] = __popc(m);
         __syncthreads();
-        unsigned woff = 0, tot = 0;
+        {   // exclusive scan of ecnt[0 .. rows*32) in place: thread t owns entries 2t, 2t+1
+            const int n = rows * 32;
+            const unsigned a = 2 * tid < n ? ecnt[2 * tid] : 0u, b2 = 2 * tid + 1 < n ? ecnt[2 * tid + 1] : 0u;
+            unsigned inc = a + b2;
 #pragma unroll
-        for (int w2 = 0; w2 < 32; ++w2) {
-            const unsigned c = wcnt[w2];
-            woff += (w2 < warp) ? c : 0u;
-            tot += c;
+            for (int off = 1; off < 32; off <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, inc, off);
+                if (lane >= off) inc += t;
+            }
+            if (lane == 31) wcnt[warp] = inc;
+            __syncthreads();
+            unsigned woff = 0;
+            for (int w2 = 0; w2 < warp; ++w2) woff += wcnt[w2];
+            const unsigned excl = woff + inc - (a + b2);
+            if (2 * tid < n) ecnt[2 * tid] = excl;
+            if (2 * tid + 1 < n) ecnt[2 * tid + 1] = excl + a;
+            __syncthreads();
         }
-        const unsigned rank = eq_run + woff + __popc(m & ((1u << lane) - 1u));
-        if (eq && rank < krem) buf[G + rank] = ((unsigned long long)key << 32) | (0xFFFFFFFFu - (unsigned)i);
-        eq_run += tot;
+        for (int v = 0; v < rows; ++v) {
+            const unsigned base_rank = ecnt[v * 32 + warp];
+            if (base_rank >= krem) break;  // ranks only grow with the index (warp-uniform)
+            const int i = v * 1024 + tid;
+            const bool eq = i < HW && skeys[i] == T;
+            const unsigned me = __ballot_sync(0xffffffffu, eq);
+            const unsigned rank = base_rank + __popc(me & ((1u << lane) - 1u));
+            if (eq && rank < krem) buf[G + rank] = ((unsigned long long)T << 32) | (0xFFFFFFFFu - (unsigned)i);
+        }
         __syncthreads();
+    } else {
+        unsigned eq_run = 0;
+        for (int base = 0; base < HW; base += 1024) {
+            const int i = base + tid;
+            const bool valid = i < HW;
+            const uint32_t key = valid ? key_at(i) : 0u;
+            const bool gt = valid && key > T;
+            const bool eq = valid && key == T;
+            if (gt) {
+                const unsigned slot = atomicAdd(&s_cnt, 1u);
+                buf[slot] = ((unsigned long long)key << 32) | (0xFFFFFFFFu - (unsigned)i);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, eq);
+            if (lane == 0) wcnt[warp] = __popc(m);
+            __syncthreads();
+            unsigned woff = 0, tot = 0;
+    #pragma unroll
+            for (int w2 = 0; w2 < 32; ++w2) {
+                const unsigned c = wcnt[w2];
+                woff += (w2 < warp) ? c : 0u;
+                tot += c;
+            }
+            const unsigned rank = eq_run + woff + __popc(m & ((1u << lane) - 1u));
+            if (eq && rank < krem) buf[G + rank] = ((unsigned long long)key << 32) | (0xFFFFFFFFu - (unsigned)i);
+            eq_run += tot;
+            __syncthreads();
+        }
     }
     int P = 1;
     while (P < K) P <<= 1;
@@ -200,11 +258,12 @@ inline cudaError_t launch_topk(const float* pk, const float* wh, const float* re
     if (HW <= TOPK_SMEM_MAX_HW) {
         static bool attr_done = false;
         if (!attr_done) {
-            cudaError_t e = cudaFuncSetAttribute(k_topk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOPK_SMEM_MAX_HW * 4);
+            cudaError_t e = cudaFuncSetAttribute(k_topk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (TOPK_SMEM_MAX_HW + TOPK_SMEM_MAX_HW / 32) * 4);
             if (e != cudaSuccess) return e;
             attr_done = true;
         }
-        return launch_pdl(k_topk<true>, dim3(B), dim3(1024), (size_t)HW * 4, s, pk, wh, reg, H, W, K, dets, inds);
+        const size_t HWp = ((size_t)HW + 1023) & ~(size_t)1023;
+        return launch_pdl(k_topk<true>, dim3(B), dim3(1024), (HWp + HWp / 32) * 4, s, pk, wh, reg, H, W, K, dets, inds);
     }
     return launch_pdl(k_topk<false>, dim3(B), dim3(1024), 0, s, pk, wh, reg, H, W, K, dets, inds);
 }

@@ -3,7 +3,7 @@
 // The register/L1 kernels (k_dw, k_dw3 in k_conv.cuh) are latency-bound: ncu shows 48 % of their warp stalls on
 // the long scoreboard at 36 % of DRAM peak -- a thread can keep only a handful of 16-byte loads in flight.  Here the
 // loads are bulk tensor copies: a CTA walks over (image, 10x10 output tile, 32-channel chunk) items, one elected
-// thread keeps NST halo tiles in flight with cp.async.bulk.tensor.4d (box = 32 channels x IW x IH, SWIZZLE_128B,
+// thread keeps NST halo tiles in flight with cp.async.bulk.tensor.4d (box = 32 channels x IW x IH, no swizzle,
 // zero fill outside the image = the reference's ZeroPad2d, model/centernet.py:63-70), and all 256 threads compute
 // from shared memory with the same 2x2-output register blocking as the fused kernel (xd_dw_phase_g).  Bytes in flight
 // per SM = NST x tile (up to ~190 KB) instead of a few KB of registers.
@@ -32,6 +32,7 @@ struct DwtParams {
     XdParams x;  // We unused; hid = C
     int nchunk;  // ceil(C / 32); TMA zero-fills the channels past C in the last chunk
     int nst;     // pipeline stages
+    int dbg;     // development only (env CF_DWT_DEBUG): 1 = skip the compute phase (TMA streaming rate of the tiling)
 };
 
 template <int KS, int S, int GEOM>
@@ -55,37 +56,41 @@ __global__ void __launch_bounds__(DWT_THREADS, 2) k_dwt(const __grid_constant__ 
     __syncthreads();
     pdl_wait();
 
-    // item = ((b * tiles_y + ty) * tiles_x + tx) * nchunk + chunk : chunks of one tile are adjacent
-    auto issue = [&](int item, int stage) {  // thread 0 only
-        const int ch = item % P.nchunk;
-        int t = item / P.nchunk;
-        const int tx = t % p.tiles_x;
-        t /= p.tiles_x;
-        const int ty = t % p.tiles_y, b = t / p.tiles_y;
-        mbar_expect_tx(bars + 8 * stage, (uint32_t)G::NPX * 128u);
-        tma_load_4d(base + stage * G::XBYTES, &tmX, ch * 32, tx * G::TW * S - G::LO, ty * G::TH * S - G::LO, b, bars + 8 * stage);
-    };
-    if (tid == 0)
-        for (int i = 0; i < nst; ++i) {
-            const long long item = (long long)blockIdx.x + (long long)i * gridDim.x;
-            if (item < p.n_items) issue((int)item, i);
-        }
-    uint32_t it = 0;
-    for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
-        const int stage = (int)(it % (uint32_t)nst);
-        mbar_wait(bars + 8 * stage, (it / (uint32_t)nst) & 1u);
+    // item = ((b * tiles_y + ty) * tiles_x + tx) * nchunk + chunk : chunks of one tile are adjacent.
+    // Thread 0 decodes an item once, when it issues the item's TMA, and leaves (chunk, tx, ty, b) beside the barriers; the
+    // other 255 threads read it after the barrier wait instead of repeating three integer divisions each (the SASS of the
+    // previous version spent ~35 % of its instructions per item on that decode).
+    int4* info = reinterpret_cast<int4*>(sm + (size_t)nst * G::XBYTES + 64);  // [nst], after the 8 barriers
+    auto issue = [&](long long item, int stage) {  // thread 0 only
         const int ch = (int)(item % P.nchunk);
         int t = (int)(item / P.nchunk);
         const int tx = t % p.tiles_x;
         t /= p.tiles_x;
         const int ty = t % p.tiles_y, b = t / p.tiles_y;
+        info[stage] = make_int4(ch, tx, ty, b);
+        mbar_expect_tx(bars + 8 * stage, (uint32_t)G::NPX * 128u);  // release: orders the info store before the phase flip
+        tma_load_4d(base + stage * G::XBYTES, &tmX, ch * 32, tx * G::TW * S - G::LO, ty * G::TH * S - G::LO, b, bars + 8 * stage);
+    };
+    if (tid == 0)
+        for (int i = 0; i < nst; ++i) {
+            const long long item = (long long)blockIdx.x + (long long)i * gridDim.x;
+            if (item < p.n_items) issue(item, i);
+        }
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        mbar_wait(bars + 8 * stage, phase);
+        const int4 inf = info[stage];
+        const int ch = inf.x, tx = inf.y, ty = inf.z, b = inf.w;
         const int cbase = ch * 32 + c4 * 4;
-        xd_dw_phase_g<G, KS, S, 2, 2, true, DWT_THREADS / 32>(sm + stage * G::XBYTES, p.Wd, p, warp, pg, c4, cbase, cbase < p.hid, b, ty, tx);
-        __syncthreads();  // every thread is done with this stage: refill it
+        if (!(P.dbg & 1))
+            xd_dw_phase_g<G, KS, S, 2, 2, true, DWT_THREADS / 32, false>(sm + stage * G::XBYTES, p.Wd, p, warp, pg, c4, cbase, cbase < p.hid, b, ty, tx);
+        __syncthreads();  // every thread is done with this stage (and has read its info): refill it
         if (tid == 0) {
             const long long nxt = item + (long long)nst * gridDim.x;
-            if (nxt < p.n_items) issue((int)nxt, stage);
+            if (nxt < p.n_items) issue(nxt, stage);
         }
+        if (++stage == nst) stage = 0, phase ^= 1u;
     }
 }
 
@@ -166,7 +171,7 @@ inline int dwt_plan(PwTcState& st, int ks, int s, const float* X, const float* W
     if (iw > 256 || ih > 256 || xb + 2048 > TC_SMEM_MAX) {  // TMA box limit / one stage must fit
         return fail(CF_EINVAL, "dwt_plan: tile geometry %d does not fit (halo %dx%d)", geom, ih, iw);
     }
-    int rc = xd_make_map(st, &dl->tmX, X, B, Hi, Wi, C, iw, ih);
+    int rc = xd_make_map(st, &dl->tmX, X, B, Hi, Wi, C, iw, ih, /*swizzle=*/false);
     if (rc) return rc;
     XdParams& p = dl->p.x;
     p.We = nullptr;
@@ -199,7 +204,9 @@ inline int dwt_plan(PwTcState& st, int ks, int s, const float* X, const float* W
     }
     if (nst < 1) return fail(CF_EINVAL, "dwt_plan: tile does not fit shared memory");
     dl->p.nst = nst;
-    dl->smem = (size_t)nst * xb + 64 + 1024;
+    dl->p.dbg = 0;
+    if (const char* ev = getenv("CF_DWT_DEBUG")) dl->p.dbg = atoi(ev);
+    dl->smem = (size_t)nst * xb + 64 + 8 * 16 + 1024;  // stages | 8 barriers | 8 item records | alignment slack
     dl->ks = ks;
     dl->s = s;
     dl->geom = geom;

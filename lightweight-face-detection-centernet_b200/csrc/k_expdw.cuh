@@ -59,7 +59,10 @@ struct XdDwShape {
     static constexpr int YT = (S == 1) ? 2 : 1;
 };
 
-template <typename G, int KS, int S, int XT, int YT, bool WD_GLOBAL, int NWARPS>
+// SWZ: the halo tile is in the TMA's SWIZZLE_128B layout (needed where the tile doubles as a tcgen05 operand).  A quarter
+// warp (8 lanes = the 8 channel vectors of one pixel) reads one whole 128-byte pixel row per LDS.128 wavefront, which is
+// bank-conflict free with or without the swizzle; without it every window address is base + an immediate.
+template <typename G, int KS, int S, int XT, int YT, bool WD_GLOBAL, int NWARPS, bool SWZ = true>
 __device__ __forceinline__ void xd_dw_phase_g(const uint8_t* Es, const float* Wd_s, const XdParams& p, int warp, int pg, int c4,
                                               int cbase, bool cvalid, int b, int ty, int tx) {
     constexpr int NBX = G::TW / XT, NBLK = (G::TH / YT) * NBX;
@@ -81,7 +84,8 @@ __device__ __forceinline__ void xd_dw_phase_g(const uint8_t* Es, const float* Wd
 #pragma unroll
             for (int cc = 0; cc < NCOL; ++cc) {
                 const int px = (r0 + rr) * G::IW + q0 + cc;
-                win[cc] = *reinterpret_cast<const float4*>(Es + px * 128 + ((c4 ^ (px & 7)) << 4));
+                win[cc] = SWZ ? *reinterpret_cast<const float4*>(Es + px * 128 + ((c4 ^ (px & 7)) << 4))
+                              : *reinterpret_cast<const float4*>(Es + px * 128 + (c4 << 4));
             }
             if (rr < KS) {
 #pragma unroll
@@ -100,13 +104,14 @@ __device__ __forceinline__ void xd_dw_phase_g(const uint8_t* Es, const float* Wd
                 }
             }
         }
+        const int yo0 = ty * G::TH + YT * by, xo0 = tx * G::TW + XT * bx;
+        float* o0 = p.D + ((size_t)(b * p.Ho + yo0) * p.Wo + xo0) * p.hid + cbase;  // one 64-bit address per block
+        const int rstride = p.Wo * p.hid;
 #pragma unroll
         for (int dy = 0; dy < YT; ++dy)
 #pragma unroll
             for (int dx = 0; dx < XT; ++dx) {
-                const int yo = ty * G::TH + YT * by + dy, xo = tx * G::TW + XT * bx + dx;
-                if (yo < p.Ho && xo < p.Wo)
-                    st4(p.D + ((size_t)(b * p.Ho + yo) * p.Wo + xo) * p.hid + cbase, swish4(acc[dy][dx]));
+                if (yo0 + dy < p.Ho && xo0 + dx < p.Wo) st4(o0 + dy * rstride + dx * p.hid, swish4(acc[dy][dx]));
             }
     }
 }
@@ -374,13 +379,13 @@ __global__ void __launch_bounds__(XD_THREADS, 1) k_expdw_tc(const __grid_constan
 
 // ---- host side --------------------------------------------------------------------------
 // fp32 NHWC tensor [B][H][W][C]: box {32 channels (zero filled past C), IW, IH, 1}, SWIZZLE_128B
-inline int xd_make_map(PwTcState& st, CUtensorMap* map, const float* ptr, int B, int H, int W, int C, int IW, int IH) {
+inline int xd_make_map(PwTcState& st, CUtensorMap* map, const float* ptr, int B, int H, int W, int C, int IW, int IH, bool swizzle = true) {
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
     cuuint32_t box[4] = {32, (cuuint32_t)IW, (cuuint32_t)IH, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = ((PFN_encodeTiled)st.encode)(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box, estr,
-                                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                              CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(CF_ECUDA, "cuTensorMapEncodeTiled(4D %dx%dx%dx%d) failed with CUresult %d", B, H, W, C, (int)r);
     return CF_OK;

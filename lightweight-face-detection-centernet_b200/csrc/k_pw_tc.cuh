@@ -65,8 +65,12 @@ struct TcParams {
     float* out;      // [M][N] (direct stores)
     int nacc;        // TMEM accumulator stages (2 or 4); stage stride = acc_stride columns
     uint32_t acc_stride;
-    int atmem;       // 1: narrow layers (NC <= 64): the split A operand is handed to the tensor core in TMEM
-                     //    (tcgen05.st by the splitter warps) instead of shared memory
+    int atmem;       // 1: the split A operand is handed to the tensor core in TMEM (tcgen05.st by the splitter warps)
+                     //    instead of shared memory: NC <= 64 (accumulators in columns [0,256), four A slots above) or
+                     //    NC <= 96 (two accumulator pairs in [0,384), two A slots above)
+    uint32_t acol;   // first TMEM column of the A ring
+    uint32_t amask;  // A ring slots - 1 (1 or 3)
+    uint32_t ashift; // log2(A ring slots)
     int dbg;         // development only (env CF_TC_DEBUG): 1 skip the A split, 2 skip the stores, 4 skip the MMAs
     int stages;
     uint32_t stage_bytes, a_bytes_stage, b_bytes_block;  // b_bytes_block = NC*128*(passes==3?2:1)
@@ -249,7 +253,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const uint32_t bar_bres = bar_tempty + 32;               // [1]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + p.off_bars + 24 * TC_MAX_STAGES + 80);
     const uint32_t bar_aready = bars + 24 * TC_MAX_STAGES + 96, bar_aempty = bar_aready + 32;  // [4] each: TMEM A ring (atmem)
-    constexpr uint32_t kATmemCol = 256;  // accumulators use columns [0,256), the A ring 4 x (32 hi + 32 lo) above
+    const uint32_t kATmemCol = p.acol;  // accumulators below, the A ring of (32 hi + 32 lo)-column slots from here
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -347,8 +351,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 const uint32_t idesc2 = umma_idesc_tf32(2 * p.NC);
                 for (int kb = 0; kb < nkb; ++kb) {
                     if (kPasses == 3 && p.atmem) {
-                        const uint32_t aslot = acnt & 3u;
-                        mbar_wait(bar_aready + 8 * aslot, (acnt >> 2) & 1u);
+                        const uint32_t aslot = acnt & p.amask;
+                        mbar_wait(bar_aready + 8 * aslot, (acnt >> p.ashift) & 1u);
                         tc_fence_after();
                         const uint32_t sb = p.resident ? bres + (uint32_t)((p.resident == 2 ? 0 : ch * nkb) + kb) * p.b_bytes_block
                                                        : stages0 + stage * p.stage_bytes + p.a_bytes_stage;
@@ -406,7 +410,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     if (p.atmem) {
                         // thread = one row of the 128 x 32 A block: read it from the TMA's swizzled image, split it and
                         // store both halves into this warp's TMEM lane quarter
-                        const uint32_t aslot = acnt & 3u;
+                        const uint32_t aslot = acnt & p.amask;
                         mbar_wait(bar_full + 8 * stage, phase);
                         const int q = warp & 3, row = q * 32 + lane;
                         const uint8_t* ar = base_ptr + p.off_stages + stage * p.stage_bytes + row * 128;
@@ -418,7 +422,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                             lo[4 * j] = v.x - hi[4 * j], lo[4 * j + 1] = v.y - hi[4 * j + 1], lo[4 * j + 2] = v.z - hi[4 * j + 2],
                                    lo[4 * j + 3] = v.w - hi[4 * j + 3];
                         }
-                        mbar_wait(bar_aempty + 8 * aslot, ((acnt >> 2) & 1u) ^ 1u);
+                        mbar_wait(bar_aempty + 8 * aslot, ((acnt >> p.ashift) & 1u) ^ 1u);
                         tc_fence_after();
                         const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + kATmemCol + aslot * 64u;
                         tmem_st32(ta, hi);
@@ -730,10 +734,13 @@ inline int tc_plan(PwTcState& st, int passes, int epi, const float* A, const flo
     // narrow layers: A operand through TMEM (both accumulator pairs fit columns [0,256), the A ring sits above them)
     const TcTune tune = tc_tune_for(K, N, passes);
     p.atmem = (passes == 3 && L.NC <= 64) ? 1 : 0;
-    if (tune.atmem >= 0) p.atmem = (tune.atmem != 0 && passes == 3 && L.NC <= 64) ? 1 : 0;
+    if (tune.atmem >= 0) p.atmem = (tune.atmem != 0 && passes == 3 && L.NC <= 96) ? 1 : 0;
     p.a_bytes_stage = p.atmem ? TC_A_BYTES : TC_A_BYTES * hl;
+    p.acol = L.NC <= 64 ? 256u : 384u;
+    p.amask = L.NC <= 64 ? 3u : 1u;
+    p.ashift = L.NC <= 64 ? 2u : 1u;
     {   // accumulator ring: as many (main+correction) pairs as fit the accumulator columns, 2 or 4
-        const uint32_t acc_cols = p.atmem ? 256u : 512u, pair = (passes == 3 ? 2u : 1u) * (uint32_t)L.NC;
+        const uint32_t acc_cols = p.atmem ? p.acol : 512u, pair = (passes == 3 ? 2u : 1u) * (uint32_t)L.NC;
         p.nacc = (4u * pair <= acc_cols) ? 4 : 2;
         if (tune.nacc) p.nacc = tune.nacc == 4 && 4u * pair <= acc_cols ? 4 : 2;
         p.acc_stride = acc_cols / (uint32_t)p.nacc;
@@ -802,15 +809,18 @@ inline const TcTuneEntry* tc_tuned_table(int* n) {
         t.nc = nc, t.atmem = atmem, t.direct = direct, t.rchunk = rchunk;
         return t;
     };
-    // us per launch, cost-model plan -> this plan (gpurun_out/r2e_tc_tune.jsonl)
+    // us per launch, cost-model plan -> this plan (gpurun_out/r2e_tc_tune.jsonl, r2h_tc_tune.jsonl).  The wide stride-16/32
+    // layers all want 96-column chunks with the A operand through TMEM: the shared-memory stage shrinks from 56-64 KB to
+    // 40 KB, i.e. four pipeline stages instead of two (these kernels are hand-off-latency bound, not L2 or tensor bound).
     static const TcTuneEntry tab[] = {
         {24, 144, mk(64, 1, 0, -1)},    // layer1.1 / layer2.0 expand   145.1 -> 139.5
         {384, 64, mk(0, -1, 0, -1)},    // layer3.1 project              34.2 -> 32.3
-        {384, 96, mk(96, -1, 1, -1)},   // layer4.0 project              40.1 -> 37.5
-        {96, 576, mk(128, -1, 0, 0)},   // layer4.1 / layer5.0 expand    60.8 -> 53.1
-        {576, 96, mk(96, -1, 1, -1)},   // layer4.1 project              64.1 -> 55.3
-        {960, 160, mk(96, -1, 1, -1)},  // layer5.1 project              57.2 -> 55.4
-        {960, 320, mk(128, -1, 1, 0)},  // layer6.0 project              77.1 -> 73.3
+        {384, 96, mk(96, 1, 0, -1)},    // layer4.0 project              40.1 -> 30.7
+        {96, 576, mk(96, 1, 0, 0)},     // layer4.1 / layer5.0 expand    60.8 -> 47.7
+        {576, 96, mk(96, 1, 0, -1)},    // layer4.1 project              64.1 -> 48.4
+        {576, 160, mk(96, 1, 0, -1)},   // layer5.0 project              32.4 -> 28.8
+        {960, 160, mk(96, 1, 0, -1)},   // layer5.1 project              57.2 -> 48.7
+        {960, 320, mk(96, 1, 0, 0)},    // layer6.0 project              77.1 -> 66.4
     };
     *n = (int)(sizeof(tab) / sizeof(tab[0]));
     return tab;

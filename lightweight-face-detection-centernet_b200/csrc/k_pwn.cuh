@@ -105,6 +105,20 @@ __global__ void __launch_bounds__(PWN_THREADS, 2) k_pwn(const __grid_constant__ 
         // ---- split: this thread's 16 elements of row (32q + lane) -> tf32 hi / lo -> TMEM ----
         mbar_wait(bars + 8 * stage, (uint32_t)(j / nst) & 1u);
         const int row = q * 32 + lane;
+        // IDAUp: this thread's low-resolution operands are fetched now, so the L2 latency runs under the split -> MMA chain
+        // instead of after the accumulator wait (up3: 90 us per launch against 48 us for the same GEMM with a linear epilogue)
+        float4 lowv[4];
+        int lowq = 0;
+        if (EPI == EPI_IDAUP && kb == 0) {
+            const int grow0 = tile * TC_BM + row;
+            if (grow0 < p.M) {
+                const int c00 = half * (p.NC >> 1);
+                const float* lp = idaup_low_ptr(grow0, c00, p.N, p.ea, &lowq);
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    if (g * 4 < (p.NC >> 1) && c00 + 4 * g < p.N) lowv[g] = ldcg4(lp + 4 * g);
+            }
+        }
         const uint8_t* ar = sm + stage * TC_A_BYTES + row * 128;
         float hi[16], lo[16];
 #pragma unroll
@@ -156,7 +170,8 @@ __global__ void __launch_bounds__(PWN_THREADS, 2) k_pwn(const __grid_constant__ 
                         if (n < p.N) {
                             float4 o = make_float4(v[4 * g] + c[4 * g], v[4 * g + 1] + c[4 * g + 1], v[4 * g + 2] + c[4 * g + 2],
                                                    v[4 * g + 3] + c[4 * g + 3]);
-                            o = apply_epi<EPI>(o, grow, n, p.N, p.ea);
+                            if (EPI == EPI_IDAUP && p.NC <= 32) o = idaup_apply(o, lowv[g], n, lowq, p.ea);  // one 16-column pass per thread
+                            else o = apply_epi<EPI>(o, grow, n, p.N, p.ea);
                             st4(p.out + (size_t)grow * p.N + n, o);
                         }
                     }

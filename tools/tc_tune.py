@@ -49,7 +49,7 @@ def variants(K, N):
     v = []
     for nc in range(32, min(128, n32) + 1, 32):
         for direct in (0, 1):
-            for atmem in ((1, 0) if nc <= 64 else (0,)):
+            for atmem in ((1, 0) if nc <= 96 else (0,)):
                 for rchunk in (1, 0):
                     v.append({"CF_TC_NC": nc, "CF_TC_DIRECT": direct, "CF_TC_ATMEM": atmem, "CF_PWN": 0, "CF_TC_RCHUNK": rchunk})
         if nc <= 64 and K <= 32 and n32 <= nc:
