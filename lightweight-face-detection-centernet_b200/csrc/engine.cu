@@ -276,10 +276,21 @@ int build_plan(cf_engine* e, const void* input, int fmt, int B, int H, int W) {
         float* out = e->stem;
         const long long thr = (long long)B * H2 * W2;
         const unsigned grid = (unsigned)((thr + 127) / 128);
-        // CF_STEM_TC=1: the role-free tcgen05 stem (k_stem_tc.cuh).  Parity-green but slower than the FFMA stem
-        // (255 vs 222 us per 32-image batch: its per-tile split -> MMA -> drain chain is serial), so it is opt-in.
+        // The tensor-core engines run the stem on tcgen05 too (k_stem_tc2: warp-specialised, pipelined; 173 us per 32-image
+        // batch against 199 us for the FFMA stem).  CF_STEM_TC=0 selects the FFMA stem, =1 the role-free first-generation
+        // tcgen05 stem (parity-green, 255 us: its gather -> split -> MMA -> drain chain is serial per tile).
         const char* ev = getenv("CF_STEM_TC");
-        if (engine_is_tc(e->pw_engine) && ev && atoi(ev) == 1) {
+        const int stem_mode = ev ? atoi(ev) : 2;
+        if (engine_is_tc(e->pw_engine) && stem_mode == 2) {
+            StcParams sp;
+            int sgrid = 0;
+            if ((rc = stc_plan(e->tc, e->w["stem.w"], input, lut, out, B, H, W, &sp, &sgrid))) return rc;
+            const int sms = e->tc.sms;
+            if (fmt == CF_IN_U8_HWC)
+                P.push_back({CLS_STEM, [=](cudaStream_t s) { return stc2_launch_t<1>(sp, sms, s); }});
+            else
+                P.push_back({CLS_STEM, [=](cudaStream_t s) { return stc2_launch_t<0>(sp, sms, s); }});
+        } else if (engine_is_tc(e->pw_engine) && stem_mode == 1) {
             StcParams sp;
             int sgrid = 0;
             if ((rc = stc_plan(e->tc, e->w["stem.w"], input, lut, out, B, H, W, &sp, &sgrid))) return rc;

@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(128) k_stem(const void* __restrict__ in, const
                                               const float* __restrict__ lut, float* __restrict__ out,
                                               int B, int H, int W) {
     __shared__ float lut_s[FMT == 1 ? 768 : 1];
+    __shared__ __align__(16) uint8_t stg_s[4][4096];  // per warp: 32 pixels x 128 B, 16-byte chunks XOR-swizzled by row
     pdl_trigger();
     if (FMT == 1) {
         for (int i = threadIdx.x; i < 768; i += 128) lut_s[i] = lut[i];
@@ -71,8 +72,10 @@ __global__ void __launch_bounds__(128) k_stem(const void* __restrict__ in, const
     }
     pdl_wait();  // `out` may still be read by the previous forward's kernels
     const int Ho = H >> 1, Wo = W >> 1;
-    const long long pix = (long long)blockIdx.x * 128 + threadIdx.x;
-    if (pix >= (long long)B * Ho * Wo) return;
+    const long long n_pix = (long long)B * Ho * Wo;
+    const long long pix_raw = (long long)blockIdx.x * 128 + threadIdx.x;
+    const bool live = pix_raw < n_pix;
+    const long long pix = live ? pix_raw : n_pix - 1;  // tail threads recompute the last pixel and store nothing
     const int xo = (int)(pix % Wo);
     const int yo = (int)((pix / Wo) % Ho);
     const int b = (int)(pix / ((long long)Wo * Ho));
@@ -106,10 +109,24 @@ __global__ void __launch_bounds__(128) k_stem(const void* __restrict__ in, const
                 for (int co = 0; co < 32; ++co) acc[co] = fmaf(v[c], sw.w[((ky * 3 + kx) * 3 + c) * 32 + co], acc[co]);
         }
     }
-    float* o = out + (size_t)pix * 32;
+    // A thread owns one pixel = 128 contiguous output bytes; storing them directly makes every STG.128 of a warp touch 32
+    // different lines (16 B each).  Transposed through shared memory, a store instruction writes 4 whole pixels = 512
+    // contiguous bytes (8 lanes per pixel).
+    const int lane = threadIdx.x & 31;
+    uint8_t* stg = stg_s[threadIdx.x >> 5];
 #pragma unroll
     for (int q = 0; q < 8; ++q)
-        st4(o + 4 * q, swish4(make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3])));
+        *reinterpret_cast<float4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+            swish4(make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]));
+    __syncwarp();
+    const long long pix0 = (long long)blockIdx.x * 128 + (threadIdx.x & ~31);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = 4 * i + (lane >> 3), c = lane & 7;
+        const float4 v = *reinterpret_cast<const float4*>(stg + r * 128 + ((c ^ (r & 7)) << 4));
+        if (pix0 + r < n_pix) st4(out + (size_t)(pix0 + r) * 32 + c * 4, v);
+    }
+    (void)live;
 }
 
 // ----------------------------------------------------------------------------------------

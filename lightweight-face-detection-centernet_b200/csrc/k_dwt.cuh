@@ -139,16 +139,17 @@ inline bool dwt_supported(int C) { return C % 4 == 0 && C >= 16; }
 inline int dwt_plan(PwTcState& st, int ks, int s, const float* X, const float* Wd, float* D, int B, int Hi, int Wi, int C, DwtLaunch* dl) {
     if (!dwt_supported(C)) return fail(CF_EINVAL, "dwt_plan: C=%d is not a multiple of 4", C);
     const int Ho = Hi / s, Wo = Wi / s;
-    // Tile geometry per layer, from a sweep on the device at batch 32 @ 640x640 (profiles/r2_tuning.md; us per launch,
-    // 10x10 -> chosen): stride-1 layers take 16x16 tiles with two CTAs x two stages per SM (3x3/32ch 207 -> 150,
-    // 3x3/144ch 258 -> 185, 5x5/192ch 131 -> 113), the 5x5 stride-2 layer 8x16 (207 -> 141); the 3x3 stride-2 layer is
-    // HBM-bound at 6.2 TB/s with any tile and the stride-16/32 maps (40x40, 20x20) are not divisible: both keep 10x10.
+    // Tile geometry per layer, from sweeps on the device at batch 32 @ 640x640 (profiles/r2_tuning.md; us per launch,
+    // 10x10 -> chosen): the 3x3 stride-1 layers take 16x16 tiles with two CTAs x two stages per SM (32ch 174 -> 141,
+    // 144ch 215 -> 167), the 5x5 layers 8x16 (stride 1, 192ch: 118 -> 100; stride 2, 144ch: 138 -> 122); the 3x3 stride-2
+    // layer is TMA/HBM-bound with any tile (209 of its 252 us are the bare tile stream) and the stride-16/32 maps
+    // (40x40, 20x20) are not divisible: both keep 10x10.
     const int gth[5] = {10, 8, 16, 8, 16}, gtw[5] = {10, 16, 16, 32, 32};
     auto divides = [&](int g) {  // ... and one halo tile fits shared memory
         const int hh = (gth[g] - 1) * s + ks, hw = (gtw[g] - 1) * s + ks;
         return Ho % gth[g] == 0 && Wo % gtw[g] == 0 && (size_t)((hh * hw * 128 + 1023) / 1024 * 1024) + 2048 <= (size_t)TC_SMEM_MAX;
     };
-    int geom = (s == 1 && divides(2)) ? 2 : (ks == 5 && divides(1)) ? 1 : 0;
+    int geom = (s == 1 && ks == 3 && divides(2)) ? 2 : (ks == 5 && divides(1)) ? 1 : 0;
     if (const char* ev = getenv("CF_DWT_GEOM")) {  // development probe: geometry index wherever it divides the map
         const int g = atoi(ev);
         if (g == 0) geom = 0;

@@ -191,6 +191,197 @@ __global__ void __launch_bounds__(STC_THREADS, 3) k_stem_tc(const StcParams p) {
     }
 }
 
+// ---- second generation: warp-specialised, pipelined ---------------------------------------------------------------
+// The role-free kernel above runs gather -> split -> TMEM store -> MMA -> drain -> store as ONE serial chain per
+// 128-pixel tile (255 us per batch, slower than the FFMA stem).  Here the chain is a pipeline, as in k_pw_tc:
+//   warps 4-11   two producer sets (tiles alternate between them): thread = one pixel, gathers its 27 inputs (prefetched
+//                one own-tile ahead), normalises, splits into tf32 hi/lo and tcgen05.st's them into a four-slot TMEM ring
+//   warp 1       one lane issues  A_hi.[W_hi|W_lo]  and  A_lo.W_hi  per 8-wide K step into a four-stage accumulator ring
+//   warps 12-19  two drain groups (accumulator stages alternate): tcgen05.ld main + correction, Swish, 128-byte row store
+//   warp 0       loads the 8 KB weight image once; warp 2 owns the TMEM allocation (512 columns, one CTA per SM)
+constexpr int STC2_THREADS = 640;
+constexpr uint32_t STC2_OFF_BARS = STC_OFF_LUT + 768 * 4;
+constexpr uint32_t STC2_OFF_STG = STC2_OFF_BARS + 256;      // 8 drain warps x 4 KB store-transpose tiles
+constexpr size_t STC2_SMEM = STC2_OFF_STG + 8 * 4096 + 1024;
+
+template <int FMT>
+__device__ __forceinline__ uint32_t stc2_gather(const StcParams& p, bool valid, int b, int yo, int xo, uint32_t (&raw)[27]) {
+    uint32_t mask = 0;
+    const bool last_y = (2 * yo + 2 >= p.H), last_x = (2 * xo + 2 >= p.W);
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+        const int ky = k / 9, r = k - ky * 9, kx = r / 3, c = r - kx * 3;
+        raw[k] = 0;
+        const bool ok = valid && !(ky == 2 && last_y) && !(kx == 2 && last_x);
+        if (ok) {
+            if (FMT == 1) raw[k] = __ldg((const uint8_t*)p.in + ((size_t)(b * p.H + 2 * yo + ky) * p.W + 2 * xo + kx) * 3 + c);
+            else raw[k] = __float_as_uint(__ldg((const float*)p.in + ((size_t)(b * 3 + c) * p.H + 2 * yo + ky) * p.W + 2 * xo + kx));
+            mask |= 1u << k;
+        }
+    }
+    return mask;
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(STC2_THREADS, 1) k_stem_tc2(const StcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bsm = base;
+    float* lut_s = reinterpret_cast<float*>(sm + STC_OFF_LUT);
+    const uint32_t bars = base + STC2_OFF_BARS;
+    const uint32_t bar_b = bars;                 // weights landed
+    const uint32_t bar_aready = bars + 8;        // [4] producers -> MMA   (4 warps arrive)
+    const uint32_t bar_aempty = bars + 40;       // [4] MMA -> producers   (tcgen05.commit)
+    const uint32_t bar_tfull = bars + 72;        // [4] MMA -> drain       (tcgen05.commit)
+    const uint32_t bar_tempty = bars + 104;      // [4] drain -> MMA       (4 warps arrive)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + STC2_OFF_BARS + 144);
+    constexpr uint32_t kACol = 256;              // accumulator pairs: 4 x 64 columns in [0,256); A ring: 4 x (32 hi + 32 lo) above
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    pdl_trigger();
+    if (tid == 0) {
+        mbar_init(bar_b, 1);
+        for (int a = 0; a < 4; ++a) {
+            mbar_init(bar_aready + 8 * a, 4);
+            mbar_init(bar_aempty + 8 * a, 1);
+            mbar_init(bar_tfull + 8 * a, 1);
+            mbar_init(bar_tempty + 8 * a, 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (FMT == 1)
+        for (int i = tid; i < 768; i += STC2_THREADS) lut_s[i] = __ldg(p.lut + i);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int n_tiles = p.n_tiles;
+    const int Ho = p.H >> 1, Wo = p.W >> 1;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(bar_b, STC_B_BYTES);
+            bulk_load(bsm, p.bimg, STC_B_BYTES, bar_b);
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(STC_NC), idesc2 = umma_idesc_tf32(2 * STC_NC);
+            mbar_wait(bar_b, 0);
+            const uint64_t b_hi = umma_desc(bsm);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                const uint32_t s4 = it & 3u, ph = (it >> 2) & 1u;
+                mbar_wait(bar_tempty + 8 * s4, ph ^ 1u);
+                mbar_wait(bar_aready + 8 * s4, ph);
+                tc_fence_after();
+                const uint32_t d_main = tmem_base + s4 * 64u, d_corr = d_main + (uint32_t)STC_NC;
+                const uint32_t a_hi = tmem_base + kACol + s4 * 64u, a_lo = a_hi + 32u;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {  // K = 27 -> four 8-wide steps (elements 27..31 are zero on both sides)
+                    const uint64_t ko = (uint64_t)(k * 2);
+                    umma_tf32_ts(d_main, a_hi + 8u * k, b_hi + ko, idesc2, k > 0 ? 1u : 0u);  // main += hi.hi ; corr += hi.lo
+                    umma_tf32_ts(d_corr, a_lo + 8u * k, b_hi + ko, idesc, 1u);                 // corr += lo.hi
+                }
+                umma_commit(bar_aempty + 8 * s4);
+                umma_commit(bar_tfull + 8 * s4);
+            }
+        }
+    } else if (warp >= 4 && warp < 12) {
+        // ================= producers: set 0 = warps 4-7, set 1 = warps 8-11 =================
+        pdl_wait();  // the image may come from the resize kernel
+        const int set = (warp - 4) >> 2, q = warp & 3;
+        const int row = q * 32 + lane;
+        uint32_t raw[27];
+        uint32_t mask = 0;
+        auto gather = [&](int tile) {  // 32-bit index math (stc_plan checks n_pix < 2^31): 64-bit divisions cost ~100 instructions each
+            const unsigned pix = (unsigned)tile * TC_BM + (unsigned)row;
+            const bool valid = pix < (unsigned)p.n_pix;
+            const unsigned t = pix / (unsigned)Wo;
+            const int xo = (int)(pix - t * (unsigned)Wo);
+            const unsigned b = t / (unsigned)Ho;
+            const int yo = (int)(t - b * (unsigned)Ho);
+            mask = stc2_gather<FMT>(p, valid, (int)b, yo, xo, raw);
+        };
+        const int first = (int)blockIdx.x + set * (int)gridDim.x;
+        if (first < n_tiles) gather(first);
+        uint32_t it = (uint32_t)set;
+        for (int tile = first; tile < n_tiles; tile += 2 * (int)gridDim.x, it += 2) {
+            float hi[32], lo[32];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                float v = 0.f;
+                if (k < 27 && (mask & (1u << k))) v = FMT == 1 ? lut_s[(k % 3) * 256 + raw[k]] : __uint_as_float(raw[k]);
+                hi[k] = tf32_hi(v);
+                lo[k] = v - hi[k];
+            }
+            if (tile + 2 * (int)gridDim.x < n_tiles) gather(tile + 2 * (int)gridDim.x);  // in flight while this tile is handed over
+            const uint32_t s4 = it & 3u, ph = (it >> 2) & 1u;
+            mbar_wait(bar_aempty + 8 * s4, ph ^ 1u);
+            tc_fence_after();
+            const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + kACol + s4 * 64u;
+            tmem_st32(ta, hi);
+            tmem_st32(ta + 32u, lo);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_aready + 8 * s4);
+        }
+    } else if (warp >= 12) {
+        // ================= drain: group g = accumulator stages g, g+2 =================
+        pdl_wait();  // `out` may still be read by the previous forward
+        const int g = (warp - 12) >> 2, q = warp & 3;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            if ((int)(it & 1u) != g) continue;
+            const uint32_t s4 = it & 3u, ph = (it >> 2) & 1u;
+            mbar_wait(bar_tfull + 8 * s4, ph);
+            tc_fence_after();
+            float v[32], c[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + s4 * 64u;
+            tmem_ld32(taddr, v);
+            tmem_ld32(taddr + (uint32_t)STC_NC, c);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * s4);  // the accumulator pair is in registers: hand it back
+            // transpose through a per-warp swizzled tile so that one STG.128 writes 4 whole pixels (512 contiguous bytes)
+            uint8_t* stg = sm + STC2_OFF_STG + (warp - 12) * 4096;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                    swish4(make_float4(v[4 * j] + c[4 * j], v[4 * j + 1] + c[4 * j + 1], v[4 * j + 2] + c[4 * j + 2], v[4 * j + 3] + c[4 * j + 3]));
+            __syncwarp();
+            const long long pix0 = (long long)tile * TC_BM + q * 32;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = 4 * i + (lane >> 3), cc = lane & 7;
+                const float4 x = *reinterpret_cast<const float4*>(stg + r * 128 + ((cc ^ (r & 7)) << 4));
+                if (pix0 + r < p.n_pix) st4(p.out + (size_t)(pix0 + r) * 32 + cc * 4, x);
+            }
+            __syncwarp();
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+template <int FMT>
+inline cudaError_t stc2_launch_t(const StcParams& p, int sms, cudaStream_t s) {
+    const int grid = p.n_tiles < sms ? p.n_tiles : sms;
+    return launch_pdl(k_stem_tc2<FMT>, dim3(grid), dim3(STC2_THREADS), STC2_SMEM, s, p);
+}
+
 template <int FMT>
 inline cudaError_t stc_launch_t(const StcParams& p, int grid, cudaStream_t s) {
     return launch_pdl(k_stem_tc<FMT>, dim3(grid), dim3(STC_THREADS), STC_SMEM, s, p);
@@ -210,6 +401,7 @@ inline int stc_plan(PwTcState& st, const float* key_w, const void* in, const flo
     p->H = H;
     p->W = W;
     p->n_pix = (long long)B * (H / 2) * (W / 2);
+    if (p->n_pix + TC_BM >= (1ll << 31)) return fail(CF_EINVAL, "stc_plan: %lld output pixels exceed the 32-bit index math", p->n_pix);
     p->n_tiles = (int)((p->n_pix + TC_BM - 1) / TC_BM);
     const int want = 3 * st.sms;
     *grid = p->n_tiles < want ? p->n_tiles : want;
