@@ -96,6 +96,8 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+// (A suspend-time hint on try_wait -- CUTLASS passes 0x989680 -- was tried and measured SLOWER here: +2.6 % on the
+// point-wise class; the default try_wait already parks the warp for a short, implementation-defined time.)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     uint64_t t0 = 0;
@@ -114,6 +116,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             else if (t - t0 > 4000000000ull) __trap();
         }
     }
+}
+// One elected lane of a CONVERGENT warp.  tcgen05.mma / commit / TMA instructions are warp-uniform in SASS: issued under
+// `if (lane == 0)` the compiler wraps every one of them in an ELECT + BRA.U.ANY loop with ~10 dependent uniform-datapath
+// instructions around it (measured ~75 cycles per MMA in the single issuing thread); under `if (elect_one())` in
+// convergent code they are emitted back to back.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -288,20 +299,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const int nkb = p.nkb;
 
     if (warp == 0) {
-        // ================= TMA producer =================
-        if (lane == 0) {
-            if (p.resident) {
-                const uint32_t chunk_bytes = (uint32_t)nkb * p.b_bytes_block;
-                const uint32_t total = p.resident == 2 ? chunk_bytes : (uint32_t)p.nchunks * chunk_bytes;
-                const uint8_t* src = reinterpret_cast<const uint8_t*>(p.bimg) +
-                                     (p.resident == 2 ? (size_t)(blockIdx.x % (unsigned)p.nchunks) * chunk_bytes : (size_t)0);
+        // ================= TMA producer: the whole warp walks the loop, one elected lane issues =================
+        if (p.resident) {
+            const uint32_t chunk_bytes = (uint32_t)nkb * p.b_bytes_block;
+            const uint32_t total = p.resident == 2 ? chunk_bytes : (uint32_t)p.nchunks * chunk_bytes;
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.bimg) +
+                                 (p.resident == 2 ? (size_t)(blockIdx.x % (unsigned)p.nchunks) * chunk_bytes : (size_t)0);
+            if (elect_one()) {
                 mbar_expect_tx(bar_bres, total);
                 for (uint32_t off = 0; off < total; off += 32768u) {
                     const uint32_t n = total - off < 32768u ? total - off : 32768u;
                     bulk_load(bres + off, src + off, n, bar_bres);
                 }
             }
-            pdl_wait();  // the weights above depend on nothing; A is the previous kernel's output
+            __syncwarp();
+        }
+        pdl_wait();  // the weights above depend on nothing; A is the previous kernel's output
+        {
             int stage = 0;
             uint32_t phase = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -310,21 +324,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                     const uint32_t sa = stages0 + stage * p.stage_bytes;
                     const uint32_t tx = TC_A_BYTES + (p.resident ? 0u : p.b_bytes_block);
-                    mbar_expect_tx(bar_full + 8 * stage, tx);
-                    tma_load_2d(sa, &tmA, kb * TC_BK, mt * TC_BM, bar_full + 8 * stage);
-                    if (!p.resident)
-                        bulk_load(sa + p.a_bytes_stage,
-                                  reinterpret_cast<const uint8_t*>(p.bimg) + (size_t)(ch * nkb + kb) * p.b_bytes_block,
-                                  p.b_bytes_block, bar_full + 8 * stage);
+                    if (elect_one()) {
+                        mbar_expect_tx(bar_full + 8 * stage, tx);
+                        tma_load_2d(sa, &tmA, kb * TC_BK, mt * TC_BM, bar_full + 8 * stage);
+                        if (!p.resident)
+                            bulk_load(sa + p.a_bytes_stage,
+                                      reinterpret_cast<const uint8_t*>(p.bimg) + (size_t)(ch * nkb + kb) * p.b_bytes_block,
+                                      p.b_bytes_block, bar_full + 8 * stage);
+                    }
+                    __syncwarp();
                     if (++stage == p.stages) stage = 0, phase ^= 1;
                 }
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
+        // ================= MMA issuer: the whole warp walks the loop, one elected lane issues =================
+        {
             const uint32_t idesc = umma_idesc_tf32(p.NC);
-            const uint32_t lo_off = (uint32_t)p.NC * 128u;  // B lo block follows B hi
             if (p.resident) mbar_wait(bar_bres, 0);
             int stage = 0;
             uint32_t phase = 0;
@@ -335,40 +351,48 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 const uint32_t as = it % (uint32_t)p.nacc, aphase = (it / (uint32_t)p.nacc) & 1u;
                 mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
                 tc_fence_after();
-                // 3-pass: the two small cross terms go to their own accumulator (columns +128).  The
+                // 3-pass: the two small cross terms go to their own accumulator (columns +NC).  The
                 // tensor core truncates its fp32 accumulator once per MMA (measured -2^-24 per step,
                 // tools/tc_accum_probe.py); keeping the 2K/8 correction steps out of the main sum
                 // leaves it K/8 truncations instead of 3K/8, and the corrections' own truncation
                 // is 2^-11 smaller.  The epilogue adds the two in fp32 (round-to-nearest).
                 // The correction accumulator sits right behind the main one (columns [NC, 2NC)) and the weight image
                 // stores the hi block right before the lo block, so  A_hi . [B_hi | B_lo]  is ONE MMA of width 2NC
-                // filling both accumulators; only  A_lo . B_hi  needs a second one.  For the narrow layers (N <= 64)
-                // an MMA is bound by streaming its 128 x 32 B A operand out of shared memory (measured ~60 cycles
-                // per instruction whatever N is, tools/tc_shape_probe.py), so two MMAs per K step instead of three
-                // is a third off the tensor-pipe time.
-                const uint32_t d_tmem = tmem_base + as * p.acc_stride;  // atmem: accumulators in [0,256), A ring above
+                // filling both accumulators; only  A_lo . B_hi  needs a second one.
+                const uint32_t d_tmem = tmem_base + as * p.acc_stride;  // atmem: accumulators below acol, A ring above
                 const uint32_t d_corr = d_tmem + (uint32_t)p.NC;
                 const uint32_t idesc2 = umma_idesc_tf32(2 * p.NC);
                 for (int kb = 0; kb < nkb; ++kb) {
+                    const int krem = p.K - kb * TC_BK;
+                    const int nks = krem >= TC_BK ? TC_BK / 8 : (krem + 7) / 8;
+                    const uint32_t first = kb > 0 ? 1u : 0u;
                     if (kPasses == 3 && p.atmem) {
                         const uint32_t aslot = acnt & p.amask;
                         mbar_wait(bar_aready + 8 * aslot, (acnt >> p.ashift) & 1u);
                         tc_fence_after();
                         const uint32_t sb = p.resident ? bres + (uint32_t)((p.resident == 2 ? 0 : ch * nkb) + kb) * p.b_bytes_block
                                                        : stages0 + stage * p.stage_bytes + p.a_bytes_stage;
-                        const int krem = p.K - kb * TC_BK;
-                        const int nks = krem >= TC_BK ? TC_BK / 8 : (krem + 7) / 8;
                         const uint64_t b_hi = umma_desc(sb);
                         const uint32_t a_hi = tmem_base + kATmemCol + aslot * 64u, a_lo = a_hi + 32u;
-                        for (int k = 0; k < nks; ++k) {
-                            const uint64_t ko = (uint64_t)(k * 2);
-                            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-                            umma_tf32_ts(d_tmem, a_hi + 8u * k, b_hi + ko, idesc2, acc);
-                            umma_tf32_ts(d_corr, a_lo + 8u * k, b_hi + ko, idesc, 1u);
+                        if (elect_one()) {
+                            if (nks == 4 && !(p.dbg & 4)) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    umma_tf32_ts(d_tmem, a_hi + 8u * k, b_hi + (uint64_t)(k * 2), idesc2, k > 0 ? 1u : first);  // main += hi.hi ; corr += hi.lo
+                                    umma_tf32_ts(d_corr, a_lo + 8u * k, b_hi + (uint64_t)(k * 2), idesc, 1u);                   // corr += lo.hi
+                                }
+                            } else {
+                                for (int k = 0; k < nks; ++k) {
+                                    if ((p.dbg & 4) && !(kb == 0 && k == 0)) break;
+                                    umma_tf32_ts(d_tmem, a_hi + 8u * k, b_hi + (uint64_t)(k * 2), idesc2, k > 0 ? 1u : first);
+                                    umma_tf32_ts(d_corr, a_lo + 8u * k, b_hi + (uint64_t)(k * 2), idesc, 1u);
+                                }
+                            }
+                            umma_commit(bar_aempty + 8 * aslot);
+                            if (!p.resident) umma_commit(bar_empty + 8 * stage);
+                            if (kb == nkb - 1) umma_commit(bar_tfull + 8 * as);
                         }
-                        umma_commit(bar_aempty + 8 * aslot);
-                        if (!p.resident) umma_commit(bar_empty + 8 * stage);
-                        if (kb == nkb - 1) umma_commit(bar_tfull + 8 * as);
+                        __syncwarp();
                         ++acnt;
                         if (++stage == p.stages) stage = 0, phase ^= 1;
                         continue;
@@ -378,23 +402,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     const uint32_t sa = stages0 + stage * p.stage_bytes;
                     const uint32_t sb = p.resident ? bres + (uint32_t)((p.resident == 2 ? 0 : ch * nkb) + kb) * p.b_bytes_block
                                                    : sa + p.a_bytes_stage;
-                    const int krem = p.K - kb * TC_BK;
-                    const int nks = krem >= TC_BK ? TC_BK / 8 : (krem + 7) / 8;
                     const uint64_t a_hi = umma_desc(sa), b_hi = umma_desc(sb);
-                    for (int k = 0; k < nks; ++k) {
-                        if ((p.dbg & 4) && !(kb == 0 && k == 0)) break;
-                        const uint64_t ko = (uint64_t)(k * 2);  // +32 bytes along K, in 16-byte units
-                        const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-                        if (kPasses == 3) {
-                            const uint64_t a_lo = umma_desc(sa + TC_A_BYTES);
-                            umma_tf32(d_tmem, a_hi + ko, b_hi + ko, idesc2, acc);  // main += hi.hi ; corr += hi.lo
-                            umma_tf32(d_corr, a_lo + ko, b_hi + ko, idesc, 1u);    // corr += lo.hi
+                    const uint64_t a_lo = umma_desc(sa + TC_A_BYTES);
+                    if (elect_one()) {
+                        if (nks == 4 && !(p.dbg & 4)) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const uint64_t ko = (uint64_t)(k * 2);  // +32 bytes along K, in 16-byte units
+                                if (kPasses == 3) {
+                                    umma_tf32(d_tmem, a_hi + ko, b_hi + ko, idesc2, k > 0 ? 1u : first);  // main += hi.hi ; corr += hi.lo
+                                    umma_tf32(d_corr, a_lo + ko, b_hi + ko, idesc, 1u);                   // corr += lo.hi
+                                } else {
+                                    umma_tf32(d_tmem, a_hi + ko, b_hi + ko, idesc, k > 0 ? 1u : first);
+                                }
+                            }
                         } else {
-                            umma_tf32(d_tmem, a_hi + ko, b_hi + ko, idesc, acc);
+                            for (int k = 0; k < nks; ++k) {
+                                if ((p.dbg & 4) && !(kb == 0 && k == 0)) break;
+                                const uint64_t ko = (uint64_t)(k * 2);
+                                if (kPasses == 3) {
+                                    umma_tf32(d_tmem, a_hi + ko, b_hi + ko, idesc2, k > 0 ? 1u : first);
+                                    umma_tf32(d_corr, a_lo + ko, b_hi + ko, idesc, 1u);
+                                } else {
+                                    umma_tf32(d_tmem, a_hi + ko, b_hi + ko, idesc, k > 0 ? 1u : first);
+                                }
+                            }
                         }
+                        umma_commit(bar_empty + 8 * stage);  // frees the smem slot when these MMAs retire
+                        if (kb == nkb - 1) umma_commit(bar_tfull + 8 * as);
                     }
-                    umma_commit(bar_empty + 8 * stage);  // frees the smem slot when these MMAs retire
-                    if (kb == nkb - 1) umma_commit(bar_tfull + 8 * as);
+                    __syncwarp();
                     if (++stage == p.stages) stage = 0, phase ^= 1;
                 }
             }
@@ -417,6 +454,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                         float hi[32], lo[32];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
+                            if (p.dbg & 1) break;  // development probe: garbage operand, no smem reads / split math
                             const float4 v = *reinterpret_cast<const float4*>(ar + ((j ^ (row & 7)) << 4));
                             hi[4 * j] = tf32_hi(v.x), hi[4 * j + 1] = tf32_hi(v.y), hi[4 * j + 2] = tf32_hi(v.z), hi[4 * j + 3] = tf32_hi(v.w);
                             lo[4 * j] = v.x - hi[4 * j], lo[4 * j + 1] = v.y - hi[4 * j + 1], lo[4 * j + 2] = v.z - hi[4 * j + 2],
@@ -425,9 +463,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                         mbar_wait(bar_aempty + 8 * aslot, ((acnt >> p.ashift) & 1u) ^ 1u);
                         tc_fence_after();
                         const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + kATmemCol + aslot * 64u;
-                        tmem_st32(ta, hi);
-                        tmem_st32(ta + 32u, lo);
-                        tmem_st_wait();
+                        if (!(p.dbg & 8)) {  // development probe 8: no TMEM stores either
+                            tmem_st32(ta, hi);
+                            tmem_st32(ta + 32u, lo);
+                            tmem_st_wait();
+                        }
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) {

@@ -135,21 +135,33 @@ __global__ void __launch_bounds__(PWN_THREADS, 2) k_pwn(const __grid_constant__ 
         tmem_st_wait();
         tc_fence_before();
         __syncthreads();  // the A block is in TMEM, the smem stage is drained
-        if (tid == 0) {
-            if (j + nst < total) issue_a(j + nst);
+        if (warp == 0) {  // convergent after the barrier: one elected lane issues (see elect_one)
             if (j == 0) mbar_wait(bar_b, 0);
             tc_fence_after();
             const uint64_t b_hi = umma_desc(bsm + (uint32_t)kb * blk_bytes);
             const uint32_t a_hi = tmem_base + kACol + aslot * 64u, a_lo = a_hi + 32u;
             const int krem = p.K - kb * TC_BK;
             const int nks = krem >= TC_BK ? TC_BK / 8 : (krem + 7) / 8;
-            for (int k = 0; k < nks; ++k) {
-                const uint64_t ko = (uint64_t)(k * 2);
-                umma_tf32_ts(d_main, a_hi + 8u * k, b_hi + ko, idesc2, (kb > 0 || k > 0) ? 1u : 0u);  // main += hi.hi ; corr += hi.lo
-                umma_tf32_ts(d_corr, a_lo + 8u * k, b_hi + ko, idesc, 1u);                              // corr += lo.hi
+            if (elect_one()) {
+                if (j + nst < total) issue_a(j + nst);
+                if (nks == 4) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t ko = (uint64_t)(k * 2);
+                        umma_tf32_ts(d_main, a_hi + 8u * k, b_hi + ko, idesc2, (kb > 0 || k > 0) ? 1u : 0u);  // main += hi.hi ; corr += hi.lo
+                        umma_tf32_ts(d_corr, a_lo + 8u * k, b_hi + ko, idesc, 1u);                              // corr += lo.hi
+                    }
+                } else {
+                    for (int k = 0; k < nks; ++k) {
+                        const uint64_t ko = (uint64_t)(k * 2);
+                        umma_tf32_ts(d_main, a_hi + 8u * k, b_hi + ko, idesc2, (kb > 0 || k > 0) ? 1u : 0u);
+                        umma_tf32_ts(d_corr, a_lo + 8u * k, b_hi + ko, idesc, 1u);
+                    }
+                }
+                umma_commit(bar_afree + 8 * aslot);
+                if (kb == nkb - 1) umma_commit(bar_acc);
             }
-            umma_commit(bar_afree + 8 * aslot);
-            if (kb == nkb - 1) umma_commit(bar_acc);
+            __syncwarp();
         }
         if (kb == nkb - 1) {
             // ---- tile done: drain main + correction, epilogue, store this thread's half of the row ----

@@ -269,8 +269,8 @@ __global__ void __launch_bounds__(STC2_THREADS, 1) k_stem_tc2(const StcParams p)
             bulk_load(bsm, p.bimg, STC_B_BYTES, bar_b);
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
+        // ================= MMA issuer: the whole warp walks the loop, one elected lane issues =================
+        {
             const uint32_t idesc = umma_idesc_tf32(STC_NC), idesc2 = umma_idesc_tf32(2 * STC_NC);
             mbar_wait(bar_b, 0);
             const uint64_t b_hi = umma_desc(bsm);
@@ -282,14 +282,17 @@ __global__ void __launch_bounds__(STC2_THREADS, 1) k_stem_tc2(const StcParams p)
                 tc_fence_after();
                 const uint32_t d_main = tmem_base + s4 * 64u, d_corr = d_main + (uint32_t)STC_NC;
                 const uint32_t a_hi = tmem_base + kACol + s4 * 64u, a_lo = a_hi + 32u;
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {  // K = 27 -> four 8-wide steps (elements 27..31 are zero on both sides)
-                    const uint64_t ko = (uint64_t)(k * 2);
-                    umma_tf32_ts(d_main, a_hi + 8u * k, b_hi + ko, idesc2, k > 0 ? 1u : 0u);  // main += hi.hi ; corr += hi.lo
-                    umma_tf32_ts(d_corr, a_lo + 8u * k, b_hi + ko, idesc, 1u);                 // corr += lo.hi
+                    for (int k = 0; k < 4; ++k) {  // K = 27 -> four 8-wide steps (elements 27..31 are zero on both sides)
+                        const uint64_t ko = (uint64_t)(k * 2);
+                        umma_tf32_ts(d_main, a_hi + 8u * k, b_hi + ko, idesc2, k > 0 ? 1u : 0u);  // main += hi.hi ; corr += hi.lo
+                        umma_tf32_ts(d_corr, a_lo + 8u * k, b_hi + ko, idesc, 1u);                 // corr += lo.hi
+                    }
+                    umma_commit(bar_aempty + 8 * s4);
+                    umma_commit(bar_tfull + 8 * s4);
                 }
-                umma_commit(bar_aempty + 8 * s4);
-                umma_commit(bar_tfull + 8 * s4);
+                __syncwarp();
             }
         }
     } else if (warp >= 4 && warp < 12) {

@@ -62,6 +62,7 @@ def main():
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "tc_tune.jsonl"))
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--only", default="")
+    ap.add_argument("--default-only", action="store_true", help="time only the library's default plan of each layer")
     a = ap.parse_args()
     lib = pkg._lib.load()
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
@@ -96,7 +97,7 @@ def main():
             ref = ref + R[idx].double()
         scale = ref.abs().max().item()
         iters = 20 if M <= 204800 else 8
-        for v in [{}] + variants(K, N):  # {} = the library's current default plan
+        for v in [{}] + ([] if a.default_only else variants(K, N)):  # {} = the library's current default plan
             key = f"{name}|{M}|{K}|{N}|{epi}|" + ",".join(f"{k}={v[k]}" for k in sorted(v))
             if key in done:
                 continue
