@@ -26,6 +26,9 @@ struct DwtGeom {
     static constexpr int NPX = IH * IW;
     static constexpr int LO = (KS - S) / 2;
     static constexpr int XBYTES = ((NPX * 128 + 1023) / 1024) * 1024;
+    // outputs per thread: 2 x 2, or 2 rows x 4 columns where a 16x16 tile then gives exactly one block per thread slot
+    // (3x3 stride 1: 24 window loads + 9 tap loads per 8 outputs instead of 32 + 18)
+    static constexpr int XT = (GEOM == 2 && KS == 3 && S == 1) ? 4 : 2, YT = 2;
 };
 
 struct DwtParams {
@@ -61,7 +64,7 @@ __global__ void __launch_bounds__(DWT_THREADS, 2) k_dwt(const __grid_constant__ 
     // other 255 threads read it after the barrier wait instead of repeating three integer divisions each (the SASS of the
     // previous version spent ~35 % of its instructions per item on that decode).
     int4* info = reinterpret_cast<int4*>(sm + (size_t)nst * G::XBYTES + 64);  // [nst], after the 8 barriers
-    auto issue = [&](long long item, int stage) {  // thread 0 only
+    auto issue = [&](long long item, int stage) {  // one elected lane of warp 0 only
         const int ch = (int)(item % P.nchunk);
         int t = (int)(item / P.nchunk);
         const int tx = t % p.tiles_x;
@@ -71,11 +74,14 @@ __global__ void __launch_bounds__(DWT_THREADS, 2) k_dwt(const __grid_constant__ 
         mbar_expect_tx(bars + 8 * stage, (uint32_t)G::NPX * 128u);  // release: orders the info store before the phase flip
         tma_load_4d(base + stage * G::XBYTES, &tmX, ch * 32, tx * G::TW * S - G::LO, ty * G::TH * S - G::LO, b, bars + 8 * stage);
     };
-    if (tid == 0)
-        for (int i = 0; i < nst; ++i) {
-            const long long item = (long long)blockIdx.x + (long long)i * gridDim.x;
-            if (item < p.n_items) issue(item, i);
-        }
+    if (warp == 0) {  // convergent: one elected lane issues (see elect_one in k_pw_tc.cuh)
+        if (elect_one())
+            for (int i = 0; i < nst; ++i) {
+                const long long item = (long long)blockIdx.x + (long long)i * gridDim.x;
+                if (item < p.n_items) issue(item, i);
+            }
+        __syncwarp();
+    }
     int stage = 0;
     uint32_t phase = 0;
     for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x) {
@@ -84,11 +90,12 @@ __global__ void __launch_bounds__(DWT_THREADS, 2) k_dwt(const __grid_constant__ 
         const int ch = inf.x, tx = inf.y, ty = inf.z, b = inf.w;
         const int cbase = ch * 32 + c4 * 4;
         if (!(P.dbg & 1))
-            xd_dw_phase_g<G, KS, S, 2, 2, true, DWT_THREADS / 32, false>(sm + stage * G::XBYTES, p.Wd, p, warp, pg, c4, cbase, cbase < p.hid, b, ty, tx);
+            xd_dw_phase_g<G, KS, S, G::XT, G::YT, true, DWT_THREADS / 32, false>(sm + stage * G::XBYTES, p.Wd, p, warp, pg, c4, cbase, cbase < p.hid, b, ty, tx);
         __syncthreads();  // every thread is done with this stage (and has read its info): refill it
-        if (tid == 0) {
+        if (warp == 0) {
             const long long nxt = item + (long long)nst * gridDim.x;
-            if (nxt < p.n_items) issue(nxt, stage);
+            if (nxt < p.n_items && elect_one()) issue(nxt, stage);
+            __syncwarp();
         }
         if (++stage == nst) stage = 0, phase ^= 1u;
     }

@@ -552,7 +552,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     }
                     continue;
                 }
-                if (lane == 0) bulk_wait_read<TC_STG_BUFS - 1>();  // the staging buffer we are about to overwrite
+                if (elect_one()) bulk_wait_read<TC_STG_BUFS - 1>();  // the staging buffer we are about to overwrite (bulk groups
+                                                                     // are per thread: the elected lane is the same one each time)
                 __syncwarp();
                 uint8_t* sp = stg_ptr + buf * TC_STG_BYTES + lane * 128;
 #pragma unroll
@@ -568,14 +569,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 }
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) {
+                if (elect_one()) {
                     tma_store_2d(&tmOut, stg + buf * TC_STG_BYTES, col0, mt * TC_BM + q * 32);  // clips rows >= M, cols >= N
                     bulk_commit();
                 }
                 buf ^= 1;
             }
         }
-        if (lane == 0) bulk_wait_all();
+        __syncwarp();
+        if (elect_one()) bulk_wait_all();
     }
 
     tc_fence_before();
