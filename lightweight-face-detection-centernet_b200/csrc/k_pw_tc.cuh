@@ -60,8 +60,8 @@ struct TcParams {
     int M, K, N, NC, nchunks, nkb, n_items;
     int resident;    // 1: the whole B image lives in smem for the kernel's lifetime; 2: the image of ONE column chunk does --
                      //    the grid is a multiple of nchunks, so a CTA's items all share the chunk blockIdx.x % nchunks
-    int direct;      // 1: narrow outputs (N <= 64): the epilogue stores rows straight from registers, the staging
-                     //    buffers' 64 KB go to two more pipeline stages
+    int direct;      // 0: swizzled smem staging + TMA store; 1: the epilogue stores rows straight from registers (the staging
+                     //    buffers' 64 KB go to more pipeline stages); 2: staging tile + coalesced register stores (probe)
     float* out;      // [M][N] (direct stores)
     int nacc;        // TMEM accumulator stages (2 or 4); stage stride = acc_stride columns
     uint32_t acc_stride;
@@ -536,7 +536,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
                 }
                 if (p.dbg & 2) continue;
-                if (p.direct) {
+                if (p.direct == 1) {
                     // one thread = one output row: up to 128 contiguous bytes per 32-column block
                     if (row < p.M) {
                         float* orow = p.out + (size_t)row * p.N + col0;
@@ -552,8 +552,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     }
                     continue;
                 }
-                if (elect_one()) bulk_wait_read<TC_STG_BUFS - 1>();  // the staging buffer we are about to overwrite (bulk groups
-                                                                     // are per thread: the elected lane is the same one each time)
+                if (p.direct != 2) {
+                    if (elect_one()) bulk_wait_read<TC_STG_BUFS - 1>();  // the staging buffer we are about to overwrite (bulk groups
+                                                                         // are per thread: the elected lane is the same one each time)
+                }
                 __syncwarp();
                 uint8_t* sp = stg_ptr + buf * TC_STG_BYTES + lane * 128;
 #pragma unroll
@@ -566,6 +568,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                         o = tc_epi<EPI>(o, row, n, p.N, p.ea);
                     }
                     *reinterpret_cast<float4*>(sp + ((j ^ (lane & 7)) << 4)) = o;  // SWIZZLE_128B
+                }
+                if (p.direct == 2) {
+                    // coalesced register stores out of the transposed tile: one STG.128 writes 4 rows x 128 contiguous bytes,
+                    // and the warp does not have to wait for a TMA store to drain its staging buffer
+                    __syncwarp();
+                    const int row0 = mt * TC_BM + q * 32;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = 4 * i + (lane >> 3), c = lane & 7;
+                        const float4 x = *reinterpret_cast<const float4*>(stg_ptr + buf * TC_STG_BYTES + r * 128 + ((c ^ (r & 7)) << 4));
+                        if (row0 + r < p.M && col0 + 4 * c < p.N) st4(p.out + (size_t)(row0 + r) * p.N + col0 + 4 * c, x);
+                    }
+                    buf ^= 1;
+                    continue;
                 }
                 fence_proxy_async();
                 __syncwarp();
@@ -787,12 +803,12 @@ inline int tc_plan(PwTcState& st, int passes, int epi, const float* A, const flo
         if (tune.nacc) p.nacc = tune.nacc == 4 && 4u * pair <= acc_cols ? 4 : 2;
         p.acc_stride = acc_cols / (uint32_t)p.nacc;
     }
-    p.direct = (N <= 64) ? 1 : 0;
-    if (tune.direct >= 0) p.direct = tune.direct ? 1 : 0;
+    p.direct = (N <= 16) ? 1 : 0;  // since the elect-based issue the TMA-store epilogue wins from N = 24 up (r2r sweep)
+    if (tune.direct >= 0) p.direct = tune.direct;  // 0 TMA stores, 1 row stores from registers, 2 transposed tile + coalesced stores
     p.out = out;
     p.dbg = 0;
     if (const char* ev = getenv("CF_TC_DEBUG")) p.dbg = atoi(ev);
-    const uint32_t stg_bytes = p.direct ? 0u : 8u * TC_STG_BUFS * TC_STG_BYTES;  // 8 epilogue warps
+    const uint32_t stg_bytes = p.direct == 1 ? 0u : 8u * TC_STG_BUFS * TC_STG_BYTES;  // 8 epilogue warps
     const uint32_t bar_bytes = 1024;
     const uint32_t avail = TC_SMEM_MAX - 1024 /*alignment slack*/ - stg_bytes - bar_bytes;
     const uint32_t b_total = (uint32_t)L.img_bytes;
@@ -856,11 +872,13 @@ inline const TcTuneEntry* tc_tuned_table(int* n) {
     // 40 KB, i.e. four pipeline stages instead of two (these kernels are hand-off-latency bound, not L2 or tensor bound).
     static const TcTuneEntry tab[] = {
         {24, 144, mk(64, 1, 0, -1)},    // layer1.1 / layer2.0 expand   145.1 -> 139.5
-        {384, 64, mk(0, -1, 0, -1)},    // layer3.1 project              34.2 -> 32.3
+        {144, 24, mk(0, -1, 1, -1)},    // layer1.1 project (+res): row stores stay marginally ahead (115.7 vs 116.2)
+        {64, 384, mk(96, 1, 0, 1)},     // layer3.1 / layer4.0 expand    26.7 -> 24.6
         {384, 96, mk(96, 1, 0, -1)},    // layer4.0 project              40.1 -> 30.7
-        {96, 576, mk(96, 1, 0, 0)},     // layer4.1 / layer5.0 expand    60.8 -> 47.7
+        {96, 576, mk(96, 1, 0, -1)},    // layer4.1 / layer5.0 expand    60.8 -> 47.7 (-> 41.0 with the resident chunk)
         {576, 96, mk(96, 1, 0, -1)},    // layer4.1 project              64.1 -> 48.4
         {576, 160, mk(96, 1, 0, -1)},   // layer5.0 project              32.4 -> 28.8
+        {160, 960, mk(96, 1, 0, 0)},    // layer5.1 / layer6.0 expand    31.8 -> 27.0
         {960, 160, mk(96, 1, 0, -1)},   // layer5.1 project              57.2 -> 48.7
         {960, 320, mk(96, 1, 0, 0)},    // layer6.0 project              77.1 -> 66.4
     };

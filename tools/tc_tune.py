@@ -48,7 +48,7 @@ def variants(K, N):
     n32 = (N + 31) // 32 * 32
     v = []
     for nc in range(32, min(128, n32) + 1, 32):
-        for direct in (0, 1):
+        for direct in (0, 1, 2):
             for atmem in ((1, 0) if nc <= 96 else (0,)):
                 for rchunk in (1, 0):
                     v.append({"CF_TC_NC": nc, "CF_TC_DIRECT": direct, "CF_TC_ATMEM": atmem, "CF_PWN": 0, "CF_TC_RCHUNK": rchunk})
