@@ -161,6 +161,36 @@ class Clocks:
                 "power_w_max": max(r[2] for r in rows), "samples": len(rows)}
 
 
+BLOCKS = [(32, 16, 1, 3, 1), (16, 24, 6, 3, 2), (24, 24, 6, 3, 1), (24, 32, 6, 5, 2), (32, 32, 6, 5, 1), (32, 64, 6, 3, 2),
+          (64, 64, 6, 3, 1), (64, 96, 6, 5, 1), (96, 96, 6, 5, 1), (96, 160, 6, 5, 2), (160, 160, 6, 5, 1), (160, 320, 6, 3, 1)]
+
+
+def launch_table(h, w):
+    """(name, algorithmic bytes per image) of every launch of one forward + path-C decode, in launch order -- the same
+    layer-wise accounting as cf_work_model (un-padded input once + output once + residual / low-res re-reads, fp32)."""
+    out = []
+    hh, ww = h // 2, w // 2
+    out.append(("stem 3->32 s2", h * w * 3 + hh * ww * 32 * 4))
+    for i, (cin, cout, t, k, s) in enumerate(BLOCKS):
+        hid = cin * t
+        if t != 1:
+            out.append((f"b{i} expand {cin}->{hid}", hh * ww * (cin + hid) * 4))
+        ho, wo = hh // s, ww // s
+        out.append((f"b{i} dw{k}x{k} s{s} {hid}ch", (hh * ww + ho * wo) * hid * 4))
+        res = cout if (cin == cout and s == 1) else 0
+        out.append((f"b{i} project {hid}->{cout}" + (" +res" if res else ""), ho * wo * (hid + cout + res) * 4))
+        hh, ww = ho, wo
+    out.append(("conv_last 320->24", hh * ww * (320 + 24) * 4))
+    for j, c in enumerate((96, 32, 24)):
+        lo = hh * ww
+        hh, ww = hh * 2, ww * 2
+        out.append((f"up{j + 1} {c}->24 (IDAUp)", (hh * ww * (c + 24) + lo * 24) * 4))
+    out.append(("heads 3x3 24->15", hh * ww * (24 + 16) * 4))
+    out.append(("peak mask", hh * ww * 2 * 4))
+    out.append(("top-k + gather", hh * ww * 4 + 100 * 6 * 4))
+    return out
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -310,12 +340,24 @@ def run_b200(a):
                                 "frac_hbm": round(v["gbs"] / hbm, 4), "TFLOPs": round(v["tflops"], 2), "launches": v["launches"]}
                             for k, v in classes.items()}}
     try:  # measured DRAM bytes of the dominant class (ncu, committed under profiles/), if it matches this run
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1c.json")))
         if (tj.get("engine"), tj.get("batch"), tj.get("h"), tj.get("w")) == (pw, B, H, W):
             roofline["traffic"] = tj["dram_bytes_per_step"].get(top)
-            roofline["traffic_source"] = "profiles/traffic_r1.json"
+            roofline["traffic_source"] = "profiles/traffic_r1c.json"
     except Exception:
         pass
+    try:  # the individual launches, timed one by one (events between launches: no overlap of neighbouring kernels)
+        ms_l, _ = eng.time_steps(5)
+        tab = launch_table(H, W)
+        if len(tab) == len(ms_l):
+            rows = [{"launch": n, "us": round(t * 1e3, 1), "alg_GB": round(by_l * B / 1e9, 4),
+                     "GBps": round(by_l * B / (t * 1e-3) / 1e9, 1), "frac_hbm": round(by_l * B / (t * 1e-3) / 1e9 / hbm, 3)}
+                    for (n, by_l), t in zip(tab, ms_l)]
+            rows.sort(key=lambda r: -r["us"])
+            roofline["top_launches"] = rows[:8]
+            roofline["dominant_launch"] = rows[0]
+    except Exception as ex:  # instrumentation only
+        roofline["top_launches_error"] = str(ex)
     by_min, _ = L.work_model(H, W, L.CF_IN_U8_HWC, 0, pw)
     by_all, fl_all = L.work_model(H, W, L.CF_IN_U8_HWC, 0, L.CF_PW_TCGEN05)  # layer-wise algorithmic bytes
     roofline["whole_step"] = {"alg_bytes_per_image": by_all, "min_bytes_per_image": by_min, "alg_flops_per_image": fl_all,
