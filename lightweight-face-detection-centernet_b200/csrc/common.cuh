@@ -123,7 +123,7 @@ struct EpiArgs {
     const float* res;   // [M,N]    residual (EPI_RESIDUAL)
     const float* bias;  // [N]      folded BN shift (BIAS_SWISH, IDAUP lateral)
     const float* low;   // [B,Ho/2,Wo/2,N] low-res input of the transposed conv (IDAUP)
-    const float* su;    // [N][2][2] folded up-sample scale (IDAUP)
+    const float* su;    // [2][2][N] folded up-sample scale, sub-pixel major (IDAUP; transposed from the blob's [N][2][2] at cf_create)
     const float* tu;    // [N]      folded up-sample shift (IDAUP)
     int Ho, Wo;         // output map size (IDAUP: m -> (b,y,x))
 };
@@ -140,15 +140,14 @@ __device__ __forceinline__ const float* idaup_low_ptr(int m, int n, int N, const
     *q = (y & 1) * 2 + (x & 1);
     return ea.low + ((size_t)(b * Hl + (y >> 1)) * Wl + (x >> 1)) * N + n;
 }
-__device__ __forceinline__ float4 idaup_apply(float4 acc, float4 lo, int n, int q, const EpiArgs& ea) {
+__device__ __forceinline__ float4 idaup_apply(float4 acc, float4 lo, int n, int q, int N, const EpiArgs& ea) {
     const float4 bb = ldg4(ea.bias + n), tt = ldg4(ea.tu + n);
-    const float s0 = __ldg(ea.su + (n + 0) * 4 + q), s1 = __ldg(ea.su + (n + 1) * 4 + q);
-    const float s2 = __ldg(ea.su + (n + 2) * 4 + q), s3 = __ldg(ea.su + (n + 3) * 4 + q);
+    const float4 ss = ldg4(ea.su + q * N + n);  // [2x2 sub-pixel][channel]: one vector load instead of four scalar ones
     float4 o;
-    o.x = fmaxf(fmaf(lo.x, s0, tt.x), 0.f) + fmaxf(acc.x + bb.x, 0.f);
-    o.y = fmaxf(fmaf(lo.y, s1, tt.y), 0.f) + fmaxf(acc.y + bb.y, 0.f);
-    o.z = fmaxf(fmaf(lo.z, s2, tt.z), 0.f) + fmaxf(acc.z + bb.z, 0.f);
-    o.w = fmaxf(fmaf(lo.w, s3, tt.w), 0.f) + fmaxf(acc.w + bb.w, 0.f);
+    o.x = fmaxf(fmaf(lo.x, ss.x, tt.x), 0.f) + fmaxf(acc.x + bb.x, 0.f);
+    o.y = fmaxf(fmaf(lo.y, ss.y, tt.y), 0.f) + fmaxf(acc.y + bb.y, 0.f);
+    o.z = fmaxf(fmaf(lo.z, ss.z, tt.z), 0.f) + fmaxf(acc.z + bb.z, 0.f);
+    o.w = fmaxf(fmaf(lo.w, ss.w, tt.w), 0.f) + fmaxf(acc.w + bb.w, 0.f);
     return o;
 }
 
@@ -166,7 +165,7 @@ __device__ __forceinline__ float4 apply_epi(float4 acc, int m, int n, int N, con
     if (EPI == EPI_IDAUP) {
         int q;
         const float4 lo = ldcg4(idaup_low_ptr(m, n, N, ea, &q));
-        return idaup_apply(acc, lo, n, q, ea);
+        return idaup_apply(acc, lo, n, q, N, ea);
     }
     return acc;
 }

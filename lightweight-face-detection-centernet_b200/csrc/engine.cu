@@ -114,6 +114,7 @@ struct cf_engine {
     float* blk[12] = {};
     float* clast = nullptr;
     float* up[3] = {};
+    float* up_sut[3] = {};  // IDAUp scales transposed to [2x2 sub-pixel][24 channels]
     // heads (planar) + decode scratch
     float *hm = nullptr, *wh = nullptr, *lm = nullptr, *reg = nullptr, *hm_sig = nullptr, *peak = nullptr;
     // staging for the host entry points
@@ -392,7 +393,7 @@ int build_plan(cf_engine* e, const void* input, int fmt, int B, int H, int W) {
         EpiArgs ea{};
         ea.bias = e->w[p + ".b"];
         ea.low = low;
-        ea.su = e->w[p + ".su"];
+        ea.su = e->up_sut[j];
         ea.tu = e->w[p + ".tu"];
         ea.Ho = h;
         ea.Wo = wd;
@@ -505,6 +506,16 @@ int cf_create(const void* weights, size_t weights_bytes, int device, int max_bat
         }
     }
 
+    for (int j = 0; j < 3; ++j) {  // up{j+1}.su is [c][a][b] in the blob; the epilogue reads one float4 of channels per sub-pixel
+        const float* hp = blob.get("up" + std::to_string(j + 1) + ".su", 24 * 4, why);
+        if (!hp) return bail(fail(CF_EWEIGHTS, "cf_create: %s", why.c_str()));
+        float t[4 * 24];
+        for (int c = 0; c < 24; ++c)
+            for (int q = 0; q < 4; ++q) t[q * 24 + c] = hp[c * 4 + q];
+        if (cudaMalloc((void**)&e->up_sut[j], sizeof t) != cudaSuccess ||
+            cudaMemcpy(e->up_sut[j], t, sizeof t, cudaMemcpyHostToDevice) != cudaSuccess)
+            return bail(fail(CF_ECUDA, "cf_create: IDAUp scale upload failed: %s", cudaGetErrorString(cudaGetLastError())));
+    }
     const size_t Bm = (size_t)max_batch;
     const size_t px2 = (size_t)(max_h / 2) * (max_w / 2);
     // largest hidden tensor: layer1.0 expand output, 96 channels at stride 2
@@ -610,6 +621,8 @@ int cf_destroy(cf_engine* e) {
     for (float* p : bufs)
         if (p) cudaFree(p);
     for (float* p : e->blk)
+        if (p) cudaFree(p);
+    for (float* p : e->up_sut)
         if (p) cudaFree(p);
     if (e->o_inds) cudaFree(e->o_inds);
     if (e->o_counts) cudaFree(e->o_counts);

@@ -39,7 +39,7 @@ constexpr int TC_BM = 128;           // rows per tile (UMMA M)
 constexpr int TC_BK = 32;            // fp32 K elements per smem block = one 128-byte swizzle row
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
 constexpr int TC_STG_BYTES = 32 * 128;          // one epilogue staging buffer: 32 rows x 32 fp32
-constexpr int TC_STG_BUFS = 2;                  // per epilogue warp
+constexpr int TC_STG_BUFS = 2;                  // per epilogue warp (TcParams::stg_bufs: 2 or 4)
 constexpr int TC_MAX_STAGES = 12;
 constexpr int TC_SMEM_MAX = 232448;             // 227 KB
 
@@ -71,6 +71,7 @@ struct TcParams {
     uint32_t acol;   // first TMEM column of the A ring
     uint32_t amask;  // A ring slots - 1 (1 or 3)
     uint32_t ashift; // log2(A ring slots)
+    int stg_bufs;    // staging buffers per epilogue warp (2 or 4)
     int dbg;         // development only (env CF_TC_DEBUG): 1 skip the A split, 2 skip the stores, 4 skip the MMAs
     int stages;
     uint32_t stage_bytes, a_bytes_stage, b_bytes_block;  // b_bytes_block = NC*128*(passes==3?2:1)
@@ -501,8 +502,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         pdl_wait();  // residual / low-res reads and the output stores touch activation memory
         const int g = (warp - 8) >> 2;
         const int q = warp & 3;  // TMEM lane quarter this warp may read
-        const uint32_t stg = stg_base + (uint32_t)(warp - 8) * (TC_STG_BUFS * TC_STG_BYTES);
-        uint8_t* stg_ptr = base_ptr + (size_t)(warp - 8) * (TC_STG_BUFS * TC_STG_BYTES);
+        const uint32_t stg = stg_base + (uint32_t)(warp - 8) * ((uint32_t)p.stg_bufs * TC_STG_BYTES);
+        uint8_t* stg_ptr = base_ptr + (size_t)(warp - 8) * ((size_t)p.stg_bufs * TC_STG_BYTES);
         int buf = 0;
         uint32_t it = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
@@ -553,7 +554,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     continue;
                 }
                 if (p.direct != 2) {
-                    if (elect_one()) bulk_wait_read<TC_STG_BUFS - 1>();  // the staging buffer we are about to overwrite (bulk groups
+                    if (elect_one()) {
+                        if (p.stg_bufs == 4) bulk_wait_read<3>();
+                        else bulk_wait_read<1>();
+                    }  // the staging buffer we are about to overwrite (bulk groups
                                                                          // are per thread: the elected lane is the same one each time)
                 }
                 __syncwarp();
@@ -580,7 +584,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                         const float4 x = *reinterpret_cast<const float4*>(stg_ptr + buf * TC_STG_BYTES + r * 128 + ((c ^ (r & 7)) << 4));
                         if (row0 + r < p.M && col0 + 4 * c < p.N) st4(p.out + (size_t)(row0 + r) * p.N + col0 + 4 * c, x);
                     }
-                    buf ^= 1;
+                    buf = (buf + 1) & (p.stg_bufs - 1);
                     continue;
                 }
                 fence_proxy_async();
@@ -589,7 +593,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     tma_store_2d(&tmOut, stg + buf * TC_STG_BYTES, col0, mt * TC_BM + q * 32);  // clips rows >= M, cols >= N
                     bulk_commit();
                 }
-                buf ^= 1;
+                buf = (buf + 1) & (p.stg_bufs - 1);
             }
         }
         __syncwarp();
@@ -677,6 +681,7 @@ struct TcTune {
     int pwn = -1;     // role-free kernel for eligible layers (-1: yes)
     int grid = 0;     // CTA count cap (0: one per SM)
     int rchunk = -1;  // per-CTA resident column chunk when the whole weight image does not fit (-1: yes)
+    int stg = 0;      // staging buffers per epilogue warp (0: two)
 };
 struct TcTuneEntry {
     int K, N;
@@ -702,6 +707,7 @@ inline TcTune tc_tune_for(int K, int N, int passes) {
     if (const char* ev = getenv("CF_PWN")) t.pwn = atoi(ev);
     if (const char* ev = getenv("CF_TC_GRID")) t.grid = atoi(ev);
     if (const char* ev = getenv("CF_TC_RCHUNK")) t.rchunk = atoi(ev);
+    if (const char* ev = getenv("CF_TC_STG")) t.stg = atoi(ev);
     const int nc_max = passes == 3 ? 128 : 192;
     if (t.nc < 0 || t.nc % 32 != 0 || t.nc > nc_max) t.nc = 0;
     return t;
@@ -808,7 +814,8 @@ inline int tc_plan(PwTcState& st, int passes, int epi, const float* A, const flo
     p.out = out;
     p.dbg = 0;
     if (const char* ev = getenv("CF_TC_DEBUG")) p.dbg = atoi(ev);
-    const uint32_t stg_bytes = p.direct == 1 ? 0u : 8u * TC_STG_BUFS * TC_STG_BYTES;  // 8 epilogue warps
+    p.stg_bufs = tune.stg == 4 ? 4 : TC_STG_BUFS;
+    const uint32_t stg_bytes = p.direct == 1 ? 0u : 8u * (uint32_t)p.stg_bufs * TC_STG_BYTES;  // 8 epilogue warps
     const uint32_t bar_bytes = 1024;
     const uint32_t avail = TC_SMEM_MAX - 1024 /*alignment slack*/ - stg_bytes - bar_bytes;
     const uint32_t b_total = (uint32_t)L.img_bytes;

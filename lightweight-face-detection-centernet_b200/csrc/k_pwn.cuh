@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(PWN_THREADS, 2) k_pwn(const __grid_constant__ 
                         if (n < p.N) {
                             float4 o = make_float4(v[4 * g] + c[4 * g], v[4 * g + 1] + c[4 * g + 1], v[4 * g + 2] + c[4 * g + 2],
                                                    v[4 * g + 3] + c[4 * g + 3]);
-                            if (EPI == EPI_IDAUP && p.NC <= 32) o = idaup_apply(o, lowv[g], n, lowq, p.ea);  // one 16-column pass per thread
+                            if (EPI == EPI_IDAUP && p.NC <= 32) o = idaup_apply(o, lowv[g], n, lowq, p.N, p.ea);  // one 16-column pass per thread
                             else o = apply_epi<EPI>(o, grow, n, p.N, p.ea);
                             st4(p.out + (size_t)grow * p.N + n, o);
                         }
