@@ -814,24 +814,27 @@ inline int tc_plan(PwTcState& st, int passes, int epi, const float* A, const flo
     p.out = out;
     p.dbg = 0;
     if (const char* ev = getenv("CF_TC_DEBUG")) p.dbg = atoi(ev);
-    p.stg_bufs = tune.stg == 4 ? 4 : TC_STG_BUFS;
-    const uint32_t stg_bytes = p.direct == 1 ? 0u : 8u * (uint32_t)p.stg_bufs * TC_STG_BYTES;  // 8 epilogue warps
     const uint32_t bar_bytes = 1024;
-    const uint32_t avail = TC_SMEM_MAX - 1024 /*alignment slack*/ - stg_bytes - bar_bytes;
     const uint32_t b_total = (uint32_t)L.img_bytes;
-    p.resident = (b_total <= 65536u && avail - b_total >= 3u * p.a_bytes_stage) ? 1 : 0;
-    // Wide layers whose image does not fit: streaming the chunk's weights again for every 128-row tile makes them
-    // L2-bandwidth bound (the weight stream is NC/64 times the A stream).  If one chunk's image fits beside two A stages,
-    // pin each CTA to one chunk instead (grid = a multiple of nchunks) and keep that chunk resident.
     const uint32_t chunk_total = (uint32_t)L.nkb * p.b_bytes_block;
-    uint32_t b_res = p.resident ? b_total : 0u;
-    if (!p.resident && tune.rchunk != 0 && L.nchunks > 1 && L.nchunks <= st.sms && chunk_total + 2u * p.a_bytes_stage <= avail) {
-        p.resident = 2;
-        b_res = chunk_total;
+    uint32_t stg_bytes = 0, b_res = 0;
+    int stages = 0;
+    for (p.stg_bufs = tune.stg == 4 ? 4 : TC_STG_BUFS; p.stg_bufs >= TC_STG_BUFS; p.stg_bufs -= 2) {  // 4 staging buffers only if they fit
+        stg_bytes = p.direct == 1 ? 0u : 8u * (uint32_t)p.stg_bufs * TC_STG_BYTES;  // 8 epilogue warps
+        const uint32_t avail = TC_SMEM_MAX - 1024 /*alignment slack*/ - stg_bytes - bar_bytes;
+        p.resident = (b_total <= 65536u && b_total + 3u * p.a_bytes_stage <= avail) ? 1 : 0;
+        // Wide layers whose image does not fit: if one column chunk's image fits beside two A stages, pin each CTA to one
+        // chunk (grid = a multiple of nchunks) and keep that chunk resident instead of streaming it again for every tile.
+        b_res = p.resident ? b_total : 0u;
+        if (!p.resident && tune.rchunk != 0 && L.nchunks > 1 && L.nchunks <= st.sms && chunk_total + 2u * p.a_bytes_stage <= avail) {
+            p.resident = 2;
+            b_res = chunk_total;
+        }
+        p.stage_bytes = p.a_bytes_stage + (p.resident ? 0u : p.b_bytes_block);
+        stages = (int)((avail - b_res) / p.stage_bytes);
+        if (stages >= 2) break;
     }
-    p.stage_bytes = p.a_bytes_stage + (p.resident ? 0u : p.b_bytes_block);
-    const uint32_t room = avail - b_res;
-    int stages = (int)(room / p.stage_bytes);
+    if (p.stg_bufs < TC_STG_BUFS) p.stg_bufs = TC_STG_BUFS;
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
     if (stages < 2) return fail(CF_EINVAL, "tc_plan: K=%d N=%d does not fit the shared-memory pipeline", K, N);
     p.stages = stages;

@@ -1,0 +1,109 @@
+"""Plan variants and fall-back paths of the CUDA engine (all through the C ABI, B200 only).
+
+* top-k on a map larger than the shared-memory key cache (k_topk<false>) and on one that fills it exactly;
+* ties AT the K-th score spread over many rows of 1024 (the block-scan rank path of k_topk<true>);
+* every launch-plan probe switch (stem kernel, k_pwn, depth-wise tile geometry, tuned GEMM table, fused-store variants)
+  gives the same head maps as the default plan -- bit-identical where only the schedule changes, inside the engine's
+  parity bar where the arithmetic order changes (FFMA stem);
+* the per-launch timing entry point returns one positive time per launch of the plan.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _decode_case(pkg, oracle, h, w, K, seed, plateau=None):
+    g = torch.Generator().manual_seed(seed)
+    heat = torch.rand(2, 1, h, w, generator=g) * 0.9 + 0.05
+    if plateau is not None:  # many exact ties at one score, scattered over the whole map
+        m = torch.rand(2, 1, h, w, generator=g) < 0.3
+        heat[m] = plateau
+    wh = torch.rand(2, 2, h, w, generator=g) * 12
+    reg = torch.rand(2, 2, h, w, generator=g)
+    want, wi = oracle.ctdet_decode(heat, wh, reg, K=K)
+    got, gi = pkg.ctdet_decode(heat.cuda(), wh.cuda(), reg.cuda(), K=K, return_inds=True)
+    assert np.array_equal(gi.cpu().numpy(), wi.numpy().astype(np.int32)), f"{h}x{w} K={K}: indices differ"
+    assert torch.equal(got.cpu(), want), f"{h}x{w} K={K}: boxes differ"
+
+
+@pytest.mark.parametrize("h,w", [(272, 240), (256, 200), (160, 160), (8, 8)])
+def test_topk_key_cache_and_global_fallback(pkg, oracle, h, w):
+    """65 280 keys > 51 200 (global re-read path), exactly 51 200 (cache full), the 640x640 map, a tiny map."""
+    _decode_case(pkg, oracle, h, w, K=min(100, h * w), seed=h * w)
+
+
+@pytest.mark.parametrize("h,w,K", [(160, 160, 100), (272, 240, 300), (96, 64, 1000)])
+def test_topk_ties_at_threshold_are_admitted_lowest_index_first(pkg, oracle, h, w, K):
+    """3x3 peak keep leaves isolated plateau pixels; with 30 % of the map on one value the K-th score IS the plateau and
+    the winners among equals must be the lowest flat indices, in order."""
+    _decode_case(pkg, oracle, h, w, K=K, seed=7 * h + w, plateau=0.97)
+    _decode_case(pkg, oracle, h, w, K=K, seed=11 * h + w, plateau=0.5)
+
+
+def _heads(pkg, weights_path, x, env):
+    old = {k: os.environ.get(k) for k in env}
+    try:
+        for k, v in env.items():
+            os.environ[k] = str(v)
+        eng = pkg.Engine(weights_path, max_batch=x.shape[0], max_h=x.shape[1], max_w=x.shape[2], device=0, pw_engine=pkg.CF_PW_TCGEN05)
+        eng.forward(x)
+        out = {k: v.clone() for k, v in eng.heads().items()}
+        dets, inds = eng.decode_topk(100)
+        out["dets"], out["inds"] = dets.clone(), inds.clone()
+        eng.close()
+        return out
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+SCHEDULE_ONLY = [{"CF_PWN": 0}, {"CF_DWT_GEOM": 0}, {"CF_DWT_GEOM": 1}, {"CF_DWT_CTAS": 1}, {"CF_TC_TABLE": 0}, {"CF_TC_RCHUNK": 0},
+                 {"CF_TC_DIRECT": 1}, {"CF_TC_DIRECT": 2}, {"CF_TC_DIRECT": 0, "CF_TC_STG": 4}, {"CF_TC_ATMEM": 0}, {"CF_STEM_TC": 1}]
+
+
+@pytest.fixture(scope="module")
+def variant_input(f5_640):
+    import cv2
+    return torch.from_numpy(np.stack([cv2.resize(f5_640[n], (384, 320)) for n in ("27", "8", "17")])).cuda()
+
+
+@pytest.fixture(scope="module")
+def default_heads(pkg, weights_path, variant_input):
+    return _heads(pkg, weights_path, variant_input, {})
+
+
+@pytest.mark.parametrize("env", SCHEDULE_ONLY, ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
+def test_plan_variants_are_bit_identical(pkg, weights_path, variant_input, default_heads, env):
+    """Column chunking, the A-operand route, the epilogue store kind, tile geometry, the role-free kernels: none of them
+    changes which products are summed in which accumulator in which order, so the head maps must not move by one bit."""
+    got = _heads(pkg, weights_path, variant_input, env)
+    for k in ("hm", "wh", "lm", "reg", "hm_sig", "dets", "inds"):
+        assert torch.equal(got[k], default_heads[k]), f"{env}: {k} differs from the default plan"
+
+
+def test_ffma_stem_within_engine_bar(pkg, weights_path, variant_input, default_heads):
+    """CF_STEM_TC=0 swaps the 3xTF32 tensor-core stem for the fp32 FFMA one: different rounding, same contract."""
+    got = _heads(pkg, weights_path, variant_input, {"CF_STEM_TC": 0})
+    for k, tol in (("hm", 5e-4), ("wh", 8e-3), ("lm", 3e-3), ("reg", 1e-4)):
+        assert (got[k] - default_heads[k]).abs().max().item() <= tol, k
+    assert (got["hm_sig"] - default_heads["hm_sig"]).abs().max().item() <= 1e-5
+
+
+def test_time_steps_reports_every_launch(pkg, weights_path, variant_input):
+    eng = pkg.Engine(weights_path, max_batch=3, max_h=320, max_w=384, device=0, pw_engine=pkg.CF_PW_TCGEN05)
+    eng.forward(variant_input)
+    eng.decode_topk(100)
+    before = eng.launches
+    ms, cls = eng.time_steps(2)
+    assert len(ms) == len(cls) == 43  # 41 network launches + peak mask + top-k
+    assert all(t > 0 for t in ms)
+    assert cls[0] == pkg._lib.CLS_STEM and cls[-1] == pkg._lib.CLS_DECODE and cls.count(pkg._lib.CLS_PW) == 27
+    assert eng.launches - before == 43 * 3  # one warm-up pass + two timed
+    eng.close()
