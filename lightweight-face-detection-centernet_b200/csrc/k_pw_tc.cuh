@@ -507,7 +507,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         int buf = 0;
         uint32_t it = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-            if ((int)(it & 1u) != g) continue;  // group g serves accumulator stages g, g+2 (nacc is even)
+            if ((int)(it & 1u) != g) continue;  // the two groups take alternate items (any accumulator stage)
             const uint32_t as = it % (uint32_t)p.nacc;
             const int mt = item / p.nchunks, ch = item - mt * p.nchunks;
             const uint32_t aphase = (it / (uint32_t)p.nacc) & 1u;
@@ -800,14 +800,18 @@ inline int tc_plan(PwTcState& st, int passes, int epi, const float* A, const flo
     p.atmem = (passes == 3 && L.NC <= 64) ? 1 : 0;
     if (tune.atmem >= 0) p.atmem = (tune.atmem != 0 && passes == 3 && L.NC <= 96) ? 1 : 0;
     p.a_bytes_stage = p.atmem ? TC_A_BYTES : TC_A_BYTES * hl;
-    p.acol = L.NC <= 64 ? 256u : 384u;
-    p.amask = L.NC <= 64 ? 3u : 1u;
-    p.ashift = L.NC <= 64 ? 2u : 1u;
+    // TMEM budget (512 columns): NC <= 64: accumulators [0,256) + four A slots; NC <= 96, or NC <= 64 with THREE accumulator
+    // pairs (tune.nacc == 3: single-K-block layers, where the accumulator round trip bounds the item rate): [0,384) + two A slots
+    const bool three = p.atmem && tune.nacc == 3 && L.NC <= 64;
+    p.acol = (L.NC <= 64 && !three) ? 256u : 384u;
+    p.amask = (L.NC <= 64 && !three) ? 3u : 1u;
+    p.ashift = (L.NC <= 64 && !three) ? 2u : 1u;
     {   // accumulator ring: as many (main+correction) pairs as fit the accumulator columns, 2 or 4
         const uint32_t acc_cols = p.atmem ? p.acol : 512u, pair = (passes == 3 ? 2u : 1u) * (uint32_t)L.NC;
         p.nacc = (4u * pair <= acc_cols) ? 4 : 2;
         if (tune.nacc) p.nacc = tune.nacc == 4 && 4u * pair <= acc_cols ? 4 : 2;
-        p.acc_stride = acc_cols / (uint32_t)p.nacc;
+        if (three && 3u * pair <= acc_cols) p.nacc = 3;
+        p.acc_stride = p.nacc == 3 ? 128u : acc_cols / (uint32_t)p.nacc;
     }
     p.direct = (N <= 16) ? 1 : 0;  // since the elect-based issue the TMA-store epilogue wins from N = 24 up (r2r sweep)
     if (tune.direct >= 0) p.direct = tune.direct;  // 0 TMA stores, 1 row stores from registers, 2 transposed tile + coalesced stores

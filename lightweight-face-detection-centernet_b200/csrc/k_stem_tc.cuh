@@ -230,11 +230,11 @@ __global__ void __launch_bounds__(STC2_THREADS, 1) k_stem_tc2(const StcParams p)
     const uint32_t bsm = base;
     float* lut_s = reinterpret_cast<float*>(sm + STC_OFF_LUT);
     const uint32_t bars = base + STC2_OFF_BARS;
-    const uint32_t bar_b = bars;                 // weights landed
-    const uint32_t bar_aready = bars + 8;        // [4] producers -> MMA   (4 warps arrive)
-    const uint32_t bar_aempty = bars + 40;       // [4] MMA -> producers   (tcgen05.commit)
-    const uint32_t bar_tfull = bars + 72;        // [4] MMA -> drain       (tcgen05.commit)
-    const uint32_t bar_tempty = bars + 104;      // [4] drain -> MMA       (4 warps arrive)
+    const uint32_t bar_aready = bars;            // [4] producers -> MMA   (4 warps arrive)
+    const uint32_t bar_aempty = bars + 32;       // [4] MMA -> producers   (tcgen05.commit)
+    const uint32_t bar_tfull = bars + 64;        // [4] MMA -> drain       (tcgen05.commit)
+    const uint32_t bar_tempty = bars + 96;       // [4] drain -> MMA       (4 warps arrive)
+    const uint32_t bar_b = bars + 128;           // weights landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + STC2_OFF_BARS + 144);
     constexpr uint32_t kACol = 256;              // accumulator pairs: 4 x 64 columns in [0,256); A ring: 4 x (32 hi + 32 lo) above
 
