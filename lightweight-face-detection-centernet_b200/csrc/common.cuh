@@ -52,34 +52,19 @@ inline bool pdl_enabled() {
     return v != 0;
 }
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, int cluster, Args... args) {
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.gridDim = grid;
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
-    cudaLaunchAttribute at[2];
-    int n = 0;
-    if (cluster > 1) {  // thread-block cluster along x (grid.x is a multiple of it)
-        at[n].id = cudaLaunchAttributeClusterDimension;
-        at[n].val.clusterDim.x = (unsigned)cluster;
-        at[n].val.clusterDim.y = 1;
-        at[n].val.clusterDim.z = 1;
-        ++n;
-    }
-    if (pdl_enabled()) {
-        at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[n].val.programmaticStreamSerializationAllowed = 1;
-        ++n;
-    }
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = (unsigned)n;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kern, args...);
-}
-template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
-    return launch_pdl_cluster(kern, grid, block, smem, s, 1, args...);
 }
 
 // ---- device math -----------------------------------------------------------------------

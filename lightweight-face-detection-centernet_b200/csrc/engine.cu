@@ -970,8 +970,8 @@ int cf_debug_pw_gemm_time(int pw_engine, int epi, const float* dA, const float* 
         } else if (!rc) {
             rc = tc_plan(st, passes, epi, dA, dW, dOut, M, K, N, ea, &tl);
             launch = [&]() { return tc_launch(tl, s); };
-            snprintf(d, sizeof d, "tc NC=%d chunks=%d stages=%d atmem=%d direct=%d resident=%d nacc=%d mc=%d grid=%d smem=%zu", tl.p.NC,
-                     tl.p.nchunks, tl.p.stages, tl.p.atmem, tl.p.direct, tl.p.resident, tl.p.nacc, tl.p.mc, tl.grid, tl.smem);
+            snprintf(d, sizeof d, "tc NC=%d chunks=%d stages=%d atmem=%d direct=%d resident=%d nacc=%d grid=%d smem=%zu", tl.p.NC,
+                     tl.p.nchunks, tl.p.stages, tl.p.atmem, tl.p.direct, tl.p.resident, tl.p.nacc, tl.grid, tl.smem);
         }
     }
     if (desc && desc_cap > 0) snprintf(desc, (size_t)desc_cap, "%s", d);

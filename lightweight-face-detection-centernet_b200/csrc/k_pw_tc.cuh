@@ -52,7 +52,6 @@ struct TcLayer {        // per weight matrix, built once
 struct PwTcState {
     void* encode = nullptr;  // cuTensorMapEncodeTiled
     int sms = 148;
-    int max_clusters2 = 74;  // co-resident clusters of two full-size CTAs (cudaOccupancyMaxActiveClusters, pw_tc_init)
     std::map<const float*, TcLayer> layers;  // keyed by the [K][N] device weight pointer
 };
 
@@ -72,9 +71,6 @@ struct TcParams {
     uint32_t acol;   // first TMEM column of the A ring
     uint32_t amask;  // A ring slots - 1 (1 or 3)
     uint32_t ashift; // log2(A ring slots)
-    int mc;          // 1: launched as clusters of two CTAs that work on neighbouring row tiles of the same column chunk in lock
-                     //    step; each loads half of every streamed weight block and multicasts it to both (halves the L2 reads of
-                     //    the weight stream, which bound the K >= 384 layers of the stride-16/32 stages at ~9 TB/s of L2 traffic)
     int stg_bufs;    // staging buffers per epilogue warp (2 or 4)
     int dbg;         // development only (env CF_TC_DEBUG): 1 skip the A split, 2 skip the stores, 4 skip the MMAs
     int stages;
@@ -151,25 +147,6 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
                  "r"(bytes), "r"(bar)
                  : "memory");
-}
-// multicast forms (thread-block cluster of two): the copy lands at the same shared-memory offset of every CTA in the mask
-// and signals the mbarrier at the same offset there; the commit arrives on the barrier of every CTA in the mask
-__device__ __forceinline__ void bulk_load_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar), "h"(mask)
-                 : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
-                 : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
@@ -296,8 +273,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_ready + 8 * s, 4);
-            mbar_init(bar_empty + 8 * s, (p.atmem && p.resident) ? 4 : (p.mc ? 2 : 1));  // atmem+resident: the splitters free the
-                                                                                         // smem stage; mc: both CTAs' MMA commits
+            mbar_init(bar_empty + 8 * s, (p.atmem && p.resident) ? 4 : 1);  // atmem: the splitters free the smem stage
         }
         for (int a = 0; a < 4; ++a) {
             mbar_init(bar_aready + 8 * a, 4);
@@ -319,13 +295,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t crank = p.mc ? cluster_ctarank() : 0u;
-    if (p.mc) cluster_sync_all();  // the peer's barriers are initialised before anything is multicast at them
 
-    // item = m_tile * nchunks + chunk; mc: item = m_tile_PAIR * nchunks + chunk, this CTA takes tile 2 * pair + rank
-    const int n_items = p.n_items;
-    const int item0 = p.mc ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-    const int istride = p.mc ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int n_items = p.n_items;  // item = m_tile * nchunks + chunk
     const int nkb = p.nkb;
 
     if (warp == 0) {
@@ -348,9 +319,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         {
             int stage = 0;
             uint32_t phase = 0;
-            for (int item = item0; item < n_items; item += istride) {
-                const int mtp = item / p.nchunks, ch = item - mtp * p.nchunks;
-                const int mt = p.mc ? 2 * mtp + (int)crank : mtp;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int mt = item / p.nchunks, ch = item - mt * p.nchunks;
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                     const uint32_t sa = stages0 + stage * p.stage_bytes;
@@ -358,15 +328,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     if (elect_one()) {
                         mbar_expect_tx(bar_full + 8 * stage, tx);
                         tma_load_2d(sa, &tmA, kb * TC_BK, mt * TC_BM, bar_full + 8 * stage);
-                        if (!p.resident) {
-                            const uint8_t* bsrc = reinterpret_cast<const uint8_t*>(p.bimg) + (size_t)(ch * nkb + kb) * p.b_bytes_block;
-                            if (p.mc) {
-                                const uint32_t half = p.b_bytes_block >> 1;
-                                bulk_load_mc(sa + p.a_bytes_stage + crank * half, bsrc + crank * half, half, bar_full + 8 * stage, (uint16_t)3);
-                            } else {
-                                bulk_load(sa + p.a_bytes_stage, bsrc, p.b_bytes_block, bar_full + 8 * stage);
-                            }
-                        }
+                        if (!p.resident)
+                            bulk_load(sa + p.a_bytes_stage,
+                                      reinterpret_cast<const uint8_t*>(p.bimg) + (size_t)(ch * nkb + kb) * p.b_bytes_block,
+                                      p.b_bytes_block, bar_full + 8 * stage);
                     }
                     __syncwarp();
                     if (++stage == p.stages) stage = 0, phase ^= 1;
@@ -381,9 +346,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             int stage = 0;
             uint32_t phase = 0;
             uint32_t it = 0, acnt = 0;
-            for (int item = item0; item < n_items; item += istride, ++it) {
-                const int mtp = item / p.nchunks, ch = item - mtp * p.nchunks;
-                const int mt = p.mc ? 2 * mtp + (int)crank : mtp;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const int mt = item / p.nchunks, ch = item - mt * p.nchunks;
                 (void)mt;
                 const uint32_t as = it % (uint32_t)p.nacc, aphase = (it / (uint32_t)p.nacc) & 1u;
                 mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
@@ -426,10 +390,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                                 }
                             }
                             umma_commit(bar_aempty + 8 * aslot);
-                            if (!p.resident) {
-                                if (p.mc) umma_commit_mc(bar_empty + 8 * stage, (uint16_t)3);  // the stage is free in BOTH CTAs' eyes
-                                else umma_commit(bar_empty + 8 * stage);
-                            }
+                            if (!p.resident) umma_commit(bar_empty + 8 * stage);
                             if (kb == nkb - 1) umma_commit(bar_tfull + 8 * as);
                         }
                         __syncwarp();
@@ -468,8 +429,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                                 }
                             }
                         }
-                        if (p.mc) umma_commit_mc(bar_empty + 8 * stage, (uint16_t)3);
-                        else umma_commit(bar_empty + 8 * stage);  // frees the smem slot when these MMAs retire
+                        umma_commit(bar_empty + 8 * stage);  // frees the smem slot when these MMAs retire
                         if (kb == nkb - 1) umma_commit(bar_tfull + 8 * as);
                     }
                     __syncwarp();
@@ -483,7 +443,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             const int t = threadIdx.x - 128;  // 0..127
             int stage = 0;
             uint32_t phase = 0, acnt = 0;
-            for (int item = item0; item < n_items; item += istride) {
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 for (int kb = 0; kb < nkb; ++kb) {
                     if (p.atmem) {
                         // thread = one row of the 128 x 32 A block: read it from the TMA's swizzled image, split it and
@@ -546,11 +506,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         uint8_t* stg_ptr = base_ptr + (size_t)(warp - 8) * ((size_t)p.stg_bufs * TC_STG_BYTES);
         int buf = 0;
         uint32_t it = 0;
-        for (int item = item0; item < n_items; item += istride, ++it) {
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             if ((int)(it & 1u) != g) continue;  // the two groups take alternate items (any accumulator stage)
             const uint32_t as = it % (uint32_t)p.nacc;
-            const int mtp = item / p.nchunks, ch = item - mtp * p.nchunks;
-                const int mt = p.mc ? 2 * mtp + (int)crank : mtp;
+            const int mt = item / p.nchunks, ch = item - mt * p.nchunks;
             const uint32_t aphase = (it / (uint32_t)p.nacc) & 1u;
             mbar_wait(bar_tfull + 8 * as, aphase);
             tc_fence_after();
@@ -643,7 +602,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 
     tc_fence_before();
     __syncthreads();
-    if (p.mc) cluster_sync_all();  // the peer may still multicast into this CTA's stages / arrive on its barriers
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -681,34 +639,6 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// how many clusters of two 512-thread, full-shared-memory CTAs the device keeps resident at once (GPCs with an odd number
-// of SMs leave one SM without a partner)
-inline void pw_tc_query_clusters(PwTcState& st) {
-    auto kern = k_pw_tc<3, EPI_LINEAR>;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX) != cudaSuccess) {
-        cudaGetLastError();
-        return;
-    }
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof cfg);
-    cfg.gridDim = dim3((unsigned)(st.sms / 2 * 2));
-    cfg.blockDim = dim3(TC_THREADS);
-    cfg.dynamicSmemBytes = TC_SMEM_MAX;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n > 0) {
-        if (n < st.max_clusters2) st.max_clusters2 = n;
-    } else {
-        cudaGetLastError();
-    }
-}
-
 inline int pw_tc_init(PwTcState& st, int device) {
     cudaDriverEntryPointQueryResult qr;
     void* fn = nullptr;
@@ -717,8 +647,6 @@ inline int pw_tc_init(PwTcState& st, int device) {
     st.encode = fn;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) st.sms = prop.multiProcessorCount;
-    st.max_clusters2 = st.sms / 2;
-    pw_tc_query_clusters(st);
     return CF_OK;
 }
 
@@ -754,7 +682,6 @@ struct TcTune {
     int grid = 0;     // CTA count cap (0: one per SM)
     int rchunk = -1;  // per-CTA resident column chunk when the whole weight image does not fit (-1: yes)
     int stg = 0;      // staging buffers per epilogue warp (0: two)
-    int mc = -1;      // clusters of two CTAs with multicast weight blocks for streamed-weight layers (-1: K >= 384)
 };
 struct TcTuneEntry {
     int K, N;
@@ -781,7 +708,6 @@ inline TcTune tc_tune_for(int K, int N, int passes) {
     if (const char* ev = getenv("CF_TC_GRID")) t.grid = atoi(ev);
     if (const char* ev = getenv("CF_TC_RCHUNK")) t.rchunk = atoi(ev);
     if (const char* ev = getenv("CF_TC_STG")) t.stg = atoi(ev);
-    if (const char* ev = getenv("CF_TC_MC")) t.mc = atoi(ev);
     const int nc_max = passes == 3 ? 128 : 192;
     if (t.nc < 0 || t.nc % 32 != 0 || t.nc > nc_max) t.nc = 0;
     return t;
@@ -916,22 +842,12 @@ inline int tc_plan(PwTcState& st, int passes, int epi, const float* A, const flo
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
     if (stages < 2) return fail(CF_EINVAL, "tc_plan: K=%d N=%d does not fit the shared-memory pipeline", K, N);
     p.stages = stages;
-    {   // cluster-of-two multicast of the streamed weight blocks
-        const int mtiles = (M + TC_BM - 1) / TC_BM;
-        const bool want = tune.mc >= 0 ? tune.mc != 0 : false;
-        p.mc = (want && passes == 3 && !p.resident && mtiles >= 2 && (p.b_bytes_block >> 1) % 16u == 0 && st.sms >= 2) ? 1 : 0;
-        if (p.mc) p.n_items = ((mtiles + 1) / 2) * L.nchunks;
-    }
     p.off_bres = stg_bytes;
     p.off_stages = stg_bytes + b_res;
     p.off_bars = p.off_stages + (uint32_t)stages * p.stage_bytes;
     tl->smem = (size_t)p.off_bars + bar_bytes + 1024;
     tl->grid = p.n_items < st.sms ? p.n_items : st.sms;
     if (p.resident == 2) tl->grid = tl->grid / L.nchunks * L.nchunks;  // n_items is a multiple of nchunks
-    if (p.mc) {
-        const int clusters = p.n_items < st.max_clusters2 ? p.n_items : st.max_clusters2;
-        tl->grid = 2 * clusters;
-    }
     if (tune.grid > 0 && tune.grid < tl->grid) tl->grid = tune.grid;
     tl->passes = passes;
     tl->epi = epi;
@@ -946,7 +862,7 @@ inline cudaError_t tc_launch_t(const TcLaunch& tl, cudaStream_t s) {
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    return launch_pdl_cluster(k_pw_tc<kPasses, EPI>, dim3(tl.grid), dim3(TC_THREADS), tl.smem, s, tl.p.mc ? 2 : 1, tl.tmA, tl.tmOut, tl.p);
+    return launch_pdl(k_pw_tc<kPasses, EPI>, dim3(tl.grid), dim3(TC_THREADS), tl.smem, s, tl.tmA, tl.tmOut, tl.p);
 }
 
 inline cudaError_t tc_launch(const TcLaunch& tl, cudaStream_t s) {

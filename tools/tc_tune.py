@@ -56,8 +56,6 @@ def variants(K, N):
             v.append({"CF_TC_NC": nc, "CF_TC_DIRECT": 0, "CF_TC_ATMEM": atmem, "CF_PWN": 0, "CF_TC_STG": 4})
         if nc <= 64:
             v.append({"CF_TC_NC": nc, "CF_TC_DIRECT": 0, "CF_TC_ATMEM": 1, "CF_PWN": 0, "CF_TC_NACC": 3})
-        for atmem in ((1, 0) if nc <= 96 else (0,)):
-            v.append({"CF_TC_NC": nc, "CF_TC_DIRECT": 0, "CF_TC_ATMEM": atmem, "CF_PWN": 0, "CF_TC_RCHUNK": 0, "CF_TC_MC": 1})
         if nc <= 64 and K <= 32 and n32 <= nc:
             v.append({"CF_TC_NC": nc, "CF_PWN": 1})
     return v
@@ -110,7 +108,7 @@ def main():
             f.write(json.dumps({"key": key, "status": "started"}) + "\n")
             f.flush()
             os.fsync(f.fileno())
-            for k in ("CF_TC_NC", "CF_TC_DIRECT", "CF_TC_ATMEM", "CF_PWN", "CF_TC_RCHUNK", "CF_TC_STG", "CF_TC_NACC", "CF_TC_MC"):
+            for k in ("CF_TC_NC", "CF_TC_DIRECT", "CF_TC_ATMEM", "CF_PWN", "CF_TC_RCHUNK", "CF_TC_STG", "CF_TC_NACC"):
                 os.environ.pop(k, None)
             for k, val in v.items():
                 os.environ[k] = str(val)
