@@ -23,6 +23,7 @@ struct PwnParams {
     const float* bimg;  // [kb][hi NC x 128 B | lo NC x 128 B]
     float* out;
     int M, K, N, NC, nkb, n_tiles, nst;
+    int three;  // 1: NC <= 32 -- 128 TMEM columns (accumulator pair + ONE A slot) and a shorter A ring, three CTAs per SM
     uint32_t off_b, off_bars, b_bytes;
     EpiArgs ea;
 };
@@ -55,7 +56,9 @@ __global__ void __launch_bounds__(PWN_THREADS, 2) k_pwn(const __grid_constant__ 
     const uint32_t bars = base + p.off_bars;  // [0..nst) A full | B full | A-slot free x2 | accumulator ready
     const uint32_t bar_b = bars + 8 * nst, bar_afree = bar_b + 8, bar_acc = bar_afree + 16;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + p.off_bars + 8 * nst + 40);
-    constexpr uint32_t kACol = 128;  // TMEM: accumulator pair in columns [0, 2NC <= 128), A ring 2 x (32 hi + 32 lo) above
+    // TMEM: accumulator pair in columns [0, 2NC), A ring of (32 hi + 32 lo)-column slots above: two slots from column 128
+    // (256 columns, two CTAs per SM) or one slot from column 64 (128 columns, three CTAs per SM)
+    const uint32_t kACol = p.three ? 64u : 128u, kTmemCols = p.three ? 128u : 256u;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = warp & 3, half = warp >> 2;  // TMEM lane quarter; which 16 of a K block's 32 elements / which column half
@@ -67,7 +70,7 @@ __global__ void __launch_bounds__(PWN_THREADS, 2) k_pwn(const __grid_constant__ 
         fence_barrier_init();
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -101,7 +104,7 @@ __global__ void __launch_bounds__(PWN_THREADS, 2) k_pwn(const __grid_constant__ 
         const int kb = (int)(j % nkb);
         const int tile = (int)blockIdx.x + (int)(j / nkb) * (int)gridDim.x;
         const int stage = (int)(j % nst);
-        const uint32_t aslot = (uint32_t)(j & 1);
+        const uint32_t aslot = p.three ? 0u : (uint32_t)(j & 1);
         // ---- split: this thread's 16 elements of row (32q + lane) -> tf32 hi / lo -> TMEM ----
         mbar_wait(bars + 8 * stage, (uint32_t)(j / nst) & 1u);
         const int row = q * 32 + lane;
@@ -127,7 +130,11 @@ __global__ void __launch_bounds__(PWN_THREADS, 2) k_pwn(const __grid_constant__ 
             hi[4 * c] = tf32_hi(v.x), hi[4 * c + 1] = tf32_hi(v.y), hi[4 * c + 2] = tf32_hi(v.z), hi[4 * c + 3] = tf32_hi(v.w);
             lo[4 * c] = v.x - hi[4 * c], lo[4 * c + 1] = v.y - hi[4 * c + 1], lo[4 * c + 2] = v.z - hi[4 * c + 2], lo[4 * c + 3] = v.w - hi[4 * c + 3];
         }
-        if (j >= 2) mbar_wait(bar_afree + 8 * aslot, (uint32_t)((j >> 1) - 1) & 1u);  // MMAs of job j-2 have read this slot
+        if (p.three) {
+            if (j >= 1) mbar_wait(bar_afree, (uint32_t)(j - 1) & 1u);  // MMAs of job j-1 have read the slot
+        } else if (j >= 2) {
+            mbar_wait(bar_afree + 8 * aslot, (uint32_t)((j >> 1) - 1) & 1u);  // MMAs of job j-2 have read this slot
+        }
         tc_fence_after();
         const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + kACol + aslot * 64u + (uint32_t)half * 16u;
         tmem_st16(ta, hi);
@@ -197,7 +204,7 @@ __global__ void __launch_bounds__(PWN_THREADS, 2) k_pwn(const __grid_constant__ 
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
     }
 }
 
@@ -235,8 +242,13 @@ inline int pwn_plan(PwTcState& st, int epi, const float* A, const float* Wkn, fl
     p.b_bytes = (uint32_t)L.img_bytes;
     p.ea = ea;
     const uint32_t b_al = (p.b_bytes + 1023u) & ~1023u;
-    const int ctas = 2;  // 256 TMEM columns per CTA (accumulator pair + two-slot A ring): two CTAs fill the SM's 512
-    int nst = ((int)(TC_SMEM_MAX / 2) - 1024 - 2048 - (int)b_al) / TC_A_BYTES;
+    // 256 TMEM columns per CTA (accumulator pair + two-slot A ring): two CTAs fill the SM's 512; or 128 columns and three CTAs.
+    // Measured: layer0 projection (linear epilogue) 141 -> 115 us with three, the IDAUp laterals 74 -> 84 us (their epilogue
+    // wants the registers / L1 of the larger share), so three CTAs only without the IDAUp epilogue.  CF_PWN_CTAS=2|3 overrides.
+    p.three = (L.NC <= 32 && epi != EPI_IDAUP) ? 1 : 0;
+    if (const char* ev = getenv("CF_PWN_CTAS")) p.three = (atoi(ev) == 3 && L.NC <= 32) ? 1 : 0;
+    const int ctas = p.three ? 3 : 2;
+    int nst = ((int)(TC_SMEM_MAX / ctas) - 1024 - 2048 - (int)b_al) / TC_A_BYTES;
     if (nst > 6) nst = 6;
     if (nst < 2) return fail(CF_EINVAL, "pwn_plan: does not fit shared memory");
     p.nst = nst;
