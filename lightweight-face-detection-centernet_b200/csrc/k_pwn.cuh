@@ -100,6 +100,8 @@ __global__ void __launch_bounds__(PWN_THREADS, 2) k_pwn(const __grid_constant__ 
     const uint32_t d_main = tmem_base, d_corr = tmem_base + (uint32_t)p.NC;
     const uint32_t blk_bytes = (uint32_t)p.NC * 256u;  // one K block of the weight image (hi | lo)
 
+    float4 lowv[4];  // IDAUp: low-resolution operands of the current tile (fetched at its first K block, used after its last)
+    int lowq = 0;
     for (long long j = 0; j < total; ++j) {
         const int kb = (int)(j % nkb);
         const int tile = (int)blockIdx.x + (int)(j / nkb) * (int)gridDim.x;
@@ -110,8 +112,6 @@ __global__ void __launch_bounds__(PWN_THREADS, 2) k_pwn(const __grid_constant__ 
         const int row = q * 32 + lane;
         // IDAUp: this thread's low-resolution operands are fetched now, so the L2 latency runs under the split -> MMA chain
         // instead of after the accumulator wait (up3: 90 us per launch against 48 us for the same GEMM with a linear epilogue)
-        float4 lowv[4];
-        int lowq = 0;
         if (EPI == EPI_IDAUP && kb == 0) {
             const int grow0 = tile * TC_BM + row;
             if (grow0 < p.M) {
@@ -217,11 +217,18 @@ struct PwnLaunch {
 };
 
 // eligible: 3-pass, one column chunk of <= 64 columns, weight image small enough to sit beside a >= 3 stage A ring
-// in half an SM's shared memory
+// in a half (or a third) of an SM's shared memory
 // Measured (tools/tc_shape_probe.py, same call): K=32,N=16: 179 -> 157 us; K=144,N=24: 159 -> 172 us; K=192,N=32: 53 -> 61 us --
 // the CTA-wide barrier per K block costs more than the hand-off chain it removes once a tile has several K blocks, so
 // only single-K-block layers (K <= 32: layer0 projection, FPN laterals up2/up3) take this kernel.
-inline bool pwn_eligible(const TcLayer& L) { return L.nchunks == 1 && L.NC <= 64 && L.nkb == 1 && L.img_bytes <= 49152; }
+inline bool pwn_eligible(const TcLayer& L) {
+    // up to three K blocks (K <= 96): with three CTAs per SM and the elect-based issue the role-free kernel now also wins on
+    // layer1.0's projection (80 -> 74 us); from five K blocks on the weight image forces two CTAs and the per-K-block CTA
+    // barrier loses again (K = 144: 123 -> 187 us).  CF_PWN_NKB overrides (development probe).
+    int max_nkb = 3;
+    if (const char* ev = getenv("CF_PWN_NKB")) max_nkb = atoi(ev);
+    return L.nchunks == 1 && L.NC <= 64 && L.nkb <= max_nkb && L.img_bytes <= 49152;
+}
 
 inline int pwn_plan(PwTcState& st, int epi, const float* A, const float* Wkn, float* out, int M, int K, int N, EpiArgs ea, PwnLaunch* pl) {
     auto it = st.layers.find(Wkn);
@@ -247,8 +254,13 @@ inline int pwn_plan(PwTcState& st, int epi, const float* A, const float* Wkn, fl
     // wants the registers / L1 of the larger share), so three CTAs only without the IDAUp epilogue.  CF_PWN_CTAS=2|3 overrides.
     p.three = (L.NC <= 32 && epi != EPI_IDAUP) ? 1 : 0;
     if (const char* ev = getenv("CF_PWN_CTAS")) p.three = (atoi(ev) == 3 && L.NC <= 32) ? 1 : 0;
-    const int ctas = p.three ? 3 : 2;
+    int ctas = p.three ? 3 : 2;
     int nst = ((int)(TC_SMEM_MAX / ctas) - 1024 - 2048 - (int)b_al) / TC_A_BYTES;
+    if (p.three && nst < 3) {  // the weight image leaves no room for a ring in a third of the shared memory
+        p.three = 0;
+        ctas = 2;
+        nst = ((int)(TC_SMEM_MAX / ctas) - 1024 - 2048 - (int)b_al) / TC_A_BYTES;
+    }
     if (nst > 6) nst = 6;
     if (nst < 2) return fail(CF_EINVAL, "pwn_plan: does not fit shared memory");
     p.nst = nst;
