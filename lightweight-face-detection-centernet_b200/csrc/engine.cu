@@ -283,7 +283,7 @@ int build_plan(cf_engine* e, const void* input, int fmt, int B, int H, int W) {
         const char* ev = getenv("CF_STEM_TC");
         const int stem_mode = ev ? atoi(ev) : 2;
         if (engine_is_tc(e->pw_engine) && stem_mode == 2) {
-            StcParams sp;
+            StcParams sp{};
             int sgrid = 0;
             if ((rc = stc_plan(e->tc, e->w["stem.w"], input, lut, out, B, H, W, &sp, &sgrid))) return rc;
             const int sms = e->tc.sms;
@@ -292,7 +292,7 @@ int build_plan(cf_engine* e, const void* input, int fmt, int B, int H, int W) {
             else
                 P.push_back({CLS_STEM, [=](cudaStream_t s) { return stc2_launch_t<0>(sp, sms, s); }});
         } else if (engine_is_tc(e->pw_engine) && stem_mode == 1) {
-            StcParams sp;
+            StcParams sp{};
             int sgrid = 0;
             if ((rc = stc_plan(e->tc, e->w["stem.w"], input, lut, out, B, H, W, &sp, &sgrid))) return rc;
             if (fmt == CF_IN_U8_HWC)
