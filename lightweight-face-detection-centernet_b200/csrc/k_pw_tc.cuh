@@ -12,18 +12,20 @@
 // shared memory by four "splitter" warps between the TMA and the MMA stage (element-wise, so the
 // swizzled layout is irrelevant to them).  kPasses == 1 is the throughput mode.
 //
-// Narrow layers (column chunk NC <= 64, i.e. the projection convs): an MMA there costs the time to stream its 128 x 32 B
-// A operand out of shared memory, three times per K step in the naive 3-pass form.  For them the splitter warps
-// hand the split operand to the tensor core through TENSOR MEMORY instead: each splitter thread owns one row of the
-// 128 x 32 block, reads it once from the TMA's swizzled image, and tcgen05.st's hi and lo halves into a four-slot
-// TMEM ring (lane = row, column = k); the MMAs take A from TMEM ([a_tmem] operand form) and only the small weight
-// tile from shared memory, the smem stage (16 KB, no lo copy) is released as soon as the splitters have read it.
+// Column chunks NC <= 96: the splitter warps hand the split operand to the tensor core through TENSOR MEMORY instead of
+// shared memory: each splitter thread owns one row of the 128 x 32 block, reads it once from the TMA's swizzled image, and
+// tcgen05.st's hi and lo halves into a TMEM ring (lane = row, column = k; four slots for NC <= 64, two for NC <= 96); the
+// MMAs take A from TMEM ([a_tmem] operand form) and only the weight tile from shared memory, and the smem stage is
+// 16 KB (no lo copy) -- which is what gives the wide stride-16/32 layers four pipeline stages instead of two.
 //
 // Warp roles (512 threads, one persistent CTA per SM):
-//   warp 0      TMA producer          warp 1      MMA issuer (one elected lane)
+//   warp 0      TMA producer          warp 1      MMA issuer            (whole warp walks the loop, elect.sync lane issues)
 //   warp 2      TMEM allocator        warp 3      idle
-//   warps 4-7   A splitters (3-pass)  warps 8-15  two epilogue groups, one per TMEM accumulator stage:
-//                                                 tcgen05.ld -> epilogue math -> swizzled smem -> TMA store
+//   warps 4-7   A splitters (3-pass)  warps 8-15  two epilogue groups taking alternate items:
+//                                                 tcgen05.ld -> epilogue math -> swizzled smem -> TMA store (or row stores)
+//
+// The launch plan of a layer -- NC, A route, epilogue store kind, weights resident / one resident chunk per CTA / streamed,
+// accumulator and staging ring depths -- is tc_plan's cost model overridden by tc_tuned_table (tools/tc_tune.py).
 #pragma once
 #include <cuda.h>
 
