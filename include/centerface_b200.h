@@ -174,6 +174,13 @@ int cf_debug_tma_stream(const float* dA, int M, int K, int stages, int box_rows,
 int cf_resize_tables(int sh, int sw, int dh, int dw, int32_t* tab, size_t tab_ints, int* area2);
 int cf_resize_u8(const uint8_t* src, int batch, int sh, int sw, uint8_t* dst, int dh, int dw, const int32_t* tab, int area2,
                  void* stream);
+/* cv2.warpAffine(img, M, (dw,dh), flags=cv2.INTER_LINEAR) on 8UC3 with the default constant-0 border: the letter-box step
+ * of the reference's loader (dataset/dataset.py:130-134, trans_input from utils/image.py:27-61), bit-exact with OpenCV 4.x.
+ * cf_warp_affine_tables builds, on the HOST and in fp64 like OpenCV, the integer tables of the inverse map from the FORWARD
+ * 2x3 matrix M (row major, 6 doubles): adelta[dw] | bdelta[dw] | X0[dh] | Y0[dh] (2*dw + 2*dh int32);
+ * cf_warp_affine_u8 warps a DEVICE batch [B,sh,sw,3] -> [B,dh,dw,3] (the same matrix for every image) with a DEVICE copy. */
+int cf_warp_affine_tables(const double* M, int dh, int dw, int32_t* tab, size_t tab_ints);
+int cf_warp_affine_u8(const uint8_t* src, int batch, int sh, int sw, uint8_t* dst, int dh, int dw, const int32_t* tab, void* stream);
 /* The whole body of CenterFace.__call__ (centerface.py:29-62) for one HOST u8 BGR image [h,w,3] at its own size:
  * H2D, resize to (net_h,net_w), normalise, network, sigmoid/clamp, threshold decode (variant A/B), NMS, //scale,
  * D2H of out_dets [cap,5], out_lms [cap,10] (may be NULL) and out_count (negative = more than cap candidates).  */

@@ -45,6 +45,8 @@ SIGNATURES = {
     "cf_debug_tma_stream": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "cf_resize_tables": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, _i]),
     "cf_resize_u8": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp]),
+    "cf_warp_affine_tables": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_size_t]),
+    "cf_warp_affine_u8": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, _vp, _vp]),
     "cf_detect_image_host": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
                                        C.c_float, C.c_int, _vp, _vp, _vp]),
     "cf_launch_count": (C.c_longlong, [_vp]),

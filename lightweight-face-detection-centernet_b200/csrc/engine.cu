@@ -8,6 +8,7 @@
 // There is no CPU fallback in this file: every entry point either launches kernels on an
 // sm_100 device or fails with an error code.
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdarg.h>
 
 #include <functional>
@@ -880,6 +881,37 @@ int cf_resize_tables(int sh, int sw, int dh, int dw, int32_t* tab, size_t tab_in
     t.build(sh, sw, dh, dw);
     memcpy(tab, t.tab.data(), t.tab.size() * sizeof(int32_t));
     *area2 = t.area2;
+    return CF_OK;
+}
+
+int cf_warp_affine_tables(const double* M, int dh, int dw, int32_t* tab, size_t tab_ints) {
+    CF_CHECK(M && tab && dh > 0 && dw > 0, CF_EINVAL, "cf_warp_affine_tables: bad arguments");
+    CF_CHECK(tab_ints >= (size_t)2 * dw + (size_t)2 * dh, CF_ECAP, "cf_warp_affine_tables: table needs %zu ints", (size_t)2 * dw + (size_t)2 * dh);
+    // cv::warpAffine without WARP_INVERSE_MAP: invert the forward matrix in fp64, then AB_BITS = 10 fixed point
+    double D = M[0] * M[4] - M[1] * M[3];
+    D = D != 0 ? 1. / D : 0;
+    const double m0 = M[4] * D, m4 = M[0] * D, m1 = M[1] * (-D), m3 = M[3] * (-D);
+    const double b1 = -m0 * M[2] - m1 * M[5], b2 = -m3 * M[2] - m4 * M[5];
+    auto rnd = [](double v) -> int32_t {  // saturate_cast<int>(double) = cvRound (round half to even) + saturation
+        const double r = nearbyint(v);
+        return r >= 2147483647.0 ? INT32_MAX : r <= -2147483648.0 ? INT32_MIN : (int32_t)r;
+    };
+    for (int x = 0; x < dw; ++x) {
+        tab[x] = rnd(m0 * x * 1024.0);
+        tab[dw + x] = rnd(m3 * x * 1024.0);
+    }
+    for (int y = 0; y < dh; ++y) {
+        tab[2 * dw + y] = rnd((m1 * y + b1) * 1024.0) + 16;
+        tab[2 * dw + dh + y] = rnd((m4 * y + b2) * 1024.0) + 16;
+    }
+    return CF_OK;
+}
+
+int cf_warp_affine_u8(const uint8_t* src, int batch, int sh, int sw, uint8_t* dst, int dh, int dw, const int32_t* tab, void* stream) {
+    CF_CHECK(src && dst && tab && batch > 0 && sh > 0 && sw > 0 && dh > 0 && dw > 0, CF_EINVAL, "cf_warp_affine_u8: bad arguments");
+    const long long n = (long long)batch * dh * dw;
+    k_warp_affine_u8<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, dst, tab, batch, sh, sw, dh, dw);
+    CF_CUDA(cudaGetLastError());
     return CF_OK;
 }
 

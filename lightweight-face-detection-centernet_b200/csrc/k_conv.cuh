@@ -47,6 +47,41 @@ __global__ void __launch_bounds__(256) k_resize_u8(const uint8_t* __restrict__ s
 }
 
 // ----------------------------------------------------------------------------------------
+// K0b pre-processing: cv2.warpAffine(img, M, (W', H'), flags=INTER_LINEAR) on 8UC3 with the default constant-0 border --
+// the letter-box step of the reference's loader (dataset/dataset.py:130-134) -- on the device and bit-exact (OpenCV
+// imgwarp.cpp: fixed-point source positions + remap's 15-bit bilinear table; restated and pinned against cv2 in
+// oracle/centerface_oracle.py::warp_affine_linear_u8).  The inverse map's per-column / per-row integer tables are built on
+// the host in fp64 exactly as OpenCV does (cf_warp_affine_tables); one thread = one output pixel x 3 channels.
+//   tab layout (int32): adelta[dw] | bdelta[dw] | X0[dh] | Y0[dh]   (positions in 1/1024 pixel, round_delta included)
+// ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_warp_affine_u8(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                                        const int32_t* __restrict__ tab, int B, int sh, int sw, int dh, int dw) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= (long long)B * dh * dw) return;
+    const int dx = (int)(i % dw);
+    const int dy = (int)((i / dw) % dh);
+    const int b = (int)(i / ((long long)dw * dh));
+    const int X = (tab[2 * dw + dy] + tab[dx]) >> 5;            // AB_BITS - INTER_BITS
+    const int Y = (tab[2 * dw + dh + dy] + tab[dw + dx]) >> 5;
+    const int sx = max(-32768, min(32767, X >> 5)), sy = max(-32768, min(32767, Y >> 5));  // saturate_cast<short>
+    const int fx = X & 31, fy = Y & 31;
+    int w00 = 32 * (32 - fx) * (32 - fy), w01 = 32 * fx * (32 - fy), w10 = 32 * (32 - fx) * fy, w11 = 32 * fx * fy;
+    if (fx == 0 && fy == 0) w00 = 32767, w11 = 1;  // saturate_cast<short>(32768) + the table's sum fix-up
+    const uint8_t* s = src + (size_t)b * sh * sw * 3;
+    const bool x0 = sx >= 0 && sx < sw, x1 = sx + 1 >= 0 && sx + 1 < sw, y0 = sy >= 0 && sy < sh, y1 = sy + 1 >= 0 && sy + 1 < sh;
+    uint8_t* o = dst + (size_t)i * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int p00 = (y0 && x0) ? s[((size_t)sy * sw + sx) * 3 + c] : 0;
+        const int p01 = (y0 && x1) ? s[((size_t)sy * sw + sx + 1) * 3 + c] : 0;
+        const int p10 = (y1 && x0) ? s[((size_t)(sy + 1) * sw + sx) * 3 + c] : 0;
+        const int p11 = (y1 && x1) ? s[((size_t)(sy + 1) * sw + sx + 1) * 3 + c] : 0;
+        const int v = (p00 * w00 + p01 * w01 + p10 * w10 + p11 * w11 + (1 << 14)) >> 15;
+        o[c] = (uint8_t)min(255, max(0, v));
+    }
+}
+
+// ----------------------------------------------------------------------------------------
 // K1 stem: ZeroPad2d(0,1,0,1) + conv3x3 s2 3->32 (no bias) + Swish   (model/centernet.py:224)
 //   FMT 0: fp32 NCHW normalised input (what EfficientNet.forward receives)
 //   FMT 1: u8 HWC BGR input; /255, -mean, /std (centerface.py:32-34) applied through a

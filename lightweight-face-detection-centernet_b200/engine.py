@@ -234,6 +234,49 @@ def resize_u8(images, dh, dw):
     return out
 
 
+def warp_affine_u8(images, M, dw, dh):
+    """cv2.warpAffine(img, M, (dw, dh), flags=cv2.INTER_LINEAR) (constant-0 border) for a cuda uint8 batch [B,h,w,3] ->
+    [B,dh,dw,3], bit-exact with OpenCV; M is the forward 2x3 matrix (the reference's trans_input, dataset/dataset.py:130-134)."""
+    import torch
+    lib = L.load()
+    assert images.is_cuda and images.dtype == torch.uint8 and images.is_contiguous() and images.shape[3] == 3
+    B, sh, sw, _ = images.shape
+    Mh = np.ascontiguousarray(np.asarray(M, dtype=np.float64).reshape(6))
+    tab = np.empty((2 * dw + 2 * dh,), np.int32)
+    L.check(lib.cf_warp_affine_tables(C.c_void_p(Mh.ctypes.data), dh, dw, C.c_void_p(tab.ctypes.data), tab.size), "cf_warp_affine_tables")
+    t_dev = torch.from_numpy(tab).to(images.device)
+    out = torch.empty((B, dh, dw, 3), dtype=torch.uint8, device=images.device)
+    with torch.cuda.device(images.device):
+        L.check(lib.cf_warp_affine_u8(C.c_void_p(images.data_ptr()), B, sh, sw, C.c_void_p(out.data_ptr()), dh, dw,
+                                      C.c_void_p(t_dev.data_ptr()), C.c_void_p(torch.cuda.current_stream(images.device).cuda_stream)),
+                "cf_warp_affine_u8")
+    return out
+
+
+def letterbox_matrix(h, w, out_w, out_h):
+    """trans_input of the reference's loader for the validation split: get_affine_transform((w/2, h/2), max(h, w), 0,
+    [out_w, out_h]) (dataset/dataset.py:113-131, utils/image.py:27-61), built with the same float32 points and the same
+    cv2.getAffineTransform call."""
+    import cv2
+    c = np.array([w / 2., h / 2.], dtype=np.float32)
+    s = max(h, w) * 1.0
+    src = np.zeros((3, 2), dtype=np.float32)
+    dst = np.zeros((3, 2), dtype=np.float32)
+    src[0, :] = c
+    src[1, :] = c + np.array([0, s * -0.5], dtype=np.float64)
+    dst[0, :] = [out_w * 0.5, out_h * 0.5]
+    dst[1, :] = np.array([out_w * 0.5, out_h * 0.5], np.float32) + np.array([0, out_w * -0.5], np.float32)
+    third = lambda a, b: b + np.array([-(a - b)[1], (a - b)[0]], dtype=np.float32)  # noqa: E731  get_3rd_point
+    src[2, :] = third(src[0, :], src[1, :])
+    dst[2, :] = third(dst[0, :], dst[1, :])
+    return cv2.getAffineTransform(np.float32(src), np.float32(dst))
+
+
+def letterbox_u8(images, out_w=640, out_h=640):
+    """The loader's letter-box of a cuda uint8 batch [B,h,w,3] of equally sized images to (out_h, out_w), on the device."""
+    return warp_affine_u8(images, letterbox_matrix(images.shape[1], images.shape[2], out_w, out_h), out_w, out_h)
+
+
 def ctdet_decode(heat, wh, reg=None, cat_spec_wh=False, K=100, return_inds=False):
     """Drop-in for centerface_ext.ctdet_decode (centerface_ext.py:52): cuda fp32 tensors
     heat [B,1,h,w] (post-sigmoid), wh/reg [B,2,h,w] -> detections [B,K,6]."""

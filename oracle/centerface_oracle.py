@@ -250,6 +250,83 @@ def resize_linear_u8(src, dh, dw):
     return out.astype(np.uint8)
 
 
+def warp_affine_tables(M, dw, dh):
+    """The integer source-coordinate tables of cv2.warpAffine(src, M, (dw,dh), flags=INTER_LINEAR) (OpenCV 4.x
+    imgwarp.cpp: the forward 2x3 matrix is inverted in fp64, then every destination pixel gets a source position in
+    1/32-pixel fixed point: AB_BITS = 10, INTER_BITS = 5, round_delta = 16):
+        X(x,y) = (X0[y] + adelta[x]) >> 5,   Y(x,y) = (Y0[y] + bdelta[x]) >> 5
+    -> (adelta[dw], bdelta[dw], X0[dh], Y0[dh]) int32.  This is the letter-box step of the reference's loader,
+    dataset/dataset.py:130-134."""
+    M = np.asarray(M, dtype=np.float64).reshape(2, 3)
+    D = M[0, 0] * M[1, 1] - M[0, 1] * M[1, 0]
+    D = 1.0 / D if D != 0 else 0.0
+    m0, m4 = M[1, 1] * D, M[0, 0] * D
+    m1, m3 = M[0, 1] * (-D), M[1, 0] * (-D)
+    b1 = -m0 * M[0, 2] - m1 * M[1, 2]
+    b2 = -m3 * M[0, 2] - m4 * M[1, 2]
+    x = np.arange(dw, dtype=np.float64)
+    y = np.arange(dh, dtype=np.float64)
+    rnd = lambda v: np.rint(v).astype(np.int64).clip(-2 ** 31, 2 ** 31 - 1).astype(np.int32)  # noqa: E731  saturate_cast<int> = cvRound
+    adelta, bdelta = rnd(m0 * x * 1024.0), rnd(m3 * x * 1024.0)
+    X0 = rnd((m1 * y + b1) * 1024.0) + 16
+    Y0 = rnd((m4 * y + b2) * 1024.0) + 16
+    return adelta, bdelta, X0, Y0
+
+
+def warp_affine_linear_u8(src, M, dw, dh):
+    """cv2.warpAffine(src, M, (dw, dh), flags=cv2.INTER_LINEAR) for 8UC3, BORDER_CONSTANT 0, bit for bit: the tables
+    above, then remap's fixed-point bilinear kernel -- 15-bit weights 32*(32-fx | fx)*(32-fy | fy) (the (0,0) entry is
+    {32767,0,0,1}: saturate_cast<short>(32768) plus the table's sum fix-up), out-of-image samples = 0,
+    (sum + 2^14) >> 15."""
+    src = np.ascontiguousarray(src, dtype=np.uint8)
+    H, W = src.shape[:2]
+    adelta, bdelta, X0, Y0 = warp_affine_tables(M, dw, dh)
+    X = (X0[:, None].astype(np.int64) + adelta[None, :]) >> 5
+    Y = (Y0[:, None].astype(np.int64) + bdelta[None, :]) >> 5
+    sx = np.clip(X >> 5, -32768, 32767)
+    sy = np.clip(Y >> 5, -32768, 32767)
+    fx, fy = X & 31, Y & 31
+    w00 = 32 * (32 - fx) * (32 - fy)
+    w01 = 32 * fx * (32 - fy)
+    w10 = 32 * (32 - fx) * fy
+    w11 = 32 * fx * fy
+    zero = (fx == 0) & (fy == 0)
+    w00 = np.where(zero, 32767, w00)
+    w11 = np.where(zero, 1, w11)
+    pad = np.zeros((H + 2, W + 2, 3), dtype=np.int64)  # constant border 0; positions further out are all-zero anyway
+    pad[1:-1, 1:-1] = src
+
+    def at(yy, xx):
+        ok = (yy >= -1) & (yy <= H) & (xx >= -1) & (xx <= W)
+        v = pad[np.clip(yy + 1, 0, H + 1), np.clip(xx + 1, 0, W + 1)]
+        return np.where(ok[..., None], v, 0)
+
+    acc = (at(sy, sx) * w00[..., None] + at(sy, sx + 1) * w01[..., None] + at(sy + 1, sx) * w10[..., None] +
+           at(sy + 1, sx + 1) * w11[..., None])
+    return np.clip((acc + (1 << 14)) >> 15, 0, 255).astype(np.uint8)
+
+
+def letterbox_matrix(h, w, out_w, out_h):
+    """trans_input of dataset/dataset.py:113-131 for the 'val' split: get_affine_transform(c, s, 0, [out_w, out_h]) with
+    c = (w/2, h/2) (float32), s = max(h, w): a uniform scale out_w/s about the centre (utils/image.py:27-61).  Returned
+    as the forward 2x3 fp64 matrix cv2.getAffineTransform gives for those three point pairs."""
+    import cv2
+    c = np.array([w / 2., h / 2.], dtype=np.float32)
+    s = max(h, w) * 1.0
+    src = np.zeros((3, 2), dtype=np.float32)
+    dst = np.zeros((3, 2), dtype=np.float32)
+    src_dir = np.array([0, s * -0.5], dtype=np.float64)   # get_dir([0, -s/2], 0)
+    dst_dir = np.array([0, out_w * -0.5], np.float32)
+    src[0, :] = c
+    src[1, :] = c + src_dir
+    dst[0, :] = [out_w * 0.5, out_h * 0.5]
+    dst[1, :] = np.array([out_w * 0.5, out_h * 0.5], np.float32) + dst_dir
+    third = lambda a, b: b + np.array([-(a - b)[1], (a - b)[0]], dtype=np.float32)  # noqa: E731  get_3rd_point
+    src[2, :] = third(src[0, :], src[1, :])
+    dst[2, :] = third(dst[0, :], dst[1, :])
+    return cv2.getAffineTransform(np.float32(src), np.float32(dst))
+
+
 def preprocess(img_u8_hwc, h_new, w_new):
     """centerface.py:30-37: cv2 bilinear stretch to (w_new,h_new) then normalise -> [1,3,H,W]."""
     import cv2

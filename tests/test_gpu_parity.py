@@ -415,3 +415,23 @@ def test_single_pass_tf32_report(pkg, oracle, weights_path, f5_640, golden, orac
           f"min IoU on matched boxes {min(ious):.4f}")
     assert sig_err < 5e-3
     e.close()
+
+
+@pytest.mark.gpu
+def test_device_warp_affine_is_bit_exact_with_cv2(pkg, oracle, images):
+    """Row f1, letter-box variant: cv2.warpAffine(img, trans_input, (640,640), INTER_LINEAR) of dataset/dataset.py:130-134 on
+    the device, for the loader's transform of every bundled JPEG and for rotated / scaled / shifted matrices, batch of 2."""
+    import cv2
+    rng = np.random.RandomState(5)
+    for name, img in images.items():
+        h, w = img.shape[:2]
+        x = torch.from_numpy(np.stack([img, img[::-1, ::-1].copy()])).cuda()
+        got = pkg.letterbox_u8(x, 640, 640).cpu().numpy()
+        M = pkg.letterbox_matrix(h, w, 640, 640)
+        for i, src in enumerate((img, img[::-1, ::-1])):
+            assert np.array_equal(got[i], cv2.warpAffine(np.ascontiguousarray(src), M, (640, 640), flags=cv2.INTER_LINEAR)), name
+        a, th = rng.uniform(0.3, 2.5), rng.uniform(-0.6, 0.6)
+        M2 = np.array([[a * np.cos(th), -a * np.sin(th), rng.uniform(-300, 300)], [a * np.sin(th), a * np.cos(th), rng.uniform(-300, 300)]])
+        got2 = pkg.warp_affine_u8(x[:1].contiguous(), M2, 416, 352).cpu().numpy()[0]
+        assert np.array_equal(got2, cv2.warpAffine(img, M2, (416, 352), flags=cv2.INTER_LINEAR)), name
+        assert np.array_equal(got2, oracle.warp_affine_linear_u8(img, M2, 416, 352))

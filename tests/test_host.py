@@ -162,3 +162,20 @@ def test_resize_tables_reproduce_cv2(pkg, images):
     tab = np.empty((3 * 245 + 4 * 176,), np.int32)
     assert lib.cf_resize_tables(352, 490, 176, 245, C.c_void_p(tab.ctypes.data), tab.size, C.byref(area2)) == 0 and area2.value == 1
     assert lib.cf_resize_tables(352, 490, 176, 245, C.c_void_p(tab.ctypes.data), 10, C.byref(area2)) == -5
+
+
+def test_warp_affine_tables_match_oracle(pkg, oracle):
+    """cf_warp_affine_tables (host side of the device letter-box) against the oracle's restatement of OpenCV's fp64 ->
+    fixed-point table construction, incl. a rotated matrix and a singular one (D = 0 -> all-zero inverse)."""
+    lib = pkg._lib.load()
+    mats = [oracle.letterbox_matrix(480, 640, 640, 640), oracle.letterbox_matrix(898, 1600, 640, 640),
+            np.array([[0.7, -0.3, 12.5], [0.3, 0.7, -40.25]]), np.array([[1.0, 2.0, 3.0], [2.0, 4.0, 5.0]])]
+    for M in mats:
+        for dw, dh in ((640, 640), (320, 256)):
+            tab = np.empty((2 * dw + 2 * dh,), np.int32)
+            Mh = np.ascontiguousarray(np.asarray(M, np.float64).reshape(6))
+            assert lib.cf_warp_affine_tables(C.c_void_p(Mh.ctypes.data), dh, dw, C.c_void_p(tab.ctypes.data), tab.size) == 0
+            a, b, x0, y0 = oracle.warp_affine_tables(M, dw, dh)
+            assert np.array_equal(tab, np.concatenate([a, b, x0, y0]))
+    assert lib.cf_warp_affine_tables(C.c_void_p(Mh.ctypes.data), 8, 8, C.c_void_p(tab.ctypes.data), 10) == -5
+    assert np.array_equal(pkg.letterbox_matrix(609, 1024, 640, 640), oracle.letterbox_matrix(609, 1024, 640, 640))

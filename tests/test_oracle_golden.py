@@ -104,3 +104,38 @@ def test_resize_restatement_is_bit_exact_against_cv2(oracle, images):
             sizes.append((h // 2, w // 2))
         for dh, dw in sizes:
             assert np.array_equal(oracle.resize_linear_u8(img, dh, dw), cv2.resize(img, (dw, dh))), (n, (h, w), (dh, dw))
+
+
+def _warp_cases(images):
+    rng = np.random.RandomState(1)
+    for name in ("27", "8", "1"):
+        img = images[name]
+        h, w = img.shape[:2]
+        yield img, None, (640, 640)  # the loader's letter-box (matrix filled in by the caller)
+        for _ in range(2):
+            a, th = rng.uniform(0.3, 2.5), rng.uniform(-0.5, 0.5)
+            M = np.array([[a * np.cos(th), -a * np.sin(th), rng.uniform(-200, 300)], [a * np.sin(th), a * np.cos(th), rng.uniform(-200, 300)]])
+            yield img, M, (320, 256)
+
+
+def test_warp_affine_restatement_is_bit_exact_against_cv2(oracle, images):
+    """SURVEY.md 8f-1, letter-box variant (dataset/dataset.py:130-134): the numpy restatement of cv2.warpAffine(INTER_LINEAR,
+    8UC3, constant border) equals OpenCV on the loader's own transform and on rotated / scaled / shifted ones."""
+    import cv2
+    n = 0
+    for img, M, (dw, dh) in _warp_cases(images):
+        if M is None:
+            M = oracle.letterbox_matrix(img.shape[0], img.shape[1], dw, dh)
+        want = cv2.warpAffine(img, M, (dw, dh), flags=cv2.INTER_LINEAR)
+        assert np.array_equal(oracle.warp_affine_linear_u8(img, M, dw, dh), want)
+        n += 1
+    assert n == 9
+
+
+def test_letterbox_matrix_is_the_uniform_scale_about_the_centre(oracle):
+    """get_affine_transform(c, max(h,w), 0, [W,H]) (utils/image.py:27-61): scale W/max(h,w), centre to centre."""
+    for h, w in ((480, 640), (609, 1024), (898, 1600), (353, 490), (640, 480)):
+        M = oracle.letterbox_matrix(h, w, 640, 640)
+        a = 640.0 / max(h, w)
+        want = np.array([[a, 0, 320 - a * w / 2], [0, a, 320 - a * h / 2]])
+        assert np.allclose(M, want, rtol=0, atol=1e-4), (h, w, M, want)
