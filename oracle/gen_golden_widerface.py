@@ -92,6 +92,15 @@ def main():
         f.write('{:.1f} {:.1f} {:.1f} {:.1f} {:.3f}\n'.format(x1, y1, (x2 - x1 + 1), (y2 - y1 + 1), s))
     out["txt_dets"] = dets
     out["txt_bytes"] = np.frombuffer(f.getvalue().encode(), dtype=np.uint8)
+    # ---- the loader's letter-box matrix (dataset/dataset.py:113-131 -> utils/image.py:27-61), from the reference's own function
+    from utils.image import get_affine_transform
+    sizes = [(353, 490), (609, 1024), (898, 1600), (480, 640), (640, 480), (1080, 1920), (333, 500)]
+    mats = []
+    for h, w in sizes:
+        c = np.array([w / 2., h / 2.], dtype=np.float32)
+        mats.append(get_affine_transform(c, max(h, w) * 1.0, 0, [640, 640]))
+    out["lb_sizes"] = np.array(sizes, dtype=np.int32)
+    out["lb_mats"] = np.stack(mats)
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "widerface_v1.npz"), **out)
     print("wrote tests/golden/widerface_v1.npz", {k: v.shape for k, v in out.items() if k.startswith(("ov0", "eval"))})
 

@@ -2,6 +2,7 @@
 produced by the reference itself (oracle/gen_golden.py asserts bit-equality at generation time).
 Runs on CPU."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -130,6 +131,14 @@ def test_warp_affine_restatement_is_bit_exact_against_cv2(oracle, images):
         assert np.array_equal(oracle.warp_affine_linear_u8(img, M, dw, dh), want)
         n += 1
     assert n == 9
+
+
+def test_letterbox_matrix_equals_the_reference(oracle):
+    """oracle.letterbox_matrix against get_affine_transform of the reference itself (utils/image.py:27-61), stored by
+    oracle/gen_golden_widerface.py: every double equal."""
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "widerface_v1.npz"))
+    for (h, w), M in zip(z["lb_sizes"], z["lb_mats"]):
+        assert np.array_equal(oracle.letterbox_matrix(int(h), int(w), 640, 640), M), (h, w)
 
 
 def test_letterbox_matrix_is_the_uniform_scale_about_the_centre(oracle):
