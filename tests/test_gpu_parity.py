@@ -435,3 +435,36 @@ def test_device_warp_affine_is_bit_exact_with_cv2(pkg, oracle, images):
         got2 = pkg.warp_affine_u8(x[:1].contiguous(), M2, 416, 352).cpu().numpy()[0]
         assert np.array_equal(got2, cv2.warpAffine(img, M2, (416, 352), flags=cv2.INTER_LINEAR)), name
         assert np.array_equal(got2, oracle.warp_affine_linear_u8(img, M2, 416, 352))
+
+
+@pytest.mark.gpu
+def test_config4_loader_flow_with_device_letterbox(pkg, oracle, sd, images, weights_path):
+    """Config 4 as the reference's loader feeds it (dataset/dataset.py:113-134): 640x480 frames -> trans_input letter-box to
+    640x640 -> normalise -> network -> path B.  The letter-box runs on the device (k_warp_affine_u8) and the u8 canvas goes
+    straight into the stem; the host twin (cv2.warpAffine + the same engine) must give bit-identical head maps, and the
+    detections must match the oracle run on the cv2-prepared input."""
+    import cv2
+    frames = np.stack([cv2.resize(images[n], (640, 480)) for n in ("27", "8", "1")])
+    M = pkg.letterbox_matrix(480, 640, 640, 640)
+    host_canvas = np.stack([cv2.warpAffine(f, M, (640, 640), flags=cv2.INTER_LINEAR) for f in frames])
+    dev_canvas = pkg.letterbox_u8(torch.from_numpy(frames).cuda(), 640, 640)
+    assert np.array_equal(dev_canvas.cpu().numpy(), host_canvas)
+    eng = pkg.Engine(weights_path, max_batch=3, max_h=640, max_w=640, device=0, pw_engine=pkg.CF_PW_TCGEN05)
+    eng.forward(dev_canvas)
+    h_dev = {k: v.clone() for k, v in eng.heads().items()}
+    eng.forward(torch.from_numpy(host_canvas).cuda())
+    h_host = eng.heads()
+    for k in h_dev:
+        assert torch.equal(h_dev[k], h_host[k]), k
+    dets, _, counts = pkg.decode_threshold(h_dev["hm_sig"], h_dev["wh"], h_dev["reg"], None, pkg.CF_DECODE_B, 0.35, 0.3, (640, 640), cap=1024)
+    dets, counts = dets.cpu().numpy(), counts.cpu().numpy()
+    for i in range(3):
+        x = torch.from_numpy(oracle.normalize_u8(host_canvas[i])).unsqueeze(0)
+        o = oracle.forward(sd, x)
+        want = oracle.decode_b(oracle.sigmoid_clamp(o["hm"])[0, 0].numpy(), o["wh"][0].numpy(), o["reg"][0].numpy(), (640, 640), 0.35)
+        want = np.asarray(want, dtype=np.float32).reshape(-1, 5)
+        assert counts[i] == len(want), (i, counts[i], len(want))
+        if len(want):
+            assert oracle.box_iou(dets[i, :counts[i], :4], want[:, :4]).min() >= 0.999
+            assert np.abs(dets[i, :counts[i], 4] - want[:, 4]).max() <= 1e-3
+    eng.close()
