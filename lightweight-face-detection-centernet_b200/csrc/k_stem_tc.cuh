@@ -200,26 +200,48 @@ __global__ void __launch_bounds__(STC_THREADS, 3) k_stem_tc(const StcParams p) {
 //   warps 12-19  two drain groups (accumulator stages alternate): tcgen05.ld main + correction, Swish, 128-byte row store
 //   warp 0       loads the 8 KB weight image once; warp 2 owns the TMEM allocation (512 columns, one CTA per SM)
 constexpr int STC2_THREADS = 640;
-constexpr uint32_t STC2_OFF_BARS = STC_OFF_LUT + 768 * 4;
+constexpr uint32_t STC2_OFF_BARS = STC_OFF_LUT + 776 * 4;    // table of 768 + entry 768 = 0.0f (taps that fall in the zero padding)
 constexpr uint32_t STC2_OFF_STG = STC2_OFF_BARS + 256;      // 8 drain warps x 4 KB store-transpose tiles
 constexpr size_t STC2_SMEM = STC2_OFF_STG + 8 * 4096 + 1024;
 
+// raw[k]: FMT 1: the tap's byte, or kPad + k%3 ... see below; FMT 0: the fp32 bit pattern (0 = 0.0f for padding).
+// Every load is unconditional and addressed as (one of three row pointers) + immediate: a tap that falls into the zero padding
+// (bottom row / right column of ZeroPad2d(0,1,0,1)) or belongs to a row past the last pixel reads a neighbouring in-image byte
+// instead and is then replaced by the index of the table's 0.0f entry -- the previous version spent ~10 instructions per tap
+// on per-tap predicates and 64-bit address arithmetic.
+// FMT 1 encoding: raw[k] = byte (table index = c * 256 + byte, c = k % 3 known at compile time) or 768 - c * 256 (-> entry 768).
 template <int FMT>
-__device__ __forceinline__ uint32_t stc2_gather(const StcParams& p, bool valid, int b, int yo, int xo, uint32_t (&raw)[27]) {
-    uint32_t mask = 0;
+__device__ __forceinline__ void stc2_gather(const StcParams& p, bool valid, int b, int yo, int xo, uint32_t (&raw)[27]) {
     const bool last_y = (2 * yo + 2 >= p.H), last_x = (2 * xo + 2 >= p.W);
+    if (FMT == 1) {
+        const int rs = p.W * 3;
+        const uint8_t* r0 = (const uint8_t*)p.in + ((size_t)(b * p.H + 2 * yo) * p.W + 2 * xo) * 3;
+        const uint8_t* r1 = r0 + rs;
+        const uint8_t* r2 = last_y ? r1 : r1 + rs;  // a safe address; the value is discarded below
 #pragma unroll
-    for (int k = 0; k < 27; ++k) {
-        const int ky = k / 9, r = k - ky * 9, kx = r / 3, c = r - kx * 3;
-        raw[k] = 0;
-        const bool ok = valid && !(ky == 2 && last_y) && !(kx == 2 && last_x);
-        if (ok) {
-            if (FMT == 1) raw[k] = __ldg((const uint8_t*)p.in + ((size_t)(b * p.H + 2 * yo + ky) * p.W + 2 * xo + kx) * 3 + c);
-            else raw[k] = __float_as_uint(__ldg((const float*)p.in + ((size_t)(b * 3 + c) * p.H + 2 * yo + ky) * p.W + 2 * xo + kx));
-            mask |= 1u << k;
+        for (int k = 0; k < 27; ++k) {
+            const int ky = k / 9, r = k - ky * 9, kx = r / 3, c = r - kx * 3;
+            const uint8_t* row = ky == 0 ? r0 : ky == 1 ? r1 : r2;
+            const int off = kx == 2 ? (last_x ? 3 + c : 6 + c) : kx * 3 + c;  // kx = 2 at the right edge: re-read column 1
+            uint32_t v = __ldg(row + off);
+            const uint32_t pad = (uint32_t)(768 - c * 256);
+            if (ky == 2) v = last_y ? pad : v;
+            if (kx == 2) v = last_x ? pad : v;
+            raw[k] = valid ? v : pad;
+        }
+    } else {
+        const size_t plane = (size_t)p.H * p.W;
+        const float* q0 = (const float*)p.in + (size_t)b * 3 * plane + (size_t)(2 * yo) * p.W + 2 * xo;
+#pragma unroll
+        for (int k = 0; k < 27; ++k) {
+            const int ky = k / 9, r = k - ky * 9, kx = r / 3, c = r - kx * 3;
+            const int kyy = (ky == 2 && last_y) ? 1 : ky, kxx = (kx == 2 && last_x) ? 1 : kx;
+            uint32_t v = __float_as_uint(__ldg(q0 + c * plane + (size_t)kyy * p.W + kxx));
+            if (ky == 2) v = last_y ? 0u : v;
+            if (kx == 2) v = last_x ? 0u : v;
+            raw[k] = valid ? v : 0u;
         }
     }
-    return mask;
 }
 
 template <int FMT>
@@ -255,7 +277,7 @@ __global__ void __launch_bounds__(STC2_THREADS, 1) k_stem_tc2(const StcParams p)
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (FMT == 1)
-        for (int i = tid; i < 768; i += STC2_THREADS) lut_s[i] = __ldg(p.lut + i);
+        for (int i = tid; i < 769; i += STC2_THREADS) lut_s[i] = i < 768 ? __ldg(p.lut + i) : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -301,15 +323,15 @@ __global__ void __launch_bounds__(STC2_THREADS, 1) k_stem_tc2(const StcParams p)
         const int set = (warp - 4) >> 2, q = warp & 3;
         const int row = q * 32 + lane;
         uint32_t raw[27];
-        uint32_t mask = 0;
         auto gather = [&](int tile) {  // 32-bit index math (stc_plan checks n_pix < 2^31): 64-bit divisions cost ~100 instructions each
-            const unsigned pix = (unsigned)tile * TC_BM + (unsigned)row;
-            const bool valid = pix < (unsigned)p.n_pix;
+            const unsigned pix_raw = (unsigned)tile * TC_BM + (unsigned)row;
+            const bool valid = pix_raw < (unsigned)p.n_pix;
+            const unsigned pix = valid ? pix_raw : (unsigned)p.n_pix - 1u;  // rows past the end re-read the last pixel (discarded)
             const unsigned t = pix / (unsigned)Wo;
             const int xo = (int)(pix - t * (unsigned)Wo);
             const unsigned b = t / (unsigned)Ho;
             const int yo = (int)(t - b * (unsigned)Ho);
-            mask = stc2_gather<FMT>(p, valid, (int)b, yo, xo, raw);
+            stc2_gather<FMT>(p, valid, (int)b, yo, xo, raw);
         };
         const int first = (int)blockIdx.x + set * (int)gridDim.x;
         if (first < n_tiles) gather(first);
@@ -319,7 +341,7 @@ __global__ void __launch_bounds__(STC2_THREADS, 1) k_stem_tc2(const StcParams p)
 #pragma unroll
             for (int k = 0; k < 32; ++k) {
                 float v = 0.f;
-                if (k < 27 && (mask & (1u << k))) v = FMT == 1 ? lut_s[(k % 3) * 256 + raw[k]] : __uint_as_float(raw[k]);
+                if (k < 27) v = FMT == 1 ? lut_s[(k % 3) * 256 + raw[k]] : __uint_as_float(raw[k]);
                 hi[k] = tf32_hi(v);
                 lo[k] = v - hi[k];
             }
