@@ -179,3 +179,23 @@ def test_warp_affine_tables_match_oracle(pkg, oracle):
             assert np.array_equal(tab, np.concatenate([a, b, x0, y0]))
     assert lib.cf_warp_affine_tables(C.c_void_p(Mh.ctypes.data), 8, 8, C.c_void_p(tab.ctypes.data), 10) == -5
     assert np.array_equal(pkg.letterbox_matrix(609, 1024, 640, 640), oracle.letterbox_matrix(609, 1024, 640, 640))
+
+
+def test_bench_launch_table_matches_work_model(pkg):
+    """bench.py's per-launch algorithmic bytes (roofline.top_launches) add up to cf_work_model's layer-wise totals: 43
+    launches per step, the network's 384.6 MB per 640x640 image, and the same per-class sums."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    L = pkg._lib
+    for h, w in ((640, 640), (480, 640), (320, 256)):
+        tab = bench.launch_table(h, w)
+        assert len(tab) == 43
+        net = sum(b for n, b in tab if n not in ("peak mask", "top-k + gather"))
+        want, _ = L.work_model(h, w, L.CF_IN_U8_HWC, L.CLS_ALL, L.CF_PW_TCGEN05)
+        assert net == want, (h, w, net, want)
+        dw = sum(b for n, b in tab if " dw" in n)
+        assert dw == L.work_model(h, w, L.CF_IN_U8_HWC, L.CLS_DW, L.CF_PW_TCGEN05)[0]
+        pw = sum(b for n, b in tab if "expand" in n or "project" in n or n.startswith(("conv_last", "up")))
+        assert pw == L.work_model(h, w, L.CF_IN_U8_HWC, L.CLS_PW, L.CF_PW_TCGEN05)[0]
