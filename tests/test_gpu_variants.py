@@ -107,3 +107,31 @@ def test_time_steps_reports_every_launch(pkg, weights_path, variant_input):
     assert cls[0] == pkg._lib.CLS_STEM and cls[-1] == pkg._lib.CLS_DECODE and cls.count(pkg._lib.CLS_PW) == 27
     assert eng.launches - before == 43 * 3  # one warm-up pass + two timed
     eng.close()
+
+
+def test_config5_small_inputs_large_batch(pkg, weights_path, f5_640):
+    """Config 5 shape: 128 images per GPU at a 320-max-side size (320x256).  Batch independence at that size: images 0, 77 and
+    127 of the batch give bit-identical head maps and top-100 boxes to the same images run alone."""
+    import cv2
+    base = [cv2.resize(f5_640[n], (320, 256)) for n in ("27", "8", "17", "1", "2")]
+    rng = np.random.RandomState(1234)
+    imgs = []
+    for i in range(128):  # SURVEY.md 8d: cycle the F5 set with flips and integer rolls
+        im = base[i % 5]
+        if rng.rand() < 0.5:
+            im = im[:, ::-1]
+        imgs.append(np.roll(im, (rng.randint(0, 32), rng.randint(0, 32)), axis=(0, 1)))
+    x = torch.from_numpy(np.ascontiguousarray(np.stack(imgs))).cuda()
+    eng = pkg.Engine(weights_path, max_batch=128, max_h=256, max_w=320, device=0, pw_engine=pkg.CF_PW_TCGEN05)
+    eng.forward(x)
+    big = {k: v.clone() for k, v in eng.heads().items()}
+    dets, inds = eng.decode_topk(100)
+    dets, inds = dets.clone(), inds.clone()
+    for i in (0, 77, 127):
+        eng.forward(x[i:i + 1].contiguous())
+        one = eng.heads()
+        for k in ("hm", "wh", "lm", "reg", "hm_sig"):
+            assert torch.equal(one[k][0], big[k][i]), (i, k)
+        d1, i1 = eng.decode_topk(100)
+        assert torch.equal(d1[0], dets[i]) and torch.equal(i1[0], inds[i]), i
+    eng.close()
