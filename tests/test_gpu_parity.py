@@ -182,6 +182,61 @@ def test_end_to_end_topk_and_boxes(eng, oracle, f5_640, golden):
         assert np.abs(dets[i][real, 4] - gd[real, 4]).max() <= 1e-3
 
 
+@pytest.fixture(scope="module")
+def f5_derived(oracle, sd, f5_640):
+    """SURVEY.md 8d parity inputs beyond the five stored images: the F5 set cycled with RandomState(1234) horizontal flips
+    (p = .5) and integer rolls in [0, 32), 16 distinct 640x640 inputs, with the oracle's result for each (CPU, ~0.2 s each)."""
+    rng = np.random.RandomState(1234)
+    u8 = []
+    for i in range(16):
+        im = f5_640[IMGS[i % 5]]
+        if rng.rand() < 0.5:
+            im = im[:, ::-1]
+        u8.append(np.roll(im, (rng.randint(0, 32), rng.randint(0, 32)), axis=(0, 1)))
+    u8 = np.ascontiguousarray(np.stack(u8))
+    ref = []
+    with torch.no_grad():
+        for im in u8:
+            o = oracle.forward(sd, torch.from_numpy(oracle.normalize_u8(im)).unsqueeze(0))
+            sig = oracle.sigmoid_clamp(o["hm"])
+            dets, inds = oracle.ctdet_decode(sig, o["wh"], o["reg"], K=100)
+            ref.append((sig[0, 0].numpy(), dets[0].numpy(), inds[0].numpy()))
+    return u8, ref
+
+
+NEAR_TIE = 5e-6  # two candidates whose oracle scores are closer than this may legitimately swap (engine error on sigma(hm) ~2e-6)
+
+
+def test_f5_derived_batch_vs_oracle(eng, oracle, f5_derived):
+    """Network + path C on 16 flipped / rolled inputs against the oracle: sigma(hm) <= 1e-3, ordered top-100 indices bit-exact,
+    boxes IoU >= 0.999.  An index mismatch is accepted only where it is a swap among near-ties: the pixel the engine ranked
+    there has an oracle score within NEAR_TIE of the oracle's score at that rank (reported; none is expected)."""
+    u8, ref = f5_derived
+    swaps = 0
+    worst_sig, worst_iou = 0.0, 1.0
+    for b0 in range(0, len(u8), 8):
+        eng.forward(torch.from_numpy(u8[b0:b0 + 8]).cuda())
+        sig = eng.heads()["hm_sig"].cpu().numpy()
+        dets, inds = eng.decode_topk(100)
+        dets, inds = dets.cpu().numpy(), inds.cpu().numpy()
+        for i in range(sig.shape[0]):
+            sig_o, dets_o, inds_o = ref[b0 + i]
+            worst_sig = max(worst_sig, float(np.abs(sig[i, 0] - sig_o).max()))
+            real = dets_o[:, 4] > 2e-4  # above the clamp floor (below it the order is among exact ties)
+            same = inds[i] == inds_o
+            for r in np.nonzero(real & ~same)[0]:
+                gap = abs(float(sig_o.flat[inds[i][r]]) - float(dets_o[r, 4]))
+                assert gap < NEAR_TIE, (b0 + i, int(r), int(inds[i][r]), int(inds_o[r]), gap)
+                swaps += 1
+            m = real & same
+            iou = oracle.box_iou(dets[i][m, :4], dets_o[m, :4])
+            worst_iou = min(worst_iou, float(iou.min()))
+            assert np.abs(dets[i][m, 4] - dets_o[m, 4]).max() <= 1e-3
+    print(eng.kind, "F5-derived x16: max |sigma(hm) - oracle|", worst_sig, "min IoU", worst_iou, "near-tie swaps", swaps)
+    assert worst_sig <= HM_SIG_TOL
+    assert worst_iou >= 0.999
+
+
 def test_u8_input_equals_f32_input(eng, oracle, f5_640):
     """The fused /255, mean/std of the u8 path is bit-identical to feeding the reference's
     normalised tensor (centerface.py:32-34)."""
