@@ -24,6 +24,7 @@
 #include "k_dwt.cuh"
 #include "k_dwp.cuh"
 #include "k_pwn.cuh"
+#include "k_mbf.cuh"
 #include "k_stem_tc.cuh"
 #include "net.hpp"
 
@@ -49,6 +50,18 @@ inline bool block_is_fused(int pw, const MBBlock& b) {
     if (b.t == 1 || !xd_supported(b.k, b.s, b.cin)) return false;
     if (pw == CF_PW_TCGEN05_FUSED) return true;
     return pw == CF_PW_TCGEN05_FUSED_TC;
+}
+
+// Whole-block fusion (k_mbf): the default tensor-core engine runs the blocks of this mask as one kernel each.  CF_MBF overrides
+// the mask (development: A/B runs against the layer-wise schedule, bit i = block i).
+constexpr unsigned kMbfDefaultMask = 0u;
+inline unsigned mbf_mask() {
+    if (const char* ev = getenv("CF_MBF")) return (unsigned)strtoul(ev, nullptr, 0);
+    return kMbfDefaultMask;
+}
+inline bool block_is_mbf(int pw, int i) {
+    const MBBlock& b = kBlocks[i];
+    return pw == CF_PW_TCGEN05 && b.t != 1 && ((mbf_mask() >> i) & 1u) && mbf_supported(b.k, b.s, b.cin, b.hid(), b.cout);
 }
 
 struct Step {
@@ -318,6 +331,18 @@ int build_plan(cf_engine* e, const void* input, int fmt, int B, int H, int W) {
         const int hid = b.hid();
         const float* dw_in = x;
         const int ho = h / b.s, wo = wd / b.s;
+        if (block_is_mbf(e->pw_engine, i)) {
+            // expand + Swish + depth-wise + Swish + projection (+ residual) in one kernel: neither hidden tensor reaches HBM
+            MbfLaunch ml;
+            if ((rc = mbf_plan(e->tc, b.k, b.s, x, e->w[p + ".exp"], e->w[p + ".dw"], e->w[p + ".proj"], e->blk[i], b.residual() ? x : nullptr, B, h,
+                               wd, b.cin, hid, b.cout, &ml)))
+                return rc;
+            P.push_back({CLS_FUSED, [ml](cudaStream_t s) { return mbf_launch(ml, s); }});
+            x = e->blk[i];
+            h = ho;
+            wd = wo;
+            continue;
+        }
         const bool fused = block_is_fused(e->pw_engine, b);
         if (fused) {
             // expand + Swish + depth-wise + Swish in one kernel; the hidden tensor stays in shared memory
@@ -586,6 +611,16 @@ int cf_create(const void* weights, size_t weights_bytes, int device, int max_bat
         };
         for (int i = 0; i < 12 && !rc; ++i) {
             const MBBlock& b = kBlocks[i];
+            if (block_is_mbf(pw_engine, i)) {  // 32-column expand chunks, one 32-column projection image per K block
+                for (const char* part : {".exp", ".proj"}) {
+                    const std::string nm = "b" + std::to_string(i) + part;
+                    const bool ex = part[1] == 'e';
+                    const int K = ex ? b.cin : b.hid(), N = ex ? b.hid() : b.cout;
+                    const float* hp = blob.get(nm, (uint64_t)K * N, why);
+                    if (!rc) rc = hp ? tc_prepare_layer(e->tc, e->w[nm], hp, K, N, 3, 32) : fail(CF_EWEIGHTS, "cf_create: %s", why.c_str());
+                }
+                continue;
+            }
             if (b.t != 1 && !block_is_fused(pw_engine, b)) rc = prep("b" + std::to_string(i) + ".exp", b.cin, b.hid());
             if (b.t != 1 && block_is_fused(pw_engine, b) && pw_engine == CF_PW_TCGEN05_FUSED_TC) {  // 32-column chunk images
                 const std::string nm = "b" + std::to_string(i) + ".exp";
@@ -1085,6 +1120,13 @@ int cf_work_model(int h, int w, int in_format, int pw_engine, int which, double*
         const MBBlock& b = kBlocks[i];
         const double hid = b.hid();
         const double ho = hh / b.s, wo = ww / b.s;
+        if (block_is_mbf(pw_engine, i)) {  // block input in, block output out (+ the residual re-read)
+            by[CLS_FUSED] += (hh * ww * b.cin + ho * wo * b.cout * (b.residual() ? 2 : 1)) * F;
+            fl[CLS_FUSED] += 2.0 * hh * ww * b.cin * hid + 2.0 * ho * wo * hid * b.k * b.k + 2.0 * ho * wo * hid * b.cout;
+            hh = ho;
+            ww = wo;
+            continue;
+        }
         if (block_is_fused(pw_engine, b)) {  // X read once, depth-wise output written once; the hidden tensor never reaches HBM
             by[CLS_FUSED] += (hh * ww * b.cin + ho * wo * hid) * F;
             fl[CLS_FUSED] += 2.0 * hh * ww * b.cin * hid + 2.0 * ho * wo * hid * b.k * b.k;

@@ -1,0 +1,545 @@
+// k_mbf: one whole MBConv block (model/centernet.py:89-140) in one kernel, for the shallow stride-2/4/8 blocks:
+//
+//     X [B,Hi,Wi,Cin]  --expand 1x1 (tcgen05, 3xTF32) + Swish-->  E (hidden, input resolution, NEVER in HBM)
+//                      --depth-wise KSxKS stride S + Swish-->     D (hidden, output resolution, NEVER in HBM)
+//                      --project 1x1 (tcgen05, 3xTF32) [+ residual]-->  Y [B,Ho,Wo,Cout]
+//
+// The layer-wise engine writes and re-reads E and D (236 MB of the 385 MB it moves per 640x640 image belong to the four
+// blocks layer1.0 .. layer2.1); here the block reads X and writes Y.  The earlier fused kernels of this library (k_expdw, k_mbx,
+// k_dwp; profiles/r1_fused_kernels.md) each fused two of the three stages and lost to the layer-wise pair on SM-side
+// execution: CTA-wide barriers between their phases, 8-16 resident warps, tiles sized by shared memory.  This kernel is a
+// warp-specialised pipeline of small, identical JOBS with mbarrier hand-offs only (no __syncthreads in steady state):
+//
+//   job = (sub-tile, 32-channel chunk).  A sub-tile is STH x STW output pixels whose input halo
+//   IH x IW = ((STH-1)S+KS) x ((STW-1)S+KS) is at most 128 pixels = ONE 128-row MMA block, so every stage of a job is one
+//   fixed-size unit: one TMA box, one TMEM A slot, one expand accumulator, one 16 KB E slot.
+//   A block = NSY x NSX sub-tiles (<= 128 output pixels) = the rows of ONE projection accumulator; jobs run chunk-major
+//   inside a block, so chunk c of all its sub-tiles fills one D operand (hi/lo, K = 32) and the projection accumulates
+//   over the chunks in TMEM.
+//
+//   warp 0        TMA producer: the X halo box of every job (zero fill outside the image = the reference's ZeroPad2d,
+//                 :63-70; swish(0 . W) = 0 because the expand conv has no bias), re-read per chunk from L2
+//   warp 1        expand issuer: the MMAs of a job as soon as its A slot is written and an accumulator is free
+//   warp 3        projection issuer: the MMAs of a (block, chunk) as soon as its D operand is complete (its own warp, so
+//                 that neither MMA stream ever waits behind the other's barrier)
+//   warps 4-7     splitters: X row -> tf32 hi + lo -> TMEM A slot (tcgen05.st, lane = halo pixel); between blocks they
+//                 drain the previous block's projection accumulator (+ residual) and store Y
+//   warps 8-15    two drain teams (alternate jobs): expand accumulator -> Swish -> swizzled E slot in shared memory
+//   warps 16-..   two depth-wise teams (alternate jobs): E slot -> KSxKS taps -> Swish -> tf32 hi/lo rows of the D operand
+//
+// 3xTF32: expand uses ONE accumulator, the two correction products first (while the accumulator is ~2^-11 of its final
+// size their per-MMA accumulator truncation, tools/tc_accum_probe.py, is negligible), then the K/8 main products; the
+// projection keeps k_pw_tc's main + correction pair because its chunks arrive over time.
+#pragma once
+#include "k_dwt.cuh"
+#include "k_pwn.cuh"
+
+namespace cf {
+
+template <int KS_, int S_, int CIN_, int STH_, int STW_, int NSY_, int NSX_, int XT_, int YT_, int TD_>
+struct MbfCfg {
+    static constexpr int KS = KS_, S = S_, CIN = CIN_, STH = STH_, STW = STW_, NSY = NSY_, NSX = NSX_, XT = XT_, YT = YT_, TD = TD_;
+    static constexpr int IH = (STH - 1) * S + KS, IW = (STW - 1) * S + KS, NPX = IH * IW;
+    static constexpr int LO = (KS - S) / 2;  // model/centernet.py:68-70
+    static constexpr int NSUB = NSY * NSX, SPX = STH * STW, DROWS = NSUB * SPX;
+    static constexpr int KSTEPS = (CIN + 7) / 8;
+    static constexpr int NDT = 2, NWT = 2;  // drain teams (4 warps each), depth-wise teams (TD warps each)
+    static constexpr int NWARPS = 16 + TD * NWT, THREADS = NWARPS * 32;
+    static constexpr int NBX = STW / XT, NITEMS = (STH / YT) * NBX * 8;  // (output block, float4 of channels)
+    // ring depths: X boxes, TMEM A slots, expand accumulators, E slots, D operands, projection accumulators
+    static constexpr int NX = 3, NA = 4, NE = 4, NES = 3, ND = 2, NP = 2;
+    static constexpr uint32_t SLOT = 16384;                         // 128 rows x 128 B
+    static constexpr uint32_t DHALF = ((DROWS + 7) / 8) * 1024u;    // the hi (or lo) half of one D operand
+    static constexpr uint32_t PCOL = 0, ECOL = PCOL + NP * 64, ACOL = ECOL + NE * 32;  // TMEM columns
+    static_assert(NPX <= 128, "a sub-tile's halo is one MMA block");
+    static_assert(DROWS <= 128, "a block's outputs are the rows of one projection accumulator");
+    static_assert(STW % XT == 0 && STH % YT == 0, "output blocks tile the sub-tile");
+    static_assert(ACOL + NA * 64 <= 512, "TMEM budget");
+    static_assert(CIN % 8 == 0 && CIN <= 32, "expand K");
+};
+
+struct MbfParams {
+    const float* we_img;  // [nch][hi 32 x 128 B | lo 32 x 128 B]   expand weights, K-major SWIZZLE_128B (tc_prepare_layer, NC = 32)
+    const float* wp_img;  // [nch][hi 32 x 128 B | lo 32 x 128 B]   projection weights, one K block per chunk, N padded to 32
+    const float* Wd;      // [KS*KS][hid]
+    float* Y;             // [B][Ho][Wo][cout]
+    const float* res;     // [B][Ho][Wo][cout] or NULL
+    int B, Hi, Wi, Ho, Wo, hid, nch, cout;
+    int blocks_x, blocks_y, n_blocks;
+    uint32_t off_e, off_d, off_we, off_wp, off_bars;  // the X ring starts at 0
+    int dbg;  // development only (env CF_MBF_DEBUG): 1 no Swish in the drain, 2 no depth-wise math, 4 no Y stores
+};
+
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ bool mbar_try_once(uint32_t bar, uint32_t parity) {  // may park the warp for a short, bounded time
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
+    const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+
+template <typename C>
+__global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ CUtensorMap tmX, const MbfParams p) {
+    constexpr int KS = C::KS, S = C::S, NX = C::NX, NA = C::NA, NE = C::NE, NES = C::NES, ND = C::ND, NP = C::NP;
+    constexpr int NSUB = C::NSUB, TD = C::TD;
+    constexpr uint32_t SLOT = C::SLOT;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_trigger();
+
+    // barriers (8 B each)
+    const uint32_t bars = base + p.off_bars;
+    const uint32_t x_full = bars, x_empty = x_full + 8 * NX;
+    const uint32_t a_full = x_empty + 8 * NX, a_empty = a_full + 8 * NA;
+    const uint32_t e_full = a_empty + 8 * NA, e_empty = e_full + 8 * NE;
+    const uint32_t es_full = e_empty + 8 * NE, es_empty = es_full + 8 * NES;
+    const uint32_t d_full = es_empty + 8 * NES, d_empty = d_full + 8 * ND;
+    const uint32_t p_full = d_empty + 8 * ND, p_empty = p_full + 8 * NP;
+    const uint32_t w_full = p_empty + 8 * NP;
+    constexpr int NBARS = 2 * (NX + NA + NE + NES + ND + NP) + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + p.off_bars + 8 * NBARS + 8);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+        for (int i = 0; i < NX; ++i) mbar_init(x_full + 8 * i, 1), mbar_init(x_empty + 8 * i, 4);
+        for (int i = 0; i < NA; ++i) mbar_init(a_full + 8 * i, 4), mbar_init(a_empty + 8 * i, 1);
+        for (int i = 0; i < NE; ++i) mbar_init(e_full + 8 * i, 1), mbar_init(e_empty + 8 * i, 4);
+        for (int i = 0; i < NES; ++i) mbar_init(es_full + 8 * i, 4), mbar_init(es_empty + 8 * i, TD);
+        for (int i = 0; i < ND; ++i) mbar_init(d_full + 8 * i, NSUB * TD), mbar_init(d_empty + 8 * i, 1);
+        for (int i = 0; i < NP; ++i) mbar_init(p_full + 8 * i, 1), mbar_init(p_empty + 8 * i, 4);
+        mbar_init(w_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int nch = p.nch;
+    const int nblk = ((int)blockIdx.x < p.n_blocks) ? (p.n_blocks - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int J = nblk * nch * NSUB;  // jobs of this CTA, in order (block i, chunk c, sub-tile s)
+    const int Q = nblk * nch;         // D operands (block, chunk), NSUB jobs each
+
+    // Every role walks the same job sequence with incremental ring cursors (slot, phase parity): no division in any loop.
+    struct Ring {
+        int slot = 0;
+        uint32_t phase = 0;
+        __device__ __forceinline__ void next(int n) {
+            if (++slot == n) slot = 0, phase ^= 1u;
+        }
+    };
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (elect_one()) {
+            const uint32_t wbytes = (uint32_t)nch * 8192u;
+            mbar_expect_tx(w_full, 2u * wbytes);
+            for (uint32_t off = 0; off < wbytes; off += 32768u) {
+                const uint32_t n = wbytes - off < 32768u ? wbytes - off : 32768u;
+                bulk_load(base + p.off_we + off, reinterpret_cast<const uint8_t*>(p.we_img) + off, n, w_full);
+                bulk_load(base + p.off_wp + off, reinterpret_cast<const uint8_t*>(p.wp_img) + off, n, w_full);
+            }
+        }
+        __syncwarp();
+        pdl_wait();  // X is the previous kernel's output
+        Ring xr;
+        for (int i = 0; i < nblk; ++i) {
+            int t = (int)blockIdx.x + i * (int)gridDim.x;
+            const int bx = t % p.blocks_x;
+            t /= p.blocks_x;
+            const int by = t % p.blocks_y, b = t / p.blocks_y;
+            const int x00 = bx * (C::NSX * C::STW * S) - C::LO, y00 = by * (C::NSY * C::STH * S) - C::LO;
+            for (int c = 0; c < nch; ++c) {
+#pragma unroll
+                for (int s = 0; s < NSUB; ++s) {
+                    const int sy = s / C::NSX, sx = s % C::NSX;  // compile-time after unrolling
+                    mbar_wait(x_empty + 8 * xr.slot, xr.phase ^ 1u);
+                    if (elect_one()) {
+                        mbar_expect_tx(x_full + 8 * xr.slot, (uint32_t)C::NPX * 128u);
+                        tma_load_4d(base + xr.slot * SLOT, &tmX, 0, x00 + sx * (C::STW * S), y00 + sy * (C::STH * S), b, x_full + 8 * xr.slot);
+                    }
+                    __syncwarp();
+                    xr.next(NX);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= expand issuer: one MMA group per job =================
+        mbar_wait(w_full, 0);
+        const uint32_t idesc32 = umma_idesc_tf32(32);
+        Ring ar, er;
+        int c = 0, s = 0;
+        for (int j = 0; j < J; ++j) {
+            mbar_wait(a_full + 8 * ar.slot, ar.phase);
+            mbar_wait(e_empty + 8 * er.slot, er.phase ^ 1u);
+            tc_fence_after();
+            const uint32_t wb = base + p.off_we + (uint32_t)c * 8192u;
+            const uint64_t b_hi = umma_desc(wb), b_lo = umma_desc(wb + 4096u);
+            const uint32_t a_hi = tmem_base + C::ACOL + (uint32_t)ar.slot * 64u, a_lo = a_hi + 32u;
+            const uint32_t d = tmem_base + C::ECOL + (uint32_t)er.slot * 32u;
+            if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < C::KSTEPS; ++k) {  // the small products first
+                    umma_tf32_ts(d, a_lo + 8u * k, b_hi + (uint64_t)(k * 2), idesc32, k > 0 ? 1u : 0u);
+                    umma_tf32_ts(d, a_hi + 8u * k, b_lo + (uint64_t)(k * 2), idesc32, 1u);
+                }
+#pragma unroll
+                for (int k = 0; k < C::KSTEPS; ++k) umma_tf32_ts(d, a_hi + 8u * k, b_hi + (uint64_t)(k * 2), idesc32, 1u);
+                umma_commit(e_full + 8 * er.slot);
+                umma_commit(a_empty + 8 * ar.slot);
+            }
+            __syncwarp();
+            ar.next(NA);
+            er.next(NE);
+            if (++s == NSUB) {
+                s = 0;
+                if (++c == nch) c = 0;
+            }
+        }
+    } else if (warp == 3) {
+        // ================= projection issuer: one MMA group per (block, chunk) =================
+        mbar_wait(w_full, 0);
+        const uint32_t idesc32 = umma_idesc_tf32(32), idesc64 = umma_idesc_tf32(64);
+        Ring dr, pr;
+        int c = 0;
+        for (int q = 0; q < Q; ++q) {
+            mbar_wait(d_full + 8 * dr.slot, dr.phase);
+            if (c == 0) mbar_wait(p_empty + 8 * pr.slot, pr.phase ^ 1u);
+            tc_fence_after();
+            const uint32_t dbase = base + p.off_d + (uint32_t)dr.slot * 2u * C::DHALF;
+            const uint64_t a_hi = umma_desc(dbase), a_lo = umma_desc(dbase + C::DHALF);
+            const uint64_t b_hi = umma_desc(base + p.off_wp + (uint32_t)c * 8192u);  // [hi 32 rows | lo 32 rows]
+            const uint32_t d_main = tmem_base + C::PCOL + (uint32_t)pr.slot * 64u, d_corr = d_main + 32u;
+            if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint64_t ko = (uint64_t)(k * 2);
+                    umma_tf32(d_main, a_hi + ko, b_hi + ko, idesc64, (c > 0 || k > 0) ? 1u : 0u);  // main += hi.hi ; corr += hi.lo
+                    umma_tf32(d_corr, a_lo + ko, b_hi + ko, idesc32, 1u);                            // corr += lo.hi
+                }
+                umma_commit(d_empty + 8 * dr.slot);
+                if (c == nch - 1) umma_commit(p_full + 8 * pr.slot);
+            }
+            __syncwarp();
+            dr.next(ND);
+            if (++c == nch) c = 0, pr.next(NP);
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ================= splitters; between blocks: projection epilogue of the previous block =================
+        pdl_wait();  // residual reads and Y stores touch activation memory
+        const int q = warp & 3, row = q * 32 + lane;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+        // accumulator row -> output pixel of the block (fixed for the kernel)
+        const int rs = row / C::SPX, rl = row - rs * C::SPX;
+        const int rsy = rs / C::NSX, rsx = rs - rsy * C::NSX;
+        const int roy = rsy * C::STH + rl / C::STW, rox = rsx * C::STW + rl % C::STW;
+        Ring pr;
+        auto epilogue = [&](int i) {
+            int t = (int)blockIdx.x + i * (int)gridDim.x;
+            const int bx = t % p.blocks_x;
+            t /= p.blocks_x;
+            const int by = t % p.blocks_y, b = t / p.blocks_y;
+            const int yo = by * (C::NSY * C::STH) + roy, xo = bx * (C::NSX * C::STW) + rox;
+            const bool valid = row < C::DROWS && yo < p.Ho && xo < p.Wo && !(p.dbg & 4);
+            const size_t pix = ((size_t)(b * p.Ho + yo) * p.Wo + xo) * (size_t)p.cout;
+            mbar_wait(p_full + 8 * pr.slot, pr.phase);
+            tc_fence_after();
+            const uint32_t taddr = lane_base + C::PCOL + (uint32_t)pr.slot * 64u;
+            for (int c0 = 0; c0 < p.cout; c0 += 8) {
+                float v[8], cr[8];
+                tmem_ld8(taddr + (uint32_t)c0, v);
+                tmem_ld8(taddr + 32u + (uint32_t)c0, cr);
+                tmem_ld_wait();
+                if (valid) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        float4 o = make_float4(v[4 * h] + cr[4 * h], v[4 * h + 1] + cr[4 * h + 1], v[4 * h + 2] + cr[4 * h + 2], v[4 * h + 3] + cr[4 * h + 3]);
+                        if (p.res) {
+                            const float4 r4 = ldcg4(p.res + pix + c0 + 4 * h);
+                            o.x += r4.x, o.y += r4.y, o.z += r4.z, o.w += r4.w;
+                        }
+                        st4(p.Y + pix + c0 + 4 * h, o);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_empty + 8 * pr.slot);
+            pr.next(NP);
+        };
+        Ring xr, ar;
+        const int xswz = row & 7;
+        for (int i = 0; i < nblk; ++i) {
+            for (int cs = 0; cs < nch * NSUB; ++cs) {
+                mbar_wait(x_full + 8 * xr.slot, xr.phase);
+                const uint8_t* xrow = sm + (size_t)xr.slot * SLOT + (size_t)row * 128;
+                float hi[8 * C::KSTEPS], lo[8 * C::KSTEPS];
+#pragma unroll
+                for (int g = 0; g < 2 * C::KSTEPS; ++g) {
+                    const float4 v = *reinterpret_cast<const float4*>(xrow + ((g ^ xswz) << 4));  // SWIZZLE_128B image written by TMA
+                    hi[4 * g] = tf32_hi(v.x), hi[4 * g + 1] = tf32_hi(v.y), hi[4 * g + 2] = tf32_hi(v.z), hi[4 * g + 3] = tf32_hi(v.w);
+                    lo[4 * g] = v.x - hi[4 * g], lo[4 * g + 1] = v.y - hi[4 * g + 1], lo[4 * g + 2] = v.z - hi[4 * g + 2], lo[4 * g + 3] = v.w - hi[4 * g + 3];
+                }
+                mbar_wait(a_empty + 8 * ar.slot, ar.phase ^ 1u);
+                tc_fence_after();
+                const uint32_t ta = lane_base + C::ACOL + (uint32_t)ar.slot * 64u;
+                if (C::KSTEPS == 4) {
+                    tmem_st16(ta, hi), tmem_st16(ta + 16u, hi + 16);
+                    tmem_st16(ta + 32u, lo), tmem_st16(ta + 48u, lo + 16);
+                } else if (C::KSTEPS == 3) {
+                    tmem_st16(ta, hi), tmem_st8(ta + 16u, hi + 16);
+                    tmem_st16(ta + 32u, lo), tmem_st8(ta + 48u, lo + 16);
+                } else {
+                    tmem_st16(ta, hi);
+                    tmem_st16(ta + 32u, lo);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(a_full + 8 * ar.slot);
+                    mbar_arrive(x_empty + 8 * xr.slot);
+                }
+                xr.next(NX);
+                ar.next(NA);
+            }
+            if (i > 0) epilogue(i - 1);  // one block behind: its projection has long been issued
+        }
+        if (nblk > 0) epilogue(nblk - 1);
+    } else if (warp >= 8 && warp < 16) {
+        // ================= drain teams: expand accumulator -> Swish -> E slot =================
+        const int team = (warp - 8) >> 2, q = warp & 3, row = q * 32 + lane;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int swz = row & 7;
+        Ring er, sr;
+        if (team == 1) er.next(NE), sr.next(NES);
+        for (int j = team; j < J; j += C::NDT) {
+            mbar_wait(e_full + 8 * er.slot, er.phase);
+            tc_fence_after();
+            float v[32];
+            tmem_ld32(lane_base + C::ECOL + (uint32_t)er.slot * 32u, v);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(e_empty + 8 * er.slot);  // the accumulator is in registers
+            mbar_wait(es_empty + 8 * sr.slot, sr.phase ^ 1u);
+            if (row < C::NPX) {
+                uint8_t* erow = sm + p.off_e + (size_t)sr.slot * SLOT + (size_t)row * 128;
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    float4 o = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+                    if (!(p.dbg & 1)) o = swish4(o);
+                    *reinterpret_cast<float4*>(erow + ((g ^ swz) << 4)) = o;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(es_full + 8 * sr.slot);
+            er.next(NE), er.next(NE);
+            sr.next(NES), sr.next(NES);
+        }
+    } else if (warp >= 16) {
+        // ================= depth-wise teams: E slot -> taps -> Swish -> hi/lo rows of the D operand =================
+        constexpr int NROW = (C::YT - 1) * S + KS, NCOL = (C::XT - 1) * S + KS;
+        const int team = (warp - 16) / TD, tw = (warp - 16) - team * TD;
+        Ring sr, dr;
+        int s = 0, c = 0;
+        auto step = [&]() {  // one job further
+            sr.next(NES);
+            if (++s == NSUB) {
+                s = 0;
+                dr.next(ND);
+                if (++c == nch) c = 0;
+            }
+        };
+        if (team == 1) step();
+        for (int j = team; j < J; j += C::NWT) {
+            mbar_wait(es_full + 8 * sr.slot, sr.phase);
+            mbar_wait(d_empty + 8 * dr.slot, dr.phase ^ 1u);  // the projection that read this operand last has retired
+            const uint8_t* Es = sm + p.off_e + (size_t)sr.slot * SLOT;
+            uint8_t* Dhi = sm + p.off_d + (size_t)dr.slot * 2u * C::DHALF;
+            uint8_t* Dlo = Dhi + C::DHALF;
+            for (int it = tw * 32 + lane; it < C::NITEMS; it += TD * 32) {
+                const int c4 = it & 7, blk = it >> 3;
+                const int by = blk / C::NBX, bx = blk - by * C::NBX;
+                const int cbase = c * 32 + c4 * 4;
+                float4 acc[C::YT][C::XT];
+#pragma unroll
+                for (int a = 0; a < C::YT; ++a)
+#pragma unroll
+                    for (int b2 = 0; b2 < C::XT; ++b2) acc[a][b2] = make_float4(0, 0, 0, 0);
+                if (cbase < p.hid && !(p.dbg & 2)) {
+                    const int r0 = C::YT * by * S, q0 = C::XT * bx * S;  // window origin inside the halo tile
+#pragma unroll
+                    for (int rr = 0; rr < NROW; ++rr) {
+                        float4 win[NCOL];
+#pragma unroll
+                        for (int cc = 0; cc < NCOL; ++cc) {
+                            const int px = (r0 + rr) * C::IW + q0 + cc;
+                            win[cc] = *reinterpret_cast<const float4*>(Es + px * 128 + ((c4 ^ (px & 7)) << 4));
+                        }
+#pragma unroll
+                        for (int dy = 0; dy < C::YT; ++dy) {
+                            const int ky = rr - dy * S;
+                            if (ky < 0 || ky >= KS) continue;
+#pragma unroll
+                            for (int kx = 0; kx < KS; ++kx) {
+                                const float4 wv = ldg4(p.Wd + (ky * KS + kx) * p.hid + cbase);
+#pragma unroll
+                                for (int dx = 0; dx < C::XT; ++dx) fma44(acc[dy][dx], win[dx * S + kx], wv);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int dy = 0; dy < C::YT; ++dy)
+#pragma unroll
+                    for (int dx = 0; dx < C::XT; ++dx) {
+                        const int r = s * C::SPX + (C::YT * by + dy) * C::STW + C::XT * bx + dx;  // D operand row = output pixel of the block
+                        const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c4 ^ (r & 7)) << 4);
+                        const float4 v = swish4(acc[dy][dx]);  // swish(0) = 0 keeps the padded channels zero
+                        const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+                        *reinterpret_cast<float4*>(Dhi + off) = h;
+                        *reinterpret_cast<float4*>(Dlo + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                    }
+            }
+            fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(d_full + 8 * dr.slot);
+                mbar_arrive(es_empty + 8 * sr.slot);
+            }
+            step(), step();
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---- host side --------------------------------------------------------------------------
+// Geometry per block type (sub-tile, block, depth-wise item shape, warps per depth-wise team):
+//   3x3 s2, Cin 16 (layer1.0): sub-tile 3 x 8 (halo 7 x 17 = 119 px), block 2 x 2 sub-tiles = 6 x 16 outputs, items of 1 x 2 outputs: 96 = 3 warps
+//   3x3 s1, Cin 24 (layer1.1): sub-tile 8 x 10 (halo 10 x 12 = 120 px), block = the sub-tile, items of 1 x 5 outputs: 128 = 4 warps
+//   5x5 s2, Cin 24 (layer2.0): sub-tile 4 x 4 (halo 11 x 11 = 121 px), block 2 x 4 sub-tiles = 8 x 16 outputs, items of one output: 128 = 4 warps
+//   5x5 s1, Cin 32 (layer2.1): sub-tile 7 x 7 (halo 11 x 11 = 121 px), block 1 x 2 sub-tiles = 7 x 14 outputs, items of 1 x 7 outputs: 56 = 2 warps
+using MbfB1 = MbfCfg<3, 2, 16, 3, 8, 2, 2, 2, 1, 3>;
+using MbfB2 = MbfCfg<3, 1, 24, 8, 10, 1, 1, 5, 1, 4>;
+using MbfB3 = MbfCfg<5, 2, 24, 4, 4, 2, 4, 1, 1, 4>;
+using MbfB4 = MbfCfg<5, 1, 32, 7, 7, 1, 2, 7, 1, 2>;
+
+struct MbfLaunch {
+    CUtensorMap tmX;
+    MbfParams p;
+    int kind = 0, grid = 0;  // kind: 1..4 = MbfB1..MbfB4
+    size_t smem = 0;
+};
+
+inline int mbf_kind(int ks, int s, int cin) {
+    if (ks == 3 && s == 2 && cin == 16) return 1;
+    if (ks == 3 && s == 1 && cin == 24) return 2;
+    if (ks == 5 && s == 2 && cin == 24) return 3;
+    if (ks == 5 && s == 1 && cin == 32) return 4;
+    return 0;
+}
+inline bool mbf_supported(int ks, int s, int cin, int hid, int cout) { return mbf_kind(ks, s, cin) != 0 && cout % 8 == 0 && cout <= 32 && hid % 4 == 0; }
+
+template <typename C>
+inline int mbf_plan_t(PwTcState& st, MbfLaunch* ml, const float* X, int B, int Hi, int Wi, int cin) {
+    MbfParams& p = ml->p;
+    int rc = xd_make_map(st, &ml->tmX, X, B, Hi, Wi, cin, C::IW, C::IH);
+    if (rc) return rc;
+    p.Ho = Hi / C::S, p.Wo = Wi / C::S;
+    p.blocks_x = cdiv(p.Wo, C::NSX * C::STW);
+    p.blocks_y = cdiv(p.Ho, C::NSY * C::STH);
+    const long long nb = (long long)B * p.blocks_x * p.blocks_y;
+    if (nb * p.nch * C::NSUB > 0x3fffffffLL) return fail(CF_EINVAL, "mbf_plan: too many jobs");
+    p.n_blocks = (int)nb;
+    p.off_e = C::NX * C::SLOT;
+    p.off_d = p.off_e + C::NES * C::SLOT;
+    p.off_we = p.off_d + C::ND * 2u * C::DHALF;
+    p.off_wp = p.off_we + (uint32_t)p.nch * 8192u;
+    p.off_bars = p.off_wp + (uint32_t)p.nch * 8192u;
+    // the MMA reads 128 rows of every D half; rows past DROWS fall into whatever follows (unused accumulator lanes), which
+    // must still be this CTA's shared memory: the weight images (>= 16 KB) follow the last half
+    ml->smem = (size_t)p.off_bars + 1024 + 1024;
+    if (ml->smem > (size_t)TC_SMEM_MAX) return fail(CF_EINVAL, "mbf_plan: %zu B of shared memory do not fit", ml->smem);
+    ml->grid = p.n_blocks < st.sms ? p.n_blocks : st.sms;
+    return CF_OK;
+}
+
+inline int mbf_plan(PwTcState& st, int ks, int s, const float* X, const float* We, const float* Wd, const float* Wp, float* Y, const float* res,
+                    int B, int Hi, int Wi, int cin, int hid, int cout, MbfLaunch* ml) {
+    if (!mbf_supported(ks, s, cin, hid, cout)) return fail(CF_EINVAL, "mbf_plan: no fused kernel for k=%d s=%d cin=%d cout=%d", ks, s, cin, cout);
+    auto ie = st.layers.find(We), ip = st.layers.find(Wp);
+    if (ie == st.layers.end() || ie->second.NC != 32 || ie->second.nkb != 1)
+        return fail(CF_EINVAL, "mbf_plan: expand weights were not prepared as 32-column images");
+    if (ip == st.layers.end() || ip->second.NC != 32 || ip->second.nchunks != 1)
+        return fail(CF_EINVAL, "mbf_plan: projection weights were not prepared as one 32-column image per K block");
+    MbfParams& p = ml->p;
+    p.we_img = ie->second.img;
+    p.wp_img = ip->second.img;
+    p.Wd = Wd;
+    p.Y = Y;
+    p.res = res;
+    p.B = B, p.Hi = Hi, p.Wi = Wi, p.hid = hid, p.cout = cout;
+    p.nch = (hid + 31) / 32;
+    p.dbg = 0;
+    if (const char* ev = getenv("CF_MBF_DEBUG")) p.dbg = atoi(ev);
+    ml->kind = mbf_kind(ks, s, cin);
+    switch (ml->kind) {
+        case 1: return mbf_plan_t<MbfB1>(st, ml, X, B, Hi, Wi, cin);
+        case 2: return mbf_plan_t<MbfB2>(st, ml, X, B, Hi, Wi, cin);
+        case 3: return mbf_plan_t<MbfB3>(st, ml, X, B, Hi, Wi, cin);
+        default: return mbf_plan_t<MbfB4>(st, ml, X, B, Hi, Wi, cin);
+    }
+}
+
+template <typename C>
+inline cudaError_t mbf_launch_t(const MbfLaunch& ml, cudaStream_t s) {
+    cudaError_t e = cudaFuncSetAttribute(k_mbf<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);  // per device: set every time
+    if (e != cudaSuccess) return e;
+    return launch_pdl(k_mbf<C>, dim3(ml.grid), dim3(C::THREADS), ml.smem, s, ml.tmX, ml.p);
+}
+
+inline cudaError_t mbf_launch(const MbfLaunch& ml, cudaStream_t s) {
+    switch (ml.kind) {
+        case 1: return mbf_launch_t<MbfB1>(ml, s);
+        case 2: return mbf_launch_t<MbfB2>(ml, s);
+        case 3: return mbf_launch_t<MbfB3>(ml, s);
+        case 4: return mbf_launch_t<MbfB4>(ml, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace cf
