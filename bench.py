@@ -165,20 +165,25 @@ BLOCKS = [(32, 16, 1, 3, 1), (16, 24, 6, 3, 2), (24, 24, 6, 3, 1), (24, 32, 6, 5
           (64, 64, 6, 3, 1), (64, 96, 6, 5, 1), (96, 96, 6, 5, 1), (96, 160, 6, 5, 2), (160, 160, 6, 5, 1), (160, 320, 6, 3, 1)]
 
 
-def launch_table(h, w):
+def launch_table(h, w, fused=()):
     """(name, algorithmic bytes per image) of every launch of one forward + path-C decode, in launch order -- the same
-    layer-wise accounting as cf_work_model (un-padded input once + output once + residual / low-res re-reads, fp32)."""
+    layer-wise accounting as cf_work_model (un-padded input once + output once + residual / low-res re-reads, fp32).
+    A block in `fused` is ONE launch credited with the layer-wise bytes of the three launches it replaces."""
     out = []
     hh, ww = h // 2, w // 2
     out.append(("stem 3->32 s2", h * w * 3 + hh * ww * 32 * 4))
     for i, (cin, cout, t, k, s) in enumerate(BLOCKS):
         hid = cin * t
-        if t != 1:
-            out.append((f"b{i} expand {cin}->{hid}", hh * ww * (cin + hid) * 4))
         ho, wo = hh // s, ww // s
-        out.append((f"b{i} dw{k}x{k} s{s} {hid}ch", (hh * ww + ho * wo) * hid * 4))
         res = cout if (cin == cout and s == 1) else 0
-        out.append((f"b{i} project {hid}->{cout}" + (" +res" if res else ""), ho * wo * (hid + cout + res) * 4))
+        rows = []
+        if t != 1:
+            rows.append((f"b{i} expand {cin}->{hid}", hh * ww * (cin + hid) * 4))
+        rows.append((f"b{i} dw{k}x{k} s{s} {hid}ch", (hh * ww + ho * wo) * hid * 4))
+        rows.append((f"b{i} project {hid}->{cout}" + (" +res" if res else ""), ho * wo * (hid + cout + res) * 4))
+        if i in fused:
+            rows = [(f"b{i} fused MBConv {cin}->{hid}->{cout} k{k} s{s}" + (" +res" if res else ""), sum(b for _, b in rows))]
+        out += rows
         hh, ww = ho, wo
     out.append(("conv_last 320->24", hh * ww * (320 + 24) * 4))
     for j, c in enumerate((96, 32, 24)):
@@ -323,7 +328,7 @@ def run_b200(a):
         # it actually has to move (`min_bytes`) are what fusion saved and are reported beside it.
         by_lw = by
         if cls == L.CLS_FUSED:
-            lw = lambda c: L.work_model(H, W, L.CF_IN_U8_HWC, c, L.CF_PW_TCGEN05)[0] - L.work_model(H, W, L.CF_IN_U8_HWC, c, pw)[0]  # noqa: E731
+            lw = lambda c: L.work_model(H, W, L.CF_IN_U8_HWC, c, L.CF_PW_TCGEN05_LAYERWISE)[0] - L.work_model(H, W, L.CF_IN_U8_HWC, c, pw)[0]  # noqa: E731
             by_lw = lw(L.CLS_PW) + lw(L.CLS_DW)
         classes[name] = {"ms_per_step": ms, "launches": n, "alg_bytes": by_lw * B, "min_bytes": by * B, "alg_flops": fl * B,
                          "gbs": by_lw * B / (ms * 1e-3) / 1e9, "tflops": fl * B / (ms * 1e-3) / 1e12}
@@ -348,7 +353,7 @@ def run_b200(a):
         pass
     try:  # the individual launches, timed one by one (events between launches: no overlap of neighbouring kernels)
         ms_l, _ = eng.time_steps(5)
-        tab = launch_table(H, W)
+        tab = launch_table(H, W, L.fused_blocks(pw))
         if len(tab) == len(ms_l):
             rows = [{"launch": n, "us": round(t * 1e3, 1), "alg_GB": round(by_l * B / 1e9, 4),
                      "GBps": round(by_l * B / (t * 1e-3) / 1e9, 1), "frac_hbm": round(by_l * B / (t * 1e-3) / 1e9 / hbm, 3)}
@@ -359,7 +364,7 @@ def run_b200(a):
     except Exception as ex:  # instrumentation only
         roofline["top_launches_error"] = str(ex)
     by_min, _ = L.work_model(H, W, L.CF_IN_U8_HWC, 0, pw)
-    by_all, fl_all = L.work_model(H, W, L.CF_IN_U8_HWC, 0, L.CF_PW_TCGEN05)  # layer-wise algorithmic bytes
+    by_all, fl_all = L.work_model(H, W, L.CF_IN_U8_HWC, 0, L.CF_PW_TCGEN05_LAYERWISE)  # layer-wise algorithmic bytes
     roofline["whole_step"] = {"alg_bytes_per_image": by_all, "min_bytes_per_image": by_min, "alg_flops_per_image": fl_all,
                               "GBps": by_all * B / (ms_per_step * 1e-3) / 1e9,
                               "frac_hbm": by_all * B / (ms_per_step * 1e-3) / 1e9 / hbm,
@@ -372,7 +377,7 @@ def run_b200(a):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": warm,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": {0: "f32", 1: "tf32x3", 2: "tf32", 3: "tf32x3+f32", 4: "tf32x3", 5: "tf32x3", 6: "tf32x3/tf32"}[pw], "data": "synthetic",
+                "dtype": {0: "f32", 1: "tf32x3", 2: "tf32", 3: "tf32x3", 6: "tf32x3/tf32"}[pw], "data": "synthetic",
                 "config": {"workload": f"batch-{B} 640x640 per GPU ({'configs[1]' if world == 1 else 'configs[2] sharding'}), "
                                        f"u8 BGR input, network + sigmoid/clamp + path-C top-{K_TOP} decode"
                                        + (", NCCL all-gather of [B,100,6] boxes" if world > 1 else ""),

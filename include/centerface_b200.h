@@ -45,16 +45,13 @@ extern "C" {
 
 /* GEMM engine for the point-wise (1x1) convolutions */
 #define CF_PW_SIMT 0      /* fp32 FFMA tiles (validation engine)                          */
-#define CF_PW_TCGEN05 1   /* tcgen05.mma kind::tf32, 3-pass split (fp32-class accuracy)   */
-#define CF_PW_TCGEN05_1P 2 /* tcgen05.mma kind::tf32 single pass (throughput mode)        */
-#define CF_PW_TCGEN05_FUSED 3 /* CF_PW_TCGEN05 + the shallow MBConv blocks (Cin<=32) run expand+Swish+
-                                 depth-wise+Swish as ONE kernel, hidden tensor kept in shared memory;
-                                 expand on the fp32 CUDA cores                                        */
-#define CF_PW_TCGEN05_FUSED_TC 4 /* same fusion, the expand conv of the fused blocks on tcgen05 (3xTF32),
-                                    accumulators drained from TMEM straight into the shared-memory tile */
-#define CF_PW_TCGEN05_MIXED 6 /* CF_PW_TCGEN05 with a single TF32 pass on the stride-16/32 stages (K or N >= 384) only */
-#define CF_PW_TCGEN05_DWP 5 /* CF_PW_TCGEN05 + the shallow blocks run depth-wise+Swish+projection(+residual) as ONE
-                               kernel: the depth-wise output is written as the tcgen05 A operand in shared memory */
+#define CF_PW_TCGEN05 1   /* tcgen05.mma kind::tf32, 3-pass split (fp32-class accuracy); the MBConv blocks of
+                             cf_fused_block_mask() run as ONE kernel each (expand + Swish + depth-wise + Swish +
+                             projection, neither hidden tensor reaches HBM).  The default.                   */
+#define CF_PW_TCGEN05_1P 2 /* tcgen05.mma kind::tf32 single pass, layer-wise (throughput probe: fails the parity contract) */
+#define CF_PW_TCGEN05_LAYERWISE 3 /* CF_PW_TCGEN05 with every block as three launches (expand, depth-wise, projection): the
+                                     schedule the fused kernel is measured against                              */
+#define CF_PW_TCGEN05_MIXED 6 /* CF_PW_TCGEN05_LAYERWISE with a single TF32 pass on the stride-16/32 stages (K or N >= 384) only */
 
 /* decode variants for cf_decode_threshold */
 #define CF_DECODE_A 0 /* centerface.py:73-109   : offsets unused, landmarks, clip to (H,W)   */
@@ -191,9 +188,17 @@ int cf_detect_image_host(cf_engine* e, const uint8_t* image, int h, int w, int n
 /* ---- instrumentation -----------------------------------------------------------------
  * Number of kernels this library launched on behalf of the handle since creation.        */
 long long cf_launch_count(cf_engine* e);
+
+/* Bit i set: MBConv block i (model/centernet.py:211-234, layer0 = block 0 .. layer6 = block 11) runs as one fused kernel under
+ * engine `pw_engine` (the built-in mask, or CF_MBF from the environment). */
+unsigned cf_fused_block_mask(int pw_engine);
+
+/* Development only: the pipeline trace of the fused MBConv kernel (k_mbf) recorded during the last forward when the plan was built
+ * with CF_MBF_TRACE=j0,nj in the environment: out[job][32] = clock64 of event 0..31 of CTA 0 (0 = not recorded). */
+int cf_debug_mbf_trace(cf_engine* e, unsigned long long* out, int n_jobs);
 /* Algorithmic bytes / flops of ONE image at (h,w) for kernel class `which` under engine `pw_engine`
  * (0 = network = 1+2+3+4+6, 1 = point-wise GEMMs, 2 = depth-wise, 3 = stem, 4 = heads,
- * 5 = path-C decode, 6 = fused expand+depth-wise blocks).  Bytes: every conv reads its un-padded input once and writes its output
+ * 5 = path-C decode, 6 = fused MBConv blocks).  Bytes: every conv reads its un-padded input once and writes its output
  * once in the engine's fp32 storage (+ residual / low-res re-reads); weights (5 MB per LAUNCH,
  * not per image) are not counted.  Flops: 2*MAC of the REFERENCE graph (model/centernet.py),
  * i.e. the four un-collapsed heads.  in_format selects the stem's input bytes.            */

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcenterface_b200.so")
 
 CF_IN_F32_NCHW, CF_IN_U8_HWC = 0, 1
-CF_PW_SIMT, CF_PW_TCGEN05, CF_PW_TCGEN05_1P, CF_PW_TCGEN05_FUSED, CF_PW_TCGEN05_FUSED_TC, CF_PW_TCGEN05_DWP, CF_PW_TCGEN05_MIXED = 0, 1, 2, 3, 4, 5, 6
+CF_PW_SIMT, CF_PW_TCGEN05, CF_PW_TCGEN05_1P, CF_PW_TCGEN05_LAYERWISE, CF_PW_TCGEN05_MIXED = 0, 1, 2, 3, 6
 CF_DECODE_A, CF_DECODE_B = 0, 1
 CLS_ALL, CLS_PW, CLS_DW, CLS_STEM, CLS_HEADS, CLS_DECODE, CLS_FUSED = range(7)
 MAX_CAP = 4096
@@ -50,6 +50,8 @@ SIGNATURES = {
     "cf_detect_image_host": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
                                        C.c_float, C.c_int, _vp, _vp, _vp]),
     "cf_launch_count": (C.c_longlong, [_vp]),
+    "cf_fused_block_mask": (C.c_uint, [C.c_int]),
+    "cf_debug_mbf_trace": (C.c_int, [_vp, _vp, C.c_int]),
     "cf_work_model": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "cf_replay_class": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "cf_time_class": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.POINTER(C.c_float), _i]),
@@ -85,6 +87,12 @@ def check(rc, what=""):
     if rc != 0:
         msg = load().cf_last_error().decode(errors="replace")
         raise CenterFaceError(f"{what or 'centerface_b200'} failed ({rc}): {msg}")
+
+
+def fused_blocks(pw_engine=CF_PW_TCGEN05):
+    """Indices of the MBConv blocks that run as one fused kernel under `pw_engine` -- cf_fused_block_mask."""
+    m = load().cf_fused_block_mask(pw_engine)
+    return [i for i in range(12) if (m >> i) & 1]
 
 
 def work_model(h, w, in_format=CF_IN_U8_HWC, which=CLS_ALL, pw_engine=CF_PW_TCGEN05):

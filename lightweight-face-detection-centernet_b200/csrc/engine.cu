@@ -19,10 +19,7 @@
 #include "k_decode.cuh"
 #include "k_pw_simt.cuh"
 #include "k_pw_tc.cuh"
-#include "k_expdw.cuh"
-#include "k_mbx.cuh"
 #include "k_dwt.cuh"
-#include "k_dwp.cuh"
 #include "k_pwn.cuh"
 #include "k_mbf.cuh"
 #include "k_stem_tc.cuh"
@@ -43,18 +40,10 @@ inline int layer_passes(int pw, int K, int N) {
     if (pw == CF_PW_TCGEN05_MIXED) return (K >= 384 || N >= 384) ? 1 : 3;
     return engine_passes(pw);
 }
-// depth-wise + projection fused (k_dwp): the shallow blocks, where the depth-wise output is large and tiles are plentiful
-inline bool block_is_dwp(int pw, int i) { return pw == CF_PW_TCGEN05_DWP && i <= 5 && dwp_supported(kBlocks[i].hid(), kBlocks[i].cout); }
-
-inline bool block_is_fused(int pw, const MBBlock& b) {
-    if (b.t == 1 || !xd_supported(b.k, b.s, b.cin)) return false;
-    if (pw == CF_PW_TCGEN05_FUSED) return true;
-    return pw == CF_PW_TCGEN05_FUSED_TC;
-}
-
-// Whole-block fusion (k_mbf): the default tensor-core engine runs the blocks of this mask as one kernel each.  CF_MBF overrides
-// the mask (development: A/B runs against the layer-wise schedule, bit i = block i).
-constexpr unsigned kMbfDefaultMask = 0u;
+// Whole-block fusion (k_mbf): the default tensor-core engine runs the blocks of this mask (bit i = block i) as one kernel each;
+// CF_PW_TCGEN05_LAYERWISE is the same engine without it.  The mask holds the blocks whose fused kernel beats its three
+// layer-wise launches on the device (profiles/r2_mbf.md); CF_MBF overrides it for A/B runs.
+constexpr unsigned kMbfDefaultMask = 0x2u;
 inline unsigned mbf_mask() {
     if (const char* ev = getenv("CF_MBF")) return (unsigned)strtoul(ev, nullptr, 0);
     return kMbfDefaultMask;
@@ -170,11 +159,15 @@ struct cf_engine {
 namespace {
 
 int run_steps(cf_engine* e, int which, cudaStream_t s) {
+    static const bool sync_each = getenv("CF_SYNC_EACH") != nullptr;  // development: attribute a device-side fault to its launch
+    int idx = 0;
     for (auto& st : e->plan) {
+        ++idx;
         if (which != CLS_ALL && st.cls != which) continue;
         if (st.cls == CLS_DECODE && which == CLS_ALL) continue;  // decode is launched by its own entry points
         cudaError_t err = st.run(s);
-        if (err != cudaSuccess) return fail(CF_ECUDA, "kernel launch failed: %s", cudaGetErrorString(err));
+        if (err == cudaSuccess && sync_each) err = cudaStreamSynchronize(s);
+        if (err != cudaSuccess) return fail(CF_ECUDA, "launch %d of the plan (class %d) failed: %s", idx - 1, st.cls, cudaGetErrorString(err));
         ++e->launches;
     }
     return CF_OK;
@@ -343,45 +336,26 @@ int build_plan(cf_engine* e, const void* input, int fmt, int B, int H, int W) {
             wd = wo;
             continue;
         }
-        const bool fused = block_is_fused(e->pw_engine, b);
-        if (fused) {
-            // expand + Swish + depth-wise + Swish in one kernel; the hidden tensor stays in shared memory
-            if (e->pw_engine == CF_PW_TCGEN05_FUSED_TC) {
-                MbxLaunch ml;
-                if ((rc = mbx_plan(e->tc, b.k, b.s, x, e->w[p + ".exp"], e->w[p + ".dw"], e->hidB, B, h, wd, b.cin, hid, &ml))) return rc;
-                P.push_back({CLS_FUSED, [ml](cudaStream_t s) { return mbx_launch(ml, s); }});
-            } else {
-                XdLaunch xl;
-                if ((rc = xd_plan(e->tc, b.k, b.s, x, e->w[p + ".exp"], e->w[p + ".dw"], e->hidB, B, h, wd, b.cin, hid, &xl))) return rc;
-                P.push_back({CLS_FUSED, [xl](cudaStream_t s) { return xd_launch(xl, s); }});
-            }
-        } else if (b.t != 1) {
+        if (b.t != 1) {
             const float* wexp = e->w[p + ".exp"];
             float* o = e->hidA;
             const int M = B * h * wd, K = b.cin;
             if ((rc = make_pw_step(e, P, EPI_SWISH, x, wexp, o, M, K, hid, EpiArgs{}))) return rc;
             dw_in = e->hidA;
         }
-        if (block_is_dwp(e->pw_engine, i)) {
-            // depth-wise + Swish + projection (+ residual) in one kernel; the depth-wise output stays in shared memory
-            DwpLaunch dl;
-            if ((rc = dwp_plan(e->tc, b.k, b.s, dw_in, e->w[p + ".dw"], e->w[p + ".proj"], e->blk[i], b.residual() ? x : nullptr, B, h, wd,
-                               hid, b.cout, &dl)))
-                return rc;
-            P.push_back({CLS_FUSED, [dl](cudaStream_t s) { return dwp_launch(dl, s); }});
-        } else {
-            if (!fused) {
-                const float* wdw = e->w[p + ".dw"];
-                float* o = e->hidB;
-                const int ks = b.k, st = b.s, hi = h, wi = wd;
-                if (engine_is_tc(e->pw_engine) && dwt_supported(hid)) {  // TMA-fed depth-wise kernel
-                    DwtLaunch dl;
-                    if ((rc = dwt_plan(e->tc, ks, st, dw_in, wdw, o, B, hi, wi, hid, &dl))) return rc;
-                    P.push_back({CLS_DW, [dl](cudaStream_t s) { return dwt_launch(dl, s); }});
-                } else {
-                    P.push_back({CLS_DW, [=](cudaStream_t s) { return launch_dw(ks, st, dw_in, wdw, o, B, hi, wi, hid, ho, wo, s); }});
-                }
+        {
+            const float* wdw = e->w[p + ".dw"];
+            float* o = e->hidB;
+            const int ks = b.k, st = b.s, hi = h, wi = wd;
+            if (engine_is_tc(e->pw_engine) && dwt_supported(hid)) {  // TMA-fed depth-wise kernel
+                DwtLaunch dl;
+                if ((rc = dwt_plan(e->tc, ks, st, dw_in, wdw, o, B, hi, wi, hid, &dl))) return rc;
+                P.push_back({CLS_DW, [dl](cudaStream_t s) { return dwt_launch(dl, s); }});
+            } else {
+                P.push_back({CLS_DW, [=](cudaStream_t s) { return launch_dw(ks, st, dw_in, wdw, o, B, hi, wi, hid, ho, wo, s); }});
             }
+        }
+        {
             const float* wpr = e->w[p + ".proj"];
             const float* a = e->hidB;
             float* o = e->blk[i];
@@ -486,7 +460,9 @@ int cf_create(const void* weights, size_t weights_bytes, int device, int max_bat
     CF_CHECK(weights != nullptr, CF_EINVAL, "cf_create: weights is NULL");
     CF_CHECK(max_batch >= 1 && max_h >= 32 && max_w >= 32 && max_h % 32 == 0 && max_w % 32 == 0, CF_EINVAL,
              "cf_create: max_batch=%d max_h=%d max_w=%d (sizes must be positive multiples of 32)", max_batch, max_h, max_w);
-    CF_CHECK(pw_engine >= CF_PW_SIMT && pw_engine <= CF_PW_TCGEN05_MIXED, CF_EINVAL, "cf_create: unknown pw_engine %d", pw_engine);
+    CF_CHECK(pw_engine == CF_PW_SIMT || pw_engine == CF_PW_TCGEN05 || pw_engine == CF_PW_TCGEN05_1P || pw_engine == CF_PW_TCGEN05_LAYERWISE ||
+                 pw_engine == CF_PW_TCGEN05_MIXED,
+             CF_EINVAL, "cf_create: unknown pw_engine %d", pw_engine);
     CF_CHECK(weights_bytes == blob_bytes(), CF_EWEIGHTS, "cf_create: blob is %zu bytes, expected %zu", weights_bytes, blob_bytes());
     Blob blob;
     std::string why;
@@ -619,21 +595,15 @@ int cf_create(const void* weights, size_t weights_bytes, int device, int max_bat
                     const float* hp = blob.get(nm, (uint64_t)K * N, why);
                     if (!rc) rc = hp ? tc_prepare_layer(e->tc, e->w[nm], hp, K, N, 3, 32) : fail(CF_EWEIGHTS, "cf_create: %s", why.c_str());
                 }
+                if (!rc) {
+                    const std::string nm = "b" + std::to_string(i) + ".dw";
+                    const float* hp = blob.get(nm, (uint64_t)b.k * b.k * b.hid(), why);
+                    rc = hp ? mbf_prepare_dw(e->tc, e->w[nm], hp, b.k * b.k, b.hid()) : fail(CF_EWEIGHTS, "cf_create: %s", why.c_str());
+                }
                 continue;
             }
-            if (b.t != 1 && !block_is_fused(pw_engine, b)) rc = prep("b" + std::to_string(i) + ".exp", b.cin, b.hid());
-            if (b.t != 1 && block_is_fused(pw_engine, b) && pw_engine == CF_PW_TCGEN05_FUSED_TC) {  // 32-column chunk images
-                const std::string nm = "b" + std::to_string(i) + ".exp";
-                const float* hp = blob.get(nm, (uint64_t)b.cin * b.hid(), why);
-                rc = hp ? tc_prepare_layer(e->tc, e->w[nm], hp, b.cin, b.hid(), 3, 32) : fail(CF_EWEIGHTS, "cf_create: %s", why.c_str());
-            }
-            if (!rc && block_is_dwp(pw_engine, i)) {  // one padded-N image per 32-channel K block
-                const std::string nm = "b" + std::to_string(i) + ".proj";
-                const float* hp = blob.get(nm, (uint64_t)b.hid() * b.cout, why);
-                rc = hp ? tc_prepare_layer(e->tc, e->w[nm], hp, b.hid(), b.cout, 3, dwp_ncp(b.cout)) : fail(CF_EWEIGHTS, "cf_create: %s", why.c_str());
-            } else if (!rc) {
-                rc = prep("b" + std::to_string(i) + ".proj", b.hid(), b.cout);
-            }
+            if (b.t != 1) rc = prep("b" + std::to_string(i) + ".exp", b.cin, b.hid());
+            if (!rc) rc = prep("b" + std::to_string(i) + ".proj", b.hid(), b.cout);
         }
         if (!rc) rc = prep("clast.w", 320, 24);
         if (!rc) {  // the stem as a K = 27 (one K block), N = 32 GEMM: k_stem_tc
@@ -1108,6 +1078,21 @@ int cf_debug_tma_stream(const float* dA, int M, int K, int stages, int box_rows,
 
 long long cf_launch_count(cf_engine* e) { return e ? e->launches : 0; }
 
+unsigned cf_fused_block_mask(int pw_engine) {
+    unsigned m = 0;
+    for (int i = 0; i < 12; ++i)
+        if (block_is_mbf(pw_engine, i)) m |= 1u << i;
+    return m;
+}
+
+int cf_debug_mbf_trace(cf_engine* e, unsigned long long* out, int n_jobs) {
+    CF_CHECK(e && out && n_jobs > 0 && n_jobs <= 4096, CF_EINVAL, "cf_debug_mbf_trace: bad arguments");
+    CF_CHECK(e->tc.trace_buf != nullptr, CF_EINVAL, "cf_debug_mbf_trace: no trace was recorded (set CF_MBF_TRACE=j0,nj before the plan is built)");
+    CF_CUDA(cudaDeviceSynchronize());
+    CF_CUDA(cudaMemcpy(out, e->tc.trace_buf, (size_t)n_jobs * 32 * 8, cudaMemcpyDeviceToHost));
+    return CF_OK;
+}
+
 int cf_work_model(int h, int w, int in_format, int pw_engine, int which, double* bytes, double* flops) {
     CF_CHECK(h >= 32 && w >= 32 && h % 32 == 0 && w % 32 == 0, CF_EINVAL, "cf_work_model: h=%d w=%d must be multiples of 32", h, w);
     CF_CHECK(which >= CLS_ALL && which < CLS_COUNT, CF_EINVAL, "cf_work_model: unknown class %d", which);
@@ -1127,26 +1112,14 @@ int cf_work_model(int h, int w, int in_format, int pw_engine, int which, double*
             ww = wo;
             continue;
         }
-        if (block_is_fused(pw_engine, b)) {  // X read once, depth-wise output written once; the hidden tensor never reaches HBM
-            by[CLS_FUSED] += (hh * ww * b.cin + ho * wo * hid) * F;
-            fl[CLS_FUSED] += 2.0 * hh * ww * b.cin * hid + 2.0 * ho * wo * hid * b.k * b.k;
-        } else {
-            if (b.t != 1) {
-                by[CLS_PW] += hh * ww * (b.cin + hid) * F;
-                fl[CLS_PW] += 2.0 * hh * ww * b.cin * hid;
-            }
-            by[CLS_DW] += (hh * ww + ho * wo) * hid * F;
-            fl[CLS_DW] += 2.0 * ho * wo * hid * b.k * b.k;
+        if (b.t != 1) {
+            by[CLS_PW] += hh * ww * (b.cin + hid) * F;
+            fl[CLS_PW] += 2.0 * hh * ww * b.cin * hid;
         }
-        if (block_is_dwp(pw_engine, i)) {  // expanded tensor in, block output out; the depth-wise output never reaches HBM
-            by[CLS_DW] -= (hh * ww + ho * wo) * hid * F;
-            fl[CLS_DW] -= 2.0 * ho * wo * hid * b.k * b.k;
-            by[CLS_FUSED] += (hh * ww * hid + ho * wo * (b.cout + (b.residual() ? b.cout : 0))) * F;
-            fl[CLS_FUSED] += 2.0 * ho * wo * hid * b.k * b.k + 2.0 * ho * wo * hid * b.cout;
-        } else {
-            by[CLS_PW] += ho * wo * (hid + b.cout + (b.residual() ? b.cout : 0)) * F;
-            fl[CLS_PW] += 2.0 * ho * wo * hid * b.cout;
-        }
+        by[CLS_DW] += (hh * ww + ho * wo) * hid * F;
+        fl[CLS_DW] += 2.0 * ho * wo * hid * b.k * b.k;
+        by[CLS_PW] += ho * wo * (hid + b.cout + (b.residual() ? b.cout : 0)) * F;
+        fl[CLS_PW] += 2.0 * ho * wo * hid * b.cout;
         hh = ho;
         ww = wo;
     }

@@ -5,12 +5,105 @@
 // loads are bulk tensor copies: a CTA walks over (image, 10x10 output tile, 32-channel chunk) items, one elected
 // thread keeps NST halo tiles in flight with cp.async.bulk.tensor.4d (box = 32 channels x IW x IH, no swizzle,
 // zero fill outside the image = the reference's ZeroPad2d, model/centernet.py:63-70), and all 256 threads compute
-// from shared memory with the same 2x2-output register blocking as the fused kernel (xd_dw_phase_g).  Bytes in flight
+// from shared memory with 2x2 (or 2x4) output register blocking (xd_dw_phase_g).  Bytes in flight
 // per SM = NST x tile (up to ~190 KB) instead of a few KB of registers.
 #pragma once
-#include "k_expdw.cuh"
+#include "k_pw_tc.cuh"
 
 namespace cf {
+
+// ---- halo-tile helpers shared with the fused MBConv kernel (k_mbf) ----------------------------------------------------
+
+struct XdParams {
+    const float* We;   // [CIN][hid]
+    const float* Wd;   // [KS*KS][hid]
+    float* D;          // [B][Ho][Wo][hid]
+    int B, Hi, Wi, Ho, Wo, hid;
+    int tiles_x, tiles_y, n_items;
+};
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
+// depth-wise KSxKS stride S + Swish from a halo tile in shared memory -> global D.  A thread owns an XT x YT block of
+// outputs for one float4 of channels; the ((YT-1)S+KS) x ((XT-1)S+KS) input window is streamed row by row.
+// SWZ: the halo tile is in the TMA's SWIZZLE_128B layout (needed where the tile doubles as a tcgen05 operand).  A quarter
+// warp (8 lanes = the 8 channel vectors of one pixel) reads one whole 128-byte pixel row per LDS.128 wavefront, which is
+// bank-conflict free with or without the swizzle; without it every window address is base + an immediate.
+template <typename G, int KS, int S, int XT, int YT, bool WD_GLOBAL, int NWARPS, bool SWZ = true>
+__device__ __forceinline__ void xd_dw_phase_g(const uint8_t* Es, const float* Wd_s, const XdParams& p, int warp, int pg, int c4,
+                                              int cbase, bool cvalid, int b, int ty, int tx) {
+    constexpr int NBX = G::TW / XT, NBLK = (G::TH / YT) * NBX;
+    static_assert(G::TW % XT == 0 && G::TH % YT == 0, "output blocks must tile the output tile");
+    constexpr int NROW = (YT - 1) * S + KS, NCOL = (XT - 1) * S + KS;
+    if (!cvalid) return;
+    for (int blk = warp * 4 + pg; blk < NBLK; blk += NWARPS * 4) {
+        const int by = blk / NBX, bx = blk - by * NBX;
+        float4 acc[YT][XT];
+#pragma unroll
+        for (int a = 0; a < YT; ++a)
+#pragma unroll
+            for (int c = 0; c < XT; ++c) acc[a][c] = make_float4(0, 0, 0, 0);
+        const int r0 = YT * by * S, q0 = XT * bx * S;  // window origin inside the halo tile
+        float4 wt[KS][KS];  // tap rows are loaded once, when the first input row needs them, and stay live for YT rows
+#pragma unroll
+        for (int rr = 0; rr < NROW; ++rr) {
+            float4 win[NCOL];
+#pragma unroll
+            for (int cc = 0; cc < NCOL; ++cc) {
+                const int px = (r0 + rr) * G::IW + q0 + cc;
+                win[cc] = SWZ ? *reinterpret_cast<const float4*>(Es + px * 128 + ((c4 ^ (px & 7)) << 4))
+                              : *reinterpret_cast<const float4*>(Es + px * 128 + (c4 << 4));
+            }
+            if (rr < KS) {
+#pragma unroll
+                for (int kx = 0; kx < KS; ++kx)
+                    wt[rr][kx] = WD_GLOBAL ? ldg4(Wd_s + (rr * KS + kx) * p.hid + cbase)
+                                           : *reinterpret_cast<const float4*>(Wd_s + (rr * KS + kx) * p.hid + cbase);
+            }
+#pragma unroll
+            for (int dy = 0; dy < YT; ++dy) {
+                const int ky = rr - dy * S;
+                if (ky < 0 || ky >= KS) continue;
+#pragma unroll
+                for (int kx = 0; kx < KS; ++kx) {
+#pragma unroll
+                    for (int dx = 0; dx < XT; ++dx) fma44(acc[dy][dx], win[dx * S + kx], wt[ky][kx]);
+                }
+            }
+        }
+        const int yo0 = ty * G::TH + YT * by, xo0 = tx * G::TW + XT * bx;
+        float* o0 = p.D + ((size_t)(b * p.Ho + yo0) * p.Wo + xo0) * p.hid + cbase;  // one 64-bit address per block
+        const int rstride = p.Wo * p.hid;
+#pragma unroll
+        for (int dy = 0; dy < YT; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < XT; ++dx) {
+                if (yo0 + dy < p.Ho && xo0 + dx < p.Wo) st4(o0 + dy * rstride + dx * p.hid, swish4(acc[dy][dx]));
+            }
+    }
+}
+
+
+// ---- host side --------------------------------------------------------------------------
+// fp32 NHWC tensor [B][H][W][C]: box {32 channels (zero filled past C), IW, IH, 1}, SWIZZLE_128B
+inline int xd_make_map(PwTcState& st, CUtensorMap* map, const float* ptr, int B, int H, int W, int C, int IW, int IH, bool swizzle = true) {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)IW, (cuuint32_t)IH, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = ((PFN_encodeTiled)st.encode)(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box, estr,
+                                              CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(CF_ECUDA, "cuTensorMapEncodeTiled(4D %dx%dx%dx%d) failed with CUresult %d", B, H, W, C, (int)r);
+    return CF_OK;
+}
+
+
 
 constexpr int DWT_THREADS = 256;
 

@@ -19,13 +19,21 @@
 //
 //   warp 0        TMA producer: the X halo box of every job (zero fill outside the image = the reference's ZeroPad2d,
 //                 :63-70; swish(0 . W) = 0 because the expand conv has no bias), re-read per chunk from L2
-//   warp 1        expand issuer: the MMAs of a job as soon as its A slot is written and an accumulator is free
-//   warp 3        projection issuer: the MMAs of a (block, chunk) as soon as its D operand is complete (its own warp, so
-//                 that neither MMA stream ever waits behind the other's barrier)
+//   warp 1        expand issuer: the MMAs of a job as soon as its A slot is written and its team's accumulator is free
+//   warp 2        projection issuer: the MMAs of a (block, chunk) as soon as its D operand is complete (its own warp, so
+//                 that neither MMA stream ever waits behind the other's barrier); also allocates / frees TMEM
 //   warps 4-7     splitters: X row -> tf32 hi + lo -> TMEM A slot (tcgen05.st, lane = halo pixel); between blocks they
 //                 drain the previous block's projection accumulator (+ residual) and store Y
-//   warps 8-15    two drain teams (alternate jobs): expand accumulator -> Swish -> swizzled E slot in shared memory
-//   warps 16-..   two depth-wise teams (alternate jobs): E slot -> KSxKS taps -> Swish -> tf32 hi/lo rows of the D operand
+//   warps 8-23    four compute teams of four warps, jobs round-robin.  A team takes its job through both element-wise
+//                 phases: expand accumulator (TMEM, a warp = a lane quarter) -> Swish -> the team's private E tile in shared
+//                 memory -> depth-wise taps -> Swish -> tf32 hi/lo rows of the D operand.  Teams are in different phases at
+//                 any time, so the MUFU-bound drain of one overlaps the LDS/FMA-bound depth-wise phase of another on every
+//                 scheduler; the only CTA-level synchronisation is two 128-thread named barriers per job inside a team.
+//
+// mbarrier waits are by phase PARITY, so a waiter must observe EVERY phase of a barrier it waits on (one that skips a phase
+// finds the parity of a phase that has not begun "already complete" -- seen as a timing-dependent deadlock in an earlier
+// version whose depth-wise teams shared E slots round-robin).  Hence every accumulator / E tile belongs to one team, and the
+// D operand hand-back is per slot when the same teams write every use of a slot, else per writer team (see d_free below).
 //
 // 3xTF32: expand uses ONE accumulator, the two correction products first (while the accumulator is ~2^-11 of its final
 // size their per-MMA accumulator truncation, tools/tc_accum_probe.py, is negligible), then the K/8 main products; the
@@ -36,24 +44,36 @@
 
 namespace cf {
 
-template <int KS_, int S_, int CIN_, int STH_, int STW_, int NSY_, int NSX_, int XT_, int YT_, int TD_>
+template <int KS_, int S_, int CIN_, int STH_, int STW_, int NSY_, int NSX_, int XT_, int YT_, int TD_, int NX_, bool WDS_>
 struct MbfCfg {
     static constexpr int KS = KS_, S = S_, CIN = CIN_, STH = STH_, STW = STW_, NSY = NSY_, NSX = NSX_, XT = XT_, YT = YT_, TD = TD_;
     static constexpr int IH = (STH - 1) * S + KS, IW = (STW - 1) * S + KS, NPX = IH * IW;
     static constexpr int LO = (KS - S) / 2;  // model/centernet.py:68-70
     static constexpr int NSUB = NSY * NSX, SPX = STH * STW, DROWS = NSUB * SPX;
     static constexpr int KSTEPS = (CIN + 7) / 8;
-    static constexpr int NDT = 2, NWT = 2;  // drain teams (4 warps each), depth-wise teams (TD warps each)
-    static constexpr int NWARPS = 16 + TD * NWT, THREADS = NWARPS * 32;
-    static constexpr int NBX = STW / XT, NITEMS = (STH / YT) * NBX * 8;  // (output block, float4 of channels)
-    // ring depths: X boxes, TMEM A slots, expand accumulators, E slots, D operands, projection accumulators
-    static constexpr int NX = 3, NA = 4, NE = 4, NES = 3, ND = 2, NP = 2;
-    static constexpr uint32_t SLOT = 16384;                         // 128 rows x 128 B
+    static constexpr int NT = 4;  // compute teams (four warps each: one per TMEM lane quarter)
+    static constexpr int NWARPS = 8 + 4 * NT, THREADS = NWARPS * 32;
+    static constexpr int NBX = STW / XT, NITEMS = (STH / YT) * NBX * 8;  // depth-wise items: (output block, float4 of channels)
+    // ring depths: X boxes, TMEM A slots, expand accumulators (one per team), D operands, projection accumulators
+    static constexpr int NX = NX_, NA = 4, NE = NT, ND = 2, NP = 2;
+    static constexpr bool WDS = WDS_;  // depth-wise taps resident in shared memory (else read through L1 from the chunk image)
+    // D operand hand-back (projection retired -> the slot may be rewritten): one barrier per SLOT when every use of a slot is
+    // written by the same set of teams ((ND * NSUB) % NT == 0), one barrier per WRITER TEAM when a D operand is one job (NSUB == 1)
+    static constexpr bool DFREE_PER_TEAM = (ND * NSUB) % NT != 0;
+    static constexpr int NDF = DFREE_PER_TEAM ? NT : ND;
+    static_assert(!DFREE_PER_TEAM || NSUB == 1, "D hand-back: per slot, or per team for one-job operands");
+    static_assert(NITEMS <= 128, "one depth-wise item per thread of a team");
+    static constexpr uint32_t SLOT = 16384;                         // X box: 128 rows x 128 B (SWIZZLE_128B, written by TMA)
+    // E slot: pixel rows at a 144-byte pitch instead of a swizzle -- the drain's stores (a lane = a pixel, 8 consecutive pixels
+    // per quarter warp) and the depth-wise loads (8 lanes = the 128 bytes of one pixel) are both bank-conflict free, and every
+    // window address is one base register + an immediate
+    static constexpr uint32_t EP = 144, ESLOT = ((NPX * EP + 1023) / 1024) * 1024;
     static constexpr uint32_t DHALF = ((DROWS + 7) / 8) * 1024u;    // the hi (or lo) half of one D operand
     static constexpr uint32_t PCOL = 0, ECOL = PCOL + NP * 64, ACOL = ECOL + NE * 32;  // TMEM columns
     static_assert(NPX <= 128, "a sub-tile's halo is one MMA block");
     static_assert(DROWS <= 128, "a block's outputs are the rows of one projection accumulator");
     static_assert(STW % XT == 0 && STH % YT == 0, "output blocks tile the sub-tile");
+    static_assert(TD_ >= 0, "legacy parameter");
     static_assert(ACOL + NA * 64 <= 512, "TMEM budget");
     static_assert(CIN % 8 == 0 && CIN <= 32, "expand K");
 };
@@ -66,32 +86,31 @@ struct MbfParams {
     const float* res;     // [B][Ho][Wo][cout] or NULL
     int B, Hi, Wi, Ho, Wo, hid, nch, cout;
     int blocks_x, blocks_y, n_blocks;
-    uint32_t off_e, off_d, off_we, off_wp, off_bars;  // the X ring starts at 0
-    int dbg;  // development only (env CF_MBF_DEBUG): 1 no Swish in the drain, 2 no depth-wise math, 4 no Y stores
+    const float* wd_img;  // [nch][KS*KS][32]   depth-wise taps per chunk, zero past hid
+    uint32_t off_e, off_d, off_we, off_wp, off_wd, off_bars;  // the X ring starts at 0
+    unsigned long long* trace;  // development only (env CF_MBF_TRACE=j0,nj): clock64 of the pipeline events of CTA 0, jobs [tr_j0, tr_j0 + tr_nj)
+    int tr_j0, tr_nj;
+    int dbg;  // development only (env CF_MBF_DEBUG; wrong results): 1 no Swish in the drain, 2 no depth-wise work, 4 no Y stores, 8 no split math, 16 no TMA loads, 32 no expand MMAs, 64 no projection MMAs
 };
 
-__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return done != 0;
+// Build (once per block) the per-chunk tap image of a depth-wise weight tensor Wd[k*k][hid]: [chunk][tap][32 channels], zero past hid.
+inline int mbf_prepare_dw(PwTcState& st, const float* key, const float* hw, int kk, int hid) {
+    if (st.dw_imgs.count(key)) return CF_OK;
+    const int nch = (hid + 31) / 32;
+    std::vector<float> img((size_t)nch * kk * 32, 0.f);
+    for (int c = 0; c < nch; ++c)
+        for (int t = 0; t < kk; ++t)
+            for (int i = 0; i < 32 && c * 32 + i < hid; ++i) img[((size_t)c * kk + t) * 32 + i] = hw[(size_t)t * hid + c * 32 + i];
+    float* d = nullptr;
+    if (cudaMalloc((void**)&d, img.size() * 4) != cudaSuccess) return fail(CF_ECUDA, "mbf_prepare_dw: cudaMalloc failed");
+    if (cudaMemcpy(d, img.data(), img.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(d);
+        return fail(CF_ECUDA, "mbf_prepare_dw: cudaMemcpy failed");
+    }
+    st.dw_imgs[key] = d;
+    return CF_OK;
 }
-__device__ __forceinline__ bool mbar_try_once(uint32_t bar, uint32_t parity) {  // may park the warp for a short, bounded time
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return done != 0;
-}
+
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
     const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
@@ -101,8 +120,8 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
 
 template <typename C>
 __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ CUtensorMap tmX, const MbfParams p) {
-    constexpr int KS = C::KS, S = C::S, NX = C::NX, NA = C::NA, NE = C::NE, NES = C::NES, ND = C::ND, NP = C::NP;
-    constexpr int NSUB = C::NSUB, TD = C::TD;
+    constexpr int KS = C::KS, S = C::S, NX = C::NX, NA = C::NA, NE = C::NE, ND = C::ND, NP = C::NP, NT = C::NT, NDF = C::NDF;
+    constexpr int NSUB = C::NSUB;
     constexpr uint32_t SLOT = C::SLOT;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -115,11 +134,10 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
     const uint32_t x_full = bars, x_empty = x_full + 8 * NX;
     const uint32_t a_full = x_empty + 8 * NX, a_empty = a_full + 8 * NA;
     const uint32_t e_full = a_empty + 8 * NA, e_empty = e_full + 8 * NE;
-    const uint32_t es_full = e_empty + 8 * NE, es_empty = es_full + 8 * NES;
-    const uint32_t d_full = es_empty + 8 * NES, d_empty = d_full + 8 * ND;
-    const uint32_t p_full = d_empty + 8 * ND, p_empty = p_full + 8 * NP;
+    const uint32_t d_full = e_empty + 8 * NE, d_free = d_full + 8 * ND;
+    const uint32_t p_full = d_free + 8 * NDF, p_empty = p_full + 8 * NP;
     const uint32_t w_full = p_empty + 8 * NP;
-    constexpr int NBARS = 2 * (NX + NA + NE + NES + ND + NP) + 1;
+    constexpr int NBARS = 2 * (NX + NA + NE + NP) + ND + NDF + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + p.off_bars + 8 * NBARS + 8);
 
     if (warp == 0 && lane == 0) {
@@ -127,8 +145,8 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
         for (int i = 0; i < NX; ++i) mbar_init(x_full + 8 * i, 1), mbar_init(x_empty + 8 * i, 4);
         for (int i = 0; i < NA; ++i) mbar_init(a_full + 8 * i, 4), mbar_init(a_empty + 8 * i, 1);
         for (int i = 0; i < NE; ++i) mbar_init(e_full + 8 * i, 1), mbar_init(e_empty + 8 * i, 4);
-        for (int i = 0; i < NES; ++i) mbar_init(es_full + 8 * i, 4), mbar_init(es_empty + 8 * i, TD);
-        for (int i = 0; i < ND; ++i) mbar_init(d_full + 8 * i, NSUB * TD), mbar_init(d_empty + 8 * i, 1);
+        for (int i = 0; i < ND; ++i) mbar_init(d_full + 8 * i, NSUB * 4);
+        for (int i = 0; i < NDF; ++i) mbar_init(d_free + 8 * i, 1);
         for (int i = 0; i < NP; ++i) mbar_init(p_full + 8 * i, 1), mbar_init(p_empty + 8 * i, 4);
         mbar_init(w_full, 1);
         fence_barrier_init();
@@ -142,6 +160,10 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // development trace: event ev of job j (one lane of one warp per role writes; 32 slots per job)
+    auto TR = [&](int ev, int j) {
+        if (p.trace && blockIdx.x == 0 && lane == 0 && (unsigned)(j - p.tr_j0) < (unsigned)p.tr_nj) p.trace[(size_t)(j - p.tr_j0) * 32 + ev] = (unsigned long long)clock64();
+    };
     const int nch = p.nch;
     const int nblk = ((int)blockIdx.x < p.n_blocks) ? (p.n_blocks - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const int J = nblk * nch * NSUB;  // jobs of this CTA, in order (block i, chunk c, sub-tile s)
@@ -159,8 +181,9 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
     if (warp == 0) {
         // ================= TMA producer =================
         if (elect_one()) {
-            const uint32_t wbytes = (uint32_t)nch * 8192u;
-            mbar_expect_tx(w_full, 2u * wbytes);
+            const uint32_t wbytes = (uint32_t)nch * 8192u, dbytes = C::WDS ? (uint32_t)nch * (KS * KS * 128u) : 0u;
+            mbar_expect_tx(w_full, 2u * wbytes + dbytes);
+            if (C::WDS) bulk_load(base + p.off_wd, p.wd_img, dbytes, w_full);
             for (uint32_t off = 0; off < wbytes; off += 32768u) {
                 const uint32_t n = wbytes - off < 32768u ? wbytes - off : 32768u;
                 bulk_load(base + p.off_we + off, reinterpret_cast<const uint8_t*>(p.we_img) + off, n, w_full);
@@ -170,6 +193,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
         __syncwarp();
         pdl_wait();  // X is the previous kernel's output
         Ring xr;
+        int jt = 0;
         for (int i = 0; i < nblk; ++i) {
             int t = (int)blockIdx.x + i * (int)gridDim.x;
             const int bx = t % p.blocks_x;
@@ -181,11 +205,18 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
                 for (int s = 0; s < NSUB; ++s) {
                     const int sy = s / C::NSX, sx = s % C::NSX;  // compile-time after unrolling
                     mbar_wait(x_empty + 8 * xr.slot, xr.phase ^ 1u);
+                    TR(0, jt);
                     if (elect_one()) {
-                        mbar_expect_tx(x_full + 8 * xr.slot, (uint32_t)C::NPX * 128u);
-                        tma_load_4d(base + xr.slot * SLOT, &tmX, 0, x00 + sx * (C::STW * S), y00 + sy * (C::STH * S), b, x_full + 8 * xr.slot);
+                        if (p.dbg & 16) {
+                            mbar_arrive(x_full + 8 * xr.slot);
+                        } else {
+                            mbar_expect_tx(x_full + 8 * xr.slot, (uint32_t)C::NPX * 128u);
+                            tma_load_4d(base + xr.slot * SLOT, &tmX, 0, x00 + sx * (C::STW * S), y00 + sy * (C::STH * S), b, x_full + 8 * xr.slot);
+                        }
                     }
                     __syncwarp();
+                    TR(1, jt);
+                    ++jt;
                     xr.next(NX);
                 }
             }
@@ -194,28 +225,33 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
         // ================= expand issuer: one MMA group per job =================
         mbar_wait(w_full, 0);
         const uint32_t idesc32 = umma_idesc_tf32(32);
-        Ring ar, er;
+        Ring ar, er;  // er.slot = the team of job j
         int c = 0, s = 0;
         for (int j = 0; j < J; ++j) {
             mbar_wait(a_full + 8 * ar.slot, ar.phase);
+            TR(5, j);
             mbar_wait(e_empty + 8 * er.slot, er.phase ^ 1u);
+            TR(6, j);
             tc_fence_after();
             const uint32_t wb = base + p.off_we + (uint32_t)c * 8192u;
             const uint64_t b_hi = umma_desc(wb), b_lo = umma_desc(wb + 4096u);
             const uint32_t a_hi = tmem_base + C::ACOL + (uint32_t)ar.slot * 64u, a_lo = a_hi + 32u;
             const uint32_t d = tmem_base + C::ECOL + (uint32_t)er.slot * 32u;
             if (elect_one()) {
+                if (!(p.dbg & 32))
 #pragma unroll
                 for (int k = 0; k < C::KSTEPS; ++k) {  // the small products first
                     umma_tf32_ts(d, a_lo + 8u * k, b_hi + (uint64_t)(k * 2), idesc32, k > 0 ? 1u : 0u);
                     umma_tf32_ts(d, a_hi + 8u * k, b_lo + (uint64_t)(k * 2), idesc32, 1u);
                 }
+                if (!(p.dbg & 32))
 #pragma unroll
                 for (int k = 0; k < C::KSTEPS; ++k) umma_tf32_ts(d, a_hi + 8u * k, b_hi + (uint64_t)(k * 2), idesc32, 1u);
                 umma_commit(e_full + 8 * er.slot);
                 umma_commit(a_empty + 8 * ar.slot);
             }
             __syncwarp();
+            TR(7, j);
             ar.next(NA);
             er.next(NE);
             if (++s == NSUB) {
@@ -223,14 +259,15 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
                 if (++c == nch) c = 0;
             }
         }
-    } else if (warp == 3) {
+    } else if (warp == 2) {
         // ================= projection issuer: one MMA group per (block, chunk) =================
         mbar_wait(w_full, 0);
         const uint32_t idesc32 = umma_idesc_tf32(32), idesc64 = umma_idesc_tf32(64);
         Ring dr, pr;
-        int c = 0;
+        int c = 0, nxt = ND % NT;  // the team that writes D operand q + ND (per-team hand-back)
         for (int q = 0; q < Q; ++q) {
             mbar_wait(d_full + 8 * dr.slot, dr.phase);
+            TR(15, q * NSUB + NSUB - 1);
             if (c == 0) mbar_wait(p_empty + 8 * pr.slot, pr.phase ^ 1u);
             tc_fence_after();
             const uint32_t dbase = base + p.off_d + (uint32_t)dr.slot * 2u * C::DHALF;
@@ -238,17 +275,20 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
             const uint64_t b_hi = umma_desc(base + p.off_wp + (uint32_t)c * 8192u);  // [hi 32 rows | lo 32 rows]
             const uint32_t d_main = tmem_base + C::PCOL + (uint32_t)pr.slot * 64u, d_corr = d_main + 32u;
             if (elect_one()) {
+                if (!(p.dbg & 64))
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const uint64_t ko = (uint64_t)(k * 2);
                     umma_tf32(d_main, a_hi + ko, b_hi + ko, idesc64, (c > 0 || k > 0) ? 1u : 0u);  // main += hi.hi ; corr += hi.lo
                     umma_tf32(d_corr, a_lo + ko, b_hi + ko, idesc32, 1u);                            // corr += lo.hi
                 }
-                umma_commit(d_empty + 8 * dr.slot);
+                umma_commit(d_free + 8 * (C::DFREE_PER_TEAM ? nxt : dr.slot));
                 if (c == nch - 1) umma_commit(p_full + 8 * pr.slot);
             }
             __syncwarp();
+            TR(16, q * NSUB + NSUB - 1);
             dr.next(ND);
+            if (++nxt == NT) nxt = 0;
             if (++c == nch) c = 0, pr.next(NP);
         }
     } else if (warp >= 4 && warp < 8) {
@@ -269,23 +309,28 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
             const int yo = by * (C::NSY * C::STH) + roy, xo = bx * (C::NSX * C::STW) + rox;
             const bool valid = row < C::DROWS && yo < p.Ho && xo < p.Wo && !(p.dbg & 4);
             const size_t pix = ((size_t)(b * p.Ho + yo) * p.Wo + xo) * (size_t)p.cout;
+            // the residual does not depend on the accumulator: its (L2) latency runs under the wait below
+            float4 rs[8];
+#pragma unroll
+            for (int h = 0; h < 8; ++h) rs[h] = (valid && p.res && 4 * h < p.cout) ? ldcg4(p.res + pix + 4 * h) : make_float4(0, 0, 0, 0);
             mbar_wait(p_full + 8 * pr.slot, pr.phase);
             tc_fence_after();
             const uint32_t taddr = lane_base + C::PCOL + (uint32_t)pr.slot * 64u;
-            for (int c0 = 0; c0 < p.cout; c0 += 8) {
-                float v[8], cr[8];
-                tmem_ld8(taddr + (uint32_t)c0, v);
-                tmem_ld8(taddr + 32u + (uint32_t)c0, cr);
-                tmem_ld_wait();
-                if (valid) {
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        float4 o = make_float4(v[4 * h] + cr[4 * h], v[4 * h + 1] + cr[4 * h + 1], v[4 * h + 2] + cr[4 * h + 2], v[4 * h + 3] + cr[4 * h + 3]);
-                        if (p.res) {
-                            const float4 r4 = ldcg4(p.res + pix + c0 + 4 * h);
-                            o.x += r4.x, o.y += r4.y, o.z += r4.z, o.w += r4.w;
+            for (int g = 0; g < 4; ++g) {
+                const int c0 = 8 * g;
+                if (c0 < p.cout) {  // warp-uniform
+                    float v[8], cr[8];
+                    tmem_ld8(taddr + (uint32_t)c0, v);
+                    tmem_ld8(taddr + 32u + (uint32_t)c0, cr);
+                    tmem_ld_wait();
+                    if (valid) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const float4 r4 = rs[2 * g + h];
+                            st4(p.Y + pix + c0 + 4 * h, make_float4(v[4 * h] + cr[4 * h] + r4.x, v[4 * h + 1] + cr[4 * h + 1] + r4.y,
+                                                                    v[4 * h + 2] + cr[4 * h + 2] + r4.z, v[4 * h + 3] + cr[4 * h + 3] + r4.w));
                         }
-                        st4(p.Y + pix + c0 + 4 * h, o);
                     }
                 }
             }
@@ -296,11 +341,14 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
         };
         Ring xr, ar;
         const int xswz = row & 7;
+        int jt = 0;
         for (int i = 0; i < nblk; ++i) {
-            for (int cs = 0; cs < nch * NSUB; ++cs) {
+            for (int cs = 0; cs < nch * NSUB; ++cs, ++jt) {
                 mbar_wait(x_full + 8 * xr.slot, xr.phase);
+                if (q == 0) TR(2, jt);
                 const uint8_t* xrow = sm + (size_t)xr.slot * SLOT + (size_t)row * 128;
                 float hi[8 * C::KSTEPS], lo[8 * C::KSTEPS];
+                if (!(p.dbg & 8))
 #pragma unroll
                 for (int g = 0; g < 2 * C::KSTEPS; ++g) {
                     const float4 v = *reinterpret_cast<const float4*>(xrow + ((g ^ xswz) << 4));  // SWIZZLE_128B image written by TMA
@@ -308,6 +356,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
                     lo[4 * g] = v.x - hi[4 * g], lo[4 * g + 1] = v.y - hi[4 * g + 1], lo[4 * g + 2] = v.z - hi[4 * g + 2], lo[4 * g + 3] = v.w - hi[4 * g + 3];
                 }
                 mbar_wait(a_empty + 8 * ar.slot, ar.phase ^ 1u);
+                if (q == 0) TR(3, jt);
                 tc_fence_after();
                 const uint32_t ta = lane_base + C::ACOL + (uint32_t)ar.slot * 64u;
                 if (C::KSTEPS == 4) {
@@ -327,115 +376,122 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
                     mbar_arrive(a_full + 8 * ar.slot);
                     mbar_arrive(x_empty + 8 * xr.slot);
                 }
+                if (q == 0) TR(4, jt);
                 xr.next(NX);
                 ar.next(NA);
             }
+            if (q == 0) TR(17, jt - 1);
             if (i > 0) epilogue(i - 1);  // one block behind: its projection has long been issued
+            if (q == 0) TR(18, jt - 1);
         }
         if (nblk > 0) epilogue(nblk - 1);
-    } else if (warp >= 8 && warp < 16) {
-        // ================= drain teams: expand accumulator -> Swish -> E slot =================
+    } else if (warp >= 8) {
+        // ================= compute teams: expand accumulator -> Swish -> E tile -> taps -> Swish -> hi/lo rows of the D operand =================
+        constexpr int NROW = (C::YT - 1) * S + KS, NCOL = (C::XT - 1) * S + KS;
         const int team = (warp - 8) >> 2, q = warp & 3, row = q * 32 + lane;
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-        const int swz = row & 7;
-        Ring er, sr;
-        if (team == 1) er.next(NE), sr.next(NES);
-        for (int j = team; j < J; j += C::NDT) {
-            mbar_wait(e_full + 8 * er.slot, er.phase);
-            tc_fence_after();
-            float v[32];
-            tmem_ld32(lane_base + C::ECOL + (uint32_t)er.slot * 32u, v);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(e_empty + 8 * er.slot);  // the accumulator is in registers
-            mbar_wait(es_empty + 8 * sr.slot, sr.phase ^ 1u);
-            if (row < C::NPX) {
-                uint8_t* erow = sm + p.off_e + (size_t)sr.slot * SLOT + (size_t)row * 128;
-#pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                    float4 o = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-                    if (!(p.dbg & 1)) o = swish4(o);
-                    *reinterpret_cast<float4*>(erow + ((g ^ swz) << 4)) = o;
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(es_full + 8 * sr.slot);
-            er.next(NE), er.next(NE);
-            sr.next(NES), sr.next(NES);
-        }
-    } else if (warp >= 16) {
-        // ================= depth-wise teams: E slot -> taps -> Swish -> hi/lo rows of the D operand =================
-        constexpr int NROW = (C::YT - 1) * S + KS, NCOL = (C::XT - 1) * S + KS;
-        const int team = (warp - 16) / TD, tw = (warp - 16) - team * TD;
-        Ring sr, dr;
-        int s = 0, c = 0;
-        auto step = [&]() {  // one job further
-            sr.next(NES);
+        uint8_t* Es = sm + p.off_e + (size_t)team * C::ESLOT;
+        auto bar_team = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + team) : "memory"); };
+        // depth-wise item of this thread (fixed): output block (by, bx) of the sub-tile, channels 4 * c4 .. + 3 of the chunk
+        const int c4 = row & 7, blk = row >> 3;
+        const int by = blk / C::NBX, bx = blk - by * C::NBX;
+        const bool has_item = row < C::NITEMS;
+        const uint8_t* eb = Es + ((C::YT * by * S) * C::IW + C::XT * bx * S) * (int)C::EP + c4 * 16;  // window origin: every load is this + an immediate
+        Ring dr;            // D operand of the current job
+        int s = 0, c = 0;   // sub-tile within the block, chunk
+        uint32_t ephase = 0, fphase = (team >= ND) ? 1u : 0u;  // per-team hand-back: teams >= ND wait for a real retirement the first time
+        auto step = [&]() {  // one job further in the CTA's job sequence
             if (++s == NSUB) {
                 s = 0;
                 dr.next(ND);
                 if (++c == nch) c = 0;
             }
         };
-        if (team == 1) step();
-        for (int j = team; j < J; j += C::NWT) {
-            mbar_wait(es_full + 8 * sr.slot, sr.phase);
-            mbar_wait(d_empty + 8 * dr.slot, dr.phase ^ 1u);  // the projection that read this operand last has retired
-            const uint8_t* Es = sm + p.off_e + (size_t)sr.slot * SLOT;
-            uint8_t* Dhi = sm + p.off_d + (size_t)dr.slot * 2u * C::DHALF;
-            uint8_t* Dlo = Dhi + C::DHALF;
-            for (int it = tw * 32 + lane; it < C::NITEMS; it += TD * 32) {
-                const int c4 = it & 7, blk = it >> 3;
-                const int by = blk / C::NBX, bx = blk - by * C::NBX;
-                const int cbase = c * 32 + c4 * 4;
-                float4 acc[C::YT][C::XT];
+        for (int t = 0; t < team; ++t) step();
+        if (C::WDS) mbar_wait(w_full, 0);  // the tap image
+        for (int j = team; j < J; j += NT) {
+            // ---- drain: this warp's lane quarter of the accumulator ----
+            mbar_wait(e_full + 8 * team, ephase);
+            if (q == 0) TR(8, j);
+            tc_fence_after();
+            float v[32];
+            tmem_ld32(lane_base + C::ECOL + (uint32_t)team * 32u, v);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(e_empty + 8 * team);  // the accumulator is in registers: the next job's MMAs may start
+            ephase ^= 1u;
+            if (q == 0) TR(9, j);
+            if (q * 32 < C::NPX && !(p.dbg & 1)) {  // warp-uniform: a quarter past the halo tile has nothing to do
 #pragma unroll
-                for (int a = 0; a < C::YT; ++a)
+                for (int g = 0; g < 32; ++g) v[g] = swishf(v[g]);
+            }
+            if (q == 0) TR(19, j);
+            bar_team();  // every warp of the team has finished the previous job's depth-wise reads of E
+            if (q == 0) TR(10, j);
+            if (row < C::NPX) {
+                uint8_t* erow = Es + (size_t)row * C::EP;
 #pragma unroll
-                    for (int b2 = 0; b2 < C::XT; ++b2) acc[a][b2] = make_float4(0, 0, 0, 0);
-                if (cbase < p.hid && !(p.dbg & 2)) {
-                    const int r0 = C::YT * by * S, q0 = C::XT * bx * S;  // window origin inside the halo tile
+                for (int g = 0; g < 8; ++g) *reinterpret_cast<float4*>(erow + 16 * g) = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+            }
+            bar_team();  // E complete
+            if (q == 0) TR(11, j);
+            // ---- depth-wise: one item per thread, results stay in registers until the D slot is free ----
+            float4 acc[C::YT][C::XT];
 #pragma unroll
-                    for (int rr = 0; rr < NROW; ++rr) {
-                        float4 win[NCOL];
+            for (int a = 0; a < C::YT; ++a)
 #pragma unroll
-                        for (int cc = 0; cc < NCOL; ++cc) {
-                            const int px = (r0 + rr) * C::IW + q0 + cc;
-                            win[cc] = *reinterpret_cast<const float4*>(Es + px * 128 + ((c4 ^ (px & 7)) << 4));
-                        }
+                for (int b2 = 0; b2 < C::XT; ++b2) acc[a][b2] = make_float4(0, 0, 0, 0);
+            if (has_item && !(p.dbg & 2)) {
+                const uint8_t* wt = (C::WDS ? sm + p.off_wd : reinterpret_cast<const uint8_t*>(p.wd_img)) + (size_t)c * (KS * KS * 128) + c4 * 16;
 #pragma unroll
-                        for (int dy = 0; dy < C::YT; ++dy) {
-                            const int ky = rr - dy * S;
-                            if (ky < 0 || ky >= KS) continue;
+                for (int rr = 0; rr < NROW; ++rr) {
+                    float4 win[NCOL];
 #pragma unroll
-                            for (int kx = 0; kx < KS; ++kx) {
-                                const float4 wv = ldg4(p.Wd + (ky * KS + kx) * p.hid + cbase);
+                    for (int cc = 0; cc < NCOL; ++cc) win[cc] = *reinterpret_cast<const float4*>(eb + (rr * C::IW + cc) * (int)C::EP);
 #pragma unroll
-                                for (int dx = 0; dx < C::XT; ++dx) fma44(acc[dy][dx], win[dx * S + kx], wv);
-                            }
+                    for (int dy = 0; dy < C::YT; ++dy) {
+                        const int ky = rr - dy * S;
+                        if (ky < 0 || ky >= KS) continue;
+#pragma unroll
+                        for (int kx = 0; kx < KS; ++kx) {
+                            const float4 wv = C::WDS ? *reinterpret_cast<const float4*>(wt + (ky * KS + kx) * 128)
+                                                     : ldg4(reinterpret_cast<const float*>(wt + (ky * KS + kx) * 128));
+#pragma unroll
+                            for (int dx = 0; dx < C::XT; ++dx) fma44(acc[dy][dx], win[dx * S + kx], wv);
                         }
                     }
                 }
+            }
+            if (q == 0) TR(12, j);
+            if (C::DFREE_PER_TEAM) {
+                mbar_wait(d_free + 8 * team, fphase ^ 1u);  // the projection that read this team's previous operand of the slot has retired
+                fphase ^= 1u;
+            } else {
+                mbar_wait(d_free + 8 * dr.slot, dr.phase ^ 1u);
+            }
+            if (q == 0) TR(13, j);
+            if (has_item) {
+                uint8_t* Dhi = sm + p.off_d + (size_t)dr.slot * 2u * C::DHALF;
+                uint8_t* Dlo = Dhi + C::DHALF;
 #pragma unroll
                 for (int dy = 0; dy < C::YT; ++dy)
 #pragma unroll
                     for (int dx = 0; dx < C::XT; ++dx) {
                         const int r = s * C::SPX + (C::YT * by + dy) * C::STW + C::XT * bx + dx;  // D operand row = output pixel of the block
                         const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c4 ^ (r & 7)) << 4);
-                        const float4 v = swish4(acc[dy][dx]);  // swish(0) = 0 keeps the padded channels zero
-                        const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+                        const float4 o = swish4(acc[dy][dx]);  // swish(0) = 0 keeps the padded channels zero
+                        const float4 h = make_float4(tf32_hi(o.x), tf32_hi(o.y), tf32_hi(o.z), tf32_hi(o.w));
                         *reinterpret_cast<float4*>(Dhi + off) = h;
-                        *reinterpret_cast<float4*>(Dlo + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                        *reinterpret_cast<float4*>(Dlo + off) = make_float4(o.x - h.x, o.y - h.y, o.z - h.z, o.w - h.w);
                     }
             }
             fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(d_full + 8 * dr.slot);
-                mbar_arrive(es_empty + 8 * sr.slot);
-            }
-            step(), step();
+            if (lane == 0) mbar_arrive(d_full + 8 * dr.slot);
+            if (q == 0) TR(14, j);
+#pragma unroll
+            for (int t = 0; t < NT; ++t) step();
         }
     }
 
@@ -448,15 +504,15 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
 }
 
 // ---- host side --------------------------------------------------------------------------
-// Geometry per block type (sub-tile, block, depth-wise item shape, warps per depth-wise team):
+// Geometry per block type (sub-tile, block, depth-wise item shape; the TD parameter is unused):
 //   3x3 s2, Cin 16 (layer1.0): sub-tile 3 x 8 (halo 7 x 17 = 119 px), block 2 x 2 sub-tiles = 6 x 16 outputs, items of 1 x 2 outputs: 96 = 3 warps
 //   3x3 s1, Cin 24 (layer1.1): sub-tile 8 x 10 (halo 10 x 12 = 120 px), block = the sub-tile, items of 1 x 5 outputs: 128 = 4 warps
 //   5x5 s2, Cin 24 (layer2.0): sub-tile 4 x 4 (halo 11 x 11 = 121 px), block 2 x 4 sub-tiles = 8 x 16 outputs, items of one output: 128 = 4 warps
 //   5x5 s1, Cin 32 (layer2.1): sub-tile 7 x 7 (halo 11 x 11 = 121 px), block 1 x 2 sub-tiles = 7 x 14 outputs, items of 1 x 7 outputs: 56 = 2 warps
-using MbfB1 = MbfCfg<3, 2, 16, 3, 8, 2, 2, 2, 1, 3>;
-using MbfB2 = MbfCfg<3, 1, 24, 8, 10, 1, 1, 5, 1, 4>;
-using MbfB3 = MbfCfg<5, 2, 24, 4, 4, 2, 4, 1, 1, 4>;
-using MbfB4 = MbfCfg<5, 1, 32, 7, 7, 1, 2, 7, 1, 2>;
+using MbfB1 = MbfCfg<3, 2, 16, 3, 8, 2, 2, 2, 1, 3, 3, true>;
+using MbfB2 = MbfCfg<3, 1, 24, 8, 10, 1, 1, 5, 1, 4, 2, false>;
+using MbfB3 = MbfCfg<5, 2, 24, 4, 4, 2, 4, 1, 1, 4, 2, false>;
+using MbfB4 = MbfCfg<5, 1, 32, 7, 7, 1, 2, 7, 1, 2, 2, false>;
 
 struct MbfLaunch {
     CUtensorMap tmX;
@@ -486,10 +542,11 @@ inline int mbf_plan_t(PwTcState& st, MbfLaunch* ml, const float* X, int B, int H
     if (nb * p.nch * C::NSUB > 0x3fffffffLL) return fail(CF_EINVAL, "mbf_plan: too many jobs");
     p.n_blocks = (int)nb;
     p.off_e = C::NX * C::SLOT;
-    p.off_d = p.off_e + C::NES * C::SLOT;
+    p.off_d = p.off_e + C::NT * C::ESLOT;
     p.off_we = p.off_d + C::ND * 2u * C::DHALF;
     p.off_wp = p.off_we + (uint32_t)p.nch * 8192u;
-    p.off_bars = p.off_wp + (uint32_t)p.nch * 8192u;
+    p.off_wd = p.off_wp + (uint32_t)p.nch * 8192u;
+    p.off_bars = (p.off_wd + (C::WDS ? (uint32_t)p.nch * (C::KS * C::KS * 128u) : 0u) + 127u) & ~127u;
     // the MMA reads 128 rows of every D half; rows past DROWS fall into whatever follows (unused accumulator lanes), which
     // must still be this CTA's shared memory: the weight images (>= 16 KB) follow the last half
     ml->smem = (size_t)p.off_bars + 1024 + 1024;
@@ -507,8 +564,11 @@ inline int mbf_plan(PwTcState& st, int ks, int s, const float* X, const float* W
     if (ip == st.layers.end() || ip->second.NC != 32 || ip->second.nchunks != 1)
         return fail(CF_EINVAL, "mbf_plan: projection weights were not prepared as one 32-column image per K block");
     MbfParams& p = ml->p;
+    auto id = st.dw_imgs.find(Wd);
+    if (id == st.dw_imgs.end()) return fail(CF_EINVAL, "mbf_plan: depth-wise taps were not prepared as a chunk image");
     p.we_img = ie->second.img;
     p.wp_img = ip->second.img;
+    p.wd_img = id->second;
     p.Wd = Wd;
     p.Y = Y;
     p.res = res;
@@ -516,6 +576,14 @@ inline int mbf_plan(PwTcState& st, int ks, int s, const float* X, const float* W
     p.nch = (hid + 31) / 32;
     p.dbg = 0;
     if (const char* ev = getenv("CF_MBF_DEBUG")) p.dbg = atoi(ev);
+    p.trace = nullptr, p.tr_j0 = p.tr_nj = 0;
+    if (const char* ev = getenv("CF_MBF_TRACE")) {  // "j0,nj": the buffer is read back with cf_debug_mbf_trace
+        if (sscanf(ev, "%d,%d", &p.tr_j0, &p.tr_nj) == 2 && p.tr_nj > 0 && p.tr_nj <= 4096) {
+            if (!st.trace_buf && cudaMalloc((void**)&st.trace_buf, 4096 * 32 * 8) != cudaSuccess) return fail(CF_ECUDA, "mbf_plan: trace buffer");
+            cudaMemset(st.trace_buf, 0, 4096 * 32 * 8);
+            p.trace = st.trace_buf;
+        }
+    }
     ml->kind = mbf_kind(ks, s, cin);
     switch (ml->kind) {
         case 1: return mbf_plan_t<MbfB1>(st, ml, X, B, Hi, Wi, cin);

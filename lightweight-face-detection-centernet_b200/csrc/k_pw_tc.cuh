@@ -55,6 +55,8 @@ struct PwTcState {
     void* encode = nullptr;  // cuTensorMapEncodeTiled
     int sms = 148;
     std::map<const float*, TcLayer> layers;  // keyed by the [K][N] device weight pointer
+    unsigned long long* trace_buf = nullptr;  // development: k_mbf pipeline trace (CF_MBF_TRACE)
+    std::map<const float*, float*> dw_imgs;  // per-chunk tap images of the fused blocks' depth-wise weights (k_mbf)
 };
 
 struct TcParams {
@@ -101,23 +103,27 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
 }
 // (A suspend-time hint on try_wait -- CUTLASS passes 0x989680 -- was tried and measured SLOWER here: +2.6 % on the
 // point-wise class; the default try_wait already parks the warp for a short, implementation-defined time.)
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {  // may park the warp for a short, bounded time
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+// Bounded wait: a protocol bug traps after ~8 s (surfacing as a CUDA error) instead of hanging the GPU.  The first try is the common
+// case; the retry loop is kept to a handful of instructions (a spinning warp shares its scheduler with working ones).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    uint64_t t0 = 0;
-    for (uint32_t it = 0;; ++it) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (done) return;
-        if ((it & 1023u) == 1023u) {
-            const uint64_t t = globaltimer_ns();
-            if (t0 == 0) t0 = t;
-            else if (t - t0 > 4000000000ull) __trap();
-        }
+    if (mbar_try(bar, parity)) return;
+    const uint64_t t0 = globaltimer_ns();
+    for (;;) {
+#pragma unroll 1
+        for (int i = 0; i < 128; ++i)
+            if (mbar_try(bar, parity)) return;
+        if (globaltimer_ns() - t0 > 8000000000ull) __trap();
     }
 }
 // One elected lane of a CONVERGENT warp.  tcgen05.mma / commit / TMA instructions are warp-uniform in SASS: issued under
@@ -656,6 +662,11 @@ inline void pw_tc_destroy(PwTcState& st) {
     for (auto& kv : st.layers)
         if (kv.second.img) cudaFree(kv.second.img);
     st.layers.clear();
+    for (auto& kv : st.dw_imgs)
+        if (kv.second) cudaFree(kv.second);
+    st.dw_imgs.clear();
+    if (st.trace_buf) cudaFree(st.trace_buf);
+    st.trace_buf = nullptr;
 }
 
 // fp32 [rows][cols] row-major tensor, box [box_rows][32 floats], SWIZZLE_128B, zero OOB fill

@@ -18,16 +18,14 @@ HM_SIG_TOL = 1e-3      # contract
 # -2^-24 per accumulation step (tools/tc_accum_probe.py), which is why 3xTF32 sits above fp32 FFMA.
 HEAD_TOL = {"simt_fp32": {"hm": 5e-5, "wh": 5e-4, "lm": 2e-4, "reg": 2e-5},
             "tcgen05_3xtf32": {"hm": 5e-4, "wh": 8e-3, "lm": 3e-3, "reg": 1e-4},
-            "tcgen05_fused": {"hm": 5e-4, "wh": 8e-3, "lm": 3e-3, "reg": 1e-4},
-            "tcgen05_fused_tc": {"hm": 5e-4, "wh": 8e-3, "lm": 3e-3, "reg": 1e-4},
-            "tcgen05_dwp": {"hm": 5e-4, "wh": 8e-3, "lm": 3e-3, "reg": 1e-4}}
-TAP_TOL = {"simt_fp32": 5e-6, "tcgen05_3xtf32": 1e-4, "tcgen05_fused": 1e-4, "tcgen05_fused_tc": 1e-4, "tcgen05_dwp": 1e-4}
+            "tcgen05_layerwise": {"hm": 5e-4, "wh": 8e-3, "lm": 3e-3, "reg": 1e-4}}
+TAP_TOL = {"simt_fp32": 5e-6, "tcgen05_3xtf32": 1e-4, "tcgen05_layerwise": 1e-4}
 
 
 # Both product engines must meet the contract: the fp32 FFMA validation engine and the tcgen05
 # 3xTF32 engine (hi/lo operand split, fp32-class).  The single-pass TF32 throughput mode is
 # measured and reported by test_single_pass_tf32_report, not gated.
-ENGINES = {"simt_fp32": 0, "tcgen05_3xtf32": 1, "tcgen05_fused": 3, "tcgen05_fused_tc": 4, "tcgen05_dwp": 5}
+ENGINES = {"simt_fp32": 0, "tcgen05_3xtf32": 1, "tcgen05_layerwise": 3}
 
 
 @pytest.fixture(scope="module", params=list(ENGINES))

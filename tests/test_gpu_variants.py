@@ -102,10 +102,12 @@ def test_time_steps_reports_every_launch(pkg, weights_path, variant_input):
     eng.decode_topk(100)
     before = eng.launches
     ms, cls = eng.time_steps(2)
-    assert len(ms) == len(cls) == 43  # 41 network launches + peak mask + top-k
+    nf = len(pkg._lib.fused_blocks(pkg.CF_PW_TCGEN05))  # a fused MBConv block is one launch instead of three
+    assert len(ms) == len(cls) == 43 - 2 * nf  # 41 layer-wise network launches + peak mask + top-k
     assert all(t > 0 for t in ms)
-    assert cls[0] == pkg._lib.CLS_STEM and cls[-1] == pkg._lib.CLS_DECODE and cls.count(pkg._lib.CLS_PW) == 27
-    assert eng.launches - before == 43 * 3  # one warm-up pass + two timed
+    assert cls[0] == pkg._lib.CLS_STEM and cls[-1] == pkg._lib.CLS_DECODE and cls.count(pkg._lib.CLS_PW) == 27 - 2 * nf
+    assert cls.count(pkg._lib.CLS_FUSED) == nf
+    assert eng.launches - before == (43 - 2 * nf) * 3  # one warm-up pass + two timed
     eng.close()
 
 

@@ -51,16 +51,18 @@ def test_create_rejects_bad_arguments_without_gpu(pkg, weights_path):
 
 
 def test_work_model_matches_survey(pkg):
-    by, fl = pkg._lib.work_model(640, 640, pkg.CF_IN_F32_NCHW, 0)
+    LW = pkg.CF_PW_TCGEN05_LAYERWISE
+    by, fl = pkg._lib.work_model(640, 640, pkg.CF_IN_F32_NCHW, 0, LW)
     assert abs(fl - 4.695e9) / 4.695e9 < 1e-3          # 4.695 GFLOP / image
-    _, fl480 = pkg._lib.work_model(480, 640, pkg.CF_IN_F32_NCHW, 0)
+    _, fl480 = pkg._lib.work_model(480, 640, pkg.CF_IN_F32_NCHW, 0, LW)
     assert abs(fl480 - 3.521e9) / 3.521e9 < 1e-3
-    parts = [pkg._lib.work_model(640, 640, pkg.CF_IN_F32_NCHW, c) for c in (1, 2, 3, 4)]
+    parts = [pkg._lib.work_model(640, 640, pkg.CF_IN_F32_NCHW, c, LW) for c in (1, 2, 3, 4)]
     assert abs(sum(p[0] for p in parts) - by) < 1 and abs(sum(p[1] for p in parts) - fl) < 1
-    # fusing expand+dw of the shallow blocks removes the hidden-tensor traffic, not the flops
-    byf, flf = pkg._lib.work_model(640, 640, pkg.CF_IN_F32_NCHW, 0, pkg.CF_PW_TCGEN05_FUSED)
-    assert abs(flf - fl) < 1 and byf < 0.65 * by
-    partsf = [pkg._lib.work_model(640, 640, pkg.CF_IN_F32_NCHW, c, pkg.CF_PW_TCGEN05_FUSED) for c in (1, 2, 3, 4, 6)]
+    # a fused MBConv block removes both hidden tensors' traffic, not the flops (default engine: layer1.0 at least)
+    assert 1 in pkg._lib.fused_blocks(pkg.CF_PW_TCGEN05) and pkg._lib.fused_blocks(LW) == []
+    byf, flf = pkg._lib.work_model(640, 640, pkg.CF_IN_F32_NCHW, 0, pkg.CF_PW_TCGEN05)
+    assert abs(flf - fl) < 1 and byf < 0.80 * by
+    partsf = [pkg._lib.work_model(640, 640, pkg.CF_IN_F32_NCHW, c, pkg.CF_PW_TCGEN05) for c in (1, 2, 3, 4, 6)]
     assert abs(sum(p[0] for p in partsf) - byf) < 1
 
 
@@ -193,9 +195,14 @@ def test_bench_launch_table_matches_work_model(pkg):
         tab = bench.launch_table(h, w)
         assert len(tab) == 43
         net = sum(b for n, b in tab if n not in ("peak mask", "top-k + gather"))
-        want, _ = L.work_model(h, w, L.CF_IN_U8_HWC, L.CLS_ALL, L.CF_PW_TCGEN05)
+        want, _ = L.work_model(h, w, L.CF_IN_U8_HWC, L.CLS_ALL, L.CF_PW_TCGEN05_LAYERWISE)
         assert net == want, (h, w, net, want)
         dw = sum(b for n, b in tab if " dw" in n)
-        assert dw == L.work_model(h, w, L.CF_IN_U8_HWC, L.CLS_DW, L.CF_PW_TCGEN05)[0]
+        assert dw == L.work_model(h, w, L.CF_IN_U8_HWC, L.CLS_DW, L.CF_PW_TCGEN05_LAYERWISE)[0]
         pw = sum(b for n, b in tab if "expand" in n or "project" in n or n.startswith(("conv_last", "up")))
-        assert pw == L.work_model(h, w, L.CF_IN_U8_HWC, L.CLS_PW, L.CF_PW_TCGEN05)[0]
+        assert pw == L.work_model(h, w, L.CF_IN_U8_HWC, L.CLS_PW, L.CF_PW_TCGEN05_LAYERWISE)[0]
+        # the default engine: every fused block is one launch credited with the bytes of the three it replaces
+        fused = L.fused_blocks(L.CF_PW_TCGEN05)
+        tabf = bench.launch_table(h, w, fused)
+        assert len(tabf) == 43 - sum(2 if bench.BLOCKS[i][2] != 1 else 1 for i in fused)
+        assert sum(b for n, b in tabf) == sum(b for n, b in tab)

@@ -23,7 +23,7 @@
 #include <cmath>
 #include <vector>
 
-#include "../lightweight-face-detection-centernet_b200/csrc/k_expdw.cuh"
+#include "../lightweight-face-detection-centernet_b200/csrc/k_dwt.cuh"
 
 using namespace cf;
 

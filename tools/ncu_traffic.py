@@ -7,7 +7,7 @@ from collections import OrderedDict
 SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1, "us": 1e3, "ms": 1e6}
 
 def cls(n):
-    if "k_mbx" in n or "k_expdw" in n or "k_dwp" in n: return "fused_blocks"
+    if "k_mbf" in n: return "fused_blocks"
     if "k_pw" in n: return "pointwise_gemm"
     if "k_dw" in n: return "depthwise"
     if "k_stem" in n: return "stem"
