@@ -104,6 +104,17 @@ int cf_ctdet_decode(const float* heat, const float* wh, const float* reg, int ba
 /* same, on the heads of the last cf_forward */
 int cf_decode_topk(cf_engine* e, int K, float* out_dets, int32_t* out_inds, void* stream);
 
+/* Replaces CenterFace.nms(boxes, scores, nms_thresh) (centerface.py:111-151; eval_widerface.py:112-152 is the same code): greedy
+ * IoU suppression with "+1" areas in float32, visiting order = np.argsort(scores) reversed with ties in (index descending) order
+ * (a stable sort; the reference's default argsort leaves the order of equal scores unspecified), suppress when ovr >= nms_threshold.
+ * boxes [n,4] (x1,y1,x2,y2), scores [n]; keep[0..*count) = indices into boxes in keep order, exactly the list the reference returns.
+ * cf_nms: DEVICE pointers, `scratch` of cf_nms_scratch_bytes(n) bytes, asynchronous on `stream`.
+ * cf_nms_host: HOST pointers (what the reference's numpy caller holds), synchronous, on `device`.                              */
+int cf_nms(const float* boxes, const float* scores, int n, float nms_threshold, int32_t* keep, int32_t* count, void* scratch,
+           size_t scratch_bytes, void* stream);
+size_t cf_nms_scratch_bytes(int n);
+int cf_nms_host(int device, const float* boxes, const float* scores, int n, float nms_threshold, int32_t* keep, int32_t* count);
+
 /* Replaces ctdet_post_process (utils/post_process.py:83-100) for the single face class: maps both corners of every
  * row of dets [B,K,6] (DEVICE, output-map units) through the per-image inverse affine trans [B,6] (DEVICE, fp64,
  * row-major 2x3 = get_affine_transform(c, s, 0, (w,h), inv=1), utils/image.py:27-61, built by the caller) and

@@ -51,6 +51,9 @@ SIGNATURES = {
                                        C.c_float, C.c_int, _vp, _vp, _vp]),
     "cf_launch_count": (C.c_longlong, [_vp]),
     "cf_fused_block_mask": (C.c_uint, [C.c_int]),
+    "cf_nms": (C.c_int, [_vp, _vp, C.c_int, C.c_float, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "cf_nms_scratch_bytes": (C.c_size_t, [C.c_int]),
+    "cf_nms_host": (C.c_int, [C.c_int, _vp, _vp, C.c_int, C.c_float, _vp, _vp]),
     "cf_debug_mbf_trace": (C.c_int, [_vp, _vp, C.c_int]),
     "cf_work_model": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "cf_replay_class": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),

@@ -101,6 +101,23 @@ class CenterFace(object):
         return d[0, :n].cpu().numpy()
 
 
+    def nms(self, boxes, scores, nms_thresh):
+        """centerface.py:111-151: greedy IoU NMS -> the list of kept indices (into ``boxes``), in keep order.  Runs on the engine's
+        GPU in the reference's float32 arithmetic ("+1" areas, ``ovr >= nms_thresh`` suppresses); equal scores are visited in
+        (index descending) order, i.e. ``np.argsort(scores, kind="stable")[::-1]``."""
+        import ctypes as C
+        boxes = np.ascontiguousarray(np.asarray(boxes, dtype=np.float32)[:, :4])
+        scores = np.ascontiguousarray(np.asarray(scores, dtype=np.float32).reshape(-1))
+        n = boxes.shape[0]
+        if scores.shape[0] != n:
+            raise ValueError(f"nms: {n} boxes but {scores.shape[0]} scores")
+        keep = np.empty(max(n, 1), dtype=np.int32)
+        cnt = C.c_int32(0)
+        L.check(L.load().cf_nms_host(self.net.device, C.c_void_p(boxes.ctypes.data), C.c_void_p(scores.ctypes.data), n, float(nms_thresh),
+                                     C.c_void_p(keep.ctypes.data), C.byref(cnt)), "cf_nms_host")
+        return list(keep[:cnt.value].astype(np.int64))
+
+
 class CenterFaceNet(object):
     """Model-level drop-in for ``efficientnet_b0()`` as eval_widerface.get_detections uses it
     (eval_widerface.py:76-90): ``model(x)[0]`` is a dict of cuda tensors 'hm','wh','lm','reg'."""

@@ -4,7 +4,10 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+
+#include <mutex>
 #include <string>
+#include <unordered_map>
 
 #include "../../include/centerface_b200.h"
 
@@ -41,6 +44,23 @@ inline int fail(int code, const char* fmt, ...) {
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// Opt a kernel in to more than 48 KB of dynamic shared memory.  Function attributes are per DEVICE (context), and an engine may be
+// created on any device of the process, from any host thread: remember per (kernel, device) what has been set.
+inline cudaError_t smem_optin(const void* func, int bytes) {
+    static std::mutex mu;
+    static std::unordered_map<const void*, unsigned long long> done;  // kernel -> bit mask of devices
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    std::lock_guard<std::mutex> lk(mu);
+    unsigned long long& m = done[func];
+    if (m & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) m |= bit;
+    return e;
+}
+
 // Kernel launch with the programmatic-stream-serialization attribute (CF_PDL=0 turns it off: plain stream order).
 // Only kernels that call pdl_wait() before touching activation memory may be launched through this.
 inline bool pdl_enabled() {
@@ -76,6 +96,44 @@ __device__ __forceinline__ float swishf(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
     return x * r;
+}
+
+// Packed fp32x2 arithmetic (sm_100: FMUL2 / FADD2 / FFMA2, one issue slot for two IEEE round-to-nearest results -- bit-identical to
+// the scalar instructions).  The fused MBConv kernel is bound by issue slots and latency, not by the FMA pipe's flop rate.
+__device__ __forceinline__ void mul2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 a, b;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\tmul.rn.f32x2 a, a, b;\n\tmov.b64 {%0, %1}, a;\n\t}"
+        : "=f"(d0), "=f"(d1)
+        : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void add2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 a, b;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\tadd.rn.f32x2 a, a, b;\n\tmov.b64 {%0, %1}, a;\n\t}"
+        : "=f"(d0), "=f"(d1)
+        : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void fma2(float& c0, float& c1, float a0, float a1, float b0, float b1) {  // c += a * b
+    asm("{\n\t.reg .b64 a, b, c;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\tmov.b64 c, {%0, %1};\n\tfma.rn.f32x2 c, a, b, c;\n\tmov.b64 {%0, %1}, c;\n\t}"
+        : "+f"(c0), "+f"(c1)
+        : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+// swishf on two values: the same five operations per value, the three FP32 ones packed
+__device__ __forceinline__ void swish2(float& x0, float& x1) {
+    float t0, t1, e0, e1, r0, r1;
+    mul2(t0, t1, x0, x1, -1.4426950408889634f, -1.4426950408889634f);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(t0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(t1));
+    add2(e0, e1, e0, e1, 1.f, 1.f);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(e0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(e1));
+    mul2(x0, x1, x0, x1, r0, r1);
+}
+__device__ __forceinline__ float4 swish4p(float4 v) {
+    swish2(v.x, v.y);
+    swish2(v.z, v.w);
+    return v;
+}
+__device__ __forceinline__ void fma44p(float4& acc, float4 a, float4 w) {
+    fma2(acc.x, acc.y, a.x, a.y, w.x, w.y);
+    fma2(acc.z, acc.w, a.z, a.w, w.z, w.w);
 }
 
 __device__ __forceinline__ float4 swish4(float4 v) {

@@ -53,6 +53,23 @@ inline bool block_is_mbf(int pw, int i) {
     return pw == CF_PW_TCGEN05 && b.t != 1 && ((mbf_mask() >> i) & 1u) && mbf_supported(b.k, b.s, b.cin, b.hid(), b.cout);
 }
 
+// Entry points that work on an engine's device switch to it for their own duration only: inside a PyTorch process a bare
+// cudaSetDevice would silently move the calling thread's current device.
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+#define CF_ON_DEVICE(dev)                                                                  \
+    DeviceGuard _dg(dev);                                                                  \
+    if (!_dg.ok) return cf::fail(CF_ECUDA, "cudaSetDevice(%d) failed: %s", dev, cudaGetErrorString(cudaGetLastError()))
+
 struct Step {
     int cls;
     std::function<cudaError_t(cudaStream_t)> run;
@@ -476,7 +493,7 @@ int cf_create(const void* weights, size_t weights_bytes, int device, int max_bat
     CF_CUDA(cudaGetDeviceProperties(&prop, device));
     CF_CHECK(prop.major == 10, CF_ENODEV, "cf_create: device %d is sm_%d%d; this library is built for sm_100a only", device,
              prop.major, prop.minor);
-    CF_CUDA(cudaSetDevice(device));
+    CF_ON_DEVICE(device);
 
     cf_engine* e = new cf_engine();
     e->device = device;
@@ -620,7 +637,7 @@ int cf_create(const void* weights, size_t weights_bytes, int device, int max_bat
 
 int cf_destroy(cf_engine* e) {
     if (!e) return CF_OK;
-    cudaSetDevice(e->device);
+    DeviceGuard _dg(e->device);
     pw_tc_destroy(e->tc);
     float* bufs[] = {e->d_w, e->stem, e->hidA, e->hidB, e->clast, e->up[0], e->up[1], e->up[2], e->hm, e->wh,
                      e->lm,  e->reg,  e->hm_sig, e->peak, e->o_dets, e->o_lms};
@@ -653,7 +670,7 @@ int cf_forward(cf_engine* e, const void* input, int in_format, int batch, int h,
     CF_CHECK(h >= 32 && w >= 32 && h % 32 == 0 && w % 32 == 0, CF_EINVAL, "cf_forward: h=%d w=%d must be positive multiples of 32", h, w);
     CF_CHECK((size_t)h * w <= (size_t)e->max_h * e->max_w, CF_ECAP, "cf_forward: %dx%d exceeds the %dx%d the engine was created for", h, w,
              e->max_h, e->max_w);
-    CF_CUDA(cudaSetDevice(e->device));
+    CF_ON_DEVICE(e->device);
     if (e->plan.empty() || e->B == 0 || e->in != input || e->fmt != in_format || e->B != batch || e->H != h || e->W != w) {
         // stash the current plan, then reuse a cached one or build a new one
         if (!e->plan.empty() && e->B != 0) {
@@ -741,8 +758,46 @@ int cf_ctdet_decode(const float* heat, const float* wh, const float* reg, int ba
 int cf_decode_topk(cf_engine* e, int K, float* out_dets, int32_t* out_inds, void* stream) {
     CF_CHECK(e != nullptr, CF_EINVAL, "cf_decode_topk: NULL engine");
     CF_CHECK(e->B > 0, CF_EINVAL, "cf_decode_topk: no cf_forward has run on this engine");
+    CF_ON_DEVICE(e->device);
     int rc = cf_ctdet_decode(e->hm_sig, e->wh, e->reg, e->B, e->H / 4, e->W / 4, K, out_dets, out_inds, e->peak, stream);
     if (rc == CF_OK) e->launches += 2;
+    return rc;
+}
+
+int cf_nms(const float* boxes, const float* scores, int n, float nms_threshold, int32_t* keep, int32_t* count, void* scratch,
+           size_t scratch_bytes, void* stream) {
+    CF_CHECK(boxes && scores && keep && count && scratch, CF_EINVAL, "cf_nms: NULL pointer");
+    CF_CHECK(n >= 0 && n <= (1 << 20), CF_EINVAL, "cf_nms: n=%d outside [0, 2^20]", n);
+    CF_CHECK(scratch_bytes >= nms_scratch_bytes(n), CF_ECAP, "cf_nms: scratch needs %zu bytes", nms_scratch_bytes(n));
+    k_nms_keep<<<1, 1024, 0, (cudaStream_t)stream>>>(boxes, scores, n, nms_threshold, (unsigned char*)scratch, keep, count);
+    CF_CUDA(cudaGetLastError());
+    return CF_OK;
+}
+
+size_t cf_nms_scratch_bytes(int n) { return n < 0 ? 0 : nms_scratch_bytes(n); }
+
+int cf_nms_host(int device, const float* boxes, const float* scores, int n, float nms_threshold, int32_t* keep, int32_t* count) {
+    CF_CHECK(count != nullptr && n >= 0 && n <= (1 << 20), CF_EINVAL, "cf_nms_host: bad arguments");
+    *count = 0;
+    if (n == 0) return CF_OK;
+    CF_CHECK(boxes && scores && keep, CF_EINVAL, "cf_nms_host: NULL pointer");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) return fail(CF_ENODEV, "cf_nms_host: no CUDA device (%s)", cudaGetErrorString(ce));
+    CF_CHECK(device >= 0 && device < ndev, CF_EINVAL, "cf_nms_host: device %d out of range (have %d)", device, ndev);
+    CF_ON_DEVICE(device);
+    const size_t sb = nms_scratch_bytes(n), bb = (size_t)n * 16, kb = (size_t)n * 4;
+    unsigned char* d = nullptr;  // boxes | scores | keep | count | scratch
+    const size_t off_s = bb, off_k = off_s + kb, off_c = off_k + kb, off_x = (off_c + 64 + 15) & ~(size_t)15;
+    CF_CUDA(cudaMalloc((void**)&d, off_x + sb));
+    int rc = CF_OK;
+    if (cudaMemcpy(d, boxes, bb, cudaMemcpyHostToDevice) != cudaSuccess || cudaMemcpy(d + off_s, scores, kb, cudaMemcpyHostToDevice) != cudaSuccess)
+        rc = fail(CF_ECUDA, "cf_nms_host: upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (!rc) rc = cf_nms((const float*)d, (const float*)(d + off_s), n, nms_threshold, (int32_t*)(d + off_k), (int32_t*)(d + off_c), d + off_x, sb, nullptr);
+    if (!rc && (cudaMemcpy(count, d + off_c, 4, cudaMemcpyDeviceToHost) != cudaSuccess ||
+                cudaMemcpy(keep, d + off_k, kb, cudaMemcpyDeviceToHost) != cudaSuccess))
+        rc = fail(CF_ECUDA, "cf_nms_host: kernel or download failed: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(d);
     return rc;
 }
 
@@ -789,8 +844,7 @@ int host_wait_oldest(cf_engine* e) {
     ++e->waited;
     return CF_OK;
 }
-int host_stage_input(cf_engine* e, const uint8_t* images, size_t bytes, int* slot_out) {
-    CF_CUDA(cudaSetDevice(e->device));
+int host_stage_input(cf_engine* e, const uint8_t* images, size_t bytes, int* slot_out) {  // the caller is on the engine's device
     if (e->submitted - e->waited >= 2) {
         int rc = host_wait_oldest(e);
         if (rc) return rc;
@@ -814,6 +868,7 @@ int cf_submit_topk_host(cf_engine* e, const uint8_t* images, int batch, int h, i
     CF_CHECK(K >= 1 && K <= 1024, CF_EINVAL, "cf_submit_topk_host: K=%d outside [1,1024]", K);
     CF_CHECK(h >= 32 && w >= 32 && h % 32 == 0 && w % 32 == 0 && (size_t)h * w <= (size_t)e->max_h * e->max_w, CF_EINVAL,
              "cf_submit_topk_host: bad size %dx%d", h, w);
+    CF_ON_DEVICE(e->device);
     int slot = 0;
     int rc = host_stage_input(e, images, (size_t)batch * h * w * 3, &slot);
     if (rc) return rc;
@@ -829,7 +884,7 @@ int cf_submit_topk_host(cf_engine* e, const uint8_t* images, int batch, int h, i
 
 int cf_wait_host(cf_engine* e) {
     CF_CHECK(e != nullptr, CF_EINVAL, "cf_wait_host: NULL engine");
-    CF_CUDA(cudaSetDevice(e->device));
+    CF_ON_DEVICE(e->device);
     return host_wait_oldest(e);
 }
 
@@ -837,6 +892,7 @@ int cf_detect_topk_host(cf_engine* e, const uint8_t* images, int batch, int h, i
                         int32_t* out_inds) {
     int rc = cf_submit_topk_host(e, images, batch, h, w, K, out_dets, out_inds);
     if (rc) return rc;
+    CF_ON_DEVICE(e->device);
     while (e->waited < e->submitted)
         if ((rc = host_wait_oldest(e))) return rc;
     return CF_OK;
@@ -849,6 +905,7 @@ int cf_detect_threshold_host(cf_engine* e, const uint8_t* images, int batch, int
     CF_CHECK(batch >= 1 && batch <= e->max_batch, CF_ECAP, "cf_detect_threshold_host: batch %d outside [1,%d]", batch, e->max_batch);
     CF_CHECK(h >= 32 && w >= 32 && h % 32 == 0 && w % 32 == 0 && (size_t)h * w <= (size_t)e->max_h * e->max_w, CF_EINVAL,
              "cf_detect_threshold_host: bad size %dx%d", h, w);
+    CF_ON_DEVICE(e->device);
     int slot = 0;
     int rc = host_stage_input(e, images, (size_t)batch * h * w * 3, &slot);
     if (rc) return rc;
@@ -927,7 +984,7 @@ int cf_detect_image_host(cf_engine* e, const uint8_t* image, int h, int w, int n
     CF_CHECK(h > 0 && w > 0, CF_EINVAL, "cf_detect_image_host: bad source size %dx%d", h, w);
     CF_CHECK(net_h >= 32 && net_w >= 32 && net_h % 32 == 0 && net_w % 32 == 0 && (size_t)net_h * net_w <= (size_t)e->max_h * e->max_w,
              CF_EINVAL, "cf_detect_image_host: bad network size %dx%d", net_h, net_w);
-    CF_CUDA(cudaSetDevice(e->device));
+    CF_ON_DEVICE(e->device);
     if (e->submitted - e->waited >= 2) {
         int rc0 = host_wait_oldest(e);
         if (rc0) return rc0;
@@ -1151,7 +1208,7 @@ int cf_replay_class(cf_engine* e, int which, int iters, void* stream) {
     CF_CHECK(e != nullptr, CF_EINVAL, "cf_replay_class: NULL engine");
     CF_CHECK(!e->plan.empty(), CF_EINVAL, "cf_replay_class: no cf_forward has run on this engine");
     CF_CHECK(which >= CLS_ALL && which < CLS_COUNT && iters >= 1, CF_EINVAL, "cf_replay_class: which=%d iters=%d", which, iters);
-    CF_CUDA(cudaSetDevice(e->device));
+    CF_ON_DEVICE(e->device);
     for (int i = 0; i < iters; ++i) {
         int rc = run_steps(e, which, (cudaStream_t)stream);
         if (rc) return rc;
@@ -1162,7 +1219,7 @@ int cf_replay_class(cf_engine* e, int which, int iters, void* stream) {
 int cf_time_class(cf_engine* e, int which, int iters, void* stream, float* ms, int* launches) {
     CF_CHECK(e != nullptr && ms != nullptr, CF_EINVAL, "cf_time_class: NULL argument");
     CF_CHECK(!e->plan.empty(), CF_EINVAL, "cf_time_class: no cf_forward has run on this engine");
-    CF_CUDA(cudaSetDevice(e->device));
+    CF_ON_DEVICE(e->device);
     cudaStream_t s = (cudaStream_t)stream;
     cudaEvent_t a, b;
     CF_CUDA(cudaEventCreate(&a));
@@ -1192,7 +1249,7 @@ int cf_time_steps(cf_engine* e, int iters, void* stream, float* ms, int* cls, in
     const int n = (int)e->plan.size();
     *n_steps = n;
     CF_CHECK(cap >= n, CF_ECAP, "cf_time_steps: the plan has %d steps, room for %d", n, cap);
-    CF_CUDA(cudaSetDevice(e->device));
+    CF_ON_DEVICE(e->device);
     cudaStream_t s = (cudaStream_t)stream;
     std::vector<cudaEvent_t> ev((size_t)n + 1);
     for (auto& x : ev) CF_CUDA(cudaEventCreate(&x));

@@ -256,12 +256,8 @@ inline cudaError_t launch_topk(const float* pk, const float* wh, const float* re
                                int32_t* inds, cudaStream_t s) {
     const int HW = H * W;
     if (HW <= TOPK_SMEM_MAX_HW) {
-        static bool attr_done = false;
-        if (!attr_done) {
-            cudaError_t e = cudaFuncSetAttribute(k_topk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (TOPK_SMEM_MAX_HW + TOPK_SMEM_MAX_HW / 32) * 4);
-            if (e != cudaSuccess) return e;
-            attr_done = true;
-        }
+        cudaError_t e = smem_optin((const void*)k_topk<true>, (TOPK_SMEM_MAX_HW + TOPK_SMEM_MAX_HW / 32) * 4);
+        if (e != cudaSuccess) return e;
         const size_t HWp = ((size_t)HW + 1023) & ~(size_t)1023;
         return launch_pdl(k_topk<true>, dim3(B), dim3(1024), (HWp + HWp / 32) * 4, s, pk, wh, reg, H, W, K, dets, inds);
     }
@@ -417,6 +413,58 @@ __global__ void __launch_bounds__(1024) k_thresh_nms(const float* __restrict__ h
         }
     }
     if (tid == 0) out_counts[b] = nk;
+}
+
+// ---- CenterFace.nms (centerface.py:111-151 == eval_widerface.py:112-152) as a stand-alone call: greedy IoU suppression of
+//      arbitrary float32 boxes [n,4] / scores [n], "+1" areas, order = stable ascending argsort reversed (score desc, index desc),
+//      suppress when ovr >= thr.  One CTA; keys / areas / flags live in `scratch` (global, n <= any) -- the n of a face detector
+//      (tens to a few thousand) makes this a latency kernel either way.  keep[] = ORIGINAL indices in keep order.
+__host__ __device__ inline size_t nms_scratch_bytes(int n) {
+    size_t P = 1;
+    while ((long long)P < n) P <<= 1;
+    return P * 8 + (size_t)n * (4 + 4) + 64;  // u64 keys[P] | float area[n] | int supp[n]
+}
+__global__ void __launch_bounds__(1024) k_nms_keep(const float* __restrict__ boxes, const float* __restrict__ scores, int n, float thr,
+                                                   unsigned char* __restrict__ scratch, int32_t* __restrict__ keep, int32_t* __restrict__ count) {
+    const int tid = threadIdx.x;
+    int P = 1;
+    while (P < n) P <<= 1;
+    unsigned long long* key = reinterpret_cast<unsigned long long*>(scratch);
+    float* area = reinterpret_cast<float*>(key + P);
+    int* supp = reinterpret_cast<int*>(area + n);
+    __shared__ int s_nk;
+    for (int i = tid; i < P; i += 1024) key[i] = i < n ? (((unsigned long long)fkey(scores[i]) << 32) | (unsigned)i) : 0ull;
+    for (int i = tid; i < n; i += 1024) {
+        const float4 b = reinterpret_cast<const float4*>(boxes)[i];
+        area[i] = __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.f), __fadd_rn(__fsub_rn(b.w, b.y), 1.f));
+        supp[i] = 0;
+    }
+    if (tid == 0) s_nk = 0;
+    __syncthreads();
+    bitonic_desc(key, P);  // n real keys all carry the fkey sign bit or its complement: they sort ahead of the zero padding
+    for (int r = 0; r < n; ++r) {
+        const int i = (int)(key[r] & 0xFFFFFFFFull);
+        if (supp[i]) continue;  // uniform: the last write to supp[] is behind a barrier
+        if (tid == 0) keep[s_nk++] = i;
+        const float4 bi = reinterpret_cast<const float4*>(boxes)[i];
+        const float ai = area[i];
+        for (int q = r + 1 + tid; q < n; q += 1024) {
+            const int j = (int)(key[q] & 0xFFFFFFFFull);
+            if (supp[j]) continue;
+            const float4 bj = reinterpret_cast<const float4*>(boxes)[j];
+            const float xx1 = fmaxf(bi.x, bj.x), yy1 = fmaxf(bi.y, bj.y);
+            const float xx2 = fminf(bi.z, bj.z), yy2 = fminf(bi.w, bj.w);
+            float w = __fadd_rn(__fsub_rn(xx2, xx1), 1.f);
+            float h = __fadd_rn(__fsub_rn(yy2, yy1), 1.f);
+            w = w > 0.f ? w : 0.f;
+            h = h > 0.f ? h : 0.f;
+            const float inter = __fmul_rn(w, h);
+            const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ai, area[j]), inter));
+            if (ovr >= thr) supp[j] = 1;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) *count = s_nk;
 }
 
 // ---- ctdet_post_process (utils/post_process.py:83-100): map the two corners of every [x1,y1,x2,y2,score,cls] row

@@ -203,12 +203,8 @@ struct DwtLaunch {
 
 template <int KS, int S, int GEOM>
 inline cudaError_t dwt_launch_t(const DwtLaunch& dl, cudaStream_t st) {
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k_dwt<KS, S, GEOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
+    cudaError_t e = smem_optin((const void*)k_dwt<KS, S, GEOM>, (int)(TC_SMEM_MAX));
+    if (e != cudaSuccess) return e;
     return launch_pdl(k_dwt<KS, S, GEOM>, dim3(dl.grid), dim3(DWT_THREADS), dl.smem, st, dl.tmX, dl.p);
 }
 

@@ -413,6 +413,16 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
             // ---- drain: this warp's lane quarter of the accumulator ----
             mbar_wait(e_full + 8 * team, ephase);
             if (q == 0) TR(8, j);
+            // probe the D hand-back now (non-blocking); the result is needed only after the depth-wise arithmetic
+            const uint32_t fbar = d_free + 8 * (C::DFREE_PER_TEAM ? team : dr.slot), fpar = (C::DFREE_PER_TEAM ? fphase : dr.phase) ^ 1u;
+            uint32_t d_ok;
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(d_ok)
+                : "r"(fbar), "r"(fpar)
+                : "memory");
             tc_fence_after();
             float v[32];
             tmem_ld32(lane_base + C::ECOL + (uint32_t)team * 32u, v);
@@ -424,7 +434,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
             if (q == 0) TR(9, j);
             if (q * 32 < C::NPX && !(p.dbg & 1)) {  // warp-uniform: a quarter past the halo tile has nothing to do
 #pragma unroll
-                for (int g = 0; g < 32; ++g) v[g] = swishf(v[g]);
+                for (int g = 0; g < 16; ++g) swish2(v[2 * g], v[2 * g + 1]);
             }
             if (q == 0) TR(19, j);
             bar_team();  // every warp of the team has finished the previous job's depth-wise reads of E
@@ -458,18 +468,14 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
                             const float4 wv = C::WDS ? *reinterpret_cast<const float4*>(wt + (ky * KS + kx) * 128)
                                                      : ldg4(reinterpret_cast<const float*>(wt + (ky * KS + kx) * 128));
 #pragma unroll
-                            for (int dx = 0; dx < C::XT; ++dx) fma44(acc[dy][dx], win[dx * S + kx], wv);
+                            for (int dx = 0; dx < C::XT; ++dx) fma44p(acc[dy][dx], win[dx * S + kx], wv);
                         }
                     }
                 }
             }
             if (q == 0) TR(12, j);
-            if (C::DFREE_PER_TEAM) {
-                mbar_wait(d_free + 8 * team, fphase ^ 1u);  // the projection that read this team's previous operand of the slot has retired
-                fphase ^= 1u;
-            } else {
-                mbar_wait(d_free + 8 * dr.slot, dr.phase ^ 1u);
-            }
+            if (!d_ok) mbar_wait(fbar, fpar);  // the projection that read the slot last (per team: this team's previous operand) has retired
+            if (C::DFREE_PER_TEAM) fphase ^= 1u;
             if (q == 0) TR(13, j);
             if (has_item) {
                 uint8_t* Dhi = sm + p.off_d + (size_t)dr.slot * 2u * C::DHALF;
@@ -480,7 +486,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
                     for (int dx = 0; dx < C::XT; ++dx) {
                         const int r = s * C::SPX + (C::YT * by + dy) * C::STW + C::XT * bx + dx;  // D operand row = output pixel of the block
                         const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c4 ^ (r & 7)) << 4);
-                        const float4 o = swish4(acc[dy][dx]);  // swish(0) = 0 keeps the padded channels zero
+                        const float4 o = swish4p(acc[dy][dx]);  // swish(0) = 0 keeps the padded channels zero
                         const float4 h = make_float4(tf32_hi(o.x), tf32_hi(o.y), tf32_hi(o.z), tf32_hi(o.w));
                         *reinterpret_cast<float4*>(Dhi + off) = h;
                         *reinterpret_cast<float4*>(Dlo + off) = make_float4(o.x - h.x, o.y - h.y, o.z - h.z, o.w - h.w);
@@ -595,7 +601,7 @@ inline int mbf_plan(PwTcState& st, int ks, int s, const float* X, const float* W
 
 template <typename C>
 inline cudaError_t mbf_launch_t(const MbfLaunch& ml, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(k_mbf<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);  // per device: set every time
+    cudaError_t e = smem_optin((const void*)k_mbf<C>, TC_SMEM_MAX);
     if (e != cudaSuccess) return e;
     return launch_pdl(k_mbf<C>, dim3(ml.grid), dim3(C::THREADS), ml.smem, s, ml.tmX, ml.p);
 }

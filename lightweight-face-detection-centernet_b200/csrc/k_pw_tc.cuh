@@ -869,12 +869,8 @@ inline int tc_plan(PwTcState& st, int passes, int epi, const float* A, const flo
 
 template <int kPasses, int EPI>
 inline cudaError_t tc_launch_t(const TcLaunch& tl, cudaStream_t s) {
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k_pw_tc<kPasses, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
+    cudaError_t e = smem_optin((const void*)k_pw_tc<kPasses, EPI>, (int)(TC_SMEM_MAX));
+    if (e != cudaSuccess) return e;
     return launch_pdl(k_pw_tc<kPasses, EPI>, dim3(tl.grid), dim3(TC_THREADS), tl.smem, s, tl.tmA, tl.tmOut, tl.p);
 }
 

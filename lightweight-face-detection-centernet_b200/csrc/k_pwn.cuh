@@ -275,12 +275,8 @@ inline int pwn_plan(PwTcState& st, int epi, const float* A, const float* Wkn, fl
 
 template <int EPI>
 inline cudaError_t pwn_launch_t(const PwnLaunch& pl, cudaStream_t s) {
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k_pwn<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX / 2);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
+    cudaError_t e = smem_optin((const void*)k_pwn<EPI>, (int)(TC_SMEM_MAX / 2));
+    if (e != cudaSuccess) return e;
     return launch_pdl(k_pwn<EPI>, dim3(pl.grid), dim3(PWN_THREADS), pl.smem, s, pl.tmA, pl.p);
 }
 

@@ -324,6 +324,98 @@ def test_centerface_call_native_sizes(pkg, oracle, sd, images, golden, weights_p
     assert d.shape == (0, 5) and l.shape == (0, 10)
 
 
+def _check_call_against_golden(pkg, img, gd, gl, weights_path, tag):
+    cf = pkg.CenterFace(img.shape[0], img.shape[1], landmarks=True, weights=weights_path)
+    dets, lms = cf(img, threshold=0.35)
+    cf.net.close()
+    assert dets.shape == gd.shape and lms.shape == gl.shape, (tag, dets.shape, gd.shape)
+    assert dets.dtype == np.float32 and lms.dtype == np.float32
+    if len(gd):
+        assert np.abs(dets[:, 4] - gd[:, 4]).max() < 1e-4, tag
+        assert (np.abs(dets[:, :4] - gd[:, :4]) <= 1.0).all(), tag  # at most a floor-boundary flip of one pixel
+        assert (dets[:, :4] == gd[:, :4]).mean() >= 0.97 and (lms == gl).mean() >= 0.97, tag
+
+
+def test_centerface_call_config5_320_max_side(pkg, images, golden, weights_path):
+    """configs[4]: the drop-in CenterFace.__call__ on the five JPEGs scaled to 320 max side (device resize to the /32 size, network,
+    path A, NMS, // scale) against the reference's stored __call__ results, same criteria as the native-size test."""
+    import cv2
+    pkg.CenterFace.print_times = False
+    for n in IMGS:
+        h, w = images[n].shape[:2]
+        f = 320.0 / max(h, w)
+        img = cv2.resize(images[n], (int(round(w * f)), int(round(h * f))))
+        assert tuple(img.shape[:2]) == tuple(golden[f"c5_320/{n}/hw"])
+        _check_call_against_golden(pkg, img, golden[f"c5_320/{n}/dets"], golden[f"c5_320/{n}/lms"], weights_path, ("c5_320", n))
+
+
+def test_centerface_call_large_native_sizes(pkg, images, golden, weights_path):
+    """The two largest JPEGs at their own size: 17.jpg (928x1600 network input, 673 detections -- the NMS stress case) and 27.jpg."""
+    pkg.CenterFace.print_times = False
+    for n in ("17", "27"):
+        _check_call_against_golden(pkg, images[n], golden[f"native/{n}/dets"], golden[f"native/{n}/lms"], weights_path, ("native", n))
+
+
+def test_batch32_against_32_oracle_results(pkg, oracle, sd, f5_640, weights_path):
+    """The benchmarked configuration (batch 32 at 640x640, default engine) against 32 oracle results computed one by one: 32
+    distinct F5-derived inputs (flips / rolls), ordered top-100 indices bit-exact (near-tie swaps reported),
+    sigma(hm) <= 1e-3, box IoU >= 0.999."""
+    rng = np.random.RandomState(4321)
+    u8 = []
+    for i in range(32):
+        im = f5_640[IMGS[i % 5]]
+        if rng.rand() < 0.5:
+            im = im[:, ::-1]
+        u8.append(np.roll(im, (rng.randint(0, 32), rng.randint(0, 32)), axis=(0, 1)))
+    u8 = np.ascontiguousarray(np.stack(u8))
+    eng = pkg.Engine(weights_path, max_batch=32, max_h=640, max_w=640, device=0)
+    eng.forward(torch.from_numpy(u8).cuda())
+    sig = eng.heads()["hm_sig"].cpu().numpy()
+    dets, inds = eng.decode_topk(100)
+    dets, inds = dets.cpu().numpy(), inds.cpu().numpy()
+    eng.close()
+    worst_sig, worst_iou, swaps = 0.0, 1.0, 0
+    with torch.no_grad():
+        for i in range(32):
+            o = oracle.forward(sd, torch.from_numpy(oracle.normalize_u8(u8[i])).unsqueeze(0))
+            so = oracle.sigmoid_clamp(o["hm"])
+            do, io = oracle.ctdet_decode(so, o["wh"], o["reg"], K=100)
+            so, do, io = so[0, 0].numpy(), do[0].numpy(), io[0].numpy()
+            worst_sig = max(worst_sig, float(np.abs(sig[i, 0] - so).max()))
+            real = do[:, 4] > 2e-4
+            same = inds[i] == io
+            for r in np.nonzero(real & ~same)[0]:
+                gap = abs(float(so.flat[inds[i][r]]) - float(do[r, 4]))
+                assert gap < NEAR_TIE, (i, int(r), int(inds[i][r]), int(io[r]), gap)
+                swaps += 1
+            m = real & same
+            worst_iou = min(worst_iou, float(oracle.box_iou(dets[i][m, :4], do[m, :4]).min()))
+            assert np.abs(dets[i][m, 4] - do[m, 4]).max() <= 1e-3
+    print("batch 32 vs 32 oracle results: max |sigma(hm) - oracle|", worst_sig, "min IoU", worst_iou, "near-tie swaps", swaps)
+    assert worst_sig <= HM_SIG_TOL and worst_iou >= 0.999
+
+
+def test_nms_method_matches_reference_keep_list(pkg, oracle, weights_path):
+    """CenterFace.nms (centerface.py:111-151) on the GPU against the oracle's restatement: random overlapping boxes, duplicated
+    scores (tie order = stable argsort reversed), empty / single inputs, and more boxes than the decode kernels' 4096 cap."""
+    pkg.CenterFace.print_times = False
+    cf = pkg.CenterFace(64, 64, landmarks=True, weights=weights_path)
+    rng = np.random.RandomState(7)
+    for n, ties in ((0, False), (1, False), (2, True), (57, False), (300, True), (1500, True), (5000, True)):
+        xy = rng.uniform(0, 600, size=(n, 2)).astype(np.float32)
+        wh = rng.uniform(4, 120, size=(n, 2)).astype(np.float32)
+        boxes = np.concatenate([xy, xy + wh], axis=1).astype(np.float32)
+        scores = rng.uniform(0.3, 1.0, size=n).astype(np.float32)
+        if ties and n > 1:
+            scores[rng.randint(0, n, size=n // 3)] = np.float32(0.9999)  # the clamp ceiling: many equal scores
+            boxes[1] = boxes[0]  # identical boxes
+        for thr in (0.3, 0.5):
+            want = oracle.nms(boxes, scores, thr) if n else []
+            got = cf.nms(boxes, scores, thr)
+            assert isinstance(got, list) and [int(k) for k in got] == [int(k) for k in want], (n, thr)
+    cf.net.close()
+
+
 def test_get_detections_vga_letterbox(pkg, oracle, golden, images, weights_path):
     """Config 4: eval_widerface.get_detections on 640x480 frames letter-boxed into 640x640, path B."""
     import cv2

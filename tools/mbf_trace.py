@@ -54,3 +54,10 @@ for a_, b_ in pairs:
     if m.any():
         d = t[m, b_] - t[m, a_]
         print(f"{names[a_]:>9s} -> {names[b_]:9s}: mean {d.mean():8.1f}  min {d.min():6d}  max {d.max():6d}")
+# whole-run view: completion rate over windows of 64 jobs
+v = t[:, 14]
+v = v[v > 0]
+if len(v) > 128:
+    print("T.dfull span", int(v.max() - v.min()), "cycles for", len(v), "jobs;", "first event at", int(t[t > 0].min() - t0))
+    for k in range(0, len(v) - 64, 64):
+        print(f"  jobs {a.j0 + k:4d}..{a.j0 + k + 63:4d}: {(v[k + 64] - v[k]) / 64:7.1f} cycles/job")
