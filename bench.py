@@ -47,11 +47,17 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="images per GPU per step")
     ap.add_argument("--pw", type=int, default=int(os.environ.get("CENTERFACE_B200_PW", -1)),
-                    help="engine: 0 fp32 SIMT, 1 tcgen05 3xTF32, 2 tcgen05 1xTF32, 3 tcgen05 3xTF32 + fused expand/dw blocks "
+                    help="engine: 0 fp32 SIMT, 1 tcgen05 3xTF32 + fused MBConv blocks, 2 tcgen05 1xTF32, 3 tcgen05 3xTF32 layer-wise "
                          "(default: library default)")
-    ap.add_argument("--cpu-sample", type=int, default=4, help="images per CPU-baseline step")
+    ap.add_argument("--cpu-sample", type=int, default=PER_GPU_BATCH, help="images per step of the cpu_baseline leg of the B200 arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
+
+
+def workload_name(batch, world):
+    """config.workload, the same string in both arms (the driver compares the arms' configs)."""
+    return (f"batch-{batch} 640x640 per GPU ({'configs[1]' if world == 1 else 'configs[2] sharding'}), "
+            f"u8 BGR input, network + sigmoid/clamp + path-C top-{K_TOP} decode" + (", NCCL all-gather of [B,100,6] boxes" if world > 1 else ""))
 
 
 def synthetic_batch(n, seed):
@@ -62,23 +68,83 @@ def synthetic_batch(n, seed):
 
 
 # ---------------------------------------------------------------------------------------------
-# reference arm: the reference's CPU path (oracle port; the reference is Python on ATen and cannot
-# travel to the GPU box) on all host cores
+# reference arm: the reference's own CPU implementation of the path on all host cores.  baseline/_ref holds the UNMODIFIED
+# reference files (staged by oracle/make_ref.py in the build container, git-ignored, shipped to the GPU box); when it is
+# absent the oracle port (oracle/centerface_oracle.py, the same ATen calls) stands in and the line says kind = "port".
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_run(steps, warmup, sample):
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def load_reference():
+    """(net, CenterFace class on CPU, ctdet_decode, mean, std) of the unmodified reference, or None."""
+    if not os.path.exists(os.path.join(REF_DIR, "centerface.py")):
+        return None
     import torch
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import centerface_oracle as O
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "refshim"))  # stub mlconfig / torchsummary (SURVEY.md F9)
+    sys.path.insert(0, REF_DIR)
+    cwd = os.getcwd()
+    os.chdir(REF_DIR)  # the checkpoint path is cwd-relative (centerface.py:23)
+    try:
+        import model.centernet as mc
+        mc.ghost_net = mc.efficientnet_b0  # lets centerface_ext import (SURVEY.md F4); its ctdet_decode is model-independent
+        import centerface as ref_cf
+        import centerface_ext as ref_ext
+
+        class CPUCenterFace(ref_cf.CenterFace):  # centerface.py:16-27 hard-codes .cuda(): restated for the CPU
+            def __init__(self, height, width, landmarks=True):
+                self.landmarks = landmarks
+                self.net = mc.efficientnet_b0()
+                self.cuda = False
+                self.net.load_state_dict(torch.load("weight/model_epoch_100.pt", map_location="cpu", weights_only=True))
+                self.net.eval()
+                self.img_h_new, self.img_w_new, self.scale_h, self.scale_w = self.transform(height, width)
+
+        cf = CPUCenterFace(H, W)
+    finally:
+        os.chdir(cwd)
+    return cf.net, cf, ref_ext.ctdet_decode, ref_cf.CenterFace.mean, ref_cf.CenterFace.std
+
+
+def cpu_reference_run(steps, warmup, sample, with_call=False):
+    import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sd = O.load_weights(WEIGHTS)
     u8 = synthetic_batch(sample, 0)
+    ref = load_reference()
+    extra = {}
+    if ref is not None:
+        net, cf, ctdet_decode, mean, std = ref
+        kind = "reference"
 
-    def step():
-        x = torch.from_numpy(np.stack([O.normalize_u8(i) for i in u8]))  # centerface.py:32-34
-        o = O.forward(sd, x)                                             # model/centernet.py:263-280
-        dets, _ = O.ctdet_decode(O.sigmoid_clamp(o["hm"]), o["wh"], o["reg"], K=K_TOP)  # centerface_ext.py:52-82
-        return dets
+        def step():
+            with torch.no_grad():
+                x = np.stack([((im / 255. - mean) / std).astype(np.float32).transpose(2, 0, 1) for im in u8])  # centerface.py:32-35
+                out = net(torch.from_numpy(x))[0]                                                             # :41
+                hm = out["hm"].sigmoid_().clamp(1e-4, 1 - 1e-4)                                               # :43
+                return ctdet_decode(hm, out["wh"], out["reg"], K=K_TOP)                                       # centerface_ext.py:52-82
+        if with_call:  # SURVEY.md 8(d)(i): the drop-in call itself (resize, normalise, forward, path A, Python NMS), F5 set at 640x640
+            import contextlib
+            import io
+            import cv2
+            imgs = [cv2.resize(cv2.imread(os.path.join(REF_DIR, "imgs", f"{n}.jpg")), (W, H)) for n in ("1", "17", "2", "27", "8")]
+            ts = []
+            with contextlib.redirect_stdout(io.StringIO()):
+                for k in range(13):
+                    t0 = time.perf_counter()
+                    cf(imgs[k % 5], threshold=0.35)
+                    ts.append(time.perf_counter() - t0)
+            extra["call_ms_per_image_f5_640"] = round(float(np.median(ts[3:])) * 1e3, 1)
+    else:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import centerface_oracle as O
+        sd = O.load_weights(WEIGHTS)
+        kind = "port"
+
+        def step():
+            x = torch.from_numpy(np.stack([O.normalize_u8(i) for i in u8]))  # centerface.py:32-34
+            o = O.forward(sd, x)                                             # model/centernet.py:263-280
+            dets, _ = O.ctdet_decode(O.sigmoid_clamp(o["hm"]), o["wh"], o["reg"], K=K_TOP)  # centerface_ext.py:52-82
+            return dets
 
     for _ in range(warmup):
         step()
@@ -86,24 +152,26 @@ def cpu_reference_run(steps, warmup, sample):
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    return {"value": sample * steps / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{steps} steps x {sample} images of the 640x640 batch-{PER_GPU_BATCH} workload "
-                      f"(normalise + forward + sigmoid/clamp + ctdet_decode K={K_TOP}), torch {torch.__version__} CPU, "
-                      f"{cores} logical cores"}, dt / steps * 1e3
+    cb = {"value": sample * steps / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+          "sample": f"{steps} steps x {sample} images of the 640x640 batch-{PER_GPU_BATCH} workload "
+                    f"(normalise + forward + sigmoid/clamp + ctdet_decode K={K_TOP}), "
+                    f"{'unmodified reference from baseline/_ref' if kind == 'reference' else 'oracle port'}, torch {torch.__version__} CPU, "
+                    f"{cores} logical cores"}
+    cb.update(extra)
+    return cb, dt / steps * 1e3
 
 
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(a.steps, 6))
-    warm = max(1, min(a.warmup, 2))
-    cb, ms = cpu_reference_run(steps, warm, a.cpu_sample)
+    steps, warm = max(1, a.steps), max(0, a.warmup)
+    cb, ms = cpu_reference_run(steps, warm, PER_GPU_BATCH)  # the whole batch-32 step, as many steps as asked for
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"batch-{PER_GPU_BATCH} 640x640 (configs[1]), bounded sample of {a.cpu_sample} images per step",
-                       "h": H, "w": W, "decode": f"path C top-{K_TOP}"},
+            "config": {"workload": workload_name(PER_GPU_BATCH, 1), "global_batch": PER_GPU_BATCH, "h": H, "w": W, "parallelism": "dp1",
+                       "where": "host CPU, all cores (the reference's own CPU path; it has no other)"},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -246,24 +314,25 @@ def run_b200(a):
         dets, _ = eng.decode_topk(K_TOP)
         return sh.gather_detections(dets, n_total=n_total)  # NCCL all-gather of the final box list (N>1)
 
-    outs = [(torch.empty((B, K_TOP, 6), dtype=torch.float32).pin_memory(),
+    # end-to-end outputs: with N > 1 every rank receives the gathered [N*B,100,6] list (the exchange step runs inside the library:
+    # ncclAllGather on the compute stream right behind the decode kernel, then ONE device-to-host copy)
+    outs = [(torch.empty((n_total, K_TOP, 6), dtype=torch.float32).pin_memory(),
              torch.empty((B, K_TOP), dtype=torch.int32).pin_memory()) for _ in range(2)]
-
-    def e2e_consume(i):
-        eng.wait_host()  # results of submission i are now in outs[i % 2]
-        if world > 1:
-            return sh.gather_detections(outs[i % 2][0].to(dev, non_blocking=True), n_total=n_total)
-        return outs[i % 2][0]
+    if world > 1:
+        eng.comm_init()
 
     def e2e_loop(steps):
         """`steps` batches through the C-ABI host entry points, double buffered: the H2D of batch i+1
         overlaps the kernels of batch i; every batch's inputs are copied from pinned host memory and its
-        boxes are read back to the host inside the timed region."""
+        boxes (N > 1: every rank's boxes) are read back to the host inside the timed region."""
         for i in range(steps):
-            eng.submit_topk_host(host[i % n_rot], K_TOP, outs[i % 2][0], outs[i % 2][1])
+            if world > 1:
+                eng.submit_topk_gather_host(host[i % n_rot], K_TOP, outs[i % 2][0], outs[i % 2][1])
+            else:
+                eng.submit_topk_host(host[i % n_rot], K_TOP, outs[i % 2][0], outs[i % 2][1])
             if i >= 1:
-                e2e_consume(i - 1)
-        e2e_consume(steps - 1)
+                eng.wait_host()  # results of submission i - 1 are now in outs[(i - 1) % 2]
+        eng.wait_host()
 
     def sync():
         torch.cuda.synchronize()
@@ -370,25 +439,44 @@ def run_b200(a):
                               "frac_hbm": by_all * B / (ms_per_step * 1e-3) / 1e9 / hbm,
                               "TFLOPs": fl_all * B / (ms_per_step * 1e-3) / 1e12}
 
+    gather_check = None
+    if world > 1:
+        # content of the exchange step: slice r of the gathered list must be rank r's own boxes -- on every rank
+        own, _ = eng.detect_topk_host(host[0].numpy(), K_TOP)
+        eng.submit_topk_gather_host(host[0], K_TOP, outs[0][0], outs[0][1])
+        eng.wait_host()
+        got = outs[0][0].numpy()
+        ok_own = bool(np.array_equal(got[rank * B:(rank + 1) * B], own))
+        digest = torch.tensor([float(np.abs(got[r * B:(r + 1) * B]).sum()) for r in range(world)], dtype=torch.float64, device=dev)
+        ref = digest.clone()
+        dist.broadcast(ref, src=0)
+        flags = torch.tensor([1.0 if ok_own else 0.0, 1.0 if bool(torch.equal(ref, digest)) else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        gather_check = {"own_slice_equal_on_every_rank": bool(flags[0].item() == 1.0),
+                        "gathered_list_equal_on_every_rank": bool(flags[1].item() == 1.0), "ranks": world}
+        if not (gather_check["own_slice_equal_on_every_rank"] and gather_check["gathered_list_equal_on_every_rank"]):
+            raise SystemExit(f"bench.py: the all-gathered box list is wrong: {gather_check}")
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        cpu_baseline, _ = cpu_reference_run(3, 1, a.cpu_sample)
+        cpu_baseline, _ = cpu_reference_run(3, 1, a.cpu_sample, with_call=True)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": warm,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": {0: "f32", 1: "tf32x3", 2: "tf32", 3: "tf32x3", 6: "tf32x3/tf32"}[pw], "data": "synthetic",
-                "config": {"workload": f"batch-{B} 640x640 per GPU ({'configs[1]' if world == 1 else 'configs[2] sharding'}), "
-                                       f"u8 BGR input, network + sigmoid/clamp + path-C top-{K_TOP} decode"
-                                       + (", NCCL all-gather of [B,100,6] boxes" if world > 1 else ""),
-                           "global_batch": n_total, "h": H, "w": W, "pw_engine": pw,
+                "config": {"workload": workload_name(B, world), "global_batch": n_total, "h": H, "w": W, "pw_engine": pw,
                            "l2": f"{n_rot} rotating input batches ({n_rot * B * H * W * 3 / 1e6:.0f} MB) and "
                                  f"{by_all * B / 1e9:.1f} GB of activation traffic per step, both > 126 MB L2",
                            "parallelism": f"dp{world}"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * H * W * 3,
-                        "d2h_bytes_per_step": B * K_TOP * (6 * 4 + 4), "api": "cf_submit_topk_host / cf_wait_host (pinned host buffers, double buffered)",
+                        "d2h_bytes_per_step": n_total * K_TOP * 6 * 4 + B * K_TOP * 4,
+                        "api": ("cf_submit_topk_gather_host (ncclAllGather inside the library, one D2H of the gathered list)" if world > 1
+                                else "cf_submit_topk_host") + " / cf_wait_host (pinned host buffers, double buffered)",
                         "steps": e2e_steps},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline}
+        if gather_check is not None:
+            line["gather_check"] = gather_check
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line), flush=True)

@@ -151,6 +151,20 @@ int cf_submit_topk_host(cf_engine* e, const uint8_t* images, int batch, int h, i
                         float* out_dets, int32_t* out_inds);
 int cf_wait_host(cf_engine* e);
 
+/* ---- multi-GPU: one process per GPU, one exchange step ---------------------------------------
+ * Images are independent and the weights replicate, so the path shards with no data-path collective; the reference has no
+ * counterpart (single device).  The only exchange is an all-gather of the final fixed-size box list:
+ *   cf_comm_unique_id          rank 0 creates the 128-byte NCCL id; the caller broadcasts it (any side channel)
+ *   cf_comm_init               every rank joins (ncclCommInitRank) -- NCCL is bound at run time (libnccl.so.2)
+ *   cf_submit_topk_gather_host as cf_submit_topk_host, then ncclAllGather of the [batch,K,6] lists on the compute stream right
+ *                              behind the decode kernel and ONE device-to-host copy of the gathered [nranks*batch,K,6] list
+ *                              (rank r's boxes at rows r*batch ..); every rank must submit the same batch and K.
+ *                              Completion: cf_wait_host.                                                                   */
+int cf_comm_unique_id(void* id128);
+int cf_comm_init(cf_engine* e, int nranks, int rank, const void* id128);
+int cf_submit_topk_gather_host(cf_engine* e, const uint8_t* images, int batch, int h, int w, int K, float* out_dets_all,
+                               int32_t* out_inds);
+
 /* Same for the threshold paths: the body of CenterFace.__call__ after cv2.resize
  * (centerface.py:32-62) for variant A, or of get_detections (eval_widerface.py:83-89) for
  * variant B, on a HOST u8 BGR batch [B,h,w,3].  Host outputs as in cf_decode_threshold.    */

@@ -51,6 +51,9 @@ SIGNATURES = {
                                        C.c_float, C.c_int, _vp, _vp, _vp]),
     "cf_launch_count": (C.c_longlong, [_vp]),
     "cf_fused_block_mask": (C.c_uint, [C.c_int]),
+    "cf_comm_unique_id": (C.c_int, [_vp]),
+    "cf_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "cf_submit_topk_gather_host": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "cf_nms": (C.c_int, [_vp, _vp, C.c_int, C.c_float, _vp, _vp, _vp, C.c_size_t, _vp]),
     "cf_nms_scratch_bytes": (C.c_size_t, [C.c_int]),
     "cf_nms_host": (C.c_int, [C.c_int, _vp, _vp, C.c_int, C.c_float, _vp, _vp]),

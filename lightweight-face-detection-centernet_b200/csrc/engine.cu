@@ -8,6 +8,7 @@
 // There is no CPU fallback in this file: every entry point either launches kernels on an
 // sm_100 device or fails with an error code.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <math.h>
 #include <stdarg.h>
 
@@ -69,6 +70,39 @@ struct DeviceGuard {
 #define CF_ON_DEVICE(dev)                                                                  \
     DeviceGuard _dg(dev);                                                                  \
     if (!_dg.ok) return cf::fail(CF_ECUDA, "cudaSetDevice(%d) failed: %s", dev, cudaGetErrorString(cudaGetLastError()))
+
+// ---- NCCL, bound at run time ---------------------------------------------------------------------------------------
+// The one exchange step of the path is an all-gather of the final box list.  The library does not link NCCL:
+// the first cf_comm_* call binds the copy that is already in the process (PyTorch loads its own) or dlopens libnccl.so.2.
+// Prototypes restated from nccl.h (NCCL 2.x ABI): ncclUniqueId is 128 opaque bytes, ncclFloat32 = 7, ncclSuccess = 0.
+struct NcclId {
+    char internal[128];
+};
+struct NcclApi {
+    int (*GetUniqueId)(NcclId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId, int) = nullptr;  // ncclUniqueId is passed BY VALUE
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+inline NcclApi& nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);  // the copy PyTorch (or the host program) already loaded
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return;
+        api.GetUniqueId = (int (*)(NcclId*))dlsym(h, "ncclGetUniqueId");
+        api.CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(h, "ncclCommInitRank");
+        api.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(h, "ncclAllGather");
+        api.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+        api.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+        api.ok = api.GetUniqueId && api.CommInitRank && api.AllGather && api.CommDestroy;
+    });
+    return api;
+}
 
 struct Step {
     int cls;
@@ -168,6 +202,10 @@ struct cf_engine {
     ResizeTables rs;
     long long submitted = 0, waited = 0;
     long long launches = 0;
+    void* comm = nullptr;      // ncclComm_t of cf_comm_init
+    int comm_ranks = 1, comm_rank = 0;
+    float* o_gather = nullptr;  // [ranks * max_batch, K <= 1024... sized at cf_comm_init for K = 100 .. 1024] gathered boxes
+    size_t o_gather_floats = 0;
     PwTcState tc;  // tensor maps etc. of the tcgen05 engine
     StemW stem_w;  // host copy: the stem weights are passed to the kernel by value
     HeadsW heads_w;  // likewise the collapsed head conv
@@ -654,6 +692,8 @@ int cf_destroy(cf_engine* e) {
         if (e->ev_copied[i]) cudaEventDestroy(e->ev_copied[i]);
         if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]);
     }
+    if (e->comm && nccl_api().ok) nccl_api().CommDestroy(e->comm);
+    if (e->o_gather) cudaFree(e->o_gather);
     if (e->src_u8) cudaFree(e->src_u8);
     if (e->rs_tab) cudaFree(e->rs_tab);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
@@ -876,6 +916,61 @@ int cf_submit_topk_host(cf_engine* e, const uint8_t* images, int batch, int h, i
     if ((rc = cf_forward(e, e->in_slot[slot], CF_IN_U8_HWC, batch, h, w, s))) return rc;
     if ((rc = cf_decode_topk(e, K, e->o_dets, e->o_inds, s))) return rc;
     CF_CUDA(cudaMemcpyAsync(out_dets, e->o_dets, (size_t)batch * K * 6 * 4, cudaMemcpyDeviceToHost, s));
+    if (out_inds) CF_CUDA(cudaMemcpyAsync(out_inds, e->o_inds, (size_t)batch * K * 4, cudaMemcpyDeviceToHost, s));
+    CF_CUDA(cudaEventRecord(e->ev_done[slot], s));
+    ++e->submitted;
+    return CF_OK;
+}
+
+int cf_comm_unique_id(void* id128) {
+    CF_CHECK(id128 != nullptr, CF_EINVAL, "cf_comm_unique_id: NULL argument");
+    NcclApi& n = nccl_api();
+    CF_CHECK(n.ok, CF_ECUDA, "cf_comm_unique_id: libnccl.so.2 is not available in this process");
+    const int r = n.GetUniqueId(reinterpret_cast<NcclId*>(id128));
+    CF_CHECK(r == 0, CF_ECUDA, "ncclGetUniqueId failed: %s", n.GetErrorString ? n.GetErrorString(r) : "?");
+    return CF_OK;
+}
+
+int cf_comm_init(cf_engine* e, int nranks, int rank, const void* id128) {
+    CF_CHECK(e && id128 && nranks >= 1 && rank >= 0 && rank < nranks, CF_EINVAL, "cf_comm_init: bad arguments (nranks=%d rank=%d)", nranks, rank);
+    CF_CHECK(e->comm == nullptr, CF_EINVAL, "cf_comm_init: the engine already has a communicator");
+    NcclApi& n = nccl_api();
+    CF_CHECK(n.ok, CF_ECUDA, "cf_comm_init: libnccl.so.2 is not available in this process");
+    CF_ON_DEVICE(e->device);
+    NcclId id;
+    memcpy(id.internal, id128, 128);
+    const int r = n.CommInitRank(&e->comm, nranks, id, rank);
+    if (r != 0) {
+        e->comm = nullptr;
+        return fail(CF_ECUDA, "ncclCommInitRank(%d of %d) failed: %s", rank, nranks, n.GetErrorString ? n.GetErrorString(r) : "?");
+    }
+    e->comm_ranks = nranks, e->comm_rank = rank;
+    e->o_gather_floats = (size_t)nranks * e->max_batch * 1024 * 6;  // K <= 1024
+    CF_CUDA(cudaMalloc((void**)&e->o_gather, e->o_gather_floats * 4));
+    return CF_OK;
+}
+
+int cf_submit_topk_gather_host(cf_engine* e, const uint8_t* images, int batch, int h, int w, int K, float* out_dets_all,
+                               int32_t* out_inds) {
+    CF_CHECK(e && images && out_dets_all, CF_EINVAL, "cf_submit_topk_gather_host: NULL argument");
+    CF_CHECK(e->comm != nullptr, CF_EINVAL, "cf_submit_topk_gather_host: no communicator (cf_comm_init)");
+    CF_CHECK(batch >= 1 && batch <= e->max_batch, CF_ECAP, "cf_submit_topk_gather_host: batch %d outside [1,%d]", batch, e->max_batch);
+    CF_CHECK(K >= 1 && K <= 1024, CF_EINVAL, "cf_submit_topk_gather_host: K=%d outside [1,1024]", K);
+    CF_CHECK(h >= 32 && w >= 32 && h % 32 == 0 && w % 32 == 0 && (size_t)h * w <= (size_t)e->max_h * e->max_w, CF_EINVAL,
+             "cf_submit_topk_gather_host: bad size %dx%d", h, w);
+    CF_ON_DEVICE(e->device);
+    int slot = 0;
+    int rc = host_stage_input(e, images, (size_t)batch * h * w * 3, &slot);
+    if (rc) return rc;
+    cudaStream_t s = e->stream;
+    if ((rc = cf_forward(e, e->in_slot[slot], CF_IN_U8_HWC, batch, h, w, s))) return rc;
+    if ((rc = cf_decode_topk(e, K, e->o_dets, e->o_inds, s))) return rc;
+    // the exchange step: every rank contributes its [batch,K,6] list, enqueued on the compute stream right behind the decode
+    // kernel (no host synchronisation in between), then ONE device-to-host copy of the gathered list
+    const size_t cnt = (size_t)batch * K * 6;
+    const int r = nccl_api().AllGather(e->o_dets, e->o_gather, cnt, /*ncclFloat32*/ 7, e->comm, s);
+    CF_CHECK(r == 0, CF_ECUDA, "ncclAllGather failed: %s", nccl_api().GetErrorString ? nccl_api().GetErrorString(r) : "?");
+    CF_CUDA(cudaMemcpyAsync(out_dets_all, e->o_gather, cnt * e->comm_ranks * 4, cudaMemcpyDeviceToHost, s));
     if (out_inds) CF_CUDA(cudaMemcpyAsync(out_inds, e->o_inds, (size_t)batch * K * 4, cudaMemcpyDeviceToHost, s));
     CF_CUDA(cudaEventRecord(e->ev_done[slot], s));
     ++e->submitted;

@@ -145,6 +145,7 @@ class Engine:
         np_, k2 = _host_ptr(out_inds)
         L.check(self.lib.cf_detect_topk_host(self.h, C.c_void_p(ip), B, H, W, K, C.c_void_p(dp), C.c_void_p(np_)),
                 "cf_detect_topk_host")
+        self._drained()
         self.shape = (B, H, W)
         return out_dets, out_inds
 
@@ -161,11 +162,45 @@ class Engine:
         self._inflight = getattr(self, "_inflight", [])
         self._inflight.append((k0, k1, k2))
 
+    def comm_init(self, group=None):
+        """Join the NCCL communicator of the library (one rank per process / GPU): rank 0 creates the id, torch.distributed (any
+        backend) carries the 128 bytes to the others -- the only use of torch.distributed on the data path is this bootstrap."""
+        import torch
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        idb = (C.c_ubyte * 128)()
+        if rank == 0:
+            L.check(self.lib.cf_comm_unique_id(idb), "cf_comm_unique_id")
+        t = torch.tensor(list(bytes(idb)), dtype=torch.uint8)
+        if dist.get_backend(group) == "nccl":
+            t = t.to(f"cuda:{self.device}")
+        dist.broadcast(t, src=0, group=group)
+        raw = bytes(t.cpu().tolist())
+        L.check(self.lib.cf_comm_init(self.h, world, rank, C.create_string_buffer(raw, 128)), "cf_comm_init")
+        self.comm_world, self.comm_rank = world, rank
+
+    def submit_topk_gather_host(self, images, K, out_dets_all, out_inds=None):
+        """submit_topk_host + the exchange step: out_dets_all [world * B, K, 6] (pinned) receives every rank's boxes."""
+        B, H, W, c = images.shape
+        assert c == 3 and out_dets_all.shape[0] == self.comm_world * B
+        ip, k0 = _host_ptr(images)
+        dp, k1 = _host_ptr(out_dets_all)
+        np_, k2 = _host_ptr(out_inds) if out_inds is not None else (None, None)
+        L.check(self.lib.cf_submit_topk_gather_host(self.h, C.c_void_p(ip), B, H, W, K, C.c_void_p(dp),
+                                                    C.c_void_p(np_) if np_ else None), "cf_submit_topk_gather_host")
+        self.shape = (B, H, W)
+        self._inflight = getattr(self, "_inflight", [])
+        self._inflight.append((k0, k1, k2))
+
     def wait_host(self):
         """Block until the oldest submit_topk_host has delivered its outputs."""
         L.check(self.lib.cf_wait_host(self.h), "cf_wait_host")
         if getattr(self, "_inflight", None):
             self._inflight.pop(0)
+
+    def _drained(self):
+        """The detect_* calls wait for every pending submission in C: the keep-alive list of the pipelined API is stale afterwards."""
+        self._inflight = []
 
     def detect_image_host(self, image, net_h, net_w, variant, threshold, nms_threshold=0.3, scale_w=0.0, scale_h=0.0, cap=1024,
                           landmarks=True):
@@ -183,6 +218,7 @@ class Engine:
                 self.h, C.c_void_p(image.ctypes.data), h, w, net_h, net_w, variant, threshold, nms_threshold, scale_w, scale_h, cap,
                 C.c_void_p(dets.ctypes.data), C.c_void_p(lms.ctypes.data) if want_lms else None, C.c_void_p(count.ctypes.data)),
                 "cf_detect_image_host")
+            self._drained()
             self.shape = (1, net_h, net_w)
             n = int(count[0])
             if n >= 0:
@@ -207,6 +243,7 @@ class Engine:
                 self.h, C.c_void_p(ip), B, H, W, variant, threshold, nms_threshold, scale_w, scale_h, cap,
                 C.c_void_p(dets.ctypes.data), C.c_void_p(lms.ctypes.data) if want_lms else None,
                 C.c_void_p(counts.ctypes.data)), "cf_detect_threshold_host")
+            self._drained()
             self.shape = (B, H, W)
             if (counts >= 0).all():
                 break
