@@ -23,6 +23,7 @@
 #include "k_dwt.cuh"
 #include "k_pwn.cuh"
 #include "k_mbf.cuh"
+#include "k_heads_tc.cuh"
 #include "k_stem_tc.cuh"
 #include "net.hpp"
 
@@ -460,7 +461,11 @@ int build_plan(cf_engine* e, const void* input, int fmt, int B, int H, int W) {
         low = e->up[j];
     }
     // heads, :240-261, :277-279 (+ sigmoid/clamp of centerface.py:43)
-    {
+    if (engine_is_tc(e->pw_engine) && !getenv("CF_HEADS_FFMA")) {  // tap-shifted tcgen05 GEMM (CF_HEADS_FFMA: the fp32 FFMA kernel, for A/B runs)
+        HeadsTcLaunch hl;
+        if ((rc = heads_tc_plan(e->tc, e->up[2], e->heads_w.b, e->hm, e->wh, e->lm, e->reg, e->hm_sig, B, h, wd, &hl))) return rc;
+        P.push_back({CLS_HEADS, [hl](cudaStream_t s) { return heads_tc_launch(hl, s); }});
+    } else {
         const float* a = e->up[2];
         const int hh = h, ww = wd;
         P.push_back({CLS_HEADS, [=](cudaStream_t s) {
@@ -667,6 +672,7 @@ int cf_create(const void* weights, size_t weights_bytes, int device, int max_bat
         }
         const int skip_c[3] = {96, 32, 24};
         for (int j = 0; j < 3 && !rc; ++j) rc = prep("up" + std::to_string(j + 1) + ".w", skip_c[j], 24);
+        if (!rc) rc = heads_tc_prepare(e->tc, e->heads_w.w);
         if (rc) return bail(rc);
     }
     *out = e;

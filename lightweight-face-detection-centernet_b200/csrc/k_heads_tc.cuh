@@ -1,9 +1,8 @@
-// Development prototype (stand-alone binary, NOT part of the product library, never measured yet): the four collapsed heads
-// (dense 3x3, 24 -> 15, + sigmoid/clamp; model/centernet.py:240-261, centerface.py:43) as ONE tcgen05 GEMM per halo tile, with the
-// nine taps as nine K blocks whose A operands are shifted windows into the same TMA-written tile.
+// k_heads_tc: the four collapsed heads (dense 3x3, 24 -> 15, + sigmoid/clamp; model/centernet.py:240-261, centerface.py:43) as ONE
+// tcgen05 GEMM per TMA halo tile, the nine taps as nine K blocks whose A operands are shifted windows into the same tile.
 //
-// Basis: tools/desc_shift_probe.cu (profiles/r1d_desc_shift_probe.md) -- a K-major SWIZZLE_128B shared-memory descriptor may start at
-// ANY 128-byte line of a swizzled tile (base_offset 0).  Plan and expected bound: profiles/r1d_headroom.md, item 1.
+// Basis: a K-major SWIZZLE_128B shared-memory descriptor may start at ANY 128-byte line of a swizzled tile (base_offset 0;
+// tools/desc_shift_probe.cu, profiles/r1d_desc_shift_probe.md).
 //
 // Geometry.  Halo tile = 9 rows x 18 columns of pixels, 32 channels (24 real, TMA zero-fills 24..31) = 162 lines of 128 B, line
 // L = hy * 18 + hx, origin (y0 - 1, x0 - 1): out-of-image pixels are zero-filled by TMA = the convolution's zero padding.  MMA row m
@@ -12,20 +11,14 @@
 // (7 rows x 16 columns) per 128-row MMA block.
 //
 // Per tile: TMA -> all threads split the tile into tf32 hi (in place) and lo (second buffer) -> one elected lane issues
-// 9 taps x 4 K steps x { A_hi.[W_hi|W_lo] (N = 32: main and correction accumulator), A_lo.W_hi (N = 16: correction) } -> the drain of
+// 9 taps x 3 K steps x { A_hi.[W_hi|W_lo] (N = 32: main and correction accumulator), A_lo.W_hi (N = 16: correction) } -> the drain of
 // the PREVIOUS tile runs under these MMAs (two accumulator slots) -> bias, sigmoid/clamp, planar stores.  Two CTAs per SM.
-//
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -o tools/build/heads_tc_probe tools/heads_tc_probe.cu -lcuda
-//   tools/build/heads_tc_probe [batch=32] [H=160] [W=160]
-#include <cstdarg>
-#include <cstdio>
-#include <cstdlib>
-#include <cmath>
-#include <vector>
+// Bound: every MMA streams a 4 KB A slice out of shared memory whatever N is -- 54 MMAs per tile; the FFMA kernel it replaces
+// (k_heads, 3456 FFMA per pixel) stays as the fp32 validation engine's head.
+#pragma once
+#include "k_dwt.cuh"
 
-#include "../lightweight-face-detection-centernet_b200/csrc/k_dwt.cuh"
-
-using namespace cf;
+namespace cf {
 
 constexpr int HT_TW = 16, HT_TH = 7;                 // outputs per tile
 constexpr int HT_WT = HT_TW + 2, HT_HT = HT_TH + 2;  // halo tile
@@ -50,6 +43,7 @@ struct HeadsTcParams {
 
 __global__ void __launch_bounds__(HT_THREADS, 2) k_heads_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ HeadsTcParams p) {
     extern __shared__ uint8_t smem_raw[];
+    pdl_trigger();
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t lo_sm = base + HT_OFF_LO, w_sm = base + HT_OFF_W, bars = base + HT_OFF_BARS;
@@ -70,6 +64,7 @@ __global__ void __launch_bounds__(HT_THREADS, 2) k_heads_tc(const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();  // the FPN map is the previous kernel's output; the head planes may still be read by the previous step's decode
 
     const int my_tiles = ((int)blockIdx.x < p.n_tiles) ? (p.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     auto tile_of = [&](int j, int* b, int* y0, int* x0) {
@@ -161,7 +156,7 @@ __global__ void __launch_bounds__(HT_THREADS, 2) k_heads_tc(const __grid_constan
                     const uint64_t a_hi = umma_desc(a_sm + shift), a_lo = umma_desc(lo_sm + shift);
                     const uint64_t b_hi = umma_desc(w_sm + (uint32_t)t * 4096u);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {  // K = 32 channels (24 real) in steps of 8
+                    for (int k = 0; k < 3; ++k) {  // K = 24 channels in steps of 8 (the tile's channels 24..31 are TMA zero fill, never read)
                         const uint64_t ko = (uint64_t)(k * 2);
                         umma_tf32(d_main, a_hi + ko, b_hi + ko, idesc32, (t > 0 || k > 0) ? 1u : 0u);  // main += hi.hi ; corr += hi.lo
                         umma_tf32(d_corr, a_lo + ko, b_hi + ko, idesc16, 1u);                           // corr += lo.hi
@@ -185,102 +180,53 @@ __global__ void __launch_bounds__(HT_THREADS, 2) k_heads_tc(const __grid_constan
     }
 }
 
-// ---- host ------------------------------------------------------------------------------------------------------------------
-#define CK(x)                                                                                   \
-    do {                                                                                        \
-        cudaError_t e_ = (x);                                                                   \
-        if (e_ != cudaSuccess) return printf("%s: %s\n", #x, cudaGetErrorString(e_)), 1;         \
-    } while (0)
+// ---- host side --------------------------------------------------------------------------
+struct HeadsTcLaunch {
+    CUtensorMap tmX;
+    HeadsTcParams p;
+    int grid = 0;
+};
 
-int main(int argc, char** argv) {
-    const int B = argc > 1 ? atoi(argv[1]) : 32, H = argc > 2 ? atoi(argv[2]) : 160, W = argc > 3 ? atoi(argv[3]) : 160;
-    PwTcState st;
-    if (pw_tc_init(st, 0)) return printf("init: %s\n", err_slot().c_str()), 1;
-    const size_t npx = (size_t)B * H * W;
-    std::vector<float> hx(npx * 24), hw(9 * 24 * 15), hb(15);
-    uint32_t s = 12345u;
-    auto rnd = [&]() { s = s * 1664525u + 1013904223u; return ((s >> 8) & 0xFFFF) / 32768.f - 1.f; };
-    for (auto& v : hx) v = rnd() * 3.f;
-    for (auto& v : hw) v = rnd() * 0.2f;
-    for (auto& v : hb) v = rnd();
-    // weight image: per tap [hi: 16 rows (n) x 32 k | lo], K-major, SWIZZLE_128B; k = channel (24..31 zero), n = 15 zero
+// weight image of the collapsed head conv (host copy hw[(tap * 24 + k) * 16 + n], n = 15 is padding): per tap
+// [hi: 16 rows (n) x 32 k | lo], K-major, SWIZZLE_128B
+inline int heads_tc_prepare(PwTcState& st, const float* hw) {
+    if (st.heads_img) return CF_OK;
     std::vector<float> img(HT_W_BYTES / 4, 0.f);
     for (int t = 0; t < 9; ++t)
         for (int n = 0; n < 15; ++n)
             for (int k = 0; k < 24; ++k) {
-                const float w = hw[(t * 24 + k) * 15 + n], h = tf32_hi(w);
+                const float w = hw[(t * 24 + k) * 16 + n], h = tf32_hi(w);
                 const int pos = n * 32 + (((k >> 2) ^ (n & 7)) << 2) + (k & 3);
                 img[t * 1024 + pos] = h;
                 img[t * 1024 + 512 + pos] = tf32_hi(w - h);
             }
-    float *dx, *dimg, *dout;
-    CK(cudaMalloc(&dx, hx.size() * 4));
-    CK(cudaMalloc(&dimg, HT_W_BYTES));
-    CK(cudaMalloc(&dout, npx * 16 * 4));
-    CK(cudaMemcpy(dx, hx.data(), hx.size() * 4, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(dimg, img.data(), HT_W_BYTES, cudaMemcpyHostToDevice));
-    CK(cudaMemset(dout, 0xff, npx * 16 * 4));
-    HeadsTcParams p = {};
-    p.wimg = dimg;
-    for (int i = 0; i < 15; ++i) p.bias[i] = hb[i];
-    p.hm = dout, p.hm_sig = dout + npx, p.wh = dout + 2 * npx, p.lm = dout + 4 * npx, p.reg = dout + 14 * npx;
-    p.B = B, p.H = H, p.W = W;
-    p.tiles_x = (W + HT_TW - 1) / HT_TW, p.tiles_y = (H + HT_TH - 1) / HT_TH, p.n_tiles = B * p.tiles_x * p.tiles_y;
-    CUtensorMap tm;
-    if (xd_make_map(st, &tm, dx, B, H, W, 24, HT_WT, HT_HT)) return printf("map: %s\n", err_slot().c_str()), 1;
-    CK(cudaFuncSetAttribute(k_heads_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_SMEM));
-    const int grid = p.n_tiles < 2 * st.sms ? p.n_tiles : 2 * st.sms;
-    k_heads_tc<<<grid, HT_THREADS, HT_SMEM>>>(tm, p);
-    CK(cudaDeviceSynchronize());
-    std::vector<float> ho(npx * 16);
-    CK(cudaMemcpy(ho.data(), dout, ho.size() * 4, cudaMemcpyDeviceToHost));
-    // fp64 check on sampled pixels (all of image 0's border + random ones)
-    const size_t plane = (size_t)H * W;
-    auto ref = [&](int b, int y, int x, int ch) {
-        double a = hb[ch];
-        for (int ky = 0; ky < 3; ++ky)
-            for (int kx = 0; kx < 3; ++kx) {
-                const int yy = y + ky - 1, xx = x + kx - 1;
-                if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-                const float* px = &hx[(((size_t)b * H + yy) * W + xx) * 24];
-                for (int k = 0; k < 24; ++k) a += (double)px[k] * hw[((ky * 3 + kx) * 24 + k) * 15 + ch];
-            }
-        return a;
-    };
-    auto got = [&](int b, int y, int x, int ch) {
-        const size_t pix = (size_t)y * W + x;
-        if (ch == 0) return ho[(size_t)b * plane + pix];
-        if (ch <= 2) return ho[2 * npx + ((size_t)b * 2 + ch - 1) * plane + pix];
-        if (ch <= 12) return ho[4 * npx + ((size_t)b * 10 + ch - 3) * plane + pix];
-        return ho[14 * npx + ((size_t)b * 2 + ch - 13) * plane + pix];
-    };
-    double worst = 0;
-    long checked = 0, bad = 0;
-    auto check = [&](int b, int y, int x) {
-        for (int ch = 0; ch < 15; ++ch) {
-            const double r = ref(b, y, x, ch), e = fabs(got(b, y, x, ch) - r);
-            if (!(e <= 1e-4)) ++bad;
-            if (e > worst || e != e) worst = e;
-            ++checked;
-        }
-    };
-    for (int x = 0; x < W; ++x) check(0, 0, x), check(0, H - 1, x);
-    for (int y = 0; y < H; ++y) check(0, y, 0), check(0, y, W - 1);
-    for (int i = 0; i < 4000; ++i) {
-        s = s * 1664525u + 1013904223u;
-        const size_t q = (size_t)(s >> 4) % npx;
-        check((int)(q / plane), (int)((q % plane) / W), (int)(q % W));
-    }
-    printf("heads_tc B=%d H=%d W=%d: %ld values checked against fp64, max abs err %.3g, %ld above 1e-4\n", B, H, W, checked, worst, bad);
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0), cudaEventCreate(&e1);
-    for (int i = 0; i < 3; ++i) k_heads_tc<<<grid, HT_THREADS, HT_SMEM>>>(tm, p);
-    cudaEventRecord(e0);
-    for (int i = 0; i < 20; ++i) k_heads_tc<<<grid, HT_THREADS, HT_SMEM>>>(tm, p);
-    cudaEventRecord(e1);
-    CK(cudaDeviceSynchronize());
-    float ms = 0;
-    cudaEventElapsedTime(&ms, e0, e1);
-    printf("time %.1f us per launch (k_heads, FFMA: 136 us at B=32 160x160), grid %d, smem %d\n", ms / 20 * 1e3, grid, HT_SMEM);
-    return bad ? 2 : 0;
+    if (cudaMalloc((void**)&st.heads_img, HT_W_BYTES) != cudaSuccess) return fail(CF_ECUDA, "heads_tc_prepare: cudaMalloc failed");
+    if (cudaMemcpy(st.heads_img, img.data(), HT_W_BYTES, cudaMemcpyHostToDevice) != cudaSuccess) return fail(CF_ECUDA, "heads_tc_prepare: cudaMemcpy failed");
+    return CF_OK;
 }
+
+inline int heads_tc_plan(PwTcState& st, const float* X, const float* bias16, float* hm, float* wh, float* lm, float* reg, float* hm_sig, int B,
+                         int H, int W, HeadsTcLaunch* hl) {
+    if (!st.heads_img) return fail(CF_EINVAL, "heads_tc_plan: weight image was not prepared");
+    int rc = xd_make_map(st, &hl->tmX, X, B, H, W, 24, HT_WT, HT_HT);
+    if (rc) return rc;
+    HeadsTcParams& p = hl->p;
+    p.wimg = st.heads_img;
+    for (int i = 0; i < 16; ++i) p.bias[i] = bias16[i];
+    p.hm = hm, p.hm_sig = hm_sig, p.wh = wh, p.lm = lm, p.reg = reg;
+    p.B = B, p.H = H, p.W = W;
+    p.tiles_x = (W + HT_TW - 1) / HT_TW, p.tiles_y = (H + HT_TH - 1) / HT_TH;
+    const long long nt = (long long)B * p.tiles_x * p.tiles_y;
+    if (nt > 0x7fffffffLL) return fail(CF_EINVAL, "heads_tc_plan: too many tiles");
+    p.n_tiles = (int)nt;
+    hl->grid = p.n_tiles < 2 * st.sms ? p.n_tiles : 2 * st.sms;
+    return CF_OK;
+}
+
+inline cudaError_t heads_tc_launch(const HeadsTcLaunch& hl, cudaStream_t s) {
+    cudaError_t e = smem_optin((const void*)k_heads_tc, HT_SMEM);
+    if (e != cudaSuccess) return e;
+    return launch_pdl(k_heads_tc, dim3(hl.grid), dim3(HT_THREADS), (size_t)HT_SMEM, s, hl.tmX, hl.p);
+}
+
+}  // namespace cf

@@ -55,6 +55,7 @@ struct PwTcState {
     void* encode = nullptr;  // cuTensorMapEncodeTiled
     int sms = 148;
     std::map<const float*, TcLayer> layers;  // keyed by the [K][N] device weight pointer
+    float* heads_img = nullptr;  // tap-major tf32 hi/lo image of the collapsed head conv (k_heads_tc)
     unsigned long long* trace_buf = nullptr;  // development: k_mbf pipeline trace (CF_MBF_TRACE)
     std::map<const float*, float*> dw_imgs;  // per-chunk tap images of the fused blocks' depth-wise weights (k_mbf)
 };
@@ -667,6 +668,8 @@ inline void pw_tc_destroy(PwTcState& st) {
     st.dw_imgs.clear();
     if (st.trace_buf) cudaFree(st.trace_buf);
     st.trace_buf = nullptr;
+    if (st.heads_img) cudaFree(st.heads_img);
+    st.heads_img = nullptr;
 }
 
 // fp32 [rows][cols] row-major tensor, box [box_rows][32 floats], SWIZZLE_128B, zero OOB fill

@@ -1,2 +1,2 @@
-timeout 120 python tools/mbf_check.py --mask 0x6 --time 2>&1 | grep -E "block[1-3] |hm_sig|inds|MBF|fused|rror"
-timeout 120 python tools/mbf_trace.py --mask 0x2 --j0 240 --nj 36 2>&1 | tail -19
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
+timeout 100 python tools/step_times.py --iters 10 2>&1 | grep -E "heads|total us|fused|rror"
