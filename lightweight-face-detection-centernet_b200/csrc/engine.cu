@@ -184,10 +184,19 @@ struct cf_engine {
     int B = 0, H = 0, W = 0, fmt = -1;
     const void* in = nullptr;
     std::vector<Step> plan;          // launch list of the current (input, format, shape)
+    // The network launches of a plan replayed as ONE CUDA graph (kernel nodes with their programmatic-dependent-launch edges):
+    // at batch 1 the forward is ~40 launches of a few microseconds each and the launch path, not the kernels, sets the latency.
+    // Captured on the plan's second run (the first, eager one has opted every kernel in to its shared memory); CF_GRAPH=0 or a
+    // failed capture falls back to eager launches.
+    cudaGraphExec_t gexec = nullptr;
+    int graph_state = 0;  // 0 not tried, 1 usable, -1 capture failed
+    int plan_runs = 0, plan_net_launches = 0;
     struct CachedPlan {
         const void* in;
         int fmt, B, H, W;
         std::vector<Step> steps;
+        cudaGraphExec_t gexec;
+        int graph_state, plan_runs, plan_net_launches;
     };
     std::vector<CachedPlan> plan_cache;  // the pipelined host path alternates between two input buffers
     // pipelined host entry points: two input slots, copy stream, events
@@ -698,6 +707,9 @@ int cf_destroy(cf_engine* e) {
         if (e->ev_copied[i]) cudaEventDestroy(e->ev_copied[i]);
         if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]);
     }
+    if (e->gexec) cudaGraphExecDestroy(e->gexec);
+    for (auto& c : e->plan_cache)
+        if (c.gexec) cudaGraphExecDestroy(c.gexec);
     if (e->comm && nccl_api().ok) nccl_api().CommDestroy(e->comm);
     if (e->o_gather) cudaFree(e->o_gather);
     if (e->src_u8) cudaFree(e->src_u8);
@@ -720,16 +732,23 @@ int cf_forward(cf_engine* e, const void* input, int in_format, int batch, int h,
     if (e->plan.empty() || e->B == 0 || e->in != input || e->fmt != in_format || e->B != batch || e->H != h || e->W != w) {
         // stash the current plan, then reuse a cached one or build a new one
         if (!e->plan.empty() && e->B != 0) {
-            if (e->plan_cache.size() >= 4) e->plan_cache.erase(e->plan_cache.begin());
-            e->plan_cache.push_back({e->in, e->fmt, e->B, e->H, e->W, std::move(e->plan)});
+            if (e->plan_cache.size() >= 4) {
+                if (e->plan_cache.front().gexec) cudaGraphExecDestroy(e->plan_cache.front().gexec);
+                e->plan_cache.erase(e->plan_cache.begin());
+            }
+            e->plan_cache.push_back({e->in, e->fmt, e->B, e->H, e->W, std::move(e->plan), e->gexec, e->graph_state, e->plan_runs, e->plan_net_launches});
+        } else if (e->gexec) {
+            cudaGraphExecDestroy(e->gexec);
         }
         e->plan.clear();
+        e->gexec = nullptr, e->graph_state = 0, e->plan_runs = 0, e->plan_net_launches = 0;
         bool hit = false;
         for (size_t i = 0; i < e->plan_cache.size(); ++i) {
             auto& c = e->plan_cache[i];
             if (c.in == input && c.fmt == in_format && c.B == batch && c.H == h && c.W == w) {
                 e->plan = std::move(c.steps);
                 e->in = c.in, e->fmt = c.fmt, e->B = c.B, e->H = c.H, e->W = c.W;
+                e->gexec = c.gexec, e->graph_state = c.graph_state, e->plan_runs = c.plan_runs, e->plan_net_launches = c.plan_net_launches;
                 e->plan_cache.erase(e->plan_cache.begin() + i);
                 hit = true;
                 break;
@@ -742,6 +761,28 @@ int cf_forward(cf_engine* e, const void* input, int in_format, int batch, int h,
                 return rc;
             }
         }
+    }
+    static const bool use_graph = !(getenv("CF_GRAPH") && atoi(getenv("CF_GRAPH")) == 0) && !getenv("CF_SYNC_EACH");
+    if (use_graph && e->graph_state == 0 && e->plan_runs >= 1) {
+        // capture on the engine's own stream (the caller's may be the legacy default stream, which cannot capture)
+        e->graph_state = -1;
+        cudaGraph_t g = nullptr;
+        if (cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+            const long long before = e->launches;
+            const int rc = run_steps(e, CLS_ALL, e->stream);
+            e->plan_net_launches = (int)(e->launches - before);
+            e->launches = before;
+            const cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
+            if (rc == CF_OK && ce == cudaSuccess && g && cudaGraphInstantiate(&e->gexec, g, 0) == cudaSuccess) e->graph_state = 1;
+            if (g) cudaGraphDestroy(g);
+        }
+        cudaGetLastError();  // a failed capture leaves the sticky-free error state clean: eager launches take over
+    }
+    ++e->plan_runs;
+    if (use_graph && e->graph_state == 1) {
+        CF_CUDA(cudaGraphLaunch(e->gexec, (cudaStream_t)stream));
+        e->launches += e->plan_net_launches;
+        return CF_OK;
     }
     return run_steps(e, CLS_ALL, (cudaStream_t)stream);
 }
