@@ -233,10 +233,11 @@ BLOCKS = [(32, 16, 1, 3, 1), (16, 24, 6, 3, 2), (24, 24, 6, 3, 1), (24, 32, 6, 5
           (64, 64, 6, 3, 1), (64, 96, 6, 5, 1), (96, 96, 6, 5, 1), (96, 160, 6, 5, 2), (160, 160, 6, 5, 1), (160, 320, 6, 3, 1)]
 
 
-def launch_table(h, w, fused=()):
+def launch_table(h, w, fused=(), dwp=()):
     """(name, algorithmic bytes per image) of every launch of one forward + path-C decode, in launch order -- the same
     layer-wise accounting as cf_work_model (un-padded input once + output once + residual / low-res re-reads, fp32).
-    A block in `fused` is ONE launch credited with the layer-wise bytes of the three launches it replaces."""
+    A block in `fused` is ONE launch credited with the layer-wise bytes of the three launches it replaces; a block in `dwp` keeps its
+    expand launch (if it has one) and runs depth-wise + projection as one launch credited with the bytes of those two."""
     out = []
     hh, ww = h // 2, w // 2
     out.append(("stem 3->32 s2", h * w * 3 + hh * ww * 32 * 4))
@@ -251,6 +252,8 @@ def launch_table(h, w, fused=()):
         rows.append((f"b{i} project {hid}->{cout}" + (" +res" if res else ""), ho * wo * (hid + cout + res) * 4))
         if i in fused:
             rows = [(f"b{i} fused MBConv {cin}->{hid}->{cout} k{k} s{s}" + (" +res" if res else ""), sum(b for _, b in rows))]
+        elif i in dwp:
+            rows = rows[:-2] + [(f"b{i} fused dw{k}x{k} s{s} + project {hid}->{cout}" + (" +res" if res else ""), sum(b for _, b in rows[-2:]))]
         out += rows
         hh, ww = ho, wo
     out.append(("conv_last 320->24", hh * ww * (320 + 24) * 4))
@@ -422,7 +425,7 @@ def run_b200(a):
         pass
     try:  # the individual launches, timed one by one (events between launches: no overlap of neighbouring kernels)
         ms_l, _ = eng.time_steps(5)
-        tab = launch_table(H, W, L.fused_blocks(pw))
+        tab = launch_table(H, W, L.fused_blocks(pw), L.dwp_blocks(pw))
         if len(tab) == len(ms_l):
             rows = [{"launch": n, "us": round(t * 1e3, 1), "alg_GB": round(by_l * B / 1e9, 4),
                      "GBps": round(by_l * B / (t * 1e-3) / 1e9, 1), "frac_hbm": round(by_l * B / (t * 1e-3) / 1e9 / hbm, 3)}

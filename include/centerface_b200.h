@@ -217,6 +217,9 @@ long long cf_launch_count(cf_engine* e);
 /* Bit i set: MBConv block i (model/centernet.py:211-234, layer0 = block 0 .. layer6 = block 11) runs as one fused kernel under
  * engine `pw_engine` (the built-in mask, or CF_MBF from the environment). */
 unsigned cf_fused_block_mask(int pw_engine);
+/* Bit i set: depth-wise + Swish + projection (+ residual) of block i run as one kernel from the hidden tensor (the expand conv, if
+ * the block has one, stays its own launch); CF_MBD overrides the built-in mask. */
+unsigned cf_dwp_block_mask(int pw_engine);
 
 /* Development only: the pipeline trace of the fused MBConv kernel (k_mbf) recorded during the last forward when the plan was built
  * with CF_MBF_TRACE=j0,nj in the environment: out[job][32] = clock64 of event 0..31 of CTA 0 (0 = not recorded). */

@@ -51,6 +51,7 @@ SIGNATURES = {
                                        C.c_float, C.c_int, _vp, _vp, _vp]),
     "cf_launch_count": (C.c_longlong, [_vp]),
     "cf_fused_block_mask": (C.c_uint, [C.c_int]),
+    "cf_dwp_block_mask": (C.c_uint, [C.c_int]),
     "cf_comm_unique_id": (C.c_int, [_vp]),
     "cf_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "cf_submit_topk_gather_host": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
@@ -98,6 +99,12 @@ def check(rc, what=""):
 def fused_blocks(pw_engine=CF_PW_TCGEN05):
     """Indices of the MBConv blocks that run as one fused kernel under `pw_engine` -- cf_fused_block_mask."""
     m = load().cf_fused_block_mask(pw_engine)
+    return [i for i in range(12) if (m >> i) & 1]
+
+
+def dwp_blocks(pw_engine=CF_PW_TCGEN05):
+    """Indices of the blocks whose depth-wise + projection run as one kernel under `pw_engine` -- cf_dwp_block_mask."""
+    m = load().cf_dwp_block_mask(pw_engine)
     return [i for i in range(12) if (m >> i) & 1]
 
 

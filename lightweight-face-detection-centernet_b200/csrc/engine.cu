@@ -50,6 +50,14 @@ inline unsigned mbf_mask() {
     if (const char* ev = getenv("CF_MBF")) return (unsigned)strtoul(ev, nullptr, 0);
     return kMbfDefaultMask;
 }
+// Depth-wise + projection of a block as one kernel (k_mbf direct mode) where the whole-block fusion does not pay: the expand conv, if
+// any, stays a k_pw_tc launch.  CF_MBD overrides the mask.
+constexpr unsigned kMbdDefaultMask = 0x1u;  // layer0 (no expand conv: the whole block is one kernel): 214 us against 143 + 115
+inline unsigned mbd_mask() {
+    if (const char* ev = getenv("CF_MBD")) return (unsigned)strtoul(ev, nullptr, 0);
+    return kMbdDefaultMask;
+}
+inline bool block_is_mbd(int pw, int i);
 inline bool block_is_mbf(int pw, int i) {
     const MBBlock& b = kBlocks[i];
     return pw == CF_PW_TCGEN05 && b.t != 1 && ((mbf_mask() >> i) & 1u) && mbf_supported(b.k, b.s, b.cin, b.hid(), b.cout);
@@ -103,6 +111,11 @@ inline NcclApi& nccl_api() {
         api.ok = api.GetUniqueId && api.CommInitRank && api.AllGather && api.CommDestroy;
     });
     return api;
+}
+
+inline bool block_is_mbd(int pw, int i) {
+    const MBBlock& b = kBlocks[i];
+    return pw == CF_PW_TCGEN05 && !block_is_mbf(pw, i) && ((mbd_mask() >> i) & 1u) && mbf_direct_supported(b.k, b.s, b.hid(), b.cout);
 }
 
 struct Step {
@@ -408,6 +421,18 @@ int build_plan(cf_engine* e, const void* input, int fmt, int B, int H, int W) {
             if ((rc = make_pw_step(e, P, EPI_SWISH, x, wexp, o, M, K, hid, EpiArgs{}))) return rc;
             dw_in = e->hidA;
         }
+        if (block_is_mbd(e->pw_engine, i)) {
+            // depth-wise + Swish + projection (+ residual) in one kernel: the depth-wise output never reaches HBM
+            MbfLaunch ml;
+            if ((rc = mbf_plan_direct(e->tc, b.k, b.s, dw_in, e->w[p + ".dw"], e->w[p + ".proj"], e->blk[i], b.residual() ? x : nullptr, B, h, wd,
+                                      hid, b.cout, &ml)))
+                return rc;
+            P.push_back({CLS_FUSED, [ml](cudaStream_t s) { return mbf_launch(ml, s); }});
+            x = e->blk[i];
+            h = ho;
+            wd = wo;
+            continue;
+        }
         {
             const float* wdw = e->w[p + ".dw"];
             float* o = e->hidB;
@@ -672,6 +697,14 @@ int cf_create(const void* weights, size_t weights_bytes, int device, int max_bat
                 continue;
             }
             if (b.t != 1) rc = prep("b" + std::to_string(i) + ".exp", b.cin, b.hid());
+            if (!rc && block_is_mbd(pw_engine, i)) {  // one 32-column projection image per K block + the tap chunk image
+                const std::string np = "b" + std::to_string(i) + ".proj", nd = "b" + std::to_string(i) + ".dw";
+                const float* hp = blob.get(np, (uint64_t)b.hid() * b.cout, why);
+                rc = hp ? tc_prepare_layer(e->tc, e->w[np], hp, b.hid(), b.cout, 3, 32) : fail(CF_EWEIGHTS, "cf_create: %s", why.c_str());
+                const float* hd = blob.get(nd, (uint64_t)b.k * b.k * b.hid(), why);
+                if (!rc) rc = hd ? mbf_prepare_dw(e->tc, e->w[nd], hd, b.k * b.k, b.hid()) : fail(CF_EWEIGHTS, "cf_create: %s", why.c_str());
+                continue;
+            }
             if (!rc) rc = prep("b" + std::to_string(i) + ".proj", b.hid(), b.cout);
         }
         if (!rc) rc = prep("clast.w", 320, 24);
@@ -1284,6 +1317,13 @@ unsigned cf_fused_block_mask(int pw_engine) {
     return m;
 }
 
+unsigned cf_dwp_block_mask(int pw_engine) {
+    unsigned m = 0;
+    for (int i = 0; i < 12; ++i)
+        if (block_is_mbd(pw_engine, i)) m |= 1u << i;
+    return m;
+}
+
 int cf_debug_mbf_trace(cf_engine* e, unsigned long long* out, int n_jobs) {
     CF_CHECK(e && out && n_jobs > 0 && n_jobs <= 4096, CF_EINVAL, "cf_debug_mbf_trace: bad arguments");
     CF_CHECK(e->tc.trace_buf != nullptr, CF_EINVAL, "cf_debug_mbf_trace: no trace was recorded (set CF_MBF_TRACE=j0,nj before the plan is built)");
@@ -1314,6 +1354,13 @@ int cf_work_model(int h, int w, int in_format, int pw_engine, int which, double*
         if (b.t != 1) {
             by[CLS_PW] += hh * ww * (b.cin + hid) * F;
             fl[CLS_PW] += 2.0 * hh * ww * b.cin * hid;
+        }
+        if (block_is_mbd(pw_engine, i)) {  // hidden tensor in, block output out (+ the residual re-read)
+            by[CLS_FUSED] += (hh * ww * hid + ho * wo * b.cout * (b.residual() ? 2 : 1)) * F;
+            fl[CLS_FUSED] += 2.0 * ho * wo * hid * b.k * b.k + 2.0 * ho * wo * hid * b.cout;
+            hh = ho;
+            ww = wo;
+            continue;
         }
         by[CLS_DW] += (hh * ww + ho * wo) * hid * F;
         fl[CLS_DW] += 2.0 * ho * wo * hid * b.k * b.k;

@@ -44,13 +44,17 @@
 
 namespace cf {
 
-template <int KS_, int S_, int CIN_, int STH_, int STW_, int NSY_, int NSX_, int XT_, int YT_, int TD_, int NX_, bool WDS_>
+template <int KS_, int S_, int CIN_, int STH_, int STW_, int NSY_, int NSX_, int XT_, int YT_, int TD_, int NX_, bool WDS_, bool EXP_ = true>
 struct MbfCfg {
     static constexpr int KS = KS_, S = S_, CIN = CIN_, STH = STH_, STW = STW_, NSY = NSY_, NSX = NSX_, XT = XT_, YT = YT_, TD = TD_;
     static constexpr int IH = (STH - 1) * S + KS, IW = (STW - 1) * S + KS, NPX = IH * IW;
     static constexpr int LO = (KS - S) / 2;  // model/centernet.py:68-70
     static constexpr int NSUB = NSY * NSX, SPX = STH * STW, DROWS = NSUB * SPX;
     static constexpr int KSTEPS = (CIN + 7) / 8;
+    // EXP: the block's expand conv runs in this kernel (X = block input).  !EXP ("direct" mode): X is the HIDDEN tensor at input
+    // resolution -- layer0 (t = 1, no expand conv) or a block whose expand conv stays a k_pw_tc launch -- and TMA writes its
+    // 32-channel halo boxes straight into the teams' E tiles (two per team): the kernel is depth-wise + Swish + projection.
+    static constexpr bool EXP = EXP_;
     static constexpr int NT = 4;  // compute teams (four warps each: one per TMEM lane quarter)
     static constexpr int NWARPS = 8 + 4 * NT, THREADS = NWARPS * 32;
     static constexpr int NBX = STW / XT, NITEMS = (STH / YT) * NBX * 8;  // depth-wise items: (output block, float4 of channels)
@@ -67,15 +71,18 @@ struct MbfCfg {
     // E slot: pixel rows at a 144-byte pitch instead of a swizzle -- the drain's stores (a lane = a pixel, 8 consecutive pixels
     // per quarter warp) and the depth-wise loads (8 lanes = the 128 bytes of one pixel) are both bank-conflict free, and every
     // window address is one base register + an immediate
-    static constexpr uint32_t EP = 144, ESLOT = ((NPX * EP + 1023) / 1024) * 1024;
+    // (direct mode: TMA writes dense 128-byte rows, which the depth-wise loads read conflict free as well)
+    static constexpr uint32_t EP = EXP ? 144 : 128, ESLOT = ((NPX * EP + 1023) / 1024) * 1024;
+    static constexpr int NEB = EXP ? 1 : 2;      // E tiles per team
+    static constexpr int NXB = EXP ? NX : NT * NEB;  // x_full / x_empty barriers: X ring slots, or one per E tile
     static constexpr uint32_t DHALF = ((DROWS + 7) / 8) * 1024u;    // the hi (or lo) half of one D operand
     static constexpr uint32_t PCOL = 0, ECOL = PCOL + NP * 64, ACOL = ECOL + NE * 32;  // TMEM columns
-    static_assert(NPX <= 128, "a sub-tile's halo is one MMA block");
+    static_assert(!EXP || NPX <= 128, "a sub-tile's halo is one MMA block");
     static_assert(DROWS <= 128, "a block's outputs are the rows of one projection accumulator");
     static_assert(STW % XT == 0 && STH % YT == 0, "output blocks tile the sub-tile");
     static_assert(TD_ >= 0, "legacy parameter");
     static_assert(ACOL + NA * 64 <= 512, "TMEM budget");
-    static_assert(CIN % 8 == 0 && CIN <= 32, "expand K");
+    static_assert(!EXP || (CIN % 8 == 0 && CIN <= 32), "expand K");
 };
 
 struct MbfParams {
@@ -131,18 +138,19 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
 
     // barriers (8 B each)
     const uint32_t bars = base + p.off_bars;
-    const uint32_t x_full = bars, x_empty = x_full + 8 * NX;
-    const uint32_t a_full = x_empty + 8 * NX, a_empty = a_full + 8 * NA;
+    constexpr int NXB = C::NXB;
+    const uint32_t x_full = bars, x_empty = x_full + 8 * NXB;
+    const uint32_t a_full = x_empty + 8 * NXB, a_empty = a_full + 8 * NA;
     const uint32_t e_full = a_empty + 8 * NA, e_empty = e_full + 8 * NE;
     const uint32_t d_full = e_empty + 8 * NE, d_free = d_full + 8 * ND;
     const uint32_t p_full = d_free + 8 * NDF, p_empty = p_full + 8 * NP;
     const uint32_t w_full = p_empty + 8 * NP;
-    constexpr int NBARS = 2 * (NX + NA + NE + NP) + ND + NDF + 1;
+    constexpr int NBARS = 2 * (NXB + NA + NE + NP) + ND + NDF + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + p.off_bars + 8 * NBARS + 8);
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
-        for (int i = 0; i < NX; ++i) mbar_init(x_full + 8 * i, 1), mbar_init(x_empty + 8 * i, 4);
+        for (int i = 0; i < NXB; ++i) mbar_init(x_full + 8 * i, 1), mbar_init(x_empty + 8 * i, 4);
         for (int i = 0; i < NA; ++i) mbar_init(a_full + 8 * i, 4), mbar_init(a_empty + 8 * i, 1);
         for (int i = 0; i < NE; ++i) mbar_init(e_full + 8 * i, 1), mbar_init(e_empty + 8 * i, 4);
         for (int i = 0; i < ND; ++i) mbar_init(d_full + 8 * i, NSUB * 4);
@@ -182,11 +190,11 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
         // ================= TMA producer =================
         if (elect_one()) {
             const uint32_t wbytes = (uint32_t)nch * 8192u, dbytes = C::WDS ? (uint32_t)nch * (KS * KS * 128u) : 0u;
-            mbar_expect_tx(w_full, 2u * wbytes + dbytes);
+            mbar_expect_tx(w_full, (C::EXP ? 2u : 1u) * wbytes + dbytes);
             if (C::WDS) bulk_load(base + p.off_wd, p.wd_img, dbytes, w_full);
             for (uint32_t off = 0; off < wbytes; off += 32768u) {
                 const uint32_t n = wbytes - off < 32768u ? wbytes - off : 32768u;
-                bulk_load(base + p.off_we + off, reinterpret_cast<const uint8_t*>(p.we_img) + off, n, w_full);
+                if (C::EXP) bulk_load(base + p.off_we + off, reinterpret_cast<const uint8_t*>(p.we_img) + off, n, w_full);
                 bulk_load(base + p.off_wp + off, reinterpret_cast<const uint8_t*>(p.wp_img) + off, n, w_full);
             }
         }
@@ -211,17 +219,20 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
                             mbar_arrive(x_full + 8 * xr.slot);
                         } else {
                             mbar_expect_tx(x_full + 8 * xr.slot, (uint32_t)C::NPX * 128u);
-                            tma_load_4d(base + xr.slot * SLOT, &tmX, 0, x00 + sx * (C::STW * S), y00 + sy * (C::STH * S), b, x_full + 8 * xr.slot);
+                            // expand mode: the block input (all its channels) into the X ring; direct mode: chunk c of the hidden
+                            // tensor into E tile xr.slot (the tiles of team t are t and t + NT: jobs go round-robin)
+                            tma_load_4d(C::EXP ? base + xr.slot * SLOT : base + p.off_e + xr.slot * C::ESLOT, &tmX, C::EXP ? 0 : c * 32,
+                                        x00 + sx * (C::STW * S), y00 + sy * (C::STH * S), b, x_full + 8 * xr.slot);
                         }
                     }
                     __syncwarp();
                     TR(1, jt);
                     ++jt;
-                    xr.next(NX);
+                    xr.next(NXB);
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 1 && C::EXP) {
         // ================= expand issuer: one MMA group per job =================
         mbar_wait(w_full, 0);
         const uint32_t idesc32 = umma_idesc_tf32(32);
@@ -342,7 +353,10 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
         Ring xr, ar;
         const int xswz = row & 7;
         int jt = 0;
-        for (int i = 0; i < nblk; ++i) {
+        if (!C::EXP) {  // direct mode: this team only drains the projection accumulators
+            for (int i = 0; i < nblk; ++i) epilogue(i);
+        }
+        for (int i = 0; i < (C::EXP ? nblk : 0); ++i) {
             for (int cs = 0; cs < nch * NSUB; ++cs, ++jt) {
                 mbar_wait(x_full + 8 * xr.slot, xr.phase);
                 if (q == 0) TR(2, jt);
@@ -384,13 +398,13 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
             if (i > 0) epilogue(i - 1);  // one block behind: its projection has long been issued
             if (q == 0) TR(18, jt - 1);
         }
-        if (nblk > 0) epilogue(nblk - 1);
+        if (C::EXP && nblk > 0) epilogue(nblk - 1);
     } else if (warp >= 8) {
         // ================= compute teams: expand accumulator -> Swish -> E tile -> taps -> Swish -> hi/lo rows of the D operand =================
         constexpr int NROW = (C::YT - 1) * S + KS, NCOL = (C::XT - 1) * S + KS;
         const int team = (warp - 8) >> 2, q = warp & 3, row = q * 32 + lane;
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-        uint8_t* Es = sm + p.off_e + (size_t)team * C::ESLOT;
+        uint8_t* Es = sm + p.off_e + (size_t)team * C::ESLOT;  // direct mode: + NT * ESLOT for the second tile
         auto bar_team = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + team) : "memory"); };
         // depth-wise item of this thread (fixed): output block (by, bx) of the sub-tile, channels 4 * c4 .. + 3 of the chunk
         const int c4 = row & 7, blk = row >> 3;
@@ -409,10 +423,17 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
         };
         for (int t = 0; t < team; ++t) step();
         if (C::WDS) mbar_wait(w_full, 0);  // the tap image
-        for (int j = team; j < J; j += NT) {
+        uint32_t kjob = 0;  // this team's job counter (direct mode: E tile = kjob & 1, its barrier phase = (kjob >> 1) & 1)
+        for (int j = team; j < J; j += NT, ++kjob) {
+            const uint32_t xslot = (uint32_t)team + (kjob & 1u) * NT;
+            const uint8_t* ebj = eb + (C::EXP ? 0u : (kjob & 1u) * NT * C::ESLOT);
+            if (!C::EXP) {
+                mbar_wait(x_full + 8 * xslot, (kjob >> 1) & 1u);  // TMA has written this job's halo box of the hidden tensor
+                if (q == 0) TR(8, j);
+            }
             // ---- drain: this warp's lane quarter of the accumulator ----
-            mbar_wait(e_full + 8 * team, ephase);
-            if (q == 0) TR(8, j);
+            if (C::EXP) mbar_wait(e_full + 8 * team, ephase);
+            if (C::EXP && q == 0) TR(8, j);
             // probe the D hand-back now (non-blocking); the result is needed only after the depth-wise arithmetic
             const uint32_t fbar = d_free + 8 * (C::DFREE_PER_TEAM ? team : dr.slot), fpar = (C::DFREE_PER_TEAM ? fphase : dr.phase) ^ 1u;
             uint32_t d_ok;
@@ -423,29 +444,31 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
                 : "=r"(d_ok)
                 : "r"(fbar), "r"(fpar)
                 : "memory");
-            tc_fence_after();
-            float v[32];
-            tmem_ld32(lane_base + C::ECOL + (uint32_t)team * 32u, v);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(e_empty + 8 * team);  // the accumulator is in registers: the next job's MMAs may start
-            ephase ^= 1u;
-            if (q == 0) TR(9, j);
-            if (q * 32 < C::NPX && !(p.dbg & 1)) {  // warp-uniform: a quarter past the halo tile has nothing to do
-#pragma unroll
-                for (int g = 0; g < 16; ++g) swish2(v[2 * g], v[2 * g + 1]);
+            if (C::EXP) {
+                tc_fence_after();
+                float v[32];
+                tmem_ld32(lane_base + C::ECOL + (uint32_t)team * 32u, v);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(e_empty + 8 * team);  // the accumulator is in registers: the next job's MMAs may start
+                ephase ^= 1u;
+                if (q == 0) TR(9, j);
+                if (q * 32 < C::NPX && !(p.dbg & 1)) {  // warp-uniform: a quarter past the halo tile has nothing to do
+    #pragma unroll
+                    for (int g = 0; g < 16; ++g) swish2(v[2 * g], v[2 * g + 1]);
+                }
+                if (q == 0) TR(19, j);
+                bar_team();  // every warp of the team has finished the previous job's depth-wise reads of E
+                if (q == 0) TR(10, j);
+                if (row < C::NPX) {
+                    uint8_t* erow = Es + (size_t)row * C::EP;
+    #pragma unroll
+                    for (int g = 0; g < 8; ++g) *reinterpret_cast<float4*>(erow + 16 * g) = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+                }
+                bar_team();  // E complete
+                if (q == 0) TR(11, j);
             }
-            if (q == 0) TR(19, j);
-            bar_team();  // every warp of the team has finished the previous job's depth-wise reads of E
-            if (q == 0) TR(10, j);
-            if (row < C::NPX) {
-                uint8_t* erow = Es + (size_t)row * C::EP;
-#pragma unroll
-                for (int g = 0; g < 8; ++g) *reinterpret_cast<float4*>(erow + 16 * g) = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-            }
-            bar_team();  // E complete
-            if (q == 0) TR(11, j);
             // ---- depth-wise: one item per thread, results stay in registers until the D slot is free ----
             float4 acc[C::YT][C::XT];
 #pragma unroll
@@ -458,7 +481,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
                 for (int rr = 0; rr < NROW; ++rr) {
                     float4 win[NCOL];
 #pragma unroll
-                    for (int cc = 0; cc < NCOL; ++cc) win[cc] = *reinterpret_cast<const float4*>(eb + (rr * C::IW + cc) * (int)C::EP);
+                    for (int cc = 0; cc < NCOL; ++cc) win[cc] = *reinterpret_cast<const float4*>(ebj + (rr * C::IW + cc) * (int)C::EP);
 #pragma unroll
                     for (int dy = 0; dy < C::YT; ++dy) {
                         const int ky = rr - dy * S;
@@ -472,6 +495,10 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
                         }
                     }
                 }
+            }
+            if (!C::EXP) {  // the window loads have been consumed: TMA may refill this tile (job j + 2 NT)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(x_empty + 8 * xslot);
             }
             if (q == 0) TR(12, j);
             if (!d_ok) mbar_wait(fbar, fpar);  // the projection that read the slot last (per team: this team's previous operand) has retired
@@ -519,11 +546,13 @@ using MbfB1 = MbfCfg<3, 2, 16, 3, 8, 2, 2, 2, 1, 3, 3, true>;
 using MbfB2 = MbfCfg<3, 1, 24, 8, 10, 1, 1, 5, 1, 4, 2, false>;
 using MbfB3 = MbfCfg<5, 2, 24, 4, 4, 2, 4, 1, 1, 4, 2, false>;
 using MbfB4 = MbfCfg<5, 1, 32, 7, 7, 1, 2, 7, 1, 2, 2, false>;
+// direct mode (depth-wise + projection from the hidden tensor): 3x3 s1 with layer1.1's geometry
+using MbfD31 = MbfCfg<3, 1, 32, 8, 10, 1, 1, 5, 1, 4, 1, false, false>;
 
 struct MbfLaunch {
     CUtensorMap tmX;
     MbfParams p;
-    int kind = 0, grid = 0;  // kind: 1..4 = MbfB1..MbfB4
+    int kind = 0, grid = 0;  // kind: 1..4 = MbfB1..MbfB4, 5 = MbfD31 (direct)
     size_t smem = 0;
 };
 
@@ -539,7 +568,8 @@ inline bool mbf_supported(int ks, int s, int cin, int hid, int cout) { return mb
 template <typename C>
 inline int mbf_plan_t(PwTcState& st, MbfLaunch* ml, const float* X, int B, int Hi, int Wi, int cin) {
     MbfParams& p = ml->p;
-    int rc = xd_make_map(st, &ml->tmX, X, B, Hi, Wi, cin, C::IW, C::IH);
+    // expand mode: X = block input, SWIZZLE_128B boxes (read by the splitters); direct mode: X = hidden tensor, plain boxes = E tiles
+    int rc = xd_make_map(st, &ml->tmX, X, B, Hi, Wi, cin, C::IW, C::IH, /*swizzle=*/C::EXP);
     if (rc) return rc;
     p.Ho = Hi / C::S, p.Wo = Wi / C::S;
     p.blocks_x = cdiv(p.Wo, C::NSX * C::STW);
@@ -547,10 +577,10 @@ inline int mbf_plan_t(PwTcState& st, MbfLaunch* ml, const float* X, int B, int H
     const long long nb = (long long)B * p.blocks_x * p.blocks_y;
     if (nb * p.nch * C::NSUB > 0x3fffffffLL) return fail(CF_EINVAL, "mbf_plan: too many jobs");
     p.n_blocks = (int)nb;
-    p.off_e = C::NX * C::SLOT;
-    p.off_d = p.off_e + C::NT * C::ESLOT;
+    p.off_e = C::EXP ? C::NX * C::SLOT : 0u;
+    p.off_d = p.off_e + C::NT * C::NEB * C::ESLOT;
     p.off_we = p.off_d + C::ND * 2u * C::DHALF;
-    p.off_wp = p.off_we + (uint32_t)p.nch * 8192u;
+    p.off_wp = p.off_we + (C::EXP ? (uint32_t)p.nch * 8192u : 0u);
     p.off_wd = p.off_wp + (uint32_t)p.nch * 8192u;
     p.off_bars = (p.off_wd + (C::WDS ? (uint32_t)p.nch * (C::KS * C::KS * 128u) : 0u) + 127u) & ~127u;
     // the MMA reads 128 rows of every D half; rows past DROWS fall into whatever follows (unused accumulator lanes), which
@@ -599,6 +629,33 @@ inline int mbf_plan(PwTcState& st, int ks, int s, const float* X, const float* W
     }
 }
 
+// Direct mode: depth-wise + Swish + projection (+ residual) of one block from its HIDDEN tensor E [B,Hi,Wi,hid] (layer0: the stem
+// output; otherwise the expand conv's output).
+inline bool mbf_direct_supported(int ks, int s, int hid, int cout) { return ks == 3 && s == 1 && cout % 8 == 0 && cout <= 32 && hid % 4 == 0; }
+inline int mbf_plan_direct(PwTcState& st, int ks, int s, const float* E, const float* Wd, const float* Wp, float* Y, const float* res, int B, int Hi,
+                           int Wi, int hid, int cout, MbfLaunch* ml) {
+    if (!mbf_direct_supported(ks, s, hid, cout)) return fail(CF_EINVAL, "mbf_plan_direct: no kernel for k=%d s=%d hid=%d cout=%d", ks, s, hid, cout);
+    auto ip = st.layers.find(Wp);
+    if (ip == st.layers.end() || ip->second.NC != 32 || ip->second.nchunks != 1)
+        return fail(CF_EINVAL, "mbf_plan_direct: projection weights were not prepared as one 32-column image per K block");
+    auto id = st.dw_imgs.find(Wd);
+    if (id == st.dw_imgs.end()) return fail(CF_EINVAL, "mbf_plan_direct: depth-wise taps were not prepared as a chunk image");
+    MbfParams& p = ml->p;
+    p.we_img = nullptr;
+    p.wp_img = ip->second.img;
+    p.wd_img = id->second;
+    p.Wd = Wd;
+    p.Y = Y;
+    p.res = res;
+    p.B = B, p.Hi = Hi, p.Wi = Wi, p.hid = hid, p.cout = cout;
+    p.nch = (hid + 31) / 32;
+    p.dbg = 0;
+    if (const char* ev = getenv("CF_MBF_DEBUG")) p.dbg = atoi(ev);
+    p.trace = nullptr, p.tr_j0 = p.tr_nj = 0;
+    ml->kind = 5;
+    return mbf_plan_t<MbfD31>(st, ml, E, B, Hi, Wi, hid);
+}
+
 template <typename C>
 inline cudaError_t mbf_launch_t(const MbfLaunch& ml, cudaStream_t s) {
     cudaError_t e = smem_optin((const void*)k_mbf<C>, TC_SMEM_MAX);
@@ -612,6 +669,7 @@ inline cudaError_t mbf_launch(const MbfLaunch& ml, cudaStream_t s) {
         case 2: return mbf_launch_t<MbfB2>(ml, s);
         case 3: return mbf_launch_t<MbfB3>(ml, s);
         case 4: return mbf_launch_t<MbfB4>(ml, s);
+        case 5: return mbf_launch_t<MbfD31>(ml, s);
     }
     return cudaErrorInvalidValue;
 }

@@ -103,11 +103,13 @@ def test_time_steps_reports_every_launch(pkg, weights_path, variant_input):
     before = eng.launches
     ms, cls = eng.time_steps(2)
     nf = len(pkg._lib.fused_blocks(pkg.CF_PW_TCGEN05))  # a fused MBConv block is one launch instead of three
-    assert len(ms) == len(cls) == 43 - 2 * nf  # 41 layer-wise network launches + peak mask + top-k
+    nd = len(pkg._lib.dwp_blocks(pkg.CF_PW_TCGEN05))    # depth-wise + projection as one launch instead of two
+    n = 43 - 2 * nf - nd                               # 41 layer-wise network launches + peak mask + top-k
+    assert len(ms) == len(cls) == n
     assert all(t > 0 for t in ms)
-    assert cls[0] == pkg._lib.CLS_STEM and cls[-1] == pkg._lib.CLS_DECODE and cls.count(pkg._lib.CLS_PW) == 27 - 2 * nf
-    assert cls.count(pkg._lib.CLS_FUSED) == nf
-    assert eng.launches - before == (43 - 2 * nf) * 3  # one warm-up pass + two timed
+    assert cls[0] == pkg._lib.CLS_STEM and cls[-1] == pkg._lib.CLS_DECODE and cls.count(pkg._lib.CLS_PW) == 27 - 2 * nf - nd
+    assert cls.count(pkg._lib.CLS_FUSED) == nf + nd
+    assert eng.launches - before == n * 3  # one warm-up pass + two timed
     eng.close()
 
 

@@ -202,7 +202,7 @@ def test_bench_launch_table_matches_work_model(pkg):
         pw = sum(b for n, b in tab if "expand" in n or "project" in n or n.startswith(("conv_last", "up")))
         assert pw == L.work_model(h, w, L.CF_IN_U8_HWC, L.CLS_PW, L.CF_PW_TCGEN05_LAYERWISE)[0]
         # the default engine: every fused block is one launch credited with the bytes of the three it replaces
-        fused = L.fused_blocks(L.CF_PW_TCGEN05)
-        tabf = bench.launch_table(h, w, fused)
-        assert len(tabf) == 43 - sum(2 if bench.BLOCKS[i][2] != 1 else 1 for i in fused)
+        fused, dwp = L.fused_blocks(L.CF_PW_TCGEN05), L.dwp_blocks(L.CF_PW_TCGEN05)
+        tabf = bench.launch_table(h, w, fused, dwp)
+        assert len(tabf) == 43 - sum(2 if bench.BLOCKS[i][2] != 1 else 1 for i in fused) - len(dwp)
         assert sum(b for n, b in tabf) == sum(b for n, b in tab)

@@ -17,6 +17,7 @@ pkg = importlib.import_module("lightweight-face-detection-centernet_b200")
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--mask", default="0x2")
+ap.add_argument("--mbd", default="0", help="blocks whose depth-wise + projection run as one kernel (CF_MBD)")
 ap.add_argument("--batch", type=int, default=4)
 ap.add_argument("--size", type=int, default=640)
 ap.add_argument("--time", action="store_true")
@@ -29,8 +30,9 @@ imgs = np.stack([cv2.resize(cv2.imdecode(z["img_" + names[i % 5]], cv2.IMREAD_CO
 x = torch.from_numpy(imgs).cuda()
 
 
-def run(mask):
+def run(mask, mbd="0"):
     os.environ["CF_MBF"] = mask
+    os.environ["CF_MBD"] = mbd
     eng = pkg.Engine(W, max_batch=a.batch, max_h=a.size, max_w=a.size, device=0)
     eng.forward(x)
     torch.cuda.synchronize()
@@ -43,7 +45,7 @@ def run(mask):
 
 
 ref = run("0")
-got = run(a.mask)
+got = run(a.mask, a.mbd)
 bad = False
 for k in ref:
     if k == "inds":
@@ -57,9 +59,10 @@ for k in ref:
     print(f"{k:8s} max|ref|={m:10.4g} max|diff|={d:10.4g} rel={d / max(m, 1e-30):9.3g} nan={nan}")
     if nan or d / max(m, 1e-30) > 1e-4:
         bad = True
-print("MBF CHECK", "FAILED" if bad else "ok", "mask", a.mask)
+print("MBF CHECK", "FAILED" if bad else "ok", "mask", a.mask, "mbd", a.mbd)
 if a.time:
     os.environ["CF_MBF"] = a.mask
+    os.environ["CF_MBD"] = a.mbd
     eng = pkg.Engine(W, max_batch=a.tbatch, max_h=a.size, max_w=a.size, device=0)
     xt = torch.from_numpy(np.random.RandomState(0).randint(0, 256, size=(a.tbatch, a.size, a.size, 3), dtype=np.uint8)).cuda()
     eng.forward(xt)

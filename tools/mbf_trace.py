@@ -15,12 +15,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 ap = argparse.ArgumentParser()
 ap.add_argument("--mask", default="0x2")
+ap.add_argument("--mbd", default="0")
 ap.add_argument("--j0", type=int, default=200)
 ap.add_argument("--nj", type=int, default=40)
 ap.add_argument("--batch", type=int, default=32)
 ap.add_argument("--size", type=int, default=640)
 a = ap.parse_args()
 os.environ["CF_MBF"] = a.mask
+os.environ["CF_MBD"] = a.mbd
 os.environ["CF_MBF_TRACE"] = f"{a.j0},{a.nj}"
 pkg = importlib.import_module("lightweight-face-detection-centernet_b200")
 eng = pkg.Engine(os.path.join(ROOT, "tests", "golden", "weights_e100.npz"), max_batch=a.batch, max_h=a.size, max_w=a.size, device=0)
