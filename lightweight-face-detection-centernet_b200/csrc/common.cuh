@@ -210,14 +210,14 @@ __device__ __forceinline__ float4 idaup_apply(float4 acc, float4 lo, int n, int 
 
 template <int EPI>
 __device__ __forceinline__ float4 apply_epi(float4 acc, int m, int n, int N, const EpiArgs& ea) {
-    if (EPI == EPI_SWISH) return swish4(acc);
+    if (EPI == EPI_SWISH) return swish4p(acc);
     if (EPI == EPI_RESIDUAL) {
         float4 r = ldcg4(ea.res + (size_t)m * N + n);
         return make_float4(acc.x + r.x, acc.y + r.y, acc.z + r.z, acc.w + r.w);
     }
     if (EPI == EPI_BIAS_SWISH) {
         float4 b = ldg4(ea.bias + n);
-        return swish4(make_float4(acc.x + b.x, acc.y + b.y, acc.z + b.z, acc.w + b.w));
+        return swish4p(make_float4(acc.x + b.x, acc.y + b.y, acc.z + b.z, acc.w + b.w));
     }
     if (EPI == EPI_IDAUP) {
         int q;

@@ -72,7 +72,7 @@ __device__ __forceinline__ void xd_dw_phase_g(const uint8_t* Es, const float* Wd
 #pragma unroll
                 for (int kx = 0; kx < KS; ++kx) {
 #pragma unroll
-                    for (int dx = 0; dx < XT; ++dx) fma44(acc[dy][dx], win[dx * S + kx], wt[ky][kx]);
+                    for (int dx = 0; dx < XT; ++dx) fma44p(acc[dy][dx], win[dx * S + kx], wt[ky][kx]);
                 }
             }
         }
@@ -83,7 +83,7 @@ __device__ __forceinline__ void xd_dw_phase_g(const uint8_t* Es, const float* Wd
         for (int dy = 0; dy < YT; ++dy)
 #pragma unroll
             for (int dx = 0; dx < XT; ++dx) {
-                if (yo0 + dy < p.Ho && xo0 + dx < p.Wo) st4(o0 + dy * rstride + dx * p.hid, swish4(acc[dy][dx]));
+                if (yo0 + dy < p.Ho && xo0 + dx < p.Wo) st4(o0 + dy * rstride + dx * p.hid, swish4p(acc[dy][dx]));
             }
     }
 }

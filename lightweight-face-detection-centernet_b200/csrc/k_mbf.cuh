@@ -59,7 +59,10 @@ struct MbfCfg {
     static constexpr int NWARPS = 8 + 4 * NT, THREADS = NWARPS * 32;
     static constexpr int NBX = STW / XT, NITEMS = (STH / YT) * NBX * 8;  // depth-wise items: (output block, float4 of channels)
     // ring depths: X boxes, TMEM A slots, expand accumulators (one per team), D operands, projection accumulators
-    static constexpr int NX = NX_, NA = 4, NE = NT, ND = 2, NP = 2;
+    // (direct mode has the shared memory and the TMEM columns for one D operand and one projection accumulator per team: with two of
+    // each, a slot's cycle -- depth-wise tail, projection, epilogue -- bounded the job rate of the one-chunk layer0)
+    static constexpr int LAG = NSUB == 1 ? 2 : 1;  // expand mode: blocks between a block's splits and its epilogue (see the splitter role)
+    static constexpr int NX = NX_, NE = NT, ND = EXP_ ? 2 : NT, NP = EXP_ ? LAG + 1 : 4, NA = NP == 3 ? 3 : 4;
     static constexpr bool WDS = WDS_;  // depth-wise taps resident in shared memory (else read through L1 from the chunk image)
     // D operand hand-back (projection retired -> the slot may be rewritten): one barrier per SLOT when every use of a slot is
     // written by the same set of teams ((ND * NSUB) % NT == 0), one barrier per WRITER TEAM when a D operand is one job (NSUB == 1)
@@ -81,7 +84,7 @@ struct MbfCfg {
     static_assert(DROWS <= 128, "a block's outputs are the rows of one projection accumulator");
     static_assert(STW % XT == 0 && STH % YT == 0, "output blocks tile the sub-tile");
     static_assert(TD_ >= 0, "legacy parameter");
-    static_assert(ACOL + NA * 64 <= 512, "TMEM budget");
+    static_assert(EXP_ ? ACOL + NA * 64 <= 512 : NP * 64 <= 512, "TMEM budget");
     static_assert(!EXP || (CIN % 8 == 0 && CIN <= 32), "expand K");
 };
 
@@ -186,6 +189,23 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
         }
     };
 
+    // This CTA's blocks are blockIdx.x, + gridDim.x, ...: (bx, by, b) advance by a fixed carry-propagating step (no division per block)
+    struct BlockWalk {
+        int bx, by, b, sx, sy, sb, nx, ny;
+        __device__ __forceinline__ void init(int first, int step, int nx_, int ny_) {
+            nx = nx_, ny = ny_;
+            bx = first % nx, by = (first / nx) % ny, b = first / (nx * ny);
+            sx = step % nx, sy = (step / nx) % ny, sb = step / (nx * ny);
+        }
+        __device__ __forceinline__ void next() {
+            bx += sx;
+            if (bx >= nx) bx -= nx, ++by;
+            by += sy;
+            if (by >= ny) by -= ny, ++b;
+            b += sb;
+        }
+    };
+
     if (warp == 0) {
         // ================= TMA producer =================
         if (elect_one()) {
@@ -202,11 +222,10 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
         pdl_wait();  // X is the previous kernel's output
         Ring xr;
         int jt = 0;
-        for (int i = 0; i < nblk; ++i) {
-            int t = (int)blockIdx.x + i * (int)gridDim.x;
-            const int bx = t % p.blocks_x;
-            t /= p.blocks_x;
-            const int by = t % p.blocks_y, b = t / p.blocks_y;
+        BlockWalk bw;
+        bw.init((int)blockIdx.x, (int)gridDim.x, p.blocks_x, p.blocks_y);
+        for (int i = 0; i < nblk; ++i, bw.next()) {
+            const int bx = bw.bx, by = bw.by, b = bw.b;
             const int x00 = bx * (C::NSX * C::STW * S) - C::LO, y00 = by * (C::NSY * C::STH * S) - C::LO;
             for (int c = 0; c < nch; ++c) {
 #pragma unroll
@@ -312,35 +331,57 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
         const int rsy = rs / C::NSX, rsx = rs - rsy * C::NSX;
         const int roy = rsy * C::STH + rl / C::STW, rox = rsx * C::STW + rl % C::STW;
         Ring pr;
-        auto epilogue = [&](int i) {
-            int t = (int)blockIdx.x + i * (int)gridDim.x;
-            const int bx = t % p.blocks_x;
-            t /= p.blocks_x;
-            const int by = t % p.blocks_y, b = t / p.blocks_y;
+        BlockWalk ew;  // the epilogues run in block order
+        ew.init((int)blockIdx.x, (int)gridDim.x, p.blocks_x, p.blocks_y);
+        auto epilogue = [&](int) {
+            const int bx = ew.bx, by = ew.by, b = ew.b;
+            ew.next();
             const int yo = by * (C::NSY * C::STH) + roy, xo = bx * (C::NSX * C::STW) + rox;
             const bool valid = row < C::DROWS && yo < p.Ho && xo < p.Wo && !(p.dbg & 4);
             const size_t pix = ((size_t)(b * p.Ho + yo) * p.Wo + xo) * (size_t)p.cout;
-            // the residual does not depend on the accumulator: its (L2) latency runs under the wait below
-            float4 rs[8];
-#pragma unroll
-            for (int h = 0; h < 8; ++h) rs[h] = (valid && p.res && 4 * h < p.cout) ? ldcg4(p.res + pix + 4 * h) : make_float4(0, 0, 0, 0);
-            mbar_wait(p_full + 8 * pr.slot, pr.phase);
-            tc_fence_after();
             const uint32_t taddr = lane_base + C::PCOL + (uint32_t)pr.slot * 64u;
+            if (p.res) {
+                // the residual does not depend on the accumulator: its (L2) latency runs under the wait below
+                float4 rs[8];
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                const int c0 = 8 * g;
-                if (c0 < p.cout) {  // warp-uniform
-                    float v[8], cr[8];
-                    tmem_ld8(taddr + (uint32_t)c0, v);
-                    tmem_ld8(taddr + 32u + (uint32_t)c0, cr);
-                    tmem_ld_wait();
-                    if (valid) {
+                for (int h = 0; h < 8; ++h) rs[h] = (valid && 4 * h < p.cout) ? ldcg4(p.res + pix + 4 * h) : make_float4(0, 0, 0, 0);
+                mbar_wait(p_full + 8 * pr.slot, pr.phase);
+                tc_fence_after();
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const float4 r4 = rs[2 * g + h];
-                            st4(p.Y + pix + c0 + 4 * h, make_float4(v[4 * h] + cr[4 * h] + r4.x, v[4 * h + 1] + cr[4 * h + 1] + r4.y,
-                                                                    v[4 * h + 2] + cr[4 * h + 2] + r4.z, v[4 * h + 3] + cr[4 * h + 3] + r4.w));
+                for (int g = 0; g < 4; ++g) {
+                    const int c0 = 8 * g;
+                    if (c0 < p.cout) {  // warp-uniform
+                        float v[8], cr[8];
+                        tmem_ld8(taddr + (uint32_t)c0, v);
+                        tmem_ld8(taddr + 32u + (uint32_t)c0, cr);
+                        tmem_ld_wait();
+                        if (valid) {
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const float4 r4 = rs[2 * g + h];
+                                st4(p.Y + pix + c0 + 4 * h, make_float4(v[4 * h] + cr[4 * h] + r4.x, v[4 * h + 1] + cr[4 * h + 1] + r4.y,
+                                                                        v[4 * h + 2] + cr[4 * h + 2] + r4.z, v[4 * h + 3] + cr[4 * h + 3] + r4.w));
+                            }
+                        }
+                    }
+                }
+            } else {
+                mbar_wait(p_full + 8 * pr.slot, pr.phase);
+                tc_fence_after();
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {  // 16 columns per TMEM round trip
+                    const int c0 = 16 * g;
+                    if (c0 < p.cout) {  // warp-uniform
+                        float v[16], cr[16];
+                        tmem_ld16(taddr + (uint32_t)c0, v);
+                        tmem_ld16(taddr + 32u + (uint32_t)c0, cr);
+                        tmem_ld_wait();
+                        if (valid) {
+#pragma unroll
+                            for (int h = 0; h < 4; ++h)
+                                if (c0 + 4 * h < p.cout)
+                                    st4(p.Y + pix + c0 + 4 * h,
+                                        make_float4(v[4 * h] + cr[4 * h], v[4 * h + 1] + cr[4 * h + 1], v[4 * h + 2] + cr[4 * h + 2], v[4 * h + 3] + cr[4 * h + 3]));
                         }
                     }
                 }
@@ -354,8 +395,16 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
         const int xswz = row & 7;
         int jt = 0;
         if (!C::EXP) {  // direct mode: this team only drains the projection accumulators
-            for (int i = 0; i < nblk; ++i) epilogue(i);
+            for (int i = 0; i < nblk; ++i) {
+                if (q == 0) TR(17, (i + 1) * nch * NSUB - 1);
+                epilogue(i);
+                if (q == 0) TR(18, (i + 1) * nch * NSUB - 1);
+            }
         }
+        // Expand mode: the epilogue of block i - LAG runs after the splits of block i.  LAG blocks must cover the pipeline behind the
+        // splitters (~10 jobs from a split to its projection's retirement): a one-job-per-chunk block (NSUB == 1) is only nch jobs
+        // long, and waiting for its projection stalled the splitters, and through them every stage (B2 trace: 4200 cycles per block).
+        int epi_done = 0;
         for (int i = 0; i < (C::EXP ? nblk : 0); ++i) {
             for (int cs = 0; cs < nch * NSUB; ++cs, ++jt) {
                 mbar_wait(x_full + 8 * xr.slot, xr.phase);
@@ -394,11 +443,13 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
                 xr.next(NX);
                 ar.next(NA);
             }
-            if (q == 0) TR(17, jt - 1);
-            if (i > 0) epilogue(i - 1);  // one block behind: its projection has long been issued
-            if (q == 0) TR(18, jt - 1);
+            if (i >= C::LAG) {
+                if (q == 0) TR(17, jt - 1);
+                epilogue(epi_done++);
+                if (q == 0) TR(18, jt - 1);
+            }
         }
-        if (C::EXP && nblk > 0) epilogue(nblk - 1);
+        while (C::EXP && epi_done < nblk) epilogue(epi_done++);  // the tail: nothing left to split
     } else if (warp >= 8) {
         // ================= compute teams: expand accumulator -> Swish -> E tile -> taps -> Swish -> hi/lo rows of the D operand =================
         constexpr int NROW = (C::YT - 1) * S + KS, NCOL = (C::XT - 1) * S + KS;
@@ -591,6 +642,18 @@ inline int mbf_plan_t(PwTcState& st, MbfLaunch* ml, const float* X, int B, int H
     return CF_OK;
 }
 
+inline int mbf_trace_setup(PwTcState& st, MbfParams& p) {  // development: CF_MBF_TRACE="j0,nj", read back with cf_debug_mbf_trace
+    p.trace = nullptr, p.tr_j0 = p.tr_nj = 0;
+    if (const char* ev = getenv("CF_MBF_TRACE")) {
+        if (sscanf(ev, "%d,%d", &p.tr_j0, &p.tr_nj) == 2 && p.tr_nj > 0 && p.tr_nj <= 4096) {
+            if (!st.trace_buf && cudaMalloc((void**)&st.trace_buf, 4096 * 32 * 8) != cudaSuccess) return fail(CF_ECUDA, "mbf_plan: trace buffer");
+            cudaMemset(st.trace_buf, 0, 4096 * 32 * 8);
+            p.trace = st.trace_buf;
+        }
+    }
+    return CF_OK;
+}
+
 inline int mbf_plan(PwTcState& st, int ks, int s, const float* X, const float* We, const float* Wd, const float* Wp, float* Y, const float* res,
                     int B, int Hi, int Wi, int cin, int hid, int cout, MbfLaunch* ml) {
     if (!mbf_supported(ks, s, cin, hid, cout)) return fail(CF_EINVAL, "mbf_plan: no fused kernel for k=%d s=%d cin=%d cout=%d", ks, s, cin, cout);
@@ -612,14 +675,7 @@ inline int mbf_plan(PwTcState& st, int ks, int s, const float* X, const float* W
     p.nch = (hid + 31) / 32;
     p.dbg = 0;
     if (const char* ev = getenv("CF_MBF_DEBUG")) p.dbg = atoi(ev);
-    p.trace = nullptr, p.tr_j0 = p.tr_nj = 0;
-    if (const char* ev = getenv("CF_MBF_TRACE")) {  // "j0,nj": the buffer is read back with cf_debug_mbf_trace
-        if (sscanf(ev, "%d,%d", &p.tr_j0, &p.tr_nj) == 2 && p.tr_nj > 0 && p.tr_nj <= 4096) {
-            if (!st.trace_buf && cudaMalloc((void**)&st.trace_buf, 4096 * 32 * 8) != cudaSuccess) return fail(CF_ECUDA, "mbf_plan: trace buffer");
-            cudaMemset(st.trace_buf, 0, 4096 * 32 * 8);
-            p.trace = st.trace_buf;
-        }
-    }
+    if (int rc = mbf_trace_setup(st, p)) return rc;
     ml->kind = mbf_kind(ks, s, cin);
     switch (ml->kind) {
         case 1: return mbf_plan_t<MbfB1>(st, ml, X, B, Hi, Wi, cin);
@@ -651,7 +707,7 @@ inline int mbf_plan_direct(PwTcState& st, int ks, int s, const float* E, const f
     p.nch = (hid + 31) / 32;
     p.dbg = 0;
     if (const char* ev = getenv("CF_MBF_DEBUG")) p.dbg = atoi(ev);
-    p.trace = nullptr, p.tr_j0 = p.tr_nj = 0;
+    if (int rc = mbf_trace_setup(st, p)) return rc;
     ml->kind = 5;
     return mbf_plan_t<MbfD31>(st, ml, E, B, Hi, Wi, hid);
 }

@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(STC2_THREADS, 1) k_stem_tc2(const StcParams p)
 #pragma unroll
             for (int j = 0; j < 8; ++j)
                 *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-                    swish4(make_float4(v[4 * j] + c[4 * j], v[4 * j + 1] + c[4 * j + 1], v[4 * j + 2] + c[4 * j + 2], v[4 * j + 3] + c[4 * j + 3]));
+                    swish4p(make_float4(v[4 * j] + c[4 * j], v[4 * j + 1] + c[4 * j + 1], v[4 * j + 2] + c[4 * j + 2], v[4 * j + 3] + c[4 * j + 3]));
             __syncwarp();
             const long long pix0 = (long long)tile * TC_BM + q * 32;
 #pragma unroll

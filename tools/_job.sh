@@ -1,3 +1,2 @@
-timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-300
-timeout 120 python tools/mbf_trace.py --mask 0 --mbd 0x1 --j0 100 --nj 40 2>&1 | tail -22
+timeout 120 python tools/mbf_check.py --mask 0x6 --mbd 0x1 --time 2>&1 | grep -E "block[0-2] |inds|MBF|fused|rror"
+timeout 120 python tools/mbf_trace.py --mask 0x4 --j0 100 --nj 40 2>&1 | tail -21

@@ -50,7 +50,7 @@ for e in (1, 4, 7, 14):
     v = col(e)
     if len(v) > 2:
         print(f"{names[e]:9s}: mean interval {np.diff(v).mean():8.1f} cycles over {len(v)} jobs")
-pairs = [(0, 1), (2, 3), (3, 4), (5, 6), (6, 7), (8, 9), (9, 19), (19, 10), (10, 11), (11, 12), (12, 13), (13, 14), (7, 8), (4, 5), (1, 2)]
+pairs = [(17, 18), (16, 18), (14, 15), (15, 16), (0, 1), (2, 3), (3, 4), (5, 6), (6, 7), (8, 9), (9, 19), (19, 10), (10, 11), (11, 12), (12, 13), (13, 14), (7, 8), (4, 5), (1, 2)]
 for a_, b_ in pairs:
     m = (t[:, a_] > 0) & (t[:, b_] > 0)
     if m.any():

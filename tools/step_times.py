@@ -12,19 +12,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 pkg = importlib.import_module("lightweight-face-detection-centernet_b200")
 
-BLOCKS = [(32, 16, 1, 3, 1), (16, 24, 6, 3, 2), (24, 24, 6, 3, 1), (24, 32, 6, 5, 2), (32, 32, 6, 5, 1), (32, 64, 6, 3, 2),
-          (64, 64, 6, 3, 1), (64, 96, 6, 5, 1), (96, 96, 6, 5, 1), (96, 160, 6, 5, 2), (160, 160, 6, 5, 1), (160, 320, 6, 3, 1)]
-
-
-def names():
-    out = ["stem 3->32 s2"]
-    for i, (cin, cout, t, k, s) in enumerate(BLOCKS):
-        if t != 1:
-            out.append(f"b{i} expand {cin}->{cin * t}")
-        out.append(f"b{i} dw{k} s{s} {cin * t}ch")
-        out.append(f"b{i} project {cin * t}->{cout}" + (" +res" if cin == cout and s == 1 else ""))
-    out += ["conv_last 320->24", "up1 96->24", "up2 32->24", "up3 24->24", "heads 3x3 24->15", "peak mask", "top-k"]
-    return out
+def names(pw, size):
+    """Launch names of the engine's plan: bench.py's table for the engine's fused-block masks + the decode kernels."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    return [n for n, _ in bench.launch_table(size, size, pkg._lib.fused_blocks(pw), pkg._lib.dwp_blocks(pw))]
 
 
 def main():
@@ -41,7 +35,7 @@ def main():
     eng.decode_topk(100)
     torch.cuda.synchronize()
     ms, cls = eng.time_steps(a.iters)
-    nm = names()
+    nm = names(a.pw, a.size)
     if len(nm) != len(ms):
         nm = [f"step {i}" for i in range(len(ms))]
     cname = {1: "pw", 2: "dw", 3: "stem", 4: "heads", 5: "decode", 6: "fused"}
