@@ -417,10 +417,10 @@ def run_b200(a):
                                 "frac_hbm": round(v["gbs"] / hbm, 4), "TFLOPs": round(v["tflops"], 2), "launches": v["launches"]}
                             for k, v in classes.items()}}
     try:  # measured DRAM bytes of the dominant class (ncu, committed under profiles/), if it matches this run
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1c.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r2.json")))
         if (tj.get("engine"), tj.get("batch"), tj.get("h"), tj.get("w")) == (pw, B, H, W):
             roofline["traffic"] = tj["dram_bytes_per_step"].get(top)
-            roofline["traffic_source"] = "profiles/traffic_r1c.json"
+            roofline["traffic_source"] = "profiles/traffic_r2.json"
     except Exception:
         pass
     try:  # the individual launches, timed one by one (events between launches: no overlap of neighbouring kernels)

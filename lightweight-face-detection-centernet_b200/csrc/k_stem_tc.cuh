@@ -200,7 +200,10 @@ __global__ void __launch_bounds__(STC_THREADS, 3) k_stem_tc(const StcParams p) {
 //   warps 12-19  two drain groups (accumulator stages alternate): tcgen05.ld main + correction, Swish, 128-byte row store
 //   warp 0       loads the 8 KB weight image once; warp 2 owns the TMEM allocation (512 columns, one CTA per SM)
 constexpr int STC2_THREADS = 640;
-constexpr uint32_t STC2_OFF_BARS = STC_OFF_LUT + 776 * 4;    // table of 768 + entry 768 = 0.0f (taps that fall in the zero padding)
+// table of 768 + entry 768 = 0.0f (taps that fall in the zero padding); the barriers start on their own 128-byte line (the table is
+// filled with generic stores after mbarrier.init: compute-sanitizer synccheck tracks barrier validity per line and reported the
+// first wait on a barrier sharing the table's last line as "missing init", profiles/r2_sanitizer.md)
+constexpr uint32_t STC2_OFF_BARS = (STC_OFF_LUT + 776 * 4 + 127u) & ~127u;
 constexpr uint32_t STC2_OFF_STG = STC2_OFF_BARS + 256;      // 8 drain warps x 4 KB store-transpose tiles
 constexpr size_t STC2_SMEM = STC2_OFF_STG + 8 * 4096 + 1024;
 
