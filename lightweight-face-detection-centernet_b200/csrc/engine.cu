@@ -45,7 +45,7 @@ inline int layer_passes(int pw, int K, int N) {
 // Whole-block fusion (k_mbf): the default tensor-core engine runs the blocks of this mask (bit i = block i) as one kernel each;
 // CF_PW_TCGEN05_LAYERWISE is the same engine without it.  The mask holds the blocks whose fused kernel beats its three
 // layer-wise launches on the device (profiles/r2_mbf.md); CF_MBF overrides it for A/B runs.
-constexpr unsigned kMbfDefaultMask = 0x2u;
+constexpr unsigned kMbfDefaultMask = 0x6u;  // layer1.0 (616 -> 460 us), layer1.1 (421 -> 382 us)
 inline unsigned mbf_mask() {
     if (const char* ev = getenv("CF_MBF")) return (unsigned)strtoul(ev, nullptr, 0);
     return kMbfDefaultMask;

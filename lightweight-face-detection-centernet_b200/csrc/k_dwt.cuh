@@ -91,13 +91,13 @@ __device__ __forceinline__ void xd_dw_phase_g(const uint8_t* Es, const float* Wd
 
 // ---- host side --------------------------------------------------------------------------
 // fp32 NHWC tensor [B][H][W][C]: box {32 channels (zero filled past C), IW, IH, 1}, SWIZZLE_128B
-inline int xd_make_map(PwTcState& st, CUtensorMap* map, const float* ptr, int B, int H, int W, int C, int IW, int IH, bool swizzle = true) {
+inline int xd_make_map(PwTcState& st, CUtensorMap* map, const float* ptr, int B, int H, int W, int C, int IW, int IH, int swizzle = 1, int box_c = 32) {  // swizzle: 0 none, 1 SWIZZLE_128B, 2 SWIZZLE_64B (box_c <= 16)
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-    cuuint32_t box[4] = {32, (cuuint32_t)IW, (cuuint32_t)IH, 1};
+    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)IW, (cuuint32_t)IH, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = ((PFN_encodeTiled)st.encode)(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box, estr,
-                                              CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                                              CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
                                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(CF_ECUDA, "cuTensorMapEncodeTiled(4D %dx%dx%dx%d) failed with CUresult %d", B, H, W, C, (int)r);
     return CF_OK;

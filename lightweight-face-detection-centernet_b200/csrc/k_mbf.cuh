@@ -44,7 +44,7 @@
 
 namespace cf {
 
-template <int KS_, int S_, int CIN_, int STH_, int STW_, int NSY_, int NSX_, int XT_, int YT_, int TD_, int NX_, bool WDS_, bool EXP_ = true>
+template <int KS_, int S_, int CIN_, int STH_, int STW_, int NSY_, int NSX_, int XT_, int YT_, int TD_, int NX_, bool WDS_, bool EXP_ = true, int NT_ = 4>
 struct MbfCfg {
     static constexpr int KS = KS_, S = S_, CIN = CIN_, STH = STH_, STW = STW_, NSY = NSY_, NSX = NSX_, XT = XT_, YT = YT_, TD = TD_;
     static constexpr int IH = (STH - 1) * S + KS, IW = (STW - 1) * S + KS, NPX = IH * IW;
@@ -55,22 +55,41 @@ struct MbfCfg {
     // resolution -- layer0 (t = 1, no expand conv) or a block whose expand conv stays a k_pw_tc launch -- and TMA writes its
     // 32-channel halo boxes straight into the teams' E tiles (two per team): the kernel is depth-wise + Swish + projection.
     static constexpr bool EXP = EXP_;
-    static constexpr int NT = 4;  // compute teams (four warps each: one per TMEM lane quarter)
+    static constexpr int NT = NT_;  // compute teams (four warps each: one per TMEM lane quarter); 4 -> 80 registers per thread, 5 -> 72
     static constexpr int NWARPS = 8 + 4 * NT, THREADS = NWARPS * 32;
     static constexpr int NBX = STW / XT, NITEMS = (STH / YT) * NBX * 8;  // depth-wise items: (output block, float4 of channels)
     // ring depths: X boxes, TMEM A slots, expand accumulators (one per team), D operands, projection accumulators
     // (direct mode has the shared memory and the TMEM columns for one D operand and one projection accumulator per team: with two of
     // each, a slot's cycle -- depth-wise tail, projection, epilogue -- bounded the job rate of the one-chunk layer0)
-    static constexpr int LAG = NSUB == 1 ? 2 : 1;  // expand mode: blocks between a block's splits and its epilogue (see the splitter role)
-    static constexpr int NX = NX_, NE = NT, ND = EXP_ ? 2 : NT, NP = EXP_ ? LAG + 1 : 4, NA = NP == 3 ? 3 : 4;
+    // Who drains a block's projection accumulator (+ residual, Y stores).  A one-job-per-chunk block (NSUB == 1) is nch jobs long,
+    // shorter than the ~10-job pipeline behind the splitters: waiting for its projection on the splitter warps stalled every stage
+    // (B2 trace: 4 200 cycles per block), and a single epilogue team bounded the one-chunk layer0 (1 000 cycles per job).  There the
+    // COMPUTE TEAM that produced a block's last chunk drains it, one job later, when it has just observed the D hand-back (the
+    // projection issuer is in order: that block's projection has retired).  Otherwise the splitters do it, one block behind.
+    static constexpr bool TEAM_EPI = EXP_ && NSUB == 1;  // direct mode: measured slower on the teams (layer0 205 -> 249 us), the splitter warps are idle there
+    static constexpr int NX = NX_, NE = NT, ND = EXP_ ? 2 : NT, NP = EXP_ ? 2 : 4;
+    // TMEM A slots (the split block input).  A slot holds one sub-tile for ALL the chunks of its block: the splitters (and the X box
+    // TMA) run once per (block, sub-tile), the expand issuer re-reads the slot with each chunk's weights and hands it back after the
+    // last one.  Slots come in groups of NSUB (one block); NG groups rotate block by block.
+    static constexpr int AW = KSTEPS <= 2 ? 32 : 64;  // columns per slot: hi | lo, 8 * KSTEPS each
+    static constexpr int NA_AVAIL = (512 - NP * 64 - NE * 32) / AW;
+    static constexpr int NG = EXP_ ? ((NA_AVAIL < 8 ? NA_AVAIL : 8) / NSUB < 4 ? (NA_AVAIL < 8 ? NA_AVAIL : 8) / NSUB : 4) : 1;
+    static constexpr int NA = EXP_ ? NG * NSUB : 4;
     static constexpr bool WDS = WDS_;  // depth-wise taps resident in shared memory (else read through L1 from the chunk image)
-    // D operand hand-back (projection retired -> the slot may be rewritten): one barrier per SLOT when every use of a slot is
-    // written by the same set of teams ((ND * NSUB) % NT == 0), one barrier per WRITER TEAM when a D operand is one job (NSUB == 1)
-    static constexpr bool DFREE_PER_TEAM = (ND * NSUB) % NT != 0;
+    // D operand hand-back (projection retired -> the slot may be rewritten).  NSUB == 1 (an operand is one job): one barrier per
+    // WRITER TEAM unless the teams map onto the slots one to one.  NSUB > 1: one barrier per SLOT; a team derives the parity it
+    // waits for from the operand index, and may skip operands (NT does not divide ND * NSUB).  That is safe while a team's
+    // consecutive jobs are at most ND operands apart (NT <= ND * NSUB): before its previous job it observed the retirement of
+    // operand >= k - 2 ND, the issuer retires in order, so the slot's barrier is at most ONE phase behind the awaited one -- the
+    // only distance at which a parity wait cannot alias.
+    static constexpr bool DFREE_PER_TEAM = NSUB == 1 && ND % NT != 0;
     static constexpr int NDF = DFREE_PER_TEAM ? NT : ND;
-    static_assert(!DFREE_PER_TEAM || NSUB == 1, "D hand-back: per slot, or per team for one-job operands");
+    static_assert(NSUB == 1 || NT <= ND * NSUB, "D hand-back by slot: a team must not fall two phases behind a slot's barrier");
+    static_assert(!EXP_ || NG >= 1, "TMEM: one block of A slots");
     static_assert(NITEMS <= 128, "one depth-wise item per thread of a team");
-    static constexpr uint32_t SLOT = 16384;                         // X box: 128 rows x 128 B (SWIZZLE_128B, written by TMA)
+    // X box (written by TMA, read by the splitters): 128 pixel rows of 128 B, SWIZZLE_128B; a 16-channel input (layer1.0) takes
+    // 64-byte rows, SWIZZLE_64B -- half the ring bytes per slot, which is what lets a deeper ring cover the TMA latency
+    static constexpr uint32_t XROW = (EXP_ && CIN_ <= 16) ? 64 : 128, SLOT = 128 * XROW;
     // E slot: pixel rows at a 144-byte pitch instead of a swizzle -- the drain's stores (a lane = a pixel, 8 consecutive pixels
     // per quarter warp) and the depth-wise loads (8 lanes = the 128 bytes of one pixel) are both bank-conflict free, and every
     // window address is one base register + an immediate
@@ -84,7 +103,7 @@ struct MbfCfg {
     static_assert(DROWS <= 128, "a block's outputs are the rows of one projection accumulator");
     static_assert(STW % XT == 0 && STH % YT == 0, "output blocks tile the sub-tile");
     static_assert(TD_ >= 0, "legacy parameter");
-    static_assert(EXP_ ? ACOL + NA * 64 <= 512 : NP * 64 <= 512, "TMEM budget");
+    static_assert(EXP_ ? ACOL + NA * AW <= 512 : NP * 64 <= 512, "TMEM budget");
     static_assert(!EXP || (CIN % 8 == 0 && CIN <= 32), "expand K");
 };
 
@@ -154,7 +173,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
         for (int i = 0; i < NXB; ++i) mbar_init(x_full + 8 * i, 1), mbar_init(x_empty + 8 * i, 4);
-        for (int i = 0; i < NA; ++i) mbar_init(a_full + 8 * i, 4), mbar_init(a_empty + 8 * i, 1);
+        for (int i = 0; i < NA; ++i) mbar_init(a_full + 8 * i, 4), mbar_init(a_empty + 8 * i, 2);  // hand-back: one commit per expand issuer
         for (int i = 0; i < NE; ++i) mbar_init(e_full + 8 * i, 1), mbar_init(e_empty + 8 * i, 4);
         for (int i = 0; i < ND; ++i) mbar_init(d_full + 8 * i, NSUB * 4);
         for (int i = 0; i < NDF; ++i) mbar_init(d_free + 8 * i, 1);
@@ -162,7 +181,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
         mbar_init(w_full, 1);
         fence_barrier_init();
     }
-    if (warp == 2) {
+    if (warp == 3) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -206,6 +225,65 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
         }
     };
 
+    // Projection epilogue of one block: this warp's lane quarter of accumulator slot `ps` (+ residual) -> Y, then the slot is handed back.
+    auto epilogue_block = [&](int ps, uint32_t pphase, int bx, int by, int b, int row, uint32_t lane_base) {
+        const int rs = row / C::SPX, rl = row - rs * C::SPX;  // accumulator row -> output pixel of the block
+        const int rsy = rs / C::NSX, rsx = rs - rsy * C::NSX;
+        const int yo = by * (C::NSY * C::STH) + rsy * C::STH + rl / C::STW, xo = bx * (C::NSX * C::STW) + rsx * C::STW + rl % C::STW;
+        const bool valid = row < C::DROWS && yo < p.Ho && xo < p.Wo && !(p.dbg & 4);
+        const size_t pix = ((size_t)(b * p.Ho + yo) * p.Wo + xo) * (size_t)p.cout;
+        const uint32_t taddr = lane_base + C::PCOL + (uint32_t)ps * 64u;
+        if (p.res) {
+            // the residual does not depend on the accumulator: its (L2) latency runs under the wait below
+            float4 rs4[8];
+#pragma unroll
+            for (int h = 0; h < 8; ++h) rs4[h] = (valid && 4 * h < p.cout) ? ldcg4(p.res + pix + 4 * h) : make_float4(0, 0, 0, 0);
+            mbar_wait(p_full + 8 * ps, pphase);
+            tc_fence_after();
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int c0 = 8 * g;
+                if (c0 < p.cout) {  // warp-uniform
+                    float v[8], cr[8];
+                    tmem_ld8(taddr + (uint32_t)c0, v);
+                    tmem_ld8(taddr + 32u + (uint32_t)c0, cr);
+                    tmem_ld_wait();
+                    if (valid) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const float4 r4 = rs4[2 * g + h];
+                            st4(p.Y + pix + c0 + 4 * h, make_float4(v[4 * h] + cr[4 * h] + r4.x, v[4 * h + 1] + cr[4 * h + 1] + r4.y,
+                                                                    v[4 * h + 2] + cr[4 * h + 2] + r4.z, v[4 * h + 3] + cr[4 * h + 3] + r4.w));
+                        }
+                    }
+                }
+            }
+        } else {
+            mbar_wait(p_full + 8 * ps, pphase);
+            tc_fence_after();
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {  // 16 columns per TMEM round trip
+                const int c0 = 16 * g;
+                if (c0 < p.cout) {  // warp-uniform
+                    float v[16], cr[16];
+                    tmem_ld16(taddr + (uint32_t)c0, v);
+                    tmem_ld16(taddr + 32u + (uint32_t)c0, cr);
+                    tmem_ld_wait();
+                    if (valid) {
+#pragma unroll
+                        for (int h = 0; h < 4; ++h)
+                            if (c0 + 4 * h < p.cout)
+                                st4(p.Y + pix + c0 + 4 * h,
+                                    make_float4(v[4 * h] + cr[4 * h], v[4 * h + 1] + cr[4 * h + 1], v[4 * h + 2] + cr[4 * h + 2], v[4 * h + 3] + cr[4 * h + 3]));
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_empty + 8 * ps);
+    };
+
     if (warp == 0) {
         // ================= TMA producer =================
         if (elect_one()) {
@@ -227,7 +305,8 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
         for (int i = 0; i < nblk; ++i, bw.next()) {
             const int bx = bw.bx, by = bw.by, b = bw.b;
             const int x00 = bx * (C::NSX * C::STW * S) - C::LO, y00 = by * (C::NSY * C::STH * S) - C::LO;
-            for (int c = 0; c < nch; ++c) {
+            for (int c = 0; c < (C::EXP ? 1 : nch); ++c) {  // expand mode: one box per (block, sub-tile), shared by the chunks
+                if (C::EXP) jt = i * nch * NSUB;
 #pragma unroll
                 for (int s = 0; s < NSUB; ++s) {
                     const int sy = s / C::NSX, sx = s % C::NSX;  // compile-time after unrolling
@@ -237,7 +316,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
                         if (p.dbg & 16) {
                             mbar_arrive(x_full + 8 * xr.slot);
                         } else {
-                            mbar_expect_tx(x_full + 8 * xr.slot, (uint32_t)C::NPX * 128u);
+                            mbar_expect_tx(x_full + 8 * xr.slot, (uint32_t)C::NPX * (C::EXP ? C::XROW : 128u));
                             // expand mode: the block input (all its channels) into the X ring; direct mode: chunk c of the hidden
                             // tensor into E tile xr.slot (the tiles of team t are t and t + NT: jobs go round-robin)
                             tma_load_4d(C::EXP ? base + xr.slot * SLOT : base + p.off_e + xr.slot * C::ESLOT, &tmX, C::EXP ? 0 : c * 32,
@@ -251,46 +330,58 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
                 }
             }
         }
-    } else if (warp == 1 && C::EXP) {
-        // ================= expand issuer: one MMA group per job =================
+    } else if ((warp == 1 || warp == 2) && C::EXP) {
+        // ================= expand issuers: one MMA group per job =================
+        // A tcgen05.mma costs its issuing thread ~55 cycles whatever its size (trace: 6 MMAs + 2 commits = 370 cycles), so one
+        // issuer bounded the job rate.  Two warps walk the same job sequence; warp w issues the jobs of the teams t % 2 == w (a
+        // fixed issuer per team: it observes every phase of that team's e_empty barrier).  Both wait for every split sub-tile and
+        // both commit its hand-back after the block's last chunk (a commit covers the thread's earlier MMAs; count 2).
+        const int w = warp - 1;
         mbar_wait(w_full, 0);
         const uint32_t idesc32 = umma_idesc_tf32(32);
-        Ring ar, er;  // er.slot = the team of job j
+        Ring gr, er;  // gr = the A slot group of the block, er.slot = the team of job j
         int c = 0, s = 0;
         for (int j = 0; j < J; ++j) {
-            mbar_wait(a_full + 8 * ar.slot, ar.phase);
-            TR(5, j);
-            mbar_wait(e_empty + 8 * er.slot, er.phase ^ 1u);
-            TR(6, j);
+            if (w == 0) TR(24, j);
+            const int aslot = gr.slot * NSUB + s;
+            if (c == 0) mbar_wait(a_full + 8 * aslot, gr.phase);  // the split sub-tile: written once, read by every chunk
+            const bool mine = (er.slot & 1) == w;
+            if (w == 0) TR(5, j);
+            if (mine) {
+                mbar_wait(e_empty + 8 * er.slot, er.phase ^ 1u);
+                TR(6, j);
+            }
             tc_fence_after();
             const uint32_t wb = base + p.off_we + (uint32_t)c * 8192u;
             const uint64_t b_hi = umma_desc(wb), b_lo = umma_desc(wb + 4096u);
-            const uint32_t a_hi = tmem_base + C::ACOL + (uint32_t)ar.slot * 64u, a_lo = a_hi + 32u;
+            const uint32_t a_hi = tmem_base + C::ACOL + (uint32_t)aslot * C::AW, a_lo = a_hi + C::AW / 2;
             const uint32_t d = tmem_base + C::ECOL + (uint32_t)er.slot * 32u;
+            if (mine) TR(25, j);
             if (elect_one()) {
-                if (!(p.dbg & 32))
+                if (mine) {
+                    if (!(p.dbg & 32))
 #pragma unroll
-                for (int k = 0; k < C::KSTEPS; ++k) {  // the small products first
-                    umma_tf32_ts(d, a_lo + 8u * k, b_hi + (uint64_t)(k * 2), idesc32, k > 0 ? 1u : 0u);
-                    umma_tf32_ts(d, a_hi + 8u * k, b_lo + (uint64_t)(k * 2), idesc32, 1u);
+                    for (int k = 0; k < C::KSTEPS; ++k) {  // the small products first
+                        umma_tf32_ts(d, a_lo + 8u * k, b_hi + (uint64_t)(k * 2), idesc32, k > 0 ? 1u : 0u);
+                        umma_tf32_ts(d, a_hi + 8u * k, b_lo + (uint64_t)(k * 2), idesc32, 1u);
+                    }
+                    if (!(p.dbg & 32))
+#pragma unroll
+                    for (int k = 0; k < C::KSTEPS; ++k) umma_tf32_ts(d, a_hi + 8u * k, b_hi + (uint64_t)(k * 2), idesc32, 1u);
+                    umma_commit(e_full + 8 * er.slot);
                 }
-                if (!(p.dbg & 32))
-#pragma unroll
-                for (int k = 0; k < C::KSTEPS; ++k) umma_tf32_ts(d, a_hi + 8u * k, b_hi + (uint64_t)(k * 2), idesc32, 1u);
-                umma_commit(e_full + 8 * er.slot);
-                umma_commit(a_empty + 8 * ar.slot);
+                if (c == nch - 1) umma_commit(a_empty + 8 * aslot);
             }
             __syncwarp();
-            TR(7, j);
-            ar.next(NA);
+            if (mine) TR(7, j);
             er.next(NE);
             if (++s == NSUB) {
                 s = 0;
-                if (++c == nch) c = 0;
+                if (++c == nch) c = 0, gr.next(C::NG);
             }
         }
-    } else if (warp == 2) {
-        // ================= projection issuer: one MMA group per (block, chunk) =================
+    } else if (warp == 3) {
+        // ================= projection issuer (warp 3: scheduler 3 carries the lightest compute load, see the item rotation below): one MMA group per (block, chunk) =================
         mbar_wait(w_full, 0);
         const uint32_t idesc32 = umma_idesc_tf32(32), idesc64 = umma_idesc_tf32(64);
         Ring dr, pr;
@@ -299,6 +390,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
             mbar_wait(d_full + 8 * dr.slot, dr.phase);
             TR(15, q * NSUB + NSUB - 1);
             if (c == 0) mbar_wait(p_empty + 8 * pr.slot, pr.phase ^ 1u);
+            TR(26, q * NSUB + NSUB - 1);
             tc_fence_after();
             const uint32_t dbase = base + p.off_d + (uint32_t)dr.slot * 2u * C::DHALF;
             const uint64_t a_hi = umma_desc(dbase), a_lo = umma_desc(dbase + C::DHALF);
@@ -326,90 +418,33 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
         pdl_wait();  // residual reads and Y stores touch activation memory
         const int q = warp & 3, row = q * 32 + lane;
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-        // accumulator row -> output pixel of the block (fixed for the kernel)
-        const int rs = row / C::SPX, rl = row - rs * C::SPX;
-        const int rsy = rs / C::NSX, rsx = rs - rsy * C::NSX;
-        const int roy = rsy * C::STH + rl / C::STW, rox = rsx * C::STW + rl % C::STW;
         Ring pr;
         BlockWalk ew;  // the epilogues run in block order
         ew.init((int)blockIdx.x, (int)gridDim.x, p.blocks_x, p.blocks_y);
         auto epilogue = [&](int) {
-            const int bx = ew.bx, by = ew.by, b = ew.b;
+            epilogue_block(pr.slot, pr.phase, ew.bx, ew.by, ew.b, row, lane_base);
             ew.next();
-            const int yo = by * (C::NSY * C::STH) + roy, xo = bx * (C::NSX * C::STW) + rox;
-            const bool valid = row < C::DROWS && yo < p.Ho && xo < p.Wo && !(p.dbg & 4);
-            const size_t pix = ((size_t)(b * p.Ho + yo) * p.Wo + xo) * (size_t)p.cout;
-            const uint32_t taddr = lane_base + C::PCOL + (uint32_t)pr.slot * 64u;
-            if (p.res) {
-                // the residual does not depend on the accumulator: its (L2) latency runs under the wait below
-                float4 rs[8];
-#pragma unroll
-                for (int h = 0; h < 8; ++h) rs[h] = (valid && 4 * h < p.cout) ? ldcg4(p.res + pix + 4 * h) : make_float4(0, 0, 0, 0);
-                mbar_wait(p_full + 8 * pr.slot, pr.phase);
-                tc_fence_after();
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const int c0 = 8 * g;
-                    if (c0 < p.cout) {  // warp-uniform
-                        float v[8], cr[8];
-                        tmem_ld8(taddr + (uint32_t)c0, v);
-                        tmem_ld8(taddr + 32u + (uint32_t)c0, cr);
-                        tmem_ld_wait();
-                        if (valid) {
-#pragma unroll
-                            for (int h = 0; h < 2; ++h) {
-                                const float4 r4 = rs[2 * g + h];
-                                st4(p.Y + pix + c0 + 4 * h, make_float4(v[4 * h] + cr[4 * h] + r4.x, v[4 * h + 1] + cr[4 * h + 1] + r4.y,
-                                                                        v[4 * h + 2] + cr[4 * h + 2] + r4.z, v[4 * h + 3] + cr[4 * h + 3] + r4.w));
-                            }
-                        }
-                    }
-                }
-            } else {
-                mbar_wait(p_full + 8 * pr.slot, pr.phase);
-                tc_fence_after();
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {  // 16 columns per TMEM round trip
-                    const int c0 = 16 * g;
-                    if (c0 < p.cout) {  // warp-uniform
-                        float v[16], cr[16];
-                        tmem_ld16(taddr + (uint32_t)c0, v);
-                        tmem_ld16(taddr + 32u + (uint32_t)c0, cr);
-                        tmem_ld_wait();
-                        if (valid) {
-#pragma unroll
-                            for (int h = 0; h < 4; ++h)
-                                if (c0 + 4 * h < p.cout)
-                                    st4(p.Y + pix + c0 + 4 * h,
-                                        make_float4(v[4 * h] + cr[4 * h], v[4 * h + 1] + cr[4 * h + 1], v[4 * h + 2] + cr[4 * h + 2], v[4 * h + 3] + cr[4 * h + 3]));
-                        }
-                    }
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(p_empty + 8 * pr.slot);
             pr.next(NP);
         };
-        Ring xr, ar;
-        const int xswz = row & 7;
+        Ring xr, gr;
+        const int xswz = C::XROW == 64 ? (row >> 1) & 3 : row & 7;  // 16-byte chunk XOR of the TMA swizzle mode
         int jt = 0;
-        if (!C::EXP) {  // direct mode: this team only drains the projection accumulators
+        if (!C::EXP && !C::TEAM_EPI) {  // direct mode: this team only drains the projection accumulators
             for (int i = 0; i < nblk; ++i) {
                 if (q == 0) TR(17, (i + 1) * nch * NSUB - 1);
                 epilogue(i);
                 if (q == 0) TR(18, (i + 1) * nch * NSUB - 1);
             }
         }
-        // Expand mode: the epilogue of block i - LAG runs after the splits of block i.  LAG blocks must cover the pipeline behind the
-        // splitters (~10 jobs from a split to its projection's retirement): a one-job-per-chunk block (NSUB == 1) is only nch jobs
-        // long, and waiting for its projection stalled the splitters, and through them every stage (B2 trace: 4200 cycles per block).
+        // Expand mode, epilogues on this team: the epilogue of block i - 1 runs after the splits of block i.
         int epi_done = 0;
         for (int i = 0; i < (C::EXP ? nblk : 0); ++i) {
-            for (int cs = 0; cs < nch * NSUB; ++cs, ++jt) {
+            jt = i * nch * NSUB;
+            for (int cs = 0; cs < NSUB; ++cs, ++jt) {  // one split per (block, sub-tile): every chunk's expand reads it
+                const int aslot = gr.slot * NSUB + cs;
                 mbar_wait(x_full + 8 * xr.slot, xr.phase);
                 if (q == 0) TR(2, jt);
-                const uint8_t* xrow = sm + (size_t)xr.slot * SLOT + (size_t)row * 128;
+                const uint8_t* xrow = sm + (size_t)xr.slot * SLOT + (size_t)row * C::XROW;
                 float hi[8 * C::KSTEPS], lo[8 * C::KSTEPS];
                 if (!(p.dbg & 8))
 #pragma unroll
@@ -418,10 +453,10 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
                     hi[4 * g] = tf32_hi(v.x), hi[4 * g + 1] = tf32_hi(v.y), hi[4 * g + 2] = tf32_hi(v.z), hi[4 * g + 3] = tf32_hi(v.w);
                     lo[4 * g] = v.x - hi[4 * g], lo[4 * g + 1] = v.y - hi[4 * g + 1], lo[4 * g + 2] = v.z - hi[4 * g + 2], lo[4 * g + 3] = v.w - hi[4 * g + 3];
                 }
-                mbar_wait(a_empty + 8 * ar.slot, ar.phase ^ 1u);
+                mbar_wait(a_empty + 8 * aslot, gr.phase ^ 1u);
                 if (q == 0) TR(3, jt);
                 tc_fence_after();
-                const uint32_t ta = lane_base + C::ACOL + (uint32_t)ar.slot * 64u;
+                const uint32_t ta = lane_base + C::ACOL + (uint32_t)aslot * C::AW;
                 if (C::KSTEPS == 4) {
                     tmem_st16(ta, hi), tmem_st16(ta + 16u, hi + 16);
                     tmem_st16(ta + 32u, lo), tmem_st16(ta + 48u, lo + 16);
@@ -430,26 +465,27 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
                     tmem_st16(ta + 32u, lo), tmem_st8(ta + 48u, lo + 16);
                 } else {
                     tmem_st16(ta, hi);
-                    tmem_st16(ta + 32u, lo);
+                    tmem_st16(ta + 16u, lo);
                 }
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
-                    mbar_arrive(a_full + 8 * ar.slot);
+                    mbar_arrive(a_full + 8 * aslot);
                     mbar_arrive(x_empty + 8 * xr.slot);
                 }
                 if (q == 0) TR(4, jt);
                 xr.next(NX);
-                ar.next(NA);
             }
-            if (i >= C::LAG) {
+            gr.next(C::NG);
+            jt = (i + 1) * nch * NSUB;
+            if (!C::TEAM_EPI && i >= 1) {
                 if (q == 0) TR(17, jt - 1);
                 epilogue(epi_done++);
                 if (q == 0) TR(18, jt - 1);
             }
         }
-        while (C::EXP && epi_done < nblk) epilogue(epi_done++);  // the tail: nothing left to split
+        while (C::EXP && !C::TEAM_EPI && epi_done < nblk) epilogue(epi_done++);  // the tail: nothing left to split
     } else if (warp >= 8) {
         // ================= compute teams: expand accumulator -> Swish -> E tile -> taps -> Swish -> hi/lo rows of the D operand =================
         constexpr int NROW = (C::YT - 1) * S + KS, NCOL = (C::XT - 1) * S + KS;
@@ -458,21 +494,35 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
         uint8_t* Es = sm + p.off_e + (size_t)team * C::ESLOT;  // direct mode: + NT * ESLOT for the second tile
         auto bar_team = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + team) : "memory"); };
         // depth-wise item of this thread (fixed): output block (by, bx) of the sub-tile, channels 4 * c4 .. + 3 of the chunk
-        const int c4 = row & 7, blk = row >> 3;
+        // A geometry with fewer than 128 items leaves warps without depth-wise work; a warp's scheduler is fixed (warp % 4, like its
+        // TMEM lane quarter), so the items rotate by one warp per team: the idle warps of different teams sit on different schedulers.
+        const int it = C::NITEMS < 128 ? (row + 32 * (team + 1)) & 127 : row;
+        const int c4 = it & 7, blk = it >> 3;
         const int by = blk / C::NBX, bx = blk - by * C::NBX;
-        const bool has_item = row < C::NITEMS;
+        const bool has_item = it < C::NITEMS;
         const uint8_t* eb = Es + ((C::YT * by * S) * C::IW + C::XT * bx * S) * (int)C::EP + c4 * 16;  // window origin: every load is this + an immediate
         Ring dr;            // D operand of the current job
         int s = 0, c = 0;   // sub-tile within the block, chunk
         uint32_t ephase = 0, fphase = (team >= ND) ? 1u : 0u;  // per-team hand-back: teams >= ND wait for a real retirement the first time
+        BlockWalk tw;  // block of the current job, its projection accumulator (TEAM_EPI)
+        tw.init((int)blockIdx.x, (int)gridDim.x, p.blocks_x, p.blocks_y);
+        Ring tpr;
         auto step = [&]() {  // one job further in the CTA's job sequence
             if (++s == NSUB) {
                 s = 0;
                 dr.next(ND);
-                if (++c == nch) c = 0;
+                if (++c == nch) {
+                    c = 0;
+                    if (C::TEAM_EPI) tw.next(), tpr.next(NP);
+                }
             }
         };
         for (int t = 0; t < team; ++t) step();
+        // TEAM_EPI: the block whose last chunk was this team's PREVIOUS job waits to be drained
+        bool epi_pending = false;
+        int e_ps = 0, e_bx = 0, e_by = 0, e_b = 0;
+        uint32_t e_ph = 0;
+        if (C::TEAM_EPI) pdl_wait();  // residual reads and Y stores touch activation memory
         if (C::WDS) mbar_wait(w_full, 0);  // the tap image
         uint32_t kjob = 0;  // this team's job counter (direct mode: E tile = kjob & 1, its barrier phase = (kjob >> 1) & 1)
         for (int j = team; j < J; j += NT, ++kjob) {
@@ -574,14 +624,26 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
             __syncwarp();
             if (lane == 0) mbar_arrive(d_full + 8 * dr.slot);
             if (q == 0) TR(14, j);
+            if (C::TEAM_EPI) {
+                // The D hand-back observed above means the in-order projection issuer has retired this team's previous job: if that
+                // was a block's last chunk, its accumulator is complete -- drain it now, behind this job's D operand.
+                if (epi_pending) {
+                    if (q == 0) TR(17, j);
+                    epilogue_block(e_ps, e_ph, e_bx, e_by, e_b, row, lane_base);
+                    if (q == 0) TR(18, j);
+                }
+                epi_pending = c == nch - 1;
+                e_ps = tpr.slot, e_ph = tpr.phase, e_bx = tw.bx, e_by = tw.by, e_b = tw.b;
+            }
 #pragma unroll
             for (int t = 0; t < NT; ++t) step();
         }
+        if (C::TEAM_EPI && epi_pending) epilogue_block(e_ps, e_ph, e_bx, e_by, e_b, row, lane_base);  // this team's last job closed a block
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) {
+    if (warp == 3) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
@@ -591,27 +653,22 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
 // Geometry per block type (sub-tile, block, depth-wise item shape; the TD parameter is unused):
 //   3x3 s2, Cin 16 (layer1.0): sub-tile 3 x 8 (halo 7 x 17 = 119 px), block 2 x 2 sub-tiles = 6 x 16 outputs, items of 1 x 2 outputs: 96 = 3 warps
 //   3x3 s1, Cin 24 (layer1.1): sub-tile 8 x 10 (halo 10 x 12 = 120 px), block = the sub-tile, items of 1 x 5 outputs: 128 = 4 warps
-//   5x5 s2, Cin 24 (layer2.0): sub-tile 4 x 4 (halo 11 x 11 = 121 px), block 2 x 4 sub-tiles = 8 x 16 outputs, items of one output: 128 = 4 warps
-//   5x5 s1, Cin 32 (layer2.1): sub-tile 7 x 7 (halo 11 x 11 = 121 px), block 1 x 2 sub-tiles = 7 x 14 outputs, items of 1 x 7 outputs: 56 = 2 warps
-using MbfB1 = MbfCfg<3, 2, 16, 3, 8, 2, 2, 2, 1, 3, 3, true>;
-using MbfB2 = MbfCfg<3, 1, 24, 8, 10, 1, 1, 5, 1, 4, 2, false>;
-using MbfB3 = MbfCfg<5, 2, 24, 4, 4, 2, 4, 1, 1, 4, 2, false>;
-using MbfB4 = MbfCfg<5, 1, 32, 7, 7, 1, 2, 7, 1, 2, 2, false>;
+// (the 5x5 blocks layer2.0 / layer2.1 have no configuration: 128-pixel halo sub-tiles recompute 1.9x / 2.5x of their expand work)
+using MbfB1 = MbfCfg<3, 2, 16, 3, 8, 2, 2, 2, 1, 3, 4, true, true, 5>;
+using MbfB2 = MbfCfg<3, 1, 24, 8, 10, 1, 1, 5, 1, 4, 1, false, true, 4>;
 // direct mode (depth-wise + projection from the hidden tensor): 3x3 s1 with layer1.1's geometry
 using MbfD31 = MbfCfg<3, 1, 32, 8, 10, 1, 1, 5, 1, 4, 1, false, false>;
 
 struct MbfLaunch {
     CUtensorMap tmX;
     MbfParams p;
-    int kind = 0, grid = 0;  // kind: 1..4 = MbfB1..MbfB4, 5 = MbfD31 (direct)
+    int kind = 0, grid = 0;  // kind: 1 = MbfB1, 2 = MbfB2, 5 = MbfD31 (direct)
     size_t smem = 0;
 };
 
 inline int mbf_kind(int ks, int s, int cin) {
     if (ks == 3 && s == 2 && cin == 16) return 1;
     if (ks == 3 && s == 1 && cin == 24) return 2;
-    if (ks == 5 && s == 2 && cin == 24) return 3;
-    if (ks == 5 && s == 1 && cin == 32) return 4;
     return 0;
 }
 inline bool mbf_supported(int ks, int s, int cin, int hid, int cout) { return mbf_kind(ks, s, cin) != 0 && cout % 8 == 0 && cout <= 32 && hid % 4 == 0; }
@@ -620,7 +677,7 @@ template <typename C>
 inline int mbf_plan_t(PwTcState& st, MbfLaunch* ml, const float* X, int B, int Hi, int Wi, int cin) {
     MbfParams& p = ml->p;
     // expand mode: X = block input, SWIZZLE_128B boxes (read by the splitters); direct mode: X = hidden tensor, plain boxes = E tiles
-    int rc = xd_make_map(st, &ml->tmX, X, B, Hi, Wi, cin, C::IW, C::IH, /*swizzle=*/C::EXP);
+    int rc = xd_make_map(st, &ml->tmX, X, B, Hi, Wi, cin, C::IW, C::IH, /*swizzle=*/C::EXP ? (C::XROW == 64 ? 2 : 1) : 0, /*box_c=*/C::EXP ? (int)C::XROW / 4 : 32);
     if (rc) return rc;
     p.Ho = Hi / C::S, p.Wo = Wi / C::S;
     p.blocks_x = cdiv(p.Wo, C::NSX * C::STW);
@@ -677,12 +734,8 @@ inline int mbf_plan(PwTcState& st, int ks, int s, const float* X, const float* W
     if (const char* ev = getenv("CF_MBF_DEBUG")) p.dbg = atoi(ev);
     if (int rc = mbf_trace_setup(st, p)) return rc;
     ml->kind = mbf_kind(ks, s, cin);
-    switch (ml->kind) {
-        case 1: return mbf_plan_t<MbfB1>(st, ml, X, B, Hi, Wi, cin);
-        case 2: return mbf_plan_t<MbfB2>(st, ml, X, B, Hi, Wi, cin);
-        case 3: return mbf_plan_t<MbfB3>(st, ml, X, B, Hi, Wi, cin);
-        default: return mbf_plan_t<MbfB4>(st, ml, X, B, Hi, Wi, cin);
-    }
+    if (ml->kind == 1) return mbf_plan_t<MbfB1>(st, ml, X, B, Hi, Wi, cin);
+    return mbf_plan_t<MbfB2>(st, ml, X, B, Hi, Wi, cin);
 }
 
 // Direct mode: depth-wise + Swish + projection (+ residual) of one block from its HIDDEN tensor E [B,Hi,Wi,hid] (layer0: the stem
@@ -723,8 +776,6 @@ inline cudaError_t mbf_launch(const MbfLaunch& ml, cudaStream_t s) {
     switch (ml.kind) {
         case 1: return mbf_launch_t<MbfB1>(ml, s);
         case 2: return mbf_launch_t<MbfB2>(ml, s);
-        case 3: return mbf_launch_t<MbfB3>(ml, s);
-        case 4: return mbf_launch_t<MbfB4>(ml, s);
         case 5: return mbf_launch_t<MbfD31>(ml, s);
     }
     return cudaErrorInvalidValue;
