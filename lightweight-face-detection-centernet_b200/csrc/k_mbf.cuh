@@ -44,7 +44,7 @@
 
 namespace cf {
 
-template <int KS_, int S_, int CIN_, int STH_, int STW_, int NSY_, int NSX_, int XT_, int YT_, int TD_, int NX_, bool WDS_, bool EXP_ = true, int NT_ = 4>
+template <int KS_, int S_, int CIN_, int STH_, int STW_, int NSY_, int NSX_, int XT_, int YT_, int TD_, int NX_, bool WDS_, bool EXP_ = true, int NT_ = 4, int ND_ = 2>
 struct MbfCfg {
     static constexpr int KS = KS_, S = S_, CIN = CIN_, STH = STH_, STW = STW_, NSY = NSY_, NSX = NSX_, XT = XT_, YT = YT_, TD = TD_;
     static constexpr int IH = (STH - 1) * S + KS, IW = (STW - 1) * S + KS, NPX = IH * IW;
@@ -67,7 +67,7 @@ struct MbfCfg {
     // COMPUTE TEAM that produced a block's last chunk drains it, one job later, when it has just observed the D hand-back (the
     // projection issuer is in order: that block's projection has retired).  Otherwise the splitters do it, one block behind.
     static constexpr bool TEAM_EPI = EXP_ && NSUB == 1;  // direct mode: measured slower on the teams (layer0 205 -> 249 us), the splitter warps are idle there
-    static constexpr int NX = NX_, NE = NT, ND = EXP_ ? 2 : NT, NP = EXP_ ? 2 : 4;
+    static constexpr int NX = NX_, NE = NT, ND = EXP_ ? ND_ : NT, NP = EXP_ ? 2 : 4;
     // TMEM A slots (the split block input).  A slot holds one sub-tile for ALL the chunks of its block: the splitters (and the X box
     // TMA) run once per (block, sub-tile), the expand issuer re-reads the slot with each chunk's weights and hands it back after the
     // last one.  Slots come in groups of NSUB (one block); NG groups rotate block by block.
@@ -147,7 +147,7 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
                  : "memory");
 }
 
-template <typename C>
+template <typename C, bool TRACE = false>
 __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ CUtensorMap tmX, const MbfParams p) {
     constexpr int KS = C::KS, S = C::S, NX = C::NX, NA = C::NA, NE = C::NE, ND = C::ND, NP = C::NP, NT = C::NT, NDF = C::NDF;
     constexpr int NSUB = C::NSUB;
@@ -191,7 +191,9 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
     const uint32_t tmem_base = *tmem_slot;
 
     // development trace: event ev of job j (one lane of one warp per role writes; 32 slots per job)
+    // (a compile-time switch: the seven-instruction test in front of every site cost the latency-bound warps ~5 % when it was a run-time one)
     auto TR = [&](int ev, int j) {
+        if constexpr (!TRACE) return;
         if (p.trace && blockIdx.x == 0 && lane == 0 && (unsigned)(j - p.tr_j0) < (unsigned)p.tr_nj) p.trace[(size_t)(j - p.tr_j0) * 32 + ev] = (unsigned long long)clock64();
     };
     const int nch = p.nch;
@@ -507,17 +509,21 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
         BlockWalk tw;  // block of the current job, its projection accumulator (TEAM_EPI)
         tw.init((int)blockIdx.x, (int)gridDim.x, p.blocks_x, p.blocks_y);
         Ring tpr;
-        auto step = [&]() {  // one job further in the CTA's job sequence
-            if (++s == NSUB) {
-                s = 0;
-                dr.next(ND);
-                if (++c == nch) {
-                    c = 0;
-                    if (C::TEAM_EPI) tw.next(), tpr.next(NP);
-                }
+        // n jobs further in the CTA's job sequence (n <= NT), in closed form: the teams run this between two jobs, and a latency-bound
+        // warp pays ~10 cycles per instruction -- the job-by-job walk cost ~1 000 cycles per job
+        auto advance = [&](int n) {
+            s += n;
+            int dq = 0;  // D operands (block, chunk) passed
+            while (s >= NSUB) s -= NSUB, ++dq;
+            dr.slot += dq;
+            while (dr.slot >= ND) dr.slot -= ND, dr.phase ^= 1u;
+            c += dq;
+            while (c >= nch) {
+                c -= nch;
+                if (C::TEAM_EPI) tw.next(), tpr.next(NP);
             }
         };
-        for (int t = 0; t < team; ++t) step();
+        advance(team);
         // TEAM_EPI: the block whose last chunk was this team's PREVIOUS job waits to be drained
         bool epi_pending = false;
         int e_ps = 0, e_bx = 0, e_by = 0, e_b = 0;
@@ -533,6 +539,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
                 if (q == 0) TR(8, j);
             }
             // ---- drain: this warp's lane quarter of the accumulator ----
+            if (C::EXP && q == 0) TR(27, j);
             if (C::EXP) mbar_wait(e_full + 8 * team, ephase);
             if (C::EXP && q == 0) TR(8, j);
             // probe the D hand-back now (non-blocking); the result is needed only after the depth-wise arithmetic
@@ -635,8 +642,8 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
                 epi_pending = c == nch - 1;
                 e_ps = tpr.slot, e_ph = tpr.phase, e_bx = tw.bx, e_by = tw.by, e_b = tw.b;
             }
-#pragma unroll
-            for (int t = 0; t < NT; ++t) step();
+            if (q == 0) TR(28, j);
+            advance(NT);
         }
         if (C::TEAM_EPI && epi_pending) epilogue_block(e_ps, e_ph, e_bx, e_by, e_b, row, lane_base);  // this team's last job closed a block
     }
@@ -655,7 +662,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
 //   3x3 s1, Cin 24 (layer1.1): sub-tile 8 x 10 (halo 10 x 12 = 120 px), block = the sub-tile, items of 1 x 5 outputs: 128 = 4 warps
 // (the 5x5 blocks layer2.0 / layer2.1 have no configuration: 128-pixel halo sub-tiles recompute 1.9x / 2.5x of their expand work)
 using MbfB1 = MbfCfg<3, 2, 16, 3, 8, 2, 2, 2, 1, 3, 4, true, true, 5>;
-using MbfB2 = MbfCfg<3, 1, 24, 8, 10, 1, 1, 5, 1, 4, 1, false, true, 4>;
+using MbfB2 = MbfCfg<3, 1, 24, 8, 10, 1, 1, 5, 1, 4, 1, false, true, 4, 3>;
 // direct mode (depth-wise + projection from the hidden tensor): 3x3 s1 with layer1.1's geometry
 using MbfD31 = MbfCfg<3, 1, 32, 8, 10, 1, 1, 5, 1, 4, 1, false, false>;
 
@@ -767,9 +774,14 @@ inline int mbf_plan_direct(PwTcState& st, int ks, int s, const float* E, const f
 
 template <typename C>
 inline cudaError_t mbf_launch_t(const MbfLaunch& ml, cudaStream_t s) {
-    cudaError_t e = smem_optin((const void*)k_mbf<C>, TC_SMEM_MAX);
+    if (ml.p.trace) {  // development build of the same kernel with the clock64 trace compiled in
+        cudaError_t e = smem_optin((const void*)k_mbf<C, true>, TC_SMEM_MAX);
+        if (e != cudaSuccess) return e;
+        return launch_pdl(k_mbf<C, true>, dim3(ml.grid), dim3(C::THREADS), ml.smem, s, ml.tmX, ml.p);
+    }
+    cudaError_t e = smem_optin((const void*)k_mbf<C, false>, TC_SMEM_MAX);
     if (e != cudaSuccess) return e;
-    return launch_pdl(k_mbf<C>, dim3(ml.grid), dim3(C::THREADS), ml.smem, s, ml.tmX, ml.p);
+    return launch_pdl(k_mbf<C, false>, dim3(ml.grid), dim3(C::THREADS), ml.smem, s, ml.tmX, ml.p);
 }
 
 inline cudaError_t mbf_launch(const MbfLaunch& ml, cudaStream_t s) {

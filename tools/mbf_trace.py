@@ -36,7 +36,7 @@ rc = eng.lib.cf_debug_mbf_trace(eng.h, buf, a.nj)
 assert rc == 0, rc
 t = np.frombuffer(buf, dtype=np.uint64).reshape(a.nj, 32).astype(np.int64)
 names = {0: "P.xempty", 1: "P.tma", 2: "S.xfull", 3: "S.aempty", 4: "S.arrive", 5: "X.afull", 6: "X.eempty", 7: "X.commit", 8: "T.efull", 9: "T.ldtm",
-         19: "T.swish", 10: "T.bar1", 11: "T.bar2", 12: "T.dw", 13: "T.dfree", 14: "T.dfull", 15: "J.dfull", 16: "J.commit", 17: "E.start", 18: "E.end", 24: "X.top", 25: "X.issue", 26: "J.pempty"}
+         19: "T.swish", 10: "T.bar1", 11: "T.bar2", 12: "T.dw", 13: "T.dfree", 14: "T.dfull", 15: "J.dfull", 16: "J.commit", 17: "E.start", 18: "E.end", 24: "X.top", 25: "X.issue", 26: "J.pempty", 27: "T.top", 28: "T.end"}
 order = [0, 1, 2, 3, 4, 24, 5, 6, 7, 8, 9, 19, 10, 11, 12, 13, 14, 15, 16, 17, 18]
 t0 = t[t > 0].min()
 print("job  " + " ".join(f"{names[e]:>9s}" for e in order))
@@ -50,7 +50,7 @@ for e in (1, 4, 7, 14):
     v = col(e)
     if len(v) > 2:
         print(f"{names[e]:9s}: mean interval {np.diff(v).mean():8.1f} cycles over {len(v)} jobs")
-pairs = [(6, 25), (25, 7), (15, 26), (26, 16), (7, 24), (17, 18), (16, 18), (14, 15), (15, 16), (0, 1), (2, 3), (3, 4), (5, 6), (6, 7), (8, 9), (9, 19), (19, 10), (10, 11), (11, 12), (12, 13), (13, 14), (7, 8), (4, 5), (1, 2)]
+pairs = [(27, 8), (14, 28), (6, 25), (25, 7), (15, 26), (26, 16), (7, 24), (17, 18), (16, 18), (14, 15), (15, 16), (0, 1), (2, 3), (3, 4), (5, 6), (6, 7), (8, 9), (9, 19), (19, 10), (10, 11), (11, 12), (12, 13), (13, 14), (7, 8), (4, 5), (1, 2)]
 for a_, b_ in pairs:
     m = (t[:, a_] > 0) & (t[:, b_] > 0)
     if m.any():
