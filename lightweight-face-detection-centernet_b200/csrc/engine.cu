@@ -372,7 +372,10 @@ int build_plan(cf_engine* e, const void* input, int fmt, int B, int H, int W) {
             int sgrid = 0;
             if ((rc = stc_plan(e->tc, e->w["stem.w"], input, lut, out, B, H, W, &sp, &sgrid))) return rc;
             const int sms = e->tc.sms;
-            if (fmt == CF_IN_U8_HWC)
+            // u8 images whose rows are whole 32-bit words take the third-generation kernel (CF_STEM_TC=2 keeps the second)
+            if (fmt == CF_IN_U8_HWC && !ev && stc3_supported(sp))
+                P.push_back({CLS_STEM, [=](cudaStream_t s) { return stc3_launch(sp, sms, s); }});
+            else if (fmt == CF_IN_U8_HWC)
                 P.push_back({CLS_STEM, [=](cudaStream_t s) { return stc2_launch_t<1>(sp, sms, s); }});
             else
                 P.push_back({CLS_STEM, [=](cudaStream_t s) { return stc2_launch_t<0>(sp, sms, s); }});

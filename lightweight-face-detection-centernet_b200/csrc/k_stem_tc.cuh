@@ -404,6 +404,241 @@ __global__ void __launch_bounds__(STC2_THREADS, 1) k_stem_tc2(const StcParams p)
     }
 }
 
+// ---- third generation (u8 input, W % 4 == 0): more warps, fewer instructions per pixel ------------------------------------
+// k_stem_tc2 runs at IPC 1.3 of 4 with MUFU, HBM and the tensor pipe all under 45 %: its 20 warps are serial chains (a lone warp
+// retires an instruction every ~10 cycles), two producer sets x ~250 instructions and two drain groups x ~250 instructions per
+// 128-pixel tile.  Here: 32 warps per SM --
+//   warps 4-19   FOUR producer sets, one per TMEM A slot.  A pixel's 3 x 9 input bytes come as three aligned 12-byte windows
+//                (9 LDG.32 instead of 27 LDG.U8); the table holds (tf32 hi, remainder) PAIRS, one LDS.64 per tap instead of a load
+//                and two ALU operations; taps in the zero padding select the table's zero page through 9 precomputed bases
+//                instead of a select per tap.  ~150 instructions per pixel.
+//   warps 20-31  THREE drain groups over a three-stage accumulator ring (stage = group), two 16-column rounds each: 48 live
+//                registers, which is what the 64-register cap of a 1 024-thread CTA allows.
+//   warp 0       weight image + MMA issue (8 MMAs per tile as before, so that u8 and fp32 inputs stay bit-identical);
+//                warp 1 owns the TMEM allocation.  (Two issuers over a six-stage single-accumulator ring were tried: same time.)
+constexpr int STC3_THREADS = 1024;
+// 1 024 entries x 16 copies x (hi, lo): [c][256] for c < 3, page 3 = zeros.  One copy per lane of a half warp: an LDS.64 of 16
+// lanes then touches every bank exactly once whatever the bytes are (uniformly random bytes -- the benchmark's synthetic images --
+// cost a single table ~3.5 wavefronts per load: 155 us against 129 us on image-like input)
+constexpr uint32_t STC3_OFF_LUT = STC_B_BYTES;
+constexpr uint32_t STC3_OFF_BARS = STC3_OFF_LUT + 1024 * 128;
+constexpr uint32_t STC3_OFF_STG = STC3_OFF_BARS + 256;         // 12 drain warps x 4 KB store-transpose tiles
+constexpr size_t STC3_SMEM = STC3_OFF_STG + 12 * 4096 + 1024;
+
+__global__ void __launch_bounds__(STC3_THREADS, 1) k_stem_tc3(const StcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bsm = base;
+    float2* lut2 = reinterpret_cast<float2*>(sm + STC3_OFF_LUT);
+    const uint32_t bars = base + STC3_OFF_BARS;
+    const uint32_t bar_aready = bars;            // [4] producer set -> MMA   (4 warps arrive)
+    const uint32_t bar_aempty = bars + 32;       // [4] MMA -> producer set   (tcgen05.commit)
+    const uint32_t bar_tfull = bars + 64;        // [3] MMA -> drain group    (tcgen05.commit)
+    const uint32_t bar_tempty = bars + 96;       // [3] drain group -> MMA    (4 warps arrive)
+    const uint32_t bar_b = bars + 128;           // weights landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + STC3_OFF_BARS + 144);
+    constexpr uint32_t kACol = 192;              // accumulator pairs: 3 x 64 columns in [0,192); A ring: 4 x (32 hi + 32 lo) above
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    pdl_trigger();
+    if (tid == 0) {
+        mbar_init(bar_b, 1);
+        for (int a = 0; a < 4; ++a) mbar_init(bar_aready + 8 * a, 4), mbar_init(bar_aempty + 8 * a, 1);
+        for (int a = 0; a < 3; ++a) mbar_init(bar_tfull + 8 * a, 1), mbar_init(bar_tempty + 8 * a, 4);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    {
+        const float v = tid < 768 ? __ldg(p.lut + tid) : 0.f;
+        const float h = tf32_hi(v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) lut2[tid * 16 + i] = make_float2(h, v - h);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int n_tiles = p.n_tiles;
+    const int Ho = p.H >> 1, Wo = p.W >> 1;
+
+    if (warp == 0) {
+        // ================= weights + MMA issuer =================
+        if (lane == 0) {
+            mbar_expect_tx(bar_b, STC_B_BYTES);
+            bulk_load(bsm, p.bimg, STC_B_BYTES, bar_b);
+        }
+        __syncwarp();
+        const uint32_t idesc = umma_idesc_tf32(STC_NC), idesc2 = umma_idesc_tf32(2 * STC_NC);
+        mbar_wait(bar_b, 0);
+        const uint64_t b_hi = umma_desc(bsm);
+        uint32_t sa = 0, pa = 0, st = 0, pt = 0;  // A slot / accumulator stage cursors with their phase parities
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            mbar_wait(bar_tempty + 8 * st, pt ^ 1u);
+            mbar_wait(bar_aready + 8 * sa, pa);
+            tc_fence_after();
+            const uint32_t d_main = tmem_base + st * 64u, d_corr = d_main + (uint32_t)STC_NC;
+            const uint32_t a_hi = tmem_base + kACol + sa * 64u, a_lo = a_hi + 32u;
+            if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {  // K = 27 -> four 8-wide steps (elements 27..31 are zero on both sides)
+                    const uint64_t ko = (uint64_t)(k * 2);
+                    umma_tf32_ts(d_main, a_hi + 8u * k, b_hi + ko, idesc2, k > 0 ? 1u : 0u);  // main += hi.hi ; corr += hi.lo
+                    umma_tf32_ts(d_corr, a_lo + 8u * k, b_hi + ko, idesc, 1u);                 // corr += lo.hi
+                }
+                umma_commit(bar_aempty + 8 * sa);
+                umma_commit(bar_tfull + 8 * st);
+            }
+            __syncwarp();
+            if (++sa == 4) sa = 0, pa ^= 1u;
+            if (++st == 3) st = 0, pt ^= 1u;
+        }
+    } else if (warp >= 4 && warp < 20) {
+        // ================= producers: set = A slot =================
+        pdl_wait();  // the image may come from the resize kernel
+        const int set = (warp - 4) >> 2, q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + kACol + (uint32_t)set * 64u;
+        uint32_t w[3][3];   // per image row: the aligned 12 bytes that hold the pixel's 9
+        uint32_t sh = 0;    // bit offset of the pixel's first byte inside the window (0..24, + 32 at the right edge + ...)
+        uint32_t edge = 0;  // bit 0: the kx == 2 taps are padding, bit 1: the ky == 2 taps are
+        auto gather = [&](int tile) {
+            const unsigned pix_raw = (unsigned)tile * TC_BM + (unsigned)row;
+            const unsigned pix = pix_raw < (unsigned)p.n_pix ? pix_raw : (unsigned)p.n_pix - 1u;  // rows past the end re-read the last pixel (their outputs are not stored)
+            const unsigned t = pix / (unsigned)Wo;
+            const int xo = (int)(pix - t * (unsigned)Wo);
+            const unsigned b = t / (unsigned)Ho;
+            const int yo = (int)(t - b * (unsigned)Ho);
+            const bool last_y = (2 * yo + 2 >= p.H), last_x = (2 * xo + 2 >= p.W);
+            edge = (last_x ? 1u : 0u) | (last_y ? 2u : 0u);
+            // right edge: the window starts one pixel to the left (its 12 aligned bytes then end with the row: W % 4 == 0); the
+            // padded column's bytes are whatever follows in the registers and select the table's zero page
+            const unsigned off = ((b * (unsigned)p.H + 2u * (unsigned)yo) * (unsigned)p.W + 2u * (unsigned)xo) * 3u - (last_x ? 3u : 0u);
+            const unsigned a0 = off & ~3u, rs = (unsigned)p.W * 3u;
+            sh = (off & 3u) * 8u + (last_x ? 24u : 0u);
+            const uint8_t* in = (const uint8_t*)p.in;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const unsigned a = a0 + (ky == 2 && last_y ? 1u : (unsigned)ky) * rs;  // bottom edge: re-read row 1 (discarded)
+#pragma unroll
+                for (int i = 0; i < 3; ++i) w[ky][i] = __ldg(reinterpret_cast<const uint32_t*>(in + a) + i);
+            }
+        };
+        const uint8_t* lutb = reinterpret_cast<const uint8_t*>(lut2) + (lane & 15) * 8;  // this lane's copy
+        const int stride = 4 * (int)gridDim.x;
+        const int first = (int)blockIdx.x + set * (int)gridDim.x;
+        if (first < n_tiles) gather(first);
+        uint32_t ph = 0;
+        for (int tile = first; tile < n_tiles; tile += stride, ph ^= 1u) {
+            // the pixel's 9 bytes of each row, shifted down to bit 0: v[ky][0] = bytes 0-3, [1] = bytes 4-7, [2] = byte 8
+            uint32_t v[3][3];
+            {
+                const bool far = sh >= 32u;
+                const uint32_t s5 = sh & 31u;
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+                    const uint32_t x0 = far ? w[ky][1] : w[ky][0], x1 = far ? w[ky][2] : w[ky][1], x2 = far ? 0u : w[ky][2];
+                    v[ky][0] = __funnelshift_r(x0, x1, s5);
+                    v[ky][1] = __funnelshift_r(x1, x2, s5);
+                    v[ky][2] = x2 >> s5;
+                }
+            }
+            const uint8_t* pgx[3];   // table page of the kx == 2 taps, ky == 2 taps, both, per channel
+            const uint8_t* pgy[3];
+            const uint8_t* pgxy[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const uint8_t* n = lutb + c * 32768;
+                const uint8_t* z = lutb + 3 * 32768;
+                pgx[c] = (edge & 1u) ? z : n;
+                pgy[c] = (edge & 2u) ? z : n;
+                pgxy[c] = edge ? z : n;
+            }
+            mbar_wait(bar_aempty + 8 * set, ph ^ 1u);
+            tc_fence_after();
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float hi[16], lo[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int k = half * 16 + i;
+                    if (k >= 27) {
+                        hi[i] = 0.f, lo[i] = 0.f;
+                        continue;
+                    }
+                    const int ky = k / 9, r = k - ky * 9, kx = r / 3, c = r - kx * 3;
+                    const uint32_t word = v[ky][r >> 2];
+                    const int bs = 8 * (r & 3) - 7;  // byte * 128 = the table entry's byte offset
+                    const uint32_t boff = (bs < 0 ? word << 7 : word >> bs) & 0x7f80u;
+                    const uint8_t* pg = ky == 2 ? (kx == 2 ? pgxy[c] : pgy[c]) : (kx == 2 ? pgx[c] : lutb + c * 32768);
+                    const float2 e = *reinterpret_cast<const float2*>(pg + boff);
+                    hi[i] = e.x, lo[i] = e.y;
+                }
+                tmem_st16(ta + 16u * half, hi);
+                tmem_st16(ta + 32u + 16u * half, lo);
+            }
+            if (tile + stride < n_tiles) gather(tile + stride);  // in flight while this tile is handed over
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_aready + 8 * set);
+        }
+    } else if (warp >= 20) {
+        // ================= drain: group = accumulator stage =================
+        pdl_wait();  // `out` may still be read by the previous forward
+        const int g = (warp - 20) >> 2, q = warp & 3;
+        uint8_t* stg = sm + STC3_OFF_STG + (warp - 20) * 4096;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)g * 64u;
+        uint32_t ph = 0;
+        for (int tile = (int)blockIdx.x + g * (int)gridDim.x; tile < n_tiles; tile += 3 * (int)gridDim.x, ph ^= 1u) {
+            mbar_wait(bar_tfull + 8 * g, ph);
+            tc_fence_after();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float v[16], c[16];
+                tmem_ld16(taddr + 16u * h, v);
+                tmem_ld16(taddr + (uint32_t)STC_NC + 16u * h, c);
+                tmem_ld_wait();
+                // transpose through a per-warp swizzled tile so that one STG.128 writes 4 whole pixels (512 contiguous bytes)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<float4*>(stg + lane * 128 + (((4 * h + j) ^ (lane & 7)) << 4)) =
+                        swish4p(make_float4(v[4 * j] + c[4 * j], v[4 * j + 1] + c[4 * j + 1], v[4 * j + 2] + c[4 * j + 2], v[4 * j + 3] + c[4 * j + 3]));
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * g);  // the accumulator pair has been read: hand it back
+            const long long pix0 = (long long)tile * TC_BM + q * 32;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = 4 * i + (lane >> 3), cc = lane & 7;
+                const float4 x = *reinterpret_cast<const float4*>(stg + r * 128 + ((cc ^ (r & 7)) << 4));
+                if (pix0 + r < p.n_pix) st4(p.out + (size_t)(pix0 + r) * 32 + cc * 4, x);
+            }
+            __syncwarp();
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// k_stem_tc3 reads aligned 32-bit words of the u8 image: W % 4 == 0 (every row then starts and ends on a word) and a 4-byte aligned base
+inline bool stc3_supported(const StcParams& p) { return p.W % 4 == 0 && ((uintptr_t)p.in & 3u) == 0 && p.n_pix * 27ll < (1ll << 31); }
+inline cudaError_t stc3_launch(const StcParams& p, int sms, cudaStream_t s) {
+    cudaError_t e = smem_optin((const void*)k_stem_tc3, (int)STC3_SMEM);
+    if (e != cudaSuccess) return e;
+    const int grid = p.n_tiles < sms ? p.n_tiles : sms;
+    return launch_pdl(k_stem_tc3, dim3(grid), dim3(STC3_THREADS), STC3_SMEM, s, p);
+}
+
 template <int FMT>
 inline cudaError_t stc2_launch_t(const StcParams& p, int sms, cudaStream_t s) {
     const int grid = p.n_tiles < sms ? p.n_tiles : sms;

@@ -1,3 +1,5 @@
 mkdir -p gpurun_out
-timeout 300 python tools/mbf_check.py --mask 0x6 --mbd 0x1 --time 2>&1 | tail -4
-timeout 300 python tools/mbf_trace.py --mask 0x4 --j0 200 --nj 60 > gpurun_out/trace_b2.log 2>&1
+timeout 600 python -m pytest tests -x -q -m gpu -k "taps or u8 or resize or batch32" 2>&1 | tail -2
+timeout 300 python tools/step_times.py 2>&1 | sed -n 3,3p
+CF_SMOOTH_INPUT=1 timeout 300 python tools/step_times.py 2>&1 | sed -n 3,3p
+CF_SMOOTH_INPUT=1 CF_STEM_TC=2 timeout 300 python tools/step_times.py 2>&1 | sed -n 3,3p

@@ -31,6 +31,9 @@ def main():
     w = os.path.join(ROOT, "tests", "golden", "weights_e100.npz")
     eng = pkg.Engine(w, max_batch=a.batch, max_h=a.size, max_w=a.size, device=0, pw_engine=a.pw)
     x = torch.from_numpy(np.random.RandomState(0).randint(0, 256, size=(a.batch, a.size, a.size, 3), dtype=np.uint8)).cuda()
+    if os.environ.get("CF_SMOOTH_INPUT"):  # probe: an image-like input (neighbouring pixels hold near-equal bytes), against the uniform-random default
+        g = np.add.outer(np.arange(a.size), np.arange(a.size)) // 5 % 256
+        x = torch.from_numpy(np.broadcast_to(g[None, :, :, None], (a.batch, a.size, a.size, 3)).astype(np.uint8).copy()).cuda()
     eng.forward(x)
     eng.decode_topk(100)
     torch.cuda.synchronize()
