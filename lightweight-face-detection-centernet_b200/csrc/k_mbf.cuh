@@ -140,12 +140,6 @@ inline int mbf_prepare_dw(PwTcState& st, const float* key, const float* hw, int 
     return CF_OK;
 }
 
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
-    const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
-                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-                 : "memory");
-}
 
 template <typename C, bool TRACE = false>
 __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ CUtensorMap tmX, const MbfParams p) {

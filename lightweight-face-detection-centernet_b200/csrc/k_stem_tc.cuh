@@ -546,25 +546,20 @@ __global__ void __launch_bounds__(STC3_THREADS, 1) k_stem_tc3(const StcParams p)
                     v[ky][2] = x2 >> s5;
                 }
             }
-            const uint8_t* pgx[3];   // table page of the kx == 2 taps, ky == 2 taps, both, per channel
-            const uint8_t* pgy[3];
-            const uint8_t* pgxy[3];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const uint8_t* n = lutb + c * 32768;
-                const uint8_t* z = lutb + 3 * 32768;
-                pgx[c] = (edge & 1u) ? z : n;
-                pgy[c] = (edge & 2u) ? z : n;
-                pgxy[c] = edge ? z : n;
-            }
+            const uint32_t edge_now = edge;
+            // the window registers are dead: the next tile's loads go out now and land during this tile's table look-ups
+            // (issued at the end of the iteration they were the head of the next one's dependency chain: 2 producer sets -> 167 us)
+            if (tile + stride < n_tiles) gather(tile + stride);
+            // padded taps read the table's zero page: a byte-offset mask per tap class (page offset c * 32 KB | 96 KB)
+            const uint32_t zx = (edge_now & 1u) ? 3u * 32768u : 0u, zy = (edge_now & 2u) ? 3u * 32768u : 0u, zxy = zx | zy;
             mbar_wait(bar_aempty + 8 * set, ph ^ 1u);
             tc_fence_after();
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                float hi[16], lo[16];
+            for (int qt = 0; qt < 4; ++qt) {  // 8 taps per TMEM store: 16 live values (the 64-register cap spilled the prefetched window otherwise)
+                float hi[8], lo[8];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int k = half * 16 + i;
+                for (int i = 0; i < 8; ++i) {
+                    const int k = qt * 8 + i;
                     if (k >= 27) {
                         hi[i] = 0.f, lo[i] = 0.f;
                         continue;
@@ -573,14 +568,14 @@ __global__ void __launch_bounds__(STC3_THREADS, 1) k_stem_tc3(const StcParams p)
                     const uint32_t word = v[ky][r >> 2];
                     const int bs = 8 * (r & 3) - 7;  // byte * 128 = the table entry's byte offset
                     const uint32_t boff = (bs < 0 ? word << 7 : word >> bs) & 0x7f80u;
-                    const uint8_t* pg = ky == 2 ? (kx == 2 ? pgxy[c] : pgy[c]) : (kx == 2 ? pgx[c] : lutb + c * 32768);
-                    const float2 e = *reinterpret_cast<const float2*>(pg + boff);
+                    // page c, or page 3 (zeros) for a padded tap: c * 32 KB | 96 KB = 96 KB for c = 0..2
+                    const uint32_t pg = (uint32_t)c * 32768u | (ky == 2 ? (kx == 2 ? zxy : zy) : (kx == 2 ? zx : 0u));
+                    const float2 e = *reinterpret_cast<const float2*>(lutb + pg + boff);
                     hi[i] = e.x, lo[i] = e.y;
                 }
-                tmem_st16(ta + 16u * half, hi);
-                tmem_st16(ta + 32u + 16u * half, lo);
+                tmem_st8(ta + 8u * qt, hi);
+                tmem_st8(ta + 32u + 8u * qt, lo);
             }
-            if (tile + stride < n_tiles) gather(tile + stride);  // in flight while this tile is handed over
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
