@@ -527,14 +527,14 @@ __global__ void __launch_bounds__(STC3_THREADS, 1) k_stem_tc3(const StcParams p)
                 for (int i = 0; i < 3; ++i) w[ky][i] = __ldg(reinterpret_cast<const uint32_t*>(in + a) + i);
             }
         };
-        const uint8_t* lutb = reinterpret_cast<const uint8_t*>(lut2) + (lane & 15) * 8;  // this lane's copy
+        const uint32_t lutb = base + STC3_OFF_LUT + (uint32_t)(lane & 15) * 8u;  // this lane's copy (32-bit shared address: no 64-bit pointer arithmetic per tap)
         const int stride = 4 * (int)gridDim.x;
         const int first = (int)blockIdx.x + set * (int)gridDim.x;
         if (first < n_tiles) gather(first);
         uint32_t ph = 0;
         for (int tile = first; tile < n_tiles; tile += stride, ph ^= 1u) {
-            // the pixel's 9 bytes of each row, shifted down to bit 0: v[ky][0] = bytes 0-3, [1] = bytes 4-7, [2] = byte 8
-            uint32_t v[3][3];
+            // the pixel's 9 bytes of each row, shifted down to bit 0: v[ky][0] = bytes 0-3, [1] = bytes 4-7; v8 = byte 8 of rows 0, 1, 2
+            uint32_t v[3][2], v8 = 0;
             {
                 const bool far = sh >= 32u;
                 const uint32_t s5 = sh & 31u;
@@ -543,7 +543,7 @@ __global__ void __launch_bounds__(STC3_THREADS, 1) k_stem_tc3(const StcParams p)
                     const uint32_t x0 = far ? w[ky][1] : w[ky][0], x1 = far ? w[ky][2] : w[ky][1], x2 = far ? 0u : w[ky][2];
                     v[ky][0] = __funnelshift_r(x0, x1, s5);
                     v[ky][1] = __funnelshift_r(x1, x2, s5);
-                    v[ky][2] = x2 >> s5;
+                    v8 |= ((x2 >> s5) & 0xffu) << (8 * ky);
                 }
             }
             const uint32_t edge_now = edge;
@@ -551,7 +551,7 @@ __global__ void __launch_bounds__(STC3_THREADS, 1) k_stem_tc3(const StcParams p)
             // (issued at the end of the iteration they were the head of the next one's dependency chain: 2 producer sets -> 167 us)
             if (tile + stride < n_tiles) gather(tile + stride);
             // padded taps read the table's zero page: a byte-offset mask per tap class (page offset c * 32 KB | 96 KB)
-            const uint32_t zx = (edge_now & 1u) ? 3u * 32768u : 0u, zy = (edge_now & 2u) ? 3u * 32768u : 0u, zxy = zx | zy;
+            const bool px = edge_now & 1u, py = edge_now & 2u;
             mbar_wait(bar_aempty + 8 * set, ph ^ 1u);
             tc_fence_after();
 #pragma unroll
@@ -565,13 +565,13 @@ __global__ void __launch_bounds__(STC3_THREADS, 1) k_stem_tc3(const StcParams p)
                         continue;
                     }
                     const int ky = k / 9, r = k - ky * 9, kx = r / 3, c = r - kx * 3;
-                    const uint32_t word = v[ky][r >> 2];
-                    const int bs = 8 * (r & 3) - 7;  // byte * 128 = the table entry's byte offset
+                    const uint32_t word = r == 8 ? v8 : v[ky][r >> 2];
+                    const int bs = 8 * (r == 8 ? ky : (r & 3)) - 7;  // byte * 128 = the table entry's byte offset
                     const uint32_t boff = (bs < 0 ? word << 7 : word >> bs) & 0x7f80u;
                     // page c, or page 3 (zeros) for a padded tap: c * 32 KB | 96 KB = 96 KB for c = 0..2
-                    const uint32_t pg = (uint32_t)c * 32768u | (ky == 2 ? (kx == 2 ? zxy : zy) : (kx == 2 ? zx : 0u));
-                    const float2 e = *reinterpret_cast<const float2*>(lutb + pg + boff);
-                    hi[i] = e.x, lo[i] = e.y;
+                    const bool pad = (ky == 2 && py) || (kx == 2 && px);
+                    const uint32_t pg = pad ? 3u * 32768u : (uint32_t)c * 32768u;
+                    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(hi[i]), "=f"(lo[i]) : "r"(lutb + pg + boff));
                 }
                 tmem_st8(ta + 8u * qt, hi);
                 tmem_st8(ta + 32u + 8u * qt, lo);
