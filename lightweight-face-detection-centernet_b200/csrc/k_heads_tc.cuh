@@ -13,8 +13,10 @@
 // Per tile: TMA -> all threads split the tile into tf32 hi (in place) and lo (second buffer) -> one elected lane issues
 // 9 taps x 3 K steps x { A_hi.[W_hi|W_lo] (N = 32: main and correction accumulator), A_lo.W_hi (N = 16: correction) } -> the drain of
 // the PREVIOUS tile runs under these MMAs (two accumulator slots) -> bias, sigmoid/clamp, planar stores.  Two CTAs per SM.
-// Bound: every MMA streams a 4 KB A slice out of shared memory whatever N is -- 54 MMAs per tile; the FFMA kernel it replaces
-// (k_heads, 3456 FFMA per pixel) stays as the fp32 validation engine's head.
+// Bound: every MMA streams a 4 KB A slice out of shared memory whatever N is -- 54 MMAs per tile at ~55 cycles each on the tensor
+// pipe that the SM's two CTAs share: 7 360 tiles x 54 x 55 cycles / 148 SMs = 77 us of the measured 87.  (A second issuing warp
+// with its own accumulator pair changed nothing, round 2: the pipe, not the issuing thread, is the limit.)  The FFMA kernel it
+// replaces (k_heads, 3456 FFMA per pixel) stays as the fp32 validation engine's head.
 #pragma once
 #include "k_dwt.cuh"
 
