@@ -452,11 +452,11 @@ __global__ void __launch_bounds__(STC3_THREADS, 1) k_stem_tc3(const StcParams p)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    {
-        const float v = tid < 768 ? __ldg(p.lut + tid) : 0.f;
+    for (int i = tid; i < 1024 * 16; i += STC3_THREADS) {  // consecutive threads fill consecutive slots (entry-major stores were 32-way conflicts: 8 us)
+        const int e = i >> 4;
+        const float v = e < 768 ? __ldg(p.lut + e) : 0.f;
         const float h = tf32_hi(v);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) lut2[tid * 16 + i] = make_float2(h, v - h);
+        lut2[i] = make_float2(h, v - h);
     }
     tc_fence_before();
     __syncthreads();
