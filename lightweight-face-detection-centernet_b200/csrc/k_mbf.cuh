@@ -44,7 +44,7 @@
 
 namespace cf {
 
-template <int KS_, int S_, int CIN_, int STH_, int STW_, int NSY_, int NSX_, int XT_, int YT_, int TD_, int NX_, bool WDS_, bool EXP_ = true, int NT_ = 4, int ND_ = 2>
+template <int KS_, int S_, int CIN_, int STH_, int STW_, int NSY_, int NSX_, int XT_, int YT_, int TD_, int NX_, bool WDS_, bool EXP_ = true, int NT_ = 4, int ND_ = 2, bool TEPI_ = true>
 struct MbfCfg {
     static constexpr int KS = KS_, S = S_, CIN = CIN_, STH = STH_, STW = STW_, NSY = NSY_, NSX = NSX_, XT = XT_, YT = YT_, TD = TD_;
     static constexpr int IH = (STH - 1) * S + KS, IW = (STW - 1) * S + KS, NPX = IH * IW;
@@ -66,8 +66,9 @@ struct MbfCfg {
     // (B2 trace: 4 200 cycles per block), and a single epilogue team bounded the one-chunk layer0 (1 000 cycles per job).  There the
     // COMPUTE TEAM that produced a block's last chunk drains it, one job later, when it has just observed the D hand-back (the
     // projection issuer is in order: that block's projection has retired).  Otherwise the splitters do it, one block behind.
-    static constexpr bool TEAM_EPI = EXP_ && NSUB == 1;  // direct mode: measured slower on the teams (layer0 205 -> 249 us), the splitter warps are idle there
-    static constexpr int NX = NX_, NE = NT, ND = EXP_ ? ND_ : NT, NP = EXP_ ? 2 : 4;
+    static constexpr int LAG = NSUB == 1 ? 2 : 1;  // splitter-side epilogues: blocks between a block's split and its epilogue
+    static constexpr bool TEAM_EPI = EXP_ && NSUB == 1 && TEPI_;  // direct mode: measured slower on the teams (layer0 205 -> 249 us), the splitter warps are idle there
+    static constexpr int NX = NX_, NE = NT, ND = EXP_ ? ND_ : NT, NP = EXP_ ? (TEAM_EPI ? 2 : LAG + 1) : 4;
     // TMEM A slots (the split block input).  A slot holds one sub-tile for ALL the chunks of its block: the splitters (and the X box
     // TMA) run once per (block, sub-tile), the expand issuer re-reads the slot with each chunk's weights and hands it back after the
     // last one.  Slots come in groups of NSUB (one block); NG groups rotate block by block.
@@ -475,7 +476,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
             }
             gr.next(C::NG);
             jt = (i + 1) * nch * NSUB;
-            if (!C::TEAM_EPI && i >= 1) {
+            if (!C::TEAM_EPI && i >= C::LAG) {
                 if (q == 0) TR(17, jt - 1);
                 epilogue(epi_done++);
                 if (q == 0) TR(18, jt - 1);
@@ -656,7 +657,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
 //   3x3 s1, Cin 24 (layer1.1): sub-tile 8 x 10 (halo 10 x 12 = 120 px), block = the sub-tile, items of 1 x 5 outputs: 128 = 4 warps
 // (the 5x5 blocks layer2.0 / layer2.1 have no configuration: 128-pixel halo sub-tiles recompute 1.9x / 2.5x of their expand work)
 using MbfB1 = MbfCfg<3, 2, 16, 3, 8, 2, 2, 2, 1, 3, 4, true, true, 5>;
-using MbfB2 = MbfCfg<3, 1, 24, 8, 10, 1, 1, 5, 1, 4, 1, false, true, 4, 3>;
+using MbfB2 = MbfCfg<3, 1, 24, 8, 10, 1, 1, 5, 1, 4, 1, false, true, 4, 3, false>;
 // direct mode (depth-wise + projection from the hidden tensor): 3x3 s1 with layer1.1's geometry
 using MbfD31 = MbfCfg<3, 1, 32, 8, 10, 1, 1, 5, 1, 4, 1, false, false>;
 

@@ -1,3 +1,2 @@
 mkdir -p gpurun_out
-timeout 900 compute-sanitizer --tool racecheck --racecheck-report analysis python tools/fwd_once.py --n 1 --batch 1 --size 160 > gpurun_out/r2f_racecheck_analysis.log 2>&1; echo racecheck rc=$?; tail -3 gpurun_out/r2f_racecheck_analysis.log
-timeout 900 compute-sanitizer --tool synccheck python tools/fwd_once.py --n 1 --batch 2 --size 320 > gpurun_out/r2f_synccheck.log 2>&1; echo synccheck rc=$?; grep -c "Barrier error" gpurun_out/r2f_synccheck.log; grep -m3 -A6 "Barrier error" gpurun_out/r2f_synccheck.log | head -30; tail -3 gpurun_out/r2f_synccheck.log
+timeout 300 python tools/mbf_check.py --mask 0x6 --mbd 0x1 --time 2>&1 | tail -4
