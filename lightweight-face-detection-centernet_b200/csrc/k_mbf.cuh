@@ -66,7 +66,7 @@ struct MbfCfg {
     // (B2 trace: 4 200 cycles per block), and a single epilogue team bounded the one-chunk layer0 (1 000 cycles per job).  There the
     // COMPUTE TEAM that produced a block's last chunk drains it, one job later, when it has just observed the D hand-back (the
     // projection issuer is in order: that block's projection has retired).  Otherwise the splitters do it, one block behind.
-    static constexpr int LAG = NSUB == 1 ? 2 : 1;  // splitter-side epilogues: blocks between a block's split and its epilogue
+    static constexpr int LAG = 2;  // splitter-side epilogues: blocks between a block's split and its epilogue
     static constexpr bool TEAM_EPI = EXP_ && NSUB == 1 && TEPI_;  // direct mode: measured slower on the teams (layer0 205 -> 249 us), the splitter warps are idle there
     static constexpr int NX = NX_, NE = NT, ND = EXP_ ? ND_ : NT, NP = EXP_ ? (TEAM_EPI ? 2 : LAG + 1) : 4;
     // TMEM A slots (the split block input).  A slot holds one sub-tile for ALL the chunks of its block: the splitters (and the X box
