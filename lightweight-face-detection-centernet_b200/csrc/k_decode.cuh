@@ -78,7 +78,7 @@ constexpr int TOPK_SMEM_MAX_HW = 51200;
 template <bool SM>
 __global__ void __launch_bounds__(1024) k_topk(const float* __restrict__ pk, const float* __restrict__ wh,
                                                const float* __restrict__ reg, int H, int W, int K,
-                                               float* __restrict__ dets, int32_t* __restrict__ inds) {
+                                               float* __restrict__ dets, int32_t* __restrict__ inds, int cand_cap) {
     extern __shared__ uint32_t skeys[];
     __shared__ unsigned hist[256];
     __shared__ unsigned long long buf[1024];
@@ -99,13 +99,72 @@ __global__ void __launch_bounds__(1024) k_topk(const float* __restrict__ pk, con
     auto key_at = [&](int i) -> uint32_t { return SM ? skeys[i] : fkey(__ldcg(p + i)); };
     const int HWp = (HW + 1023) & ~1023;  // whole warps walk the tail together (ballots below)
 
+    // Candidate list (SM only).  After the peak mask ~90-95 % of a map is +0.0; when at least K scores are positive the K winners
+    // are among them, so the positive keys are compacted ONCE, in index order, and the radix passes and the tie admission walk
+    // that list (1-3 rows of 1024 instead of 25 per pass).  Fewer than K positives, or more than the list holds: the full walk.
+    unsigned* ecnt = SM ? skeys + HWp : nullptr;        // [rows * 32] per (row of 1024, warp) counts, rows = HWp / 1024 <= 50
+    unsigned* cand = SM ? ecnt + (HWp >> 5) : nullptr;  // [cand_cap] indices of the positive keys, ascending
+    const int rows = HWp >> 10;
+    // exclusive scan of ecnt[0 .. rows*32) in place (thread t owns entries 2t, 2t+1); returns the total through s_cnt
+    auto scan_ecnt = [&]() {
+        const int n = rows * 32;
+        const unsigned a = 2 * tid < n ? ecnt[2 * tid] : 0u, b2 = 2 * tid + 1 < n ? ecnt[2 * tid + 1] : 0u;
+        unsigned inc = a + b2;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, inc, off);
+            if (lane >= off) inc += t;
+        }
+        if (lane == 31) wcnt[warp] = inc;
+        __syncthreads();
+        unsigned woff = 0;
+        for (int w2 = 0; w2 < warp; ++w2) woff += wcnt[w2];
+        const unsigned excl = woff + inc - (a + b2);
+        if (2 * tid < n) ecnt[2 * tid] = excl;
+        if (2 * tid + 1 < n) ecnt[2 * tid + 1] = excl + a;
+        if (tid == 1023) s_cnt = woff + inc;
+        __syncthreads();
+    };
+    int ncand = -1;  // >= 0: the list is in use
+    if (SM) {
+        constexpr uint32_t KEY0 = 0x80000000u;  // fkey(+0.0f): the masked-out pixels (sigmoid scores are > 0)
+        for (int v = 0; v < rows; ++v) {
+            const int i = v * 1024 + tid;
+            const unsigned m = __ballot_sync(0xffffffffu, i < HW && skeys[i] > KEY0);
+            if (lane == 0) ecnt[v * 32 + warp] = __popc(m);
+        }
+        __syncthreads();
+        scan_ecnt();
+        const unsigned npos = s_cnt;
+        __syncthreads();
+        if (npos >= (unsigned)K && npos <= (unsigned)cand_cap) {
+            ncand = (int)npos;
+            for (int v = 0; v < rows; ++v) {
+                const int i = v * 1024 + tid;
+                const bool pos = i < HW && skeys[i] > KEY0;
+                const unsigned m = __ballot_sync(0xffffffffu, pos);
+                if (pos) cand[ecnt[v * 32 + warp] + __popc(m & ((1u << lane) - 1u))] = (unsigned)i;
+            }
+            __syncthreads();
+        }
+    }
+    const int NW = ncand >= 0 ? ((ncand + 1023) & ~1023) : HWp;  // what the passes walk: list positions or pixels
+    auto item = [&](int j, bool* in) -> uint32_t {                // key of walk position j
+        if (ncand >= 0) {
+            *in = j < ncand;
+            return *in ? skeys[cand[j]] : 0u;
+        }
+        *in = j < HW;
+        return *in ? key_at(j) : 0u;
+    };
+
     unsigned prefix = 0, mask = 0, krem = K;
     for (int pass = 3; pass >= 0; --pass) {
         if (tid < 256) hist[tid] = 0;
         __syncthreads();
-        for (int i = tid; i < HWp; i += 1024) {
-            const bool in = i < HW;
-            const uint32_t key = in ? key_at(i) : 0u;
+        for (int i = tid; i < NW; i += 1024) {
+            bool in;
+            const uint32_t key = item(i, &in);
             const bool hit = in && (key & mask) == prefix;
             const unsigned bin = (key >> (8 * pass)) & 255u;
             const unsigned act = __ballot_sync(0xffffffffu, hit);
@@ -146,11 +205,40 @@ __global__ void __launch_bounds__(1024) k_topk(const float* __restrict__ pk, con
     if (tid == 0) s_cnt = 0;
     for (int i = tid; i < 1024; i += 1024) buf[i] = 0ull;
     __syncthreads();
-    if (SM) {
+    if (SM && ncand >= 0) {
+        // the list is in index order: winners above the threshold in any order, ties AT the threshold lowest list position first
+        unsigned eq_run = 0;
+        for (int base = 0; base < NW; base += 1024) {
+            const int j = base + tid;
+            const bool valid = j < ncand;
+            const unsigned i = valid ? cand[j] : 0u;
+            const uint32_t key = valid ? skeys[i] : 0u;
+            const bool gt = valid && key > T, eq = valid && key == T;
+            const unsigned mg = __ballot_sync(0xffffffffu, gt);
+            if (mg) {
+                unsigned basee = 0;
+                if (lane == 0) basee = atomicAdd(&s_cnt, (unsigned)__popc(mg));
+                basee = __shfl_sync(0xffffffffu, basee, 0);
+                if (gt) buf[basee + __popc(mg & ((1u << lane) - 1u))] = ((unsigned long long)key << 32) | (0xFFFFFFFFu - i);
+            }
+            const unsigned me = __ballot_sync(0xffffffffu, eq);
+            if (lane == 0) wcnt[warp] = __popc(me);
+            __syncthreads();
+            unsigned woff = 0, tot = 0;
+#pragma unroll
+            for (int w2 = 0; w2 < 32; ++w2) {
+                const unsigned c = wcnt[w2];
+                woff += (w2 < warp) ? c : 0u;
+                tot += c;
+            }
+            const unsigned rank = eq_run + woff + __popc(me & ((1u << lane) - 1u));
+            if (eq && rank < krem) buf[G + rank] = ((unsigned long long)T << 32) | (0xFFFFFFFFu - i);
+            eq_run += tot;
+            __syncthreads();
+        }
+    } else if (SM) {
         // winners above the threshold take slots in any order (they are sorted below); ties AT the threshold are admitted
         // lowest index first: per (row of 1024, warp) tie counts -> block-wide exclusive scan -> rank = base + lane rank
-        unsigned* ecnt = skeys + HWp;  // [rows * 32], rows = HWp / 1024 <= 50
-        const int rows = HWp >> 10;
         for (int v = 0; v < rows; ++v) {
             const int i = v * 1024 + tid;
             const bool valid = i < HW;
@@ -167,22 +255,11 @@ __global__ void __launch_bounds__(1024) k_topk(const float* __restrict__ pk, con
             if (lane == 0) ecnt[v * 32 + warp] = __popc(me);
         }
         __syncthreads();
-        {   // exclusive scan of ecnt[0 .. rows*32) in place: thread t owns entries 2t, 2t+1
-            const int n = rows * 32;
-            const unsigned a = 2 * tid < n ? ecnt[2 * tid] : 0u, b2 = 2 * tid + 1 < n ? ecnt[2 * tid + 1] : 0u;
-            unsigned inc = a + b2;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const unsigned t = __shfl_up_sync(0xffffffffu, inc, off);
-                if (lane >= off) inc += t;
-            }
-            if (lane == 31) wcnt[warp] = inc;
+        {
+            const unsigned gt_total = s_cnt;  // the scan reports its total through s_cnt: keep the winners' slot counter
             __syncthreads();
-            unsigned woff = 0;
-            for (int w2 = 0; w2 < warp; ++w2) woff += wcnt[w2];
-            const unsigned excl = woff + inc - (a + b2);
-            if (2 * tid < n) ecnt[2 * tid] = excl;
-            if (2 * tid + 1 < n) ecnt[2 * tid + 1] = excl + a;
+            scan_ecnt();
+            if (tid == 0) s_cnt = gt_total;
             __syncthreads();
         }
         for (int v = 0; v < rows; ++v) {
@@ -259,9 +336,12 @@ inline cudaError_t launch_topk(const float* pk, const float* wh, const float* re
         cudaError_t e = smem_optin((const void*)k_topk<true>, (TOPK_SMEM_MAX_HW + TOPK_SMEM_MAX_HW / 32) * 4);
         if (e != cudaSuccess) return e;
         const size_t HWp = ((size_t)HW + 1023) & ~(size_t)1023;
-        return launch_pdl(k_topk<true>, dim3(B), dim3(1024), (HWp + HWp / 32) * 4, s, pk, wh, reg, H, W, K, dets, inds);
+        // candidate list: what the opted-in shared memory leaves beside the keys, at most 8 192 entries
+        const size_t room = ((size_t)TOPK_SMEM_MAX_HW + TOPK_SMEM_MAX_HW / 32 - HWp - HWp / 32);
+        const int cand_cap = (int)(room < 8192 ? room : 8192);
+        return launch_pdl(k_topk<true>, dim3(B), dim3(1024), (HWp + HWp / 32 + (size_t)cand_cap) * 4, s, pk, wh, reg, H, W, K, dets, inds, cand_cap);
     }
-    return launch_pdl(k_topk<false>, dim3(B), dim3(1024), 0, s, pk, wh, reg, H, W, K, dets, inds);
+    return launch_pdl(k_topk<false>, dim3(B), dim3(1024), 0, s, pk, wh, reg, H, W, K, dets, inds, 0);
 }
 
 // numpy float32 floor_divide (npy_floor_dividef -> npy_divmodf), used by centerface.py:56-58

@@ -1,2 +1,3 @@
 mkdir -p gpurun_out
-timeout 300 python tools/mbf_check.py --mask 0x6 --mbd 0x1 --time 2>&1 | tail -4
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+timeout 300 python tools/step_times.py 2>&1 | grep -E "peak|top-k|total"
