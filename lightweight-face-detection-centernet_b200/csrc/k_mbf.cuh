@@ -12,28 +12,37 @@
 //
 //   job = (sub-tile, 32-channel chunk).  A sub-tile is STH x STW output pixels whose input halo
 //   IH x IW = ((STH-1)S+KS) x ((STW-1)S+KS) is at most 128 pixels = ONE 128-row MMA block, so every stage of a job is one
-//   fixed-size unit: one TMA box, one TMEM A slot, one expand accumulator, one 16 KB E slot.
+//   fixed-size unit: one expand accumulator (32 TMEM columns), one E tile (17 KB).
 //   A block = NSY x NSX sub-tiles (<= 128 output pixels) = the rows of ONE projection accumulator; jobs run chunk-major
 //   inside a block, so chunk c of all its sub-tiles fills one D operand (hi/lo, K = 32) and the projection accumulates
-//   over the chunks in TMEM.
+//   over the chunks in TMEM.  A sub-tile's X box is loaded and split ONCE per block: its TMEM A slot is read by the expand
+//   MMAs of every chunk.
 //
-//   warp 0        TMA producer: the X halo box of every job (zero fill outside the image = the reference's ZeroPad2d,
-//                 :63-70; swish(0 . W) = 0 because the expand conv has no bias), re-read per chunk from L2
-//   warp 1        expand issuer: the MMAs of a job as soon as its A slot is written and its team's accumulator is free
-//   warp 2        projection issuer: the MMAs of a (block, chunk) as soon as its D operand is complete (its own warp, so
+//   warp 0        TMA producer: the X halo box of every (block, sub-tile) (zero fill outside the image = the reference's
+//                 ZeroPad2d, :63-70; swish(0 . W) = 0 because the expand conv has no bias); the weight images once
+//   warps 1, 2    expand issuers: the MMAs of a job as soon as its sub-tile is split and its team's accumulator is free;
+//                 warp w serves the teams t % 2 == w (a tcgen05.mma costs its issuing thread ~55 cycles whatever its size)
+//   warp 3        projection issuer: the MMAs of a (block, chunk) as soon as its D operand is complete (its own warp, so
 //                 that neither MMA stream ever waits behind the other's barrier); also allocates / frees TMEM
-//   warps 4-7     splitters: X row -> tf32 hi + lo -> TMEM A slot (tcgen05.st, lane = halo pixel); between blocks they
-//                 drain the previous block's projection accumulator (+ residual) and store Y
-//   warps 8-23    four compute teams of four warps, jobs round-robin.  A team takes its job through both element-wise
-//                 phases: expand accumulator (TMEM, a warp = a lane quarter) -> Swish -> the team's private E tile in shared
-//                 memory -> depth-wise taps -> Swish -> tf32 hi/lo rows of the D operand.  Teams are in different phases at
-//                 any time, so the MUFU-bound drain of one overlaps the LDS/FMA-bound depth-wise phase of another on every
-//                 scheduler; the only CTA-level synchronisation is two 128-thread named barriers per job inside a team.
+//   warps 4-7     splitters: X row -> tf32 hi + lo -> TMEM A slot (tcgen05.st, lane = halo pixel), once per (block,
+//                 sub-tile); after a block's splits they drain the projection accumulator of the block LAG = 2 blocks back
+//                 (+ residual) and store Y
+//   warps 8-      four or five compute teams of four warps, jobs round-robin.  A team takes its job through both
+//                 element-wise phases: expand accumulator (TMEM, a warp = a lane quarter) -> Swish -> the team's private E
+//                 tile in shared memory -> depth-wise taps -> Swish -> tf32 hi/lo rows of the D operand.  Teams are in
+//                 different phases at any time, so the MUFU-bound drain of one overlaps the LDS/FMA-bound depth-wise phase
+//                 of another on every scheduler; the only CTA-level synchronisation is two 128-thread named barriers per
+//                 job inside a team.
+//   Direct mode (EXP = false: depth-wise + projection from a hidden tensor in HBM): no expand roles, TMA writes the E tiles.
+//
+//   The development trace (clock64 of every hand-off, tools/mbf_trace.py) is a separate template instantiation: a warp of
+//   this kernel is a latency-bound chain that pays ~10 cycles per instruction, and the run-time test in front of ~10 trace
+//   sites per job cost 5 %.  History and measurements: profiles/r2_mbf.md.
 //
 // mbarrier waits are by phase PARITY, so a waiter must observe EVERY phase of a barrier it waits on (one that skips a phase
 // finds the parity of a phase that has not begun "already complete" -- seen as a timing-dependent deadlock in an earlier
-// version whose depth-wise teams shared E slots round-robin).  Hence every accumulator / E tile belongs to one team, and the
-// D operand hand-back is per slot when the same teams write every use of a slot, else per writer team (see d_free below).
+// version whose depth-wise teams shared E slots round-robin).  Hence every accumulator / E tile belongs to one team, every
+// barrier has one fixed waiter role, and the D operand hand-back is per writer team or per slot (see DFREE_PER_TEAM below).
 //
 // 3xTF32: expand uses ONE accumulator, the two correction products first (while the accumulator is ~2^-11 of its final
 // size their per-MMA accumulator truncation, tools/tc_accum_probe.py, is negligible), then the K/8 main products; the
