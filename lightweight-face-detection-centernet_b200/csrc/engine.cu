@@ -700,6 +700,11 @@ int cf_create(const void* weights, size_t weights_bytes, int device, int max_bat
                 continue;
             }
             if (b.t != 1) rc = prep("b" + std::to_string(i) + ".exp", b.cin, b.hid());
+            if (!rc && !block_is_mbd(pw_engine, i)) {  // the tap chunk image: k_dwt reads its taps from shared memory
+                const std::string nd = "b" + std::to_string(i) + ".dw";
+                const float* hd = blob.get(nd, (uint64_t)b.k * b.k * b.hid(), why);
+                rc = hd ? mbf_prepare_dw(e->tc, e->w[nd], hd, b.k * b.k, b.hid()) : fail(CF_EWEIGHTS, "cf_create: %s", why.c_str());
+            }
             if (!rc && block_is_mbd(pw_engine, i)) {  // one 32-column projection image per K block + the tap chunk image
                 const std::string np = "b" + std::to_string(i) + ".proj", nd = "b" + std::to_string(i) + ".dw";
                 const float* hp = blob.get(np, (uint64_t)b.hid() * b.cout, why);

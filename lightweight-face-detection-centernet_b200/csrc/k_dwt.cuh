@@ -34,7 +34,7 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
 // SWZ: the halo tile is in the TMA's SWIZZLE_128B layout (needed where the tile doubles as a tcgen05 operand).  A quarter
 // warp (8 lanes = the 8 channel vectors of one pixel) reads one whole 128-byte pixel row per LDS.128 wavefront, which is
 // bank-conflict free with or without the swizzle; without it every window address is base + an immediate.
-template <typename G, int KS, int S, int XT, int YT, bool WD_GLOBAL, int NWARPS, bool SWZ = true>
+template <typename G, int KS, int S, int XT, int YT, bool WD_GLOBAL, int NWARPS, bool SWZ = true, bool WCHUNK = false>
 __device__ __forceinline__ void xd_dw_phase_g(const uint8_t* Es, const float* Wd_s, const XdParams& p, int warp, int pg, int c4,
                                               int cbase, bool cvalid, int b, int ty, int tx) {
     constexpr int NBX = G::TW / XT, NBLK = (G::TH / YT) * NBX;
@@ -62,8 +62,9 @@ __device__ __forceinline__ void xd_dw_phase_g(const uint8_t* Es, const float* Wd
             if (rr < KS) {
 #pragma unroll
                 for (int kx = 0; kx < KS; ++kx)
-                    wt[rr][kx] = WD_GLOBAL ? ldg4(Wd_s + (rr * KS + kx) * p.hid + cbase)
-                                           : *reinterpret_cast<const float4*>(Wd_s + (rr * KS + kx) * p.hid + cbase);
+                    wt[rr][kx] = WCHUNK      ? *reinterpret_cast<const float4*>(Wd_s + (rr * KS + kx) * 32 + c4 * 4)  // the chunk's tap image in shared memory
+                                 : WD_GLOBAL ? ldg4(Wd_s + (rr * KS + kx) * p.hid + cbase)
+                                             : *reinterpret_cast<const float4*>(Wd_s + (rr * KS + kx) * p.hid + cbase);
             }
 #pragma unroll
             for (int dy = 0; dy < YT; ++dy) {
@@ -105,6 +106,25 @@ inline int xd_make_map(PwTcState& st, CUtensorMap* map, const float* ptr, int B,
 
 
 
+// Build (once per block) the per-chunk tap image of a depth-wise weight tensor Wd[k*k][hid]: [chunk][tap][32 channels], zero past hid.
+inline int mbf_prepare_dw(PwTcState& st, const float* key, const float* hw, int kk, int hid) {
+    if (st.dw_imgs.count(key)) return CF_OK;
+    const int nch = (hid + 31) / 32;
+    std::vector<float> img((size_t)nch * kk * 32, 0.f);
+    for (int c = 0; c < nch; ++c)
+        for (int t = 0; t < kk; ++t)
+            for (int i = 0; i < 32 && c * 32 + i < hid; ++i) img[((size_t)c * kk + t) * 32 + i] = hw[(size_t)t * hid + c * 32 + i];
+    float* d = nullptr;
+    if (cudaMalloc((void**)&d, img.size() * 4) != cudaSuccess) return fail(CF_ECUDA, "mbf_prepare_dw: cudaMalloc failed");
+    if (cudaMemcpy(d, img.data(), img.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(d);
+        return fail(CF_ECUDA, "mbf_prepare_dw: cudaMemcpy failed");
+    }
+    st.dw_imgs[key] = d;
+    return CF_OK;
+}
+
+
 constexpr int DWT_THREADS = 256;
 
 // Output tile per item.  GEOM 0: 10 x 10, divides every map of the network (320, 160, 80, 40, 20) but fills only 25 of the
@@ -128,6 +148,8 @@ struct DwtParams {
     XdParams x;  // We unused; hid = C
     int nchunk;  // ceil(C / 32); TMA zero-fills the channels past C in the last chunk
     int nst;     // pipeline stages
+    const float* wd_img;  // [chunk][tap][32] tap image (mbf_prepare_dw) or NULL: taps through L1 from Wd
+    uint32_t sb;          // bytes per stage: halo tile (+ the chunk's taps when wd_img)
     int dbg;     // development only (env CF_DWT_DEBUG): 1 = skip the compute phase (TMA streaming rate of the tiling)
 };
 
@@ -139,7 +161,8 @@ __global__ void __launch_bounds__(DWT_THREADS, 2) k_dwt(const __grid_constant__ 
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
     const int nst = P.nst;
-    const uint32_t bars = base + (uint32_t)nst * G::XBYTES;
+    const uint32_t SB = P.sb;
+    const uint32_t bars = base + (uint32_t)nst * SB;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int c4 = lane & 7, pg = lane >> 3;
@@ -156,7 +179,7 @@ __global__ void __launch_bounds__(DWT_THREADS, 2) k_dwt(const __grid_constant__ 
     // Thread 0 decodes an item once, when it issues the item's TMA, and leaves (chunk, tx, ty, b) beside the barriers; the
     // other 255 threads read it after the barrier wait instead of repeating three integer divisions each (the SASS of the
     // previous version spent ~35 % of its instructions per item on that decode).
-    int4* info = reinterpret_cast<int4*>(sm + (size_t)nst * G::XBYTES + 64);  // [nst], after the 8 barriers
+    int4* info = reinterpret_cast<int4*>(sm + (size_t)nst * SB + 64);  // [nst], after the 8 barriers
     auto issue = [&](long long item, int stage) {  // one elected lane of warp 0 only
         const int ch = (int)(item % P.nchunk);
         int t = (int)(item / P.nchunk);
@@ -164,8 +187,12 @@ __global__ void __launch_bounds__(DWT_THREADS, 2) k_dwt(const __grid_constant__ 
         t /= p.tiles_x;
         const int ty = t % p.tiles_y, b = t / p.tiles_y;
         info[stage] = make_int4(ch, tx, ty, b);
-        mbar_expect_tx(bars + 8 * stage, (uint32_t)G::NPX * 128u);  // release: orders the info store before the phase flip
-        tma_load_4d(base + stage * G::XBYTES, &tmX, ch * 32, tx * G::TW * S - G::LO, ty * G::TH * S - G::LO, b, bars + 8 * stage);
+        // (release: orders the info store before the phase flip)
+        mbar_expect_tx(bars + 8 * stage, (uint32_t)G::NPX * 128u + (P.wd_img ? (uint32_t)(KS * KS * 128) : 0u));
+        tma_load_4d(base + stage * SB, &tmX, ch * 32, tx * G::TW * S - G::LO, ty * G::TH * S - G::LO, b, bars + 8 * stage);
+        // the chunk's KS*KS x 32 taps ride along: read with LDS in the compute phase (through L1 they were long-scoreboard stalls
+        // in front of the FFMAs: the same change took 12 % off the fused layer1.1 kernel)
+        if (P.wd_img) bulk_load(base + stage * SB + G::XBYTES, P.wd_img + (size_t)ch * (KS * KS * 32), (uint32_t)(KS * KS * 128), bars + 8 * stage);
     };
     if (warp == 0) {  // convergent: one elected lane issues (see elect_one in k_pw_tc.cuh)
         if (elect_one())
@@ -182,8 +209,13 @@ __global__ void __launch_bounds__(DWT_THREADS, 2) k_dwt(const __grid_constant__ 
         const int4 inf = info[stage];
         const int ch = inf.x, tx = inf.y, ty = inf.z, b = inf.w;
         const int cbase = ch * 32 + c4 * 4;
-        if (!(P.dbg & 1))
-            xd_dw_phase_g<G, KS, S, G::XT, G::YT, true, DWT_THREADS / 32, false>(sm + stage * G::XBYTES, p.Wd, p, warp, pg, c4, cbase, cbase < p.hid, b, ty, tx);
+        if (!(P.dbg & 1)) {
+            if (P.wd_img)
+                xd_dw_phase_g<G, KS, S, G::XT, G::YT, false, DWT_THREADS / 32, false, true>(
+                    sm + stage * SB, reinterpret_cast<const float*>(sm + stage * SB + G::XBYTES), p, warp, pg, c4, cbase, cbase < p.hid, b, ty, tx);
+            else
+                xd_dw_phase_g<G, KS, S, G::XT, G::YT, true, DWT_THREADS / 32, false>(sm + stage * SB, p.Wd, p, warp, pg, c4, cbase, cbase < p.hid, b, ty, tx);
+        }
         __syncthreads();  // every thread is done with this stage (and has read its info): refill it
         if (warp == 0) {
             const long long nxt = item + (long long)nst * gridDim.x;
@@ -286,6 +318,15 @@ inline int dwt_plan(PwTcState& st, int ks, int s, const float* X, const float* W
     const long long items = (long long)B * p.tiles_x * p.tiles_y * dl->p.nchunk;
     if (items > 0x7fffffffLL) return fail(CF_EINVAL, "dwt_plan: too many tiles");
     p.n_items = (int)items;
+    {   // taps in shared memory when the block's tap image was prepared (cf_create does it for every block)
+        auto it = st.dw_imgs.find(Wd);
+        dl->p.wd_img = it == st.dw_imgs.end() ? nullptr : it->second;
+        if (const char* ev = getenv("CF_DWT_WDS")) {
+            if (atoi(ev) == 0) dl->p.wd_img = nullptr;
+        }
+        if (dl->p.wd_img) xb += (ks * ks * 128 + 1023) / 1024 * 1024;
+    }
+    dl->p.sb = (uint32_t)xb;
     // two CTAs per SM when at least three stages fit in half of the shared memory, else one CTA with all of it
     const int per_cta2 = (TC_SMEM_MAX / 2 - 2048) / xb;
     int ctas_per_sm = 2, nst = per_cta2;

@@ -132,25 +132,6 @@ struct MbfParams {
     int dbg;  // development only (env CF_MBF_DEBUG; wrong results): 1 no Swish in the drain, 2 no depth-wise work, 4 no Y stores, 8 no split math, 16 no TMA loads, 32 no expand MMAs, 64 no projection MMAs
 };
 
-// Build (once per block) the per-chunk tap image of a depth-wise weight tensor Wd[k*k][hid]: [chunk][tap][32 channels], zero past hid.
-inline int mbf_prepare_dw(PwTcState& st, const float* key, const float* hw, int kk, int hid) {
-    if (st.dw_imgs.count(key)) return CF_OK;
-    const int nch = (hid + 31) / 32;
-    std::vector<float> img((size_t)nch * kk * 32, 0.f);
-    for (int c = 0; c < nch; ++c)
-        for (int t = 0; t < kk; ++t)
-            for (int i = 0; i < 32 && c * 32 + i < hid; ++i) img[((size_t)c * kk + t) * 32 + i] = hw[(size_t)t * hid + c * 32 + i];
-    float* d = nullptr;
-    if (cudaMalloc((void**)&d, img.size() * 4) != cudaSuccess) return fail(CF_ECUDA, "mbf_prepare_dw: cudaMalloc failed");
-    if (cudaMemcpy(d, img.data(), img.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
-        cudaFree(d);
-        return fail(CF_ECUDA, "mbf_prepare_dw: cudaMemcpy failed");
-    }
-    st.dw_imgs[key] = d;
-    return CF_OK;
-}
-
-
 template <typename C, bool TRACE = false>
 __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ CUtensorMap tmX, const MbfParams p) {
     constexpr int KS = C::KS, S = C::S, NX = C::NX, NA = C::NA, NE = C::NE, ND = C::ND, NP = C::NP, NT = C::NT, NDF = C::NDF;
@@ -666,9 +647,9 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
 //   3x3 s1, Cin 24 (layer1.1): sub-tile 8 x 10 (halo 10 x 12 = 120 px), block = the sub-tile, items of 1 x 5 outputs: 128 = 4 warps
 // (the 5x5 blocks layer2.0 / layer2.1 have no configuration: 128-pixel halo sub-tiles recompute 1.9x / 2.5x of their expand work)
 using MbfB1 = MbfCfg<3, 2, 16, 3, 8, 2, 2, 2, 1, 3, 4, true, true, 5>;
-using MbfB2 = MbfCfg<3, 1, 24, 8, 10, 1, 1, 5, 1, 4, 1, false, true, 4, 3, false>;
+using MbfB2 = MbfCfg<3, 1, 24, 8, 10, 1, 1, 5, 1, 4, 1, true, true, 4, 2, false>;
 // direct mode (depth-wise + projection from the hidden tensor): 3x3 s1 with layer1.1's geometry
-using MbfD31 = MbfCfg<3, 1, 32, 8, 10, 1, 1, 5, 1, 4, 1, false, false>;
+using MbfD31 = MbfCfg<3, 1, 32, 8, 10, 1, 1, 5, 1, 4, 1, true, false>;
 
 struct MbfLaunch {
     CUtensorMap tmX;
