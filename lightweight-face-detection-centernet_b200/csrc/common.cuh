@@ -197,9 +197,13 @@ __device__ __forceinline__ const float* idaup_low_ptr(int m, int n, int N, const
     *q = (y & 1) * 2 + (x & 1);
     return ea.low + ((size_t)(b * Hl + (y >> 1)) * Wl + (x >> 1)) * N + n;
 }
-__device__ __forceinline__ float4 idaup_apply(float4 acc, float4 lo, int n, int q, int N, const EpiArgs& ea) {
-    const float4 bb = ldg4(ea.bias + n), tt = ldg4(ea.tu + n);
-    const float4 ss = ldg4(ea.su + q * N + n);  // [2x2 sub-pixel][channel]: one vector load instead of four scalar ones
+// cst (optional): a shared-memory copy [bias N | tu N | su 4N] of the three constant vectors -- through L1 they are nine
+// long-scoreboard loads at the very end of a tile's dependency chain
+__device__ __forceinline__ float4 idaup_apply(float4 acc, float4 lo, int n, int q, int N, const EpiArgs& ea, const float* cst = nullptr) {
+    const float4 bb = cst ? *reinterpret_cast<const float4*>(cst + n) : ldg4(ea.bias + n);
+    const float4 tt = cst ? *reinterpret_cast<const float4*>(cst + N + n) : ldg4(ea.tu + n);
+    const float4 ss = cst ? *reinterpret_cast<const float4*>(cst + 2 * N + q * N + n)
+                          : ldg4(ea.su + q * N + n);  // [2x2 sub-pixel][channel]: one vector load instead of four scalar ones
     float4 o;
     o.x = fmaxf(fmaf(lo.x, ss.x, tt.x), 0.f) + fmaxf(acc.x + bb.x, 0.f);
     o.y = fmaxf(fmaf(lo.y, ss.y, tt.y), 0.f) + fmaxf(acc.y + bb.y, 0.f);

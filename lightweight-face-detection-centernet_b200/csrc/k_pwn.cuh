@@ -79,6 +79,13 @@ __global__ void __launch_bounds__(PWN_THREADS, 2) k_pwn(const __grid_constant__ 
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    // IDAUp: the epilogue's constant vectors (weights, not activations: no dependency on the previous kernel) in shared memory,
+    // behind the barriers (N <= 32: 6 N floats fit the barrier block's kilobyte)
+    float* cst = (EPI == EPI_IDAUP && p.N <= 32 && p.N % 4 == 0) ? reinterpret_cast<float*>(sm + p.off_bars + 256) : nullptr;
+    if (cst) {
+        for (int i = tid; i < 6 * p.N; i += PWN_THREADS)
+            cst[i] = i < p.N ? __ldg(p.ea.bias + i) : i < 2 * p.N ? __ldg(p.ea.tu + i - p.N) : __ldg(p.ea.su + i - 2 * p.N);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -195,7 +202,7 @@ __global__ void __launch_bounds__(PWN_THREADS, 2) k_pwn(const __grid_constant__ 
                         if (n < p.N) {
                             float4 o = make_float4(v[4 * g] + c[4 * g], v[4 * g + 1] + c[4 * g + 1], v[4 * g + 2] + c[4 * g + 2],
                                                    v[4 * g + 3] + c[4 * g + 3]);
-                            if (EPI == EPI_IDAUP && p.NC <= 32) o = idaup_apply(o, lowv[g], n, lowq, p.N, p.ea);  // one 16-column pass per thread
+                            if (EPI == EPI_IDAUP && p.NC <= 32) o = idaup_apply(o, lowv[g], n, lowq, p.N, p.ea, cst);  // one 16-column pass per thread
                             else o = apply_epi<EPI>(o, grow, n, p.N, p.ea);
                             st4(p.out + (size_t)grow * p.N + n, o);
                         }

@@ -1,4 +1,3 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-timeout 300 python tools/step_times.py 2>&1 | grep -E " dw|total"
-CF_DWT_WDS=0 timeout 300 python tools/step_times.py 2>&1 | grep -E "total"
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -2
+timeout 300 python tools/step_times.py 2>&1 | grep -E " up|clast|conv_last|total"
