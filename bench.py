@@ -416,6 +416,28 @@ def run_b200(a):
                 "classes": {k: {"ms": round(v["ms_per_step"], 4), "share": round(v["share"], 4), "GBps": round(v["gbs"], 1),
                                 "frac_hbm": round(v["gbs"] / hbm, 4), "TFLOPs": round(v["tflops"], 2), "launches": v["launches"]}
                             for k, v in classes.items()}}
+    # The fused MBConv kernels move a fraction of the layer-wise bytes (frac_hbm above 1 is that saving, not a faster memory): what
+    # bounds them is the SM's special-function pipe -- 2 MUFU ops (ex2, rcp) per Swish at 16 lanes/clk/SM.  Algorithmic count: every
+    # hidden element once at input resolution (expand Swish, not for layer0 where t = 1) and once at output resolution.
+    try:
+        fz = classes.get("fused_blocks")
+        if fz:
+            hid = {0: (32, 2, 1, False), 1: (96, 2, 2, True), 2: (144, 4, 1, True)}  # block: hidden channels, input stride, dw stride, has expand
+            mask_f, mask_d = L.fused_blocks(pw), L.dwp_blocks(pw)
+            sw = 0
+            for i, (c, div, st, ex) in hid.items():
+                pin, pout = (H // div) * (W // div), (H // (div * st)) * (W // (div * st))
+                if i in mask_f:
+                    sw += c * ((pin if ex else 0) + pout)
+                elif i in mask_d:
+                    sw += c * pout
+            prop = torch.cuda.get_device_properties(0)
+            mufu_peak = 16.0 * prop.multi_processor_count * (clocks.get("sm_mhz") or 1965.0) * 1e6  # ops/s
+            ach = 2.0 * sw * B / (fz["ms_per_step"] * 1e-3)
+            roofline["fused_blocks_sfu"] = {"bound": "sfu (MUFU ex2 + rcp per Swish)", "achieved": round(ach / 1e12, 3), "peak": round(mufu_peak / 1e12, 3),
+                                            "unit": "Tops/s", "frac": round(ach / mufu_peak, 3), "swish_per_image": sw}
+    except Exception as ex:  # instrumentation only
+        roofline["fused_blocks_sfu_error"] = str(ex)
     try:  # measured DRAM bytes of the dominant class (ncu, committed under profiles/), if it matches this run
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r2.json")))
         if (tj.get("engine"), tj.get("batch"), tj.get("h"), tj.get("w")) == (pw, B, H, W):
