@@ -77,6 +77,10 @@ struct TcParams {
     uint32_t amask;  // A ring slots - 1 (1 or 3)
     uint32_t ashift; // log2(A ring slots)
     int stg_bufs;    // staging buffers per epilogue warp (2 or 4)
+    int single;      // 1 (3-pass, ONE K block): one accumulator -- the two correction products of every K step first, then the main
+                     //    products (as k_mbf's expand: while the accumulator holds only corrections their per-MMA truncation is
+                     //    2^-11 smaller) -- so the epilogue reads one accumulator and adds nothing.  The expand layers with K <= 32
+                     //    are bound by their two epilogue groups' instruction chains (ncu + instruction count: ~230 per 32 columns)
     int dbg;         // development only (env CF_TC_DEBUG): 1 skip the A split, 2 skip the stores, 4 skip the MMAs
     int stages;
     uint32_t stage_bytes, a_bytes_stage, b_bytes_block;  // b_bytes_block = NC*128*(passes==3?2:1)
@@ -385,7 +389,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                         const uint64_t b_hi = umma_desc(sb);
                         const uint32_t a_hi = tmem_base + kATmemCol + aslot * 64u, a_lo = a_hi + 32u;
                         if (elect_one()) {
-                            if (nks == 4 && !(p.dbg & 4)) {
+                            if (p.single) {  // nkb == 1: corrections first, then the main products, one accumulator
+                                const uint64_t b_lo = umma_desc(sb + (uint32_t)p.NC * 128u);
+                                for (int k = 0; k < nks; ++k) {
+                                    umma_tf32_ts(d_tmem, a_lo + 8u * k, b_hi + (uint64_t)(k * 2), idesc, k > 0 ? 1u : 0u);
+                                    umma_tf32_ts(d_tmem, a_hi + 8u * k, b_lo + (uint64_t)(k * 2), idesc, 1u);
+                                }
+                                for (int k = 0; k < nks; ++k) umma_tf32_ts(d_tmem, a_hi + 8u * k, b_hi + (uint64_t)(k * 2), idesc, 1u);
+                            } else if (nks == 4 && !(p.dbg & 4)) {
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
                                     umma_tf32_ts(d_tmem, a_hi + 8u * k, b_hi + (uint64_t)(k * 2), idesc2, k > 0 ? 1u : first);  // main += hi.hi ; corr += hi.lo
@@ -415,7 +426,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     const uint64_t a_hi = umma_desc(sa), b_hi = umma_desc(sb);
                     const uint64_t a_lo = umma_desc(sa + TC_A_BYTES);
                     if (elect_one()) {
-                        if (nks == 4 && !(p.dbg & 4)) {
+                        if (kPasses == 3 && p.single) {  // same order as the TMEM-A route: bit-identical results
+                            const uint64_t b_lo = umma_desc(sb + (uint32_t)p.NC * 128u);
+                            for (int k = 0; k < nks; ++k) {
+                                const uint64_t ko = (uint64_t)(k * 2);
+                                umma_tf32(d_tmem, a_lo + ko, b_hi + ko, idesc, k > 0 ? 1u : 0u);
+                                umma_tf32(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+                            }
+                            for (int k = 0; k < nks; ++k) umma_tf32(d_tmem, a_hi + (uint64_t)(k * 2), b_hi + (uint64_t)(k * 2), idesc, 1u);
+                        } else if (nks == 4 && !(p.dbg & 4)) {
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 const uint64_t ko = (uint64_t)(k * 2);  // +32 bytes along K, in 16-byte units
@@ -530,7 +549,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 float v[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (as * p.acc_stride + (uint32_t)(cb * 32));
                 tmem_ld32(taddr, v);
-                if (kPasses == 3) {
+                if (kPasses == 3 && !p.single) {
                     float c[32];
                     tmem_ld32(taddr + (uint32_t)p.NC, c);
                     tmem_ld_wait();
@@ -750,7 +769,13 @@ inline int tc_prepare_layer(PwTcState& st, const float* key, const float* hw, in
     L.K = K;
     L.N = N;
     tc_choose_chunks(K, N, passes, &L.NC, &L.nchunks);
+    // One K block (K <= 32) runs with a single accumulator (TcParams::single), so a chunk may be up to 192 columns wide: the expand
+    // layers 24 -> 144 and 32 -> 192 become ONE item per 128-row tile instead of two or three (A read once, a third of the hand-offs,
+    // no padded columns).  CF_TC_WIDE=0 keeps the tuned narrow chunks.
+    bool wide = passes == 3 && K <= TC_BK && !force_nc && N > 96 && N <= 192;
+    if (const char* ev = getenv("CF_TC_WIDE")) wide = wide && atoi(ev) != 0;
     if (!force_nc) force_nc = tc_tune_for(K, N, passes).nc;
+    if (wide) force_nc = (N + 31) / 32 * 32;
     if (force_nc) L.NC = force_nc, L.nchunks = (N + force_nc - 1) / force_nc;
     L.nkb = (K + TC_BK - 1) / TC_BK;
     const size_t blk = (size_t)L.NC * 128;  // bytes of one hi (or lo) block
@@ -813,8 +838,10 @@ inline int tc_plan(PwTcState& st, int passes, int epi, const float* A, const flo
     p.b_bytes_block = (uint32_t)L.NC * 128u * 2u;
     // narrow layers: A operand through TMEM (both accumulator pairs fit columns [0,256), the A ring sits above them)
     const TcTune tune = tc_tune_for(K, N, passes);
+    const bool wide = passes == 3 && L.nkb == 1 && L.NC > 96;  // single accumulator, one wide chunk (tc_prepare_layer)
     p.atmem = (passes == 3 && L.NC <= 64) ? 1 : 0;
     if (tune.atmem >= 0) p.atmem = (tune.atmem != 0 && passes == 3 && L.NC <= 96) ? 1 : 0;
+    if (wide) p.atmem = 1;
     p.a_bytes_stage = p.atmem ? TC_A_BYTES : TC_A_BYTES * hl;
     // TMEM budget (512 columns): NC <= 64: accumulators [0,256) + four A slots; NC <= 96, or NC <= 64 with THREE accumulator
     // pairs (tune.nacc == 3: single-K-block layers, where the accumulator round trip bounds the item rate): [0,384) + two A slots
@@ -823,7 +850,7 @@ inline int tc_plan(PwTcState& st, int passes, int epi, const float* A, const flo
     p.amask = (L.NC <= 64 && !three) ? 3u : 1u;
     p.ashift = (L.NC <= 64 && !three) ? 2u : 1u;
     {   // accumulator ring: as many (main+correction) pairs as fit the accumulator columns, 2 or 4
-        const uint32_t acc_cols = p.atmem ? p.acol : 512u, pair = (passes == 3 ? 2u : 1u) * (uint32_t)L.NC;
+        const uint32_t acc_cols = p.atmem ? p.acol : 512u, pair = ((passes == 3 && !wide) ? 2u : 1u) * (uint32_t)L.NC;
         p.nacc = (4u * pair <= acc_cols) ? 4 : 2;
         if (tune.nacc) p.nacc = tune.nacc == 4 && 4u * pair <= acc_cols ? 4 : 2;
         if (three && 3u * pair <= acc_cols) p.nacc = 3;
@@ -832,6 +859,7 @@ inline int tc_plan(PwTcState& st, int passes, int epi, const float* A, const flo
     p.direct = (N <= 16) ? 1 : 0;  // since the elect-based issue the TMA-store epilogue wins from N = 24 up (r2r sweep)
     if (tune.direct >= 0) p.direct = tune.direct;  // 0 TMA stores, 1 row stores from registers, 2 transposed tile + coalesced stores
     p.out = out;
+    p.single = (passes == 3 && L.nkb == 1) ? 1 : 0;
     p.dbg = 0;
     if (const char* ev = getenv("CF_TC_DEBUG")) p.dbg = atoi(ev);
     const uint32_t bar_bytes = 1024;

@@ -164,7 +164,15 @@ __global__ void __launch_bounds__(PWN_THREADS, 2) k_pwn(const __grid_constant__ 
             const int nks = krem >= TC_BK ? TC_BK / 8 : (krem + 7) / 8;
             if (elect_one()) {
                 if (j + nst < total) issue_a(j + nst);
-                if (nks == 4) {
+                if (nkb == 1) {  // one K block: corrections first, then the main products, ONE accumulator (as k_pw_tc's `single`)
+                    const uint64_t b_lo = umma_desc(bsm + (uint32_t)kb * blk_bytes + (uint32_t)p.NC * 128u);
+                    for (int k = 0; k < nks; ++k) {
+                        const uint64_t ko = (uint64_t)(k * 2);
+                        umma_tf32_ts(d_main, a_lo + 8u * k, b_hi + ko, idesc, k > 0 ? 1u : 0u);
+                        umma_tf32_ts(d_main, a_hi + 8u * k, b_lo + ko, idesc, 1u);
+                    }
+                    for (int k = 0; k < nks; ++k) umma_tf32_ts(d_main, a_hi + 8u * k, b_hi + (uint64_t)(k * 2), idesc, 1u);
+                } else if (nks == 4) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t ko = (uint64_t)(k * 2);
@@ -193,7 +201,11 @@ __global__ void __launch_bounds__(PWN_THREADS, 2) k_pwn(const __grid_constant__ 
                 float v[16], c[16];
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
                 tmem_ld16(taddr, v);
-                tmem_ld16(taddr + (uint32_t)p.NC, c);
+                if (nkb > 1) tmem_ld16(taddr + (uint32_t)p.NC, c);
+                else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) c[i] = 0.f;
+                }
                 tmem_ld_wait();
                 if (grow < p.M) {
 #pragma unroll
