@@ -12,9 +12,10 @@ boxes, + for N>1 the NCCL all-gather of the box lists) over one synthetic batch 
 `value`  : inputs resident in HBM, timed with CUDA events on the launching stream, max over ranks.
 `e2e`    : the same step through the C-ABI host entry points cf_submit_topk_host / cf_wait_host with
            pinned HOST buffers (every batch's H2D and D2H inside the timed region, double buffered).
-`roofline`: the dominant kernel class, algorithmic bytes (cf_work_model x batch) / CUDA-event time of
-           that class's launches, against MEASURED_PEAKS.json.
-`cpu_baseline` / `--impl reference`: the oracle port of the reference's CPU path on the host cores.
+`roofline`: the dominant kernel class, its own algorithmic bytes (cf_work_model x batch: a fused MBConv launch reads its
+           block input and writes its block output) / CUDA-event time of that class's launches, against
+           MEASURED_PEAKS.json; the special-function-unit roofline of the fused launches beside it.
+`cpu_baseline` / `--impl reference`: the UNMODIFIED reference from baseline/_ref on the host cores (oracle port as fall-back).
 """
 import argparse
 import importlib
@@ -233,11 +234,12 @@ BLOCKS = [(32, 16, 1, 3, 1), (16, 24, 6, 3, 2), (24, 24, 6, 3, 1), (24, 32, 6, 5
           (64, 64, 6, 3, 1), (64, 96, 6, 5, 1), (96, 96, 6, 5, 1), (96, 160, 6, 5, 2), (160, 160, 6, 5, 1), (160, 320, 6, 3, 1)]
 
 
-def launch_table(h, w, fused=(), dwp=()):
+def launch_table(h, w, fused=(), dwp=(), own=False):
     """(name, algorithmic bytes per image) of every launch of one forward + path-C decode, in launch order -- the same
     layer-wise accounting as cf_work_model (un-padded input once + output once + residual / low-res re-reads, fp32).
     A block in `fused` is ONE launch credited with the layer-wise bytes of the three launches it replaces; a block in `dwp` keeps its
-    expand launch (if it has one) and runs depth-wise + projection as one launch credited with the bytes of those two."""
+    expand launch (if it has one) and runs depth-wise + projection as one launch credited with the bytes of those two.
+    own=True: a fused launch counts only what it has to move itself (its input once + its output once + the residual)."""
     out = []
     hh, ww = h // 2, w // 2
     out.append(("stem 3->32 s2", h * w * 3 + hh * ww * 32 * 4))
@@ -251,9 +253,11 @@ def launch_table(h, w, fused=(), dwp=()):
         rows.append((f"b{i} dw{k}x{k} s{s} {hid}ch", (hh * ww + ho * wo) * hid * 4))
         rows.append((f"b{i} project {hid}->{cout}" + (" +res" if res else ""), ho * wo * (hid + cout + res) * 4))
         if i in fused:
-            rows = [(f"b{i} fused MBConv {cin}->{hid}->{cout} k{k} s{s}" + (" +res" if res else ""), sum(b for _, b in rows))]
+            by = (hh * ww * cin + ho * wo * (cout + res)) * 4 if own else sum(b for _, b in rows)
+            rows = [(f"b{i} fused MBConv {cin}->{hid}->{cout} k{k} s{s}" + (" +res" if res else ""), by)]
         elif i in dwp:
-            rows = rows[:-2] + [(f"b{i} fused dw{k}x{k} s{s} + project {hid}->{cout}" + (" +res" if res else ""), sum(b for _, b in rows[-2:]))]
+            by = (hh * ww * hid + ho * wo * (cout + res)) * 4 if own else sum(b for _, b in rows[-2:])
+            rows = rows[:-2] + [(f"b{i} fused dw{k}x{k} s{s} + project {hid}->{cout}" + (" +res" if res else ""), by)]
         out += rows
         hh, ww = ho, wo
     out.append(("conv_last 320->24", hh * ww * (320 + 24) * 4))
@@ -291,6 +295,8 @@ def run_b200(a):
         raise SystemExit(f"--gpus {a.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {a.gpus}")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; this arm has no CPU fallback (use --impl reference for the CPU path)")
+    # host side of the end-to-end path: this rank's pinned buffers on the GPU's own NUMA node (restored before the CPU legs)
+    aff_old, aff_new = (None, None) if os.environ.get("CF_BENCH_BIND", "1") == "0" else sh.bind_host_to_gpu(local)
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -395,15 +401,17 @@ def run_b200(a):
         by, fl = L.work_model(H, W, L.CF_IN_U8_HWC, cls, pw)
         if n == 0:
             continue
-        # Algorithmic bytes = SURVEY.md 8(d)'s LAYER-WISE figure (every conv reads its input once and writes its
-        # output once).  A fused kernel is credited with the layer-wise bytes of the layers it replaces; the bytes
-        # it actually has to move (`min_bytes`) are what fusion saved and are reported beside it.
+        # Algorithmic bytes of a kernel = SURVEY.md 8(d): the kernel's OWN un-padded input read once + output written once
+        # (+ residual re-read).  For a fused MBConv launch that is the block's input and output -- the hidden tensors never
+        # reach HBM -- so its HBM fraction is small by construction and the bound that explains it is the special-function
+        # pipe (`fused_blocks_sfu` below).  `layerwise_bytes` = the bytes of the launches it replaces, reported beside it
+        # (round 1's schedule moved them; `layerwise_equiv_GBps` can exceed the HBM peak: that is the saving, not bandwidth).
         by_lw = by
         if cls == L.CLS_FUSED:
             lw = lambda c: L.work_model(H, W, L.CF_IN_U8_HWC, c, L.CF_PW_TCGEN05_LAYERWISE)[0] - L.work_model(H, W, L.CF_IN_U8_HWC, c, pw)[0]  # noqa: E731
             by_lw = lw(L.CLS_PW) + lw(L.CLS_DW)
-        classes[name] = {"ms_per_step": ms, "launches": n, "alg_bytes": by_lw * B, "min_bytes": by * B, "alg_flops": fl * B,
-                         "gbs": by_lw * B / (ms * 1e-3) / 1e9, "tflops": fl * B / (ms * 1e-3) / 1e12}
+        classes[name] = {"ms_per_step": ms, "launches": n, "alg_bytes": by * B, "layerwise_bytes": by_lw * B, "alg_flops": fl * B,
+                         "gbs": by * B / (ms * 1e-3) / 1e9, "gbs_lw": by_lw * B / (ms * 1e-3) / 1e9, "tflops": fl * B / (ms * 1e-3) / 1e12}
     net_ms = sum(c["ms_per_step"] for k, c in classes.items())
     for c in classes.values():
         c["share"] = c["ms_per_step"] / net_ms
@@ -411,13 +419,16 @@ def run_b200(a):
     tc = classes[top]
     roofline = {"kernel": top, "bound": "hbm", "achieved": tc["gbs"], "peak": hbm, "unit": "GB/s", "frac": tc["gbs"] / hbm,
                 "traffic": None, "peak_source": peak_src, "launches": tc["launches"], "ms": tc["ms_per_step"],
-                "alg_bytes_per_step": tc["alg_bytes"], "min_bytes_per_step": tc["min_bytes"], "share_of_step": tc["share"],
+                "alg_bytes_per_step": tc["alg_bytes"], "layerwise_bytes_per_step": tc["layerwise_bytes"],
+                "layerwise_equiv_GBps": tc["gbs_lw"], "share_of_step": tc["share"],
                 "tensor_frac_of_sustained_bf16": tc["tflops"] / tf,
                 "classes": {k: {"ms": round(v["ms_per_step"], 4), "share": round(v["share"], 4), "GBps": round(v["gbs"], 1),
-                                "frac_hbm": round(v["gbs"] / hbm, 4), "TFLOPs": round(v["tflops"], 2), "launches": v["launches"]}
+                                "frac_hbm": round(v["gbs"] / hbm, 4), "layerwise_equiv_GBps": round(v["gbs_lw"], 1),
+                                "TFLOPs": round(v["tflops"], 2), "launches": v["launches"]}
                             for k, v in classes.items()}}
-    # The fused MBConv kernels move a fraction of the layer-wise bytes (frac_hbm above 1 is that saving, not a faster memory): what
-    # bounds them is the SM's special-function pipe -- 2 MUFU ops (ex2, rcp) per Swish at 16 lanes/clk/SM.  Algorithmic count: every
+    # The fused MBConv kernels move a fraction of the layer-wise bytes: what bounds them is the SM's special-function pipe -- the
+    # reference's Swish = one exponential + one reciprocal per hidden element, counted as 2 MUFU ops at 16 lanes/clk/SM
+    # (layer1.0's kernel shares one reciprocal among four values, i.e. issues 1.25: the algorithmic count stays 2).  Every
     # hidden element once at input resolution (expand Swish, not for layer0 where t = 1) and once at output resolution.
     try:
         fz = classes.get("fused_blocks")
@@ -447,11 +458,15 @@ def run_b200(a):
         pass
     try:  # the individual launches, timed one by one (events between launches: no overlap of neighbouring kernels)
         ms_l, _ = eng.time_steps(5)
-        tab = launch_table(H, W, L.fused_blocks(pw), L.dwp_blocks(pw))
+        tab = launch_table(H, W, L.fused_blocks(pw), L.dwp_blocks(pw), own=True)
+        tab_lw = launch_table(H, W, L.fused_blocks(pw), L.dwp_blocks(pw))
         if len(tab) == len(ms_l):
             rows = [{"launch": n, "us": round(t * 1e3, 1), "alg_GB": round(by_l * B / 1e9, 4),
                      "GBps": round(by_l * B / (t * 1e-3) / 1e9, 1), "frac_hbm": round(by_l * B / (t * 1e-3) / 1e9 / hbm, 3)}
                     for (n, by_l), t in zip(tab, ms_l)]
+            for r, (_, by_l), (_, by_w) in zip(rows, tab, tab_lw):
+                if by_w != by_l:  # a fused launch: the bytes of the launches it replaces, for comparison with round 1's schedule
+                    r["layerwise_GB"] = round(by_w * B / 1e9, 4)
             rows.sort(key=lambda r: -r["us"])
             roofline["top_launches"] = rows[:8]
             roofline["dominant_launch"] = rows[0]
@@ -459,9 +474,12 @@ def run_b200(a):
         roofline["top_launches_error"] = str(ex)
     by_min, _ = L.work_model(H, W, L.CF_IN_U8_HWC, 0, pw)
     by_all, fl_all = L.work_model(H, W, L.CF_IN_U8_HWC, 0, L.CF_PW_TCGEN05_LAYERWISE)  # layer-wise algorithmic bytes
-    roofline["whole_step"] = {"alg_bytes_per_image": by_all, "min_bytes_per_image": by_min, "alg_flops_per_image": fl_all,
-                              "GBps": by_all * B / (ms_per_step * 1e-3) / 1e9,
-                              "frac_hbm": by_all * B / (ms_per_step * 1e-3) / 1e9 / hbm,
+    # whole step: the bytes this schedule has to move (fused blocks: block input + output) against the HBM peak; the layer-wise
+    # figure of SURVEY.md 8(d) (384.6 MB per image, what round 1 moved) beside it
+    roofline["whole_step"] = {"alg_bytes_per_image": by_min, "layerwise_bytes_per_image": by_all, "alg_flops_per_image": fl_all,
+                              "GBps": by_min * B / (ms_per_step * 1e-3) / 1e9,
+                              "frac_hbm": by_min * B / (ms_per_step * 1e-3) / 1e9 / hbm,
+                              "layerwise_equiv_GBps": by_all * B / (ms_per_step * 1e-3) / 1e9,
                               "TFLOPs": fl_all * B / (ms_per_step * 1e-3) / 1e12}
 
     gather_check = None
@@ -482,6 +500,8 @@ def run_b200(a):
         if not (gather_check["own_slice_equal_on_every_rank"] and gather_check["gathered_list_equal_on_every_rank"]):
             raise SystemExit(f"bench.py: the all-gathered box list is wrong: {gather_check}")
 
+    if aff_old is not None and aff_new != aff_old:
+        os.sched_setaffinity(0, aff_old)  # the CPU legs use every host core
     cpu_baseline = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cpu_baseline, _ = cpu_reference_run(3, 1, a.cpu_sample, with_call=True)
@@ -492,13 +512,14 @@ def run_b200(a):
                 "dtype": {0: "f32", 1: "tf32x3", 2: "tf32", 3: "tf32x3", 6: "tf32x3/tf32"}[pw], "data": "synthetic",
                 "config": {"workload": workload_name(B, world), "global_batch": n_total, "h": H, "w": W, "pw_engine": pw,
                            "l2": f"{n_rot} rotating input batches ({n_rot * B * H * W * 3 / 1e6:.0f} MB) and "
-                                 f"{by_all * B / 1e9:.1f} GB of activation traffic per step, both > 126 MB L2",
+                                 f"{by_min * B / 1e9:.1f} GB of activation traffic per step, both > 126 MB L2",
                            "parallelism": f"dp{world}"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * H * W * 3,
                         "d2h_bytes_per_step": n_total * K_TOP * 6 * 4 + B * K_TOP * 4,
                         "api": ("cf_submit_topk_gather_host (ncclAllGather inside the library, one D2H of the gathered list)" if world > 1
                                 else "cf_submit_topk_host") + " / cf_wait_host (pinned host buffers, double buffered)",
-                        "steps": e2e_steps},
+                        "steps": e2e_steps,
+                        "host_cpus_bound_to_gpu_numa_node": (len(aff_new) if aff_new is not None else None)},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline}
         if gather_check is not None:
             line["gather_check"] = gather_check

@@ -101,6 +101,13 @@ int cf_tap(cf_engine* e, const char* name, float** ptr, int* h, int* w, int* c);
  * at least B*h*w floats (cf_decode_topk uses the engine's own).  K <= 1024 and K <= h*w. */
 int cf_ctdet_decode(const float* heat, const float* wh, const float* reg, int batch, int h, int w,
                     int K, float* out_dets, int32_t* out_inds, float* scratch, void* stream);
+/* The class-aware form of the same function (centerface_ext.py:11-27 with cat > 1, :72-77): heat [B,classes,h,w], top-K per
+ * class then top-K of the classes*K candidates (= the image's global top-K; ties: lower class, then lower pixel index),
+ * out_dets[..,5] = class, out_inds = pixel index inside the class plane.  cat_spec_wh != 0: wh is [B,2*classes,h,w] and a
+ * detection reads its own class's (w,h) planes; else wh is [B,2,h,w].  `scratch`: B*classes*h*w floats.
+ * classes = 1, cat_spec_wh = 0 is cf_ctdet_decode.                                                                         */
+int cf_ctdet_decode_classes(const float* heat, const float* wh, const float* reg, int batch, int classes, int h, int w,
+                            int K, int cat_spec_wh, float* out_dets, int32_t* out_inds, float* scratch, void* stream);
 /* same, on the heads of the last cf_forward */
 int cf_decode_topk(cf_engine* e, int K, float* out_dets, int32_t* out_inds, void* stream);
 
@@ -183,6 +190,11 @@ int cf_debug_pw_gemm(int pw_engine, int epi, const float* dA, const float* hW, f
  * plan time select plan variants.  (tools/tc_tune.py)                                                                 */
 int cf_debug_pw_gemm_time(int pw_engine, int epi, const float* dA, const float* hW, float* dOut, int M, int K, int N,
                           const float* dRes, void* stream, int iters, float* ms, char* desc, int desc_cap);
+
+/* Validation hook: y[i] = Swish(x[i]) (model/centernet.py:39-40) with the device formulation `variant` -- 0: ex2 + rcp per
+ * value (every kernel's default), 1: one reciprocal per four values (swish4q: the fused layer1.0 kernel and the epilogue of
+ * the one-K-block expand layers).  x, y are DEVICE arrays of n floats, n a multiple of 4.  Synchronous.                   */
+int cf_debug_swish(const float* dX, float* dY, long long n, int variant);
 
 /* Development probe: stream a device [M][K] fp32 matrix through a `stages`-deep TMA ring of box_rows x 32-float boxes
  * with one thread per CTA and no consumer work; *ms = mean kernel time.  (tools/tma_probe.py)            */

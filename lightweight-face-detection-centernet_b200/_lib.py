@@ -30,6 +30,7 @@ SIGNATURES = {
     "cf_heads": (C.c_int, [_vp] + [C.POINTER(_vp)] * 5),
     "cf_tap": (C.c_int, [_vp, C.c_char_p, C.POINTER(_vp), _i, _i, _i]),
     "cf_ctdet_decode": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
+    "cf_ctdet_decode_classes": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "cf_decode_topk": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp]),
     "cf_ctdet_post_process": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp]),
     "cf_decode_threshold": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
@@ -42,6 +43,7 @@ SIGNATURES = {
     "cf_debug_pw_gemm": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "cf_debug_pw_gemm_time": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int,
                                         C.POINTER(C.c_float), C.c_char_p, C.c_int]),
+    "cf_debug_swish": (C.c_int, [_vp, _vp, C.c_longlong, C.c_int]),
     "cf_debug_tma_stream": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "cf_resize_tables": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, _i]),
     "cf_resize_u8": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp]),

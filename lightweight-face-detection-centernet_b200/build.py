@@ -31,7 +31,8 @@ def build(force=False, verbose=False):
     if not force and not is_stale():
         return LIB
     srcs, _ = sources()
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
+    extra = os.environ.get("CF_NVCC_FLAGS", "").split()  # development A/B builds, e.g. -DCF_MBF_SWISHQ=0
+    cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)

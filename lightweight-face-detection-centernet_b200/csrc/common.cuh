@@ -131,6 +131,37 @@ __device__ __forceinline__ float4 swish4p(float4 v) {
     swish2(v.z, v.w);
     return v;
 }
+// Swish on four values with ONE reciprocal: with d_i = 1 + 2^(-x_i log2 e), 1/d_0 = d_1 . (d_2 d_3) . rcp(d_0 d_1 d_2 d_3) and so on:
+// 4 MUFU.EX2 + 1 MUFU.RCP instead of 4 + 4 (-37.5 % of the special-function work that bounds the fused MBConv kernels), the
+// same twenty issue slots per four values as two swish2 + the clamps.  The exponent argument is clamped at 31, so that the
+// product of four d stays below 2^127 (no inf . 0): sigmoid bottoms out at 2^-31 for x < -21.5, an absolute error below
+// |x| . 4.7e-10 where the exact result is within 1e-8 of zero.  Five more roundings than swishf (a few 1e-7 relative at worst;
+// tests/test_gpu_variants.py::test_swish_one_reciprocal_per_four holds both forms against fp64).  Used only where a Swish site
+// is MUFU-bound and shallow: the fused layer1.0 kernel (362 -> 346 us) and the epilogue of the one-K-block expand layers
+// (24 -> 144: 115 -> 109 us; 32 -> 192: 44 -> 41); the stem (producer-bound) and the depth-wise kernels measured flat or slower.
+__device__ __forceinline__ void swish4q(float& x0, float& x1, float& x2, float& x3) {
+    float t0, t1, t2, t3, d0, d1, d2, d3, p01, p23, r, r01, r23, i0, i1, i2, i3;
+    mul2(t0, t1, x0, x1, -1.4426950408889634f, -1.4426950408889634f);
+    mul2(t2, t3, x2, x3, -1.4426950408889634f, -1.4426950408889634f);
+    t0 = fminf(t0, 31.f), t1 = fminf(t1, 31.f), t2 = fminf(t2, 31.f), t3 = fminf(t3, 31.f);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(d0) : "f"(t0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(d1) : "f"(t1));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(d2) : "f"(t2));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(d3) : "f"(t3));
+    add2(d0, d1, d0, d1, 1.f, 1.f);
+    add2(d2, d3, d2, d3, 1.f, 1.f);
+    mul2(p01, p23, d0, d2, d1, d3);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p01 * p23));
+    mul2(r01, r23, p23, p01, r, r);  // 1 / (d0 d1), 1 / (d2 d3)
+    mul2(i0, i1, d1, d0, r01, r01);
+    mul2(i2, i3, d3, d2, r23, r23);
+    mul2(x0, x1, x0, x1, i0, i1);
+    mul2(x2, x3, x2, x3, i2, i3);
+}
+__device__ __forceinline__ float4 swish4qv(float4 v) {
+    swish4q(v.x, v.y, v.z, v.w);
+    return v;
+}
 __device__ __forceinline__ void fma44p(float4& acc, float4 a, float4 w) {
     fma2(acc.x, acc.y, a.x, a.y, w.x, w.y);
     fma2(acc.z, acc.w, a.z, a.w, w.z, w.w);

@@ -870,17 +870,24 @@ int cf_tap(cf_engine* e, const char* name, float** ptr, int* h, int* w, int* c) 
     return CF_OK;
 }
 
-int cf_ctdet_decode(const float* heat, const float* wh, const float* reg, int batch, int h, int w, int K,
-                    float* out_dets, int32_t* out_inds, float* scratch, void* stream) {
+int cf_ctdet_decode_classes(const float* heat, const float* wh, const float* reg, int batch, int classes, int h, int w, int K,
+                            int cat_spec_wh, float* out_dets, int32_t* out_inds, float* scratch, void* stream) {
     CF_CHECK(heat && wh && out_dets && scratch, CF_EINVAL, "cf_ctdet_decode: NULL pointer");
     int rc = check_decode_args(batch, h, w);
     if (rc) return rc;
+    CF_CHECK(classes >= 1 && classes <= 1024 && (long long)classes * h * w <= (1ll << 30), CF_EINVAL, "cf_ctdet_decode: %d classes", classes);
     CF_CHECK(K >= 1 && K <= 1024 && K <= h * w, CF_EINVAL, "cf_ctdet_decode: K=%d outside [1,min(1024,h*w)]", K);
     cudaStream_t s = (cudaStream_t)stream;
-    const long long n = (long long)batch * h * w;
-    CF_CUDA(launch_pdl(k_peak_mask, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, heat, scratch, batch, h, w));
-    CF_CUDA(launch_topk(scratch, wh, reg, batch, h, w, K, out_dets, out_inds, s));
+    const long long n = (long long)batch * classes * h * w;
+    // _nms works per (image, class) plane (max_pool2d, centerface_ext.py:44-50): B*C planes of h x w
+    CF_CUDA(launch_pdl(k_peak_mask, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, heat, scratch, batch * classes, h, w));
+    CF_CUDA(launch_topk(scratch, wh, reg, batch, h, w, K, out_dets, out_inds, s, classes, cat_spec_wh ? 2 * classes : 2));
     return CF_OK;
+}
+
+int cf_ctdet_decode(const float* heat, const float* wh, const float* reg, int batch, int h, int w, int K,
+                    float* out_dets, int32_t* out_inds, float* scratch, void* stream) {
+    return cf_ctdet_decode_classes(heat, wh, reg, batch, 1, h, w, K, 0, out_dets, out_inds, scratch, stream);
 }
 
 int cf_decode_topk(cf_engine* e, int K, float* out_dets, int32_t* out_inds, void* stream) {
@@ -1282,6 +1289,21 @@ int cf_debug_pw_gemm_time(int pw_engine, int epi, const float* dA, const float* 
 int cf_debug_pw_gemm(int pw_engine, int epi, const float* dA, const float* hW, float* dOut, int M, int K, int N,
                      const float* dRes, void* stream) {
     return cf_debug_pw_gemm_time(pw_engine, epi, dA, hW, dOut, M, K, N, dRes, stream, 0, nullptr, nullptr, 0);
+}
+
+namespace cf {
+__global__ void k_debug_swish(const float4* x, float4* y, long long n4, int variant) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
+        y[i] = variant ? swish4qv(x[i]) : swish4p(x[i]);
+}
+}  // namespace cf
+
+int cf_debug_swish(const float* dX, float* dY, long long n, int variant) {
+    CF_CHECK(dX && dY && n > 0 && n % 4 == 0 && (variant == 0 || variant == 1), CF_EINVAL, "cf_debug_swish: bad arguments");
+    k_debug_swish<<<(unsigned)std::min<long long>((n / 4 + 255) / 256, 4096), 256>>>(reinterpret_cast<const float4*>(dX), reinterpret_cast<float4*>(dY), n / 4, variant);
+    CF_CUDA(cudaGetLastError());
+    CF_CUDA(cudaDeviceSynchronize());
+    return CF_OK;
 }
 
 int cf_debug_tma_stream(const float* dA, int M, int K, int stages, int box_rows, int ctas_per_sm, float* ms) {

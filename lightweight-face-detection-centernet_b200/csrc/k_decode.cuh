@@ -78,14 +78,18 @@ constexpr int TOPK_SMEM_MAX_HW = 51200;
 template <bool SM>
 __global__ void __launch_bounds__(1024) k_topk(const float* __restrict__ pk, const float* __restrict__ wh,
                                                const float* __restrict__ reg, int H, int W, int K,
-                                               float* __restrict__ dets, int32_t* __restrict__ inds, int cand_cap) {
+                                               float* __restrict__ dets, int32_t* __restrict__ inds, int cand_cap, int C, int wh_planes) {
     extern __shared__ uint32_t skeys[];
     __shared__ unsigned hist[256];
     __shared__ unsigned long long buf[1024];
     __shared__ unsigned wcnt[32];
     __shared__ unsigned s_prefix, s_krem, s_cnt;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int HW = H * W;
+    // C classes (centerface_ext.py:11-27): top-K per class, then top-K of those C*K candidates = the global top-K of the
+    // image's C*H*W scores; ties go to the lower class, then the lower pixel index (the candidate order of :20) = the lower
+    // index of the flattened [C][H*W] map, which is the order this kernel admits ties in.  The face model has C = 1.
+    const int HW1 = H * W;
+    const int HW = C * HW1;
     const int b = blockIdx.x;
     const float* p = pk + (size_t)b * HW;
     pdl_trigger();
@@ -306,32 +310,35 @@ __global__ void __launch_bounds__(1024) k_topk(const float* __restrict__ pk, con
 
     for (int r = tid; r < K; r += 1024) {
         const unsigned long long c = buf[r];
-        const int idx = (int)(0xFFFFFFFFu - (unsigned)(c & 0xFFFFFFFFull));
+        const int full = (int)(0xFFFFFFFFu - (unsigned)(c & 0xFFFFFFFFull));
+        const int cls = C == 1 ? 0 : full / HW1;           // :21 topk_clses
+        const int idx = C == 1 ? full : full - cls * HW1;  // :16 topk_inds % (height * width)
         const float score = fkey_inv((uint32_t)(c >> 32));
         float xs = (float)(idx % W), ys = (float)(idx / W);  // centerface_ext.py:18-19
         if (reg) {
-            xs = __fadd_rn(xs, __ldcg(reg + ((size_t)b * 2 + 0) * HW + idx));  // :62
-            ys = __fadd_rn(ys, __ldcg(reg + ((size_t)b * 2 + 1) * HW + idx));  // :63
+            xs = __fadd_rn(xs, __ldcg(reg + ((size_t)b * 2 + 0) * HW1 + idx));  // :62
+            ys = __fadd_rn(ys, __ldcg(reg + ((size_t)b * 2 + 1) * HW1 + idx));  // :63
         } else {
             xs += 0.5f;
             ys += 0.5f;
         }
-        const float hw = __ldcg(wh + ((size_t)b * 2 + 0) * HW + idx) / 2.f;
-        const float hh = __ldcg(wh + ((size_t)b * 2 + 1) * HW + idx) / 2.f;
+        const int wp = wh_planes == 2 ? 0 : 2 * cls;  // cat_spec_wh (:72-75): the class's own (w, h) planes of wh [B,2C,H,W]
+        const float hw = __ldcg(wh + ((size_t)b * wh_planes + wp + 0) * HW1 + idx) / 2.f;
+        const float hh = __ldcg(wh + ((size_t)b * wh_planes + wp + 1) * HW1 + idx) / 2.f;
         float* d = dets + ((size_t)b * K + r) * 6;
         d[0] = __fsub_rn(xs, hw);
         d[1] = __fsub_rn(ys, hh);
         d[2] = __fadd_rn(xs, hw);
         d[3] = __fadd_rn(ys, hh);
         d[4] = score;
-        d[5] = 0.f;
+        d[5] = (float)cls;
         if (inds) inds[(size_t)b * K + r] = idx;
     }
 }
 
 inline cudaError_t launch_topk(const float* pk, const float* wh, const float* reg, int B, int H, int W, int K, float* dets,
-                               int32_t* inds, cudaStream_t s) {
-    const int HW = H * W;
+                               int32_t* inds, cudaStream_t s, int C = 1, int wh_planes = 2) {
+    const int HW = C * H * W;
     if (HW <= TOPK_SMEM_MAX_HW) {
         cudaError_t e = smem_optin((const void*)k_topk<true>, (TOPK_SMEM_MAX_HW + TOPK_SMEM_MAX_HW / 32) * 4);
         if (e != cudaSuccess) return e;
@@ -339,9 +346,9 @@ inline cudaError_t launch_topk(const float* pk, const float* wh, const float* re
         // candidate list: what the opted-in shared memory leaves beside the keys, at most 8 192 entries
         const size_t room = ((size_t)TOPK_SMEM_MAX_HW + TOPK_SMEM_MAX_HW / 32 - HWp - HWp / 32);
         const int cand_cap = (int)(room < 8192 ? room : 8192);
-        return launch_pdl(k_topk<true>, dim3(B), dim3(1024), (HWp + HWp / 32 + (size_t)cand_cap) * 4, s, pk, wh, reg, H, W, K, dets, inds, cand_cap);
+        return launch_pdl(k_topk<true>, dim3(B), dim3(1024), (HWp + HWp / 32 + (size_t)cand_cap) * 4, s, pk, wh, reg, H, W, K, dets, inds, cand_cap, C, wh_planes);
     }
-    return launch_pdl(k_topk<false>, dim3(B), dim3(1024), 0, s, pk, wh, reg, H, W, K, dets, inds, 0);
+    return launch_pdl(k_topk<false>, dim3(B), dim3(1024), 0, s, pk, wh, reg, H, W, K, dets, inds, 0, C, wh_planes);
 }
 
 // numpy float32 floor_divide (npy_floor_dividef -> npy_divmodf), used by centerface.py:56-58

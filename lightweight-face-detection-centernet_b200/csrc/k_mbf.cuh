@@ -51,6 +51,13 @@
 #include "k_dwt.cuh"
 #include "k_pwn.cuh"
 
+// Swish of the compute teams with one reciprocal per four values (common.cuh, swish4q) where the teams' two Swish phases keep the
+// special-function pipe busiest: layer1.0 (MUFU 67 %: 362 -> 346 us).  layer1.1 (MUFU 44 %) and layer0 measured flat (281 -> 284,
+// 205 -> 204) and keep swish2.  CF_MBF_SWISHQ=0 = swish2 everywhere, for A/B builds.
+#ifndef CF_MBF_SWISHQ
+#define CF_MBF_SWISHQ 1
+#endif
+
 namespace cf {
 
 template <int KS_, int S_, int CIN_, int STH_, int STW_, int NSY_, int NSX_, int XT_, int YT_, int TD_, int NX_, bool WDS_, bool EXP_ = true, int NT_ = 4, int ND_ = 2, bool TEPI_ = true>
@@ -64,6 +71,7 @@ struct MbfCfg {
     // resolution -- layer0 (t = 1, no expand conv) or a block whose expand conv stays a k_pw_tc launch -- and TMA writes its
     // 32-channel halo boxes straight into the teams' E tiles (two per team): the kernel is depth-wise + Swish + projection.
     static constexpr bool EXP = EXP_;
+    static constexpr bool SWQ = CF_MBF_SWISHQ && EXP_ && S_ == 2;  // one-reciprocal Swish (see above)
     static constexpr int NT = NT_;  // compute teams (four warps each: one per TMEM lane quarter); 4 -> 80 registers per thread, 5 -> 72
     static constexpr int NWARPS = 8 + 4 * NT, THREADS = NWARPS * 32;
     static constexpr int NBX = STW / XT, NITEMS = (STH / YT) * NBX * 8;  // depth-wise items: (output block, float4 of channels)
@@ -549,7 +557,10 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
                 if (q == 0) TR(9, j);
                 if (q * 32 < C::NPX && !(p.dbg & 1)) {  // warp-uniform: a quarter past the halo tile has nothing to do
     #pragma unroll
-                    for (int g = 0; g < 16; ++g) swish2(v[2 * g], v[2 * g + 1]);
+                    for (int g = 0; g < 8; ++g) {
+                        if (C::SWQ) swish4q(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+                        else swish2(v[4 * g], v[4 * g + 1]), swish2(v[4 * g + 2], v[4 * g + 3]);
+                    }
                 }
                 if (q == 0) TR(19, j);
                 bar_team();  // every warp of the team has finished the previous job's depth-wise reads of E
@@ -606,7 +617,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
                     for (int dx = 0; dx < C::XT; ++dx) {
                         const int r = s * C::SPX + (C::YT * by + dy) * C::STW + C::XT * bx + dx;  // D operand row = output pixel of the block
                         const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c4 ^ (r & 7)) << 4);
-                        const float4 o = swish4p(acc[dy][dx]);  // swish(0) = 0 keeps the padded channels zero
+                        const float4 o = C::SWQ ? swish4qv(acc[dy][dx]) : swish4p(acc[dy][dx]);  // swish(0) = 0 keeps the padded channels zero
                         const float4 h = make_float4(tf32_hi(o.x), tf32_hi(o.y), tf32_hi(o.z), tf32_hi(o.w));
                         *reinterpret_cast<float4*>(Dhi + off) = h;
                         *reinterpret_cast<float4*>(Dlo + off) = make_float4(o.x - h.x, o.y - h.y, o.z - h.z, o.w - h.w);

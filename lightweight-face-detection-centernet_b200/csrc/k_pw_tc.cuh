@@ -596,6 +596,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     const int n = col0 + 4 * j;
                     if (EPI != EPI_LINEAR && EPI != EPI_SWISH) {
                         if (row < p.M && n < p.N) o = tc_epi<EPI>(o, row, n, p.N, p.ea);
+                    } else if (EPI == EPI_SWISH && p.single) {
+                        o = swish4qv(o);  // the one-K-block expand layers (24 -> 144, 32 -> 192) are MUFU-bound: one reciprocal per four values
                     } else {
                         o = tc_epi<EPI>(o, row, n, p.N, p.ea);
                     }

@@ -315,24 +315,25 @@ def letterbox_u8(images, out_w=640, out_h=640):
 
 
 def ctdet_decode(heat, wh, reg=None, cat_spec_wh=False, K=100, return_inds=False):
-    """Drop-in for centerface_ext.ctdet_decode (centerface_ext.py:52): cuda fp32 tensors
-    heat [B,1,h,w] (post-sigmoid), wh/reg [B,2,h,w] -> detections [B,K,6]."""
+    """Drop-in for centerface_ext.ctdet_decode (centerface_ext.py:52): cuda fp32 tensors heat [B,C,h,w] (post-sigmoid; the
+    face model has C = 1), wh [B,2,h,w] (or [B,2C,h,w] with cat_spec_wh), reg [B,2,h,w] or None -> detections [B,K,6]."""
     import torch
-    assert not cat_spec_wh, "single-class model: cat_spec_wh is not used by the reference path"
     lib = L.load()
-    assert heat.is_cuda and heat.dtype == torch.float32 and heat.shape[1] == 1
+    assert heat.is_cuda and heat.dtype == torch.float32 and heat.dim() == 4
+    B, cat, h, w = heat.shape
+    assert tuple(wh.shape) == (B, 2 * cat if cat_spec_wh else 2, h, w), f"wh {tuple(wh.shape)} does not match heat {tuple(heat.shape)}"
+    assert reg is None or tuple(reg.shape) == (B, 2, h, w)
     heat, wh = heat.contiguous(), wh.contiguous()
     reg = reg.contiguous() if reg is not None else None
-    B, _, h, w = heat.shape
     dets = torch.empty((B, K, 6), dtype=torch.float32, device=heat.device)
     inds = torch.empty((B, K), dtype=torch.int32, device=heat.device)
-    scratch = torch.empty((B, h, w), dtype=torch.float32, device=heat.device)
+    scratch = torch.empty((B, cat, h, w), dtype=torch.float32, device=heat.device)
     with torch.cuda.device(heat.device):
-        L.check(lib.cf_ctdet_decode(C.c_void_p(heat.data_ptr()), C.c_void_p(wh.data_ptr()),
-                                    C.c_void_p(reg.data_ptr()) if reg is not None else None, B, h, w, K,
-                                    C.c_void_p(dets.data_ptr()), C.c_void_p(inds.data_ptr()),
-                                    C.c_void_p(scratch.data_ptr()),
-                                    C.c_void_p(torch.cuda.current_stream(heat.device).cuda_stream)), "cf_ctdet_decode")
+        L.check(lib.cf_ctdet_decode_classes(C.c_void_p(heat.data_ptr()), C.c_void_p(wh.data_ptr()),
+                                            C.c_void_p(reg.data_ptr()) if reg is not None else None, B, cat, h, w, K,
+                                            1 if cat_spec_wh else 0, C.c_void_p(dets.data_ptr()), C.c_void_p(inds.data_ptr()),
+                                            C.c_void_p(scratch.data_ptr()),
+                                            C.c_void_p(torch.cuda.current_stream(heat.device).cuda_stream)), "cf_ctdet_decode_classes")
     return (dets, inds) if return_inds else dets
 
 

@@ -5,6 +5,43 @@ backend over NVLink on the GPU box, ``gloo`` in the CPU tests."""
 from __future__ import annotations
 
 
+def bind_host_to_gpu(device_index):
+    """Pin the calling process to the CPUs NVML reports as local to GPU ``device_index`` (its NUMA node), so that the pinned
+    host buffers allocated afterwards -- the per-step H2D source of the end-to-end path -- sit behind the GPU's own PCIe root
+    complex instead of across the socket interconnect.  With eight ranks each copying 39 MB per 2.3 ms step this is the
+    difference between eight local streams and 120 GB/s through one socket.  Returns (previous affinity, new affinity), or
+    (None, None) when NVML, the affinity call or the container's cpuset do not allow it: purely an optimisation."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = device_index
+            if visible:  # NVML enumerates all devices of the box, CUDA only the visible ones
+                tok = visible.split(",")[device_index].strip()
+                if tok.isdigit():
+                    idx = int(tok)
+                else:
+                    idx = None
+                    h = pynvml.nvmlDeviceGetHandleByUUID(tok.encode() if hasattr(tok, "encode") else tok)
+            if idx is not None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            ncpu = os.cpu_count() or 1
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        finally:
+            pynvml.nvmlShutdown()
+        local = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        old = os.sched_getaffinity(0)
+        new = local & old
+        if not new or new == old:
+            return (old, old) if new else (None, None)
+        os.sched_setaffinity(0, new)
+        return old, new
+    except Exception:
+        return None, None
+
+
 def shard_range(n_items, rank, world):
     """Contiguous shard [lo,hi) of ``n_items`` for ``rank``; the first ``n_items % world`` ranks get
     one extra item so ragged batches are covered."""

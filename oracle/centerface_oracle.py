@@ -462,25 +462,28 @@ def peak_nms(heat):
 
 
 def topk(scores, K):
-    """_topk, centerface_ext.py:11-27, single class.  torch.topk's order among equal scores
-    is unspecified; the oracle fixes it as (score desc, flat index asc) with a stable sort.
-    Returns scores [B,K], inds [B,K] int64, ys, xs float32."""
+    """_topk, centerface_ext.py:11-27.  torch.topk's order among equal scores is unspecified; the oracle fixes it as
+    (score desc, flat index asc) with a stable sort, in both stages: per class over the H*W pixels (:14), then over the
+    C*K class-major candidates (:20) -- so ties go to the lower class, then the lower pixel.
+    Returns scores [B,K], inds [B,K] int64 (pixel index inside the class plane), classes [B,K] int32, ys, xs float32."""
     b, c, h, w = scores.shape
-    assert c == 1
-    flat = scores.reshape(b, -1)
-    s, idx = torch.sort(flat, dim=1, descending=True, stable=True)
-    s, idx = s[:, :K], idx[:, :K]
-    ys = (idx / w).int().float()  # :18 true division then truncation
-    xs = (idx % w).int().float()  # :19
-    return s, idx, ys, xs
+    s, idx = torch.sort(scores.reshape(b, c, -1), dim=2, descending=True, stable=True)
+    s, idx = s[:, :, :K], idx[:, :, :K]     # :14 (already < h*w: the % of :16 is the identity)
+    ys = (idx / w).int().float()            # :18 true division then truncation
+    xs = (idx % w).int().float()            # :19
+    s2, pick = torch.sort(s.reshape(b, -1), dim=1, descending=True, stable=True)
+    s2, pick = s2[:, :K], pick[:, :K]       # :20
+    clses = (pick / K).int()                # :21
+    take = lambda t: t.reshape(b, -1).gather(1, pick)  # noqa: E731  :22-25
+    return s2, take(idx), clses, take(ys), take(xs)
 
 
-def ctdet_decode(heat, wh, reg=None, K=100):
-    """ctdet_decode, centerface_ext.py:52-82 (cat_spec_wh=False, one class).
-    heat [B,1,h,w] post-sigmoid, wh/reg [B,2,h,w] -> detections [B,K,6], inds [B,K]."""
-    b, _, h, w = heat.shape
+def ctdet_decode(heat, wh, reg=None, K=100, cat_spec_wh=False):
+    """ctdet_decode, centerface_ext.py:52-82.  heat [B,C,h,w] post-sigmoid (the face model: C = 1), wh [B,2,h,w]
+    (or [B,2C,h,w] with cat_spec_wh), reg [B,2,h,w] -> detections [B,K,6], inds [B,K]."""
+    b, cat, h, w = heat.shape
     heat = peak_nms(heat)
-    scores, inds, ys, xs = topk(heat, K)
+    scores, inds, clses, ys, xs = topk(heat, K)
 
     def gather(feat):  # _transpose_and_gather_feat :37-42
         feat = feat.permute(0, 2, 3, 1).contiguous().view(b, -1, feat.size(1))
@@ -494,9 +497,11 @@ def ctdet_decode(heat, wh, reg=None, K=100):
         xs = xs.view(b, K, 1) + 0.5
         ys = ys.view(b, K, 1) + 0.5
     g = gather(wh)
+    if cat_spec_wh:  # :72-75
+        g = g.view(b, K, cat, 2).gather(2, clses.view(b, K, 1, 1).expand(b, K, 1, 2).long()).view(b, K, 2)
     bboxes = torch.cat([xs - g[..., 0:1] / 2, ys - g[..., 1:2] / 2,
                         xs + g[..., 0:1] / 2, ys + g[..., 1:2] / 2], dim=2)
-    dets = torch.cat([bboxes, scores.view(b, K, 1), torch.zeros(b, K, 1)], dim=2)
+    dets = torch.cat([bboxes, scores.view(b, K, 1), clses.view(b, K, 1).float()], dim=2)
     return dets, inds
 
 

@@ -4,6 +4,8 @@ committed golden vectors of the reference.
 Tolerances (BASELINE.json north_star): sigmoid heat-map <= 1e-3, emitted boxes IoU >= 0.999,
 top-k indices bit-exact; decode kernels fed the reference's own head maps are bit-exact in every
 output word.  The fp32 engine is held to a much tighter bar than the contract (see each test)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -96,6 +98,30 @@ def test_decode_ties_constant_map_and_few_peaks(pkg, oracle):
     assert gi[0].tolist() == list(range(50))
     assert np.array_equal(gi.cpu().numpy(), wi.numpy().astype(np.int32))
     assert torch.equal(got.cpu(), want)
+
+
+def test_ctdet_decode_classes_vs_reference_golden(pkg, oracle):
+    """ctdet_decode with C > 1 and cat_spec_wh (centerface_ext.py:11-27, :72-77) through cf_ctdet_decode_classes against
+    outputs of the REFERENCE (tests/golden/multiclass_v1.npz, oracle/gen_golden_multiclass.py): boxes, scores, classes and
+    pixel indices bit-exact.  Then ties across classes (lower class first, then lower pixel: the oracle's total order) and
+    a map larger than the shared-memory key cache (3 x 160 x 160 keys: the global re-read path)."""
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "multiclass_v1.npz"))
+    for n in sorted({k.split("/")[0] for k in z.files}):
+        B, C, h, w, K, cat, with_reg = z[f"{n}/meta"].tolist()
+        reg = torch.from_numpy(z[f"{n}/reg"]).cuda() if with_reg else None
+        got, gi = pkg.ctdet_decode(torch.from_numpy(z[f"{n}/heat"]).cuda(), torch.from_numpy(z[f"{n}/wh"]).cuda(), reg,
+                                   cat_spec_wh=bool(cat), K=K, return_inds=True)
+        assert np.array_equal(gi.cpu().numpy(), z[f"{n}/inds"]), f"{n}: indices"
+        assert np.array_equal(got.cpu().numpy(), z[f"{n}/dets"]), f"{n}: detections"
+    g = torch.Generator().manual_seed(11)
+    for (B, C, h, w, K) in ((2, 3, 24, 40, 50), (1, 3, 160, 160, 100), (2, 4, 8, 8, 64)):
+        heat = (torch.rand(B, C, h, w, generator=g) * 16).floor() / 20 + 0.05  # 16 score levels: ties everywhere, in and across classes
+        wh = torch.rand(B, 2 * C, h, w, generator=g) * 10
+        reg = torch.rand(B, 2, h, w, generator=g)
+        want, wi = oracle.ctdet_decode(heat, wh, reg, K=K, cat_spec_wh=True)
+        got, gi = pkg.ctdet_decode(heat.cuda(), wh.cuda(), reg.cuda(), cat_spec_wh=True, K=K, return_inds=True)
+        assert np.array_equal(gi.cpu().numpy(), wi.numpy().astype(np.int32)), (B, C, h, w, K)
+        assert torch.equal(got.cpu(), want), (B, C, h, w, K)
 
 
 def test_threshold_paths_edge_cases(pkg, oracle):

@@ -65,7 +65,7 @@ def _heads(pkg, weights_path, x, env):
 
 
 SCHEDULE_ONLY = [{"CF_PWN": 0}, {"CF_DWT_GEOM": 0}, {"CF_DWT_GEOM": 1}, {"CF_DWT_CTAS": 1}, {"CF_TC_TABLE": 0}, {"CF_TC_RCHUNK": 0},
-                 {"CF_TC_DIRECT": 1}, {"CF_TC_DIRECT": 2}, {"CF_TC_DIRECT": 0, "CF_TC_STG": 4}, {"CF_TC_ATMEM": 0}, {"CF_STEM_TC": 1}, {"CF_STEM_TC": 2}, {"CF_TC_NACC": 3}, {"CF_PWN_CTAS": 3}, {"CF_PWN_CTAS": 2}, {"CF_PWN_NKB": 1}, {"CF_PWN_NKB": 6}]
+                 {"CF_TC_DIRECT": 1}, {"CF_TC_DIRECT": 2}, {"CF_TC_DIRECT": 0, "CF_TC_STG": 4}, {"CF_TC_ATMEM": 0}, {"CF_STEM_TC": 1}, {"CF_STEM_TC": 2}, {"CF_TC_NACC": 3}, {"CF_PWN_CTAS": 3}, {"CF_PWN_CTAS": 2}, {"CF_PWN_NKB": 1}, {"CF_PWN_NKB": 6}, {"CF_DWT_W4": 0}, {"CF_DWT_W4": 3}]
 
 
 @pytest.fixture(scope="module")
@@ -94,6 +94,38 @@ def test_ffma_stem_within_engine_bar(pkg, weights_path, variant_input, default_h
     for k, tol in (("hm", 5e-4), ("wh", 8e-3), ("lm", 3e-3), ("reg", 1e-4)):
         assert (got[k] - default_heads[k]).abs().max().item() <= tol, k
     assert (got["hm_sig"] - default_heads["hm_sig"]).abs().max().item() <= 1e-5
+
+
+def test_swish_one_reciprocal_per_four():
+    """swish4q (one MUFU.RCP per four values: the fused layer1.0 kernel and the epilogue of the one-K-block expand layers)
+    against fp64 x*sigmoid(x) (model/centernet.py:39-40), beside the default ex2 + rcp form: same accuracy class (a few 1e-7
+    relative), the clamp at 2^-31 only where the exact value is below 1e-8, zero stays zero (the padded channels rely on it),
+    and no NaN / inf from mixed huge and tiny magnitudes inside one group of four."""
+    import importlib
+    from conftest import PKG_NAME
+    lib = importlib.import_module(PKG_NAME + "._lib")
+    g = torch.Generator().manual_seed(7)
+    x = torch.cat([torch.randn(1 << 20, generator=g) * 3, torch.randn(1 << 18, generator=g) * 30, torch.linspace(-120, 120, 1 << 16),
+                   torch.tensor([0.0, -0.0, 1e-30, -1e-30, 88.0, -88.0, 1e6, -1e6, 1e12, -1e12, 3e38, -3e38, -21.4, -21.6, 20.0, -100.0])])
+    x = x[torch.randperm(x.numel(), generator=g)][: x.numel() // 4 * 4].contiguous()  # huge and tiny values share groups of four
+    xd = x.cuda()
+    want = (x.double() * torch.sigmoid(x.double()))
+    errs = {}
+    for variant in (0, 1):
+        y = torch.empty_like(xd)
+        lib.check(lib.load().cf_debug_swish(xd.data_ptr(), y.data_ptr(), xd.numel(), variant), "cf_debug_swish")
+        y = y.cpu().double()
+        assert torch.isfinite(y).all(), f"variant {variant}: non-finite output"
+        assert (y[x == 0] == 0).all()
+        err = (y - want).abs()
+        bulk = x.abs() <= 21
+        errs[variant] = (err[bulk] / want[bulk].abs().clamp_min(1e-30)).max().item()
+        tail = ~bulk
+        # past the clamp: absolute error below |x| * 2^-31 (variant 1) -- and far below one fp32 ulp of any O(1) activation
+        assert (err[tail] <= x[tail].abs().double() * 4.7e-10 + want[tail].abs() * 1e-6).all(), f"variant {variant}: tail"
+    print(f"swish max relative error on |x| <= 21: ex2+rcp {errs[0]:.2e}, one reciprocal per four {errs[1]:.2e}")
+    # (the argument rounding of x * log2 e alone is 7e-7 relative at x = -21)
+    assert errs[0] <= 2e-6 and errs[1] <= errs[0] + 6e-7
 
 
 def test_time_steps_reports_every_launch(pkg, weights_path, variant_input):

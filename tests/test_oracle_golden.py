@@ -80,8 +80,28 @@ def test_post_process(oracle, golden):
 def test_topk_tie_rule(oracle):
     """(score desc, flat index asc) on ties -- the documented total order."""
     heat = torch.full((1, 1, 8, 8), 0.5)
-    s, idx, ys, xs = oracle.topk(heat, 5)
-    assert idx[0].tolist() == [0, 1, 2, 3, 4]
+    s, idx, cls, ys, xs = oracle.topk(heat, 5)
+    assert idx[0].tolist() == [0, 1, 2, 3, 4] and cls[0].tolist() == [0] * 5
+    # several classes: the lower class first, then the lower pixel (the class-major candidate order of centerface_ext.py:20)
+    heat = torch.full((1, 3, 4, 4), 0.5)
+    heat[0, 2, 1, 1] = 0.9
+    s, idx, cls, ys, xs = oracle.topk(heat, 4)
+    assert cls[0].tolist() == [2, 0, 0, 0] and idx[0].tolist() == [5, 0, 1, 2]
+
+
+def test_ctdet_decode_classes_match_reference_golden(oracle):
+    """C > 1 and cat_spec_wh (centerface_ext.py:11-27, :72-77) against outputs of the reference itself
+    (oracle/gen_golden_multiclass.py -> tests/golden/multiclass_v1.npz): bit-exact."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "multiclass_v1.npz"))
+    names = sorted({k.split("/")[0] for k in z.files})
+    assert len(names) == 5
+    for n in names:
+        B, C, h, w, K, cat, with_reg = z[f"{n}/meta"].tolist()
+        reg = torch.from_numpy(z[f"{n}/reg"]) if with_reg else None
+        dets, inds = oracle.ctdet_decode(torch.from_numpy(z[f"{n}/heat"]), torch.from_numpy(z[f"{n}/wh"]), reg, K=K, cat_spec_wh=bool(cat))
+        assert np.array_equal(dets.numpy(), z[f"{n}/dets"]), n
+        assert np.array_equal(inds.numpy().astype(np.int32), z[f"{n}/inds"]), n
 
 
 def test_peak_nms_plateau_and_border(oracle):
