@@ -205,6 +205,7 @@ enum Epi : int {
     EPI_RESIDUAL = 2,    // project + skip add, :137
     EPI_BIAS_SWISH = 3,  // conv_last: conv + folded BN + Swish, :178-184
     EPI_IDAUP = 4,       // IDAUp: relu(BN(lateral)) + relu(BN(convT2x2 dw(low))), :186-204
+    EPI_SWISHQ = 5,      // EPI_SWISH with one reciprocal per four values (swish4q); chosen by k_pw_tc's plan for the one-K-block expand layers
 };
 
 struct EpiArgs {
@@ -246,6 +247,7 @@ __device__ __forceinline__ float4 idaup_apply(float4 acc, float4 lo, int n, int 
 template <int EPI>
 __device__ __forceinline__ float4 apply_epi(float4 acc, int m, int n, int N, const EpiArgs& ea) {
     if (EPI == EPI_SWISH) return swish4p(acc);
+    if (EPI == EPI_SWISHQ) return swish4qv(acc);
     if (EPI == EPI_RESIDUAL) {
         float4 r = ldcg4(ea.res + (size_t)m * N + n);
         return make_float4(acc.x + r.x, acc.y + r.y, acc.z + r.z, acc.w + r.w);

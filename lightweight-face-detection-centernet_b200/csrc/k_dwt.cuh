@@ -144,7 +144,7 @@ struct DwtGeom {
     // (3x3 stride 1: 24 window loads + 9 tap loads per 8 outputs instead of 32 + 18)
     // 5x5 stride 1 with 2 x 4 blocks: 48 window loads + 25 tap loads per 8 outputs instead of 36 + 25 per 4 -- the compute phase of
     // these layers is bound by the shared-memory pipe (one LDS.128 wavefront per quarter warp), not by the FMA pipe
-    static constexpr int XT = ((GEOM == 2 && (KS == 3 || KS == 5) && S == 1) || GEOM == 5) ? 4 : 2, YT = 2;
+    static constexpr int XT = (S == 1 && (GEOM == 2 || GEOM == 5)) ? 4 : 2, YT = 2;
 };
 
 struct DwtParams {
@@ -281,12 +281,16 @@ inline int dwt_plan(PwTcState& st, int ks, int s, const float* X, const float* W
         const int hh = (gth[g] - 1) * s + ks, hw = (gtw[g] - 1) * s + ks;
         return Ho % gth[g] == 0 && Wo % gtw[g] == 0 && (size_t)((hh * hw * 128 + 1023) / 1024 * 1024) + 2048 <= (size_t)TC_SMEM_MAX;
     };
+    // Round 2, late: 2 x 4 output blocks for the 5x5 stride-1 layers as well (their compute phase is bound by the shared-memory
+    // pipe: 48 + 25 LDS.128 per 8 outputs instead of 36 + 25 per 4) -- 16x16 tiles on the 80x80 map (192ch: 92 -> 73 us), 10x20 on the
+    // 40x40 / 20x20 maps (384ch 58 -> 54, 576ch 82 -> 78, 960ch 39 -> 37).  CF_DWT_W4: bit 0 / bit 1 enable those two (default 7: all three),
+    // bit 2 = 10x20 tiles of 2 x 4 blocks for the 3x3 stride-1 layers on the 40x40 / 20x20 maps too (384ch 39 -> 35, 960ch 27 -> 25).
+    int w4 = 7;
+    if (const char* ev = getenv("CF_DWT_W4")) w4 = atoi(ev);
     int geom = (s == 1 && ks == 3 && divides(2)) ? 2 : (ks == 5 && divides(1)) ? 1 : 0;
-    if (const char* ev = getenv("CF_DWT_W4")) {  // development probe: 2 x 4 output blocks for the 5x5 stride-1 layers (bit 0: 16x16 tiles where they divide, bit 1: 10x20)
-        const int m = atoi(ev);
-        if (ks == 5 && s == 1 && (m & 1) && divides(2)) geom = 2;
-        else if (ks == 5 && s == 1 && (m & 2) && divides(5)) geom = 5;
-    }
+    if (ks == 5 && s == 1 && (w4 & 1) && divides(2)) geom = 2;
+    else if (ks == 5 && s == 1 && (w4 & 2) && divides(5)) geom = 5;
+    else if (ks == 3 && s == 1 && (w4 & 4) && !divides(2) && divides(5)) geom = 5;
     if (const char* ev = getenv("CF_DWT_GEOM")) {  // development probe: geometry index wherever it divides the map
         const int g = atoi(ev);
         if (g == 0) geom = 0;

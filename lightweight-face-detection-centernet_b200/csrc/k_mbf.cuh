@@ -658,6 +658,9 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_mbf(const __grid_constant__ C
 //   3x3 s1, Cin 24 (layer1.1): sub-tile 8 x 10 (halo 10 x 12 = 120 px), block = the sub-tile, items of 1 x 5 outputs: 128 = 4 warps
 // (the 5x5 blocks layer2.0 / layer2.1 have no configuration: 128-pixel halo sub-tiles recompute 1.9x / 2.5x of their expand work)
 using MbfB1 = MbfCfg<3, 2, 16, 3, 8, 2, 2, 2, 1, 3, 4, true, true, 5>;
+// (depth-wise items of 2 x 5 outputs instead of 1 x 5 -- 38 % fewer shared-memory loads per output, the change that took 20 % off
+// k_dwt's 5x5 layers -- measured SLOWER here: layer1.1 279 -> 352 us, layer0 204 -> 254: half of a team's threads then walk a
+// chain twice as long, and a team is bound by its per-thread latency chain, not by the shared-memory pipe)
 using MbfB2 = MbfCfg<3, 1, 24, 8, 10, 1, 1, 5, 1, 4, 1, true, true, 4, 2, false>;
 // direct mode (depth-wise + projection from the hidden tensor): 3x3 s1 with layer1.1's geometry
 using MbfD31 = MbfCfg<3, 1, 32, 8, 10, 1, 1, 5, 1, 4, 1, true, false>;

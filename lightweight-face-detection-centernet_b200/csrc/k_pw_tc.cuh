@@ -594,10 +594,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 for (int j = 0; j < 8; ++j) {
                     float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                     const int n = col0 + 4 * j;
-                    if (EPI != EPI_LINEAR && EPI != EPI_SWISH) {
+                    if (EPI != EPI_LINEAR && EPI != EPI_SWISH && EPI != EPI_SWISHQ) {
                         if (row < p.M && n < p.N) o = tc_epi<EPI>(o, row, n, p.N, p.ea);
-                    } else if (EPI == EPI_SWISH && p.single) {
-                        o = swish4qv(o);  // the one-K-block expand layers (24 -> 144, 32 -> 192) are MUFU-bound: one reciprocal per four values
                     } else {
                         o = tc_epi<EPI>(o, row, n, p.N, p.ea);
                     }
@@ -896,7 +894,10 @@ inline int tc_plan(PwTcState& st, int passes, int epi, const float* A, const flo
     if (p.resident == 2) tl->grid = tl->grid / L.nchunks * L.nchunks;  // n_items is a multiple of nchunks
     if (tune.grid > 0 && tune.grid < tl->grid) tl->grid = tune.grid;
     tl->passes = passes;
-    tl->epi = epi;
+    // the one-K-block expand layers (24 -> 144: 115 -> 109 us, 32 -> 192: 44 -> 41) are MUFU-bound in the epilogue: one reciprocal
+    // per four values there (a separate instantiation: as a run-time switch it cost every Swish layer 10 %); CF_TC_SWISHQ=0 = off
+    static const bool swq = [] { const char* ev = getenv("CF_TC_SWISHQ"); return !ev || atoi(ev) != 0; }();
+    tl->epi = (epi == EPI_SWISH && passes == 3 && p.single && swq) ? (int)EPI_SWISHQ : epi;
     return CF_OK;
 }
 
@@ -910,7 +911,7 @@ inline cudaError_t tc_launch_t(const TcLaunch& tl, cudaStream_t s) {
 inline cudaError_t tc_launch(const TcLaunch& tl, cudaStream_t s) {
 #define CF_TC_CASE(P, E) \
     if (tl.passes == P && tl.epi == E) return tc_launch_t<P, E>(tl, s);
-    CF_TC_CASE(3, EPI_LINEAR) CF_TC_CASE(3, EPI_SWISH) CF_TC_CASE(3, EPI_RESIDUAL) CF_TC_CASE(3, EPI_BIAS_SWISH) CF_TC_CASE(3, EPI_IDAUP)
+    CF_TC_CASE(3, EPI_LINEAR) CF_TC_CASE(3, EPI_SWISH) CF_TC_CASE(3, EPI_RESIDUAL) CF_TC_CASE(3, EPI_BIAS_SWISH) CF_TC_CASE(3, EPI_IDAUP) CF_TC_CASE(3, EPI_SWISHQ)
     CF_TC_CASE(1, EPI_LINEAR) CF_TC_CASE(1, EPI_SWISH) CF_TC_CASE(1, EPI_RESIDUAL) CF_TC_CASE(1, EPI_BIAS_SWISH) CF_TC_CASE(1, EPI_IDAUP)
 #undef CF_TC_CASE
     return cudaErrorInvalidValue;
