@@ -344,7 +344,7 @@ inline int dwt_plan(PwTcState& st, int ks, int s, const float* X, const float* W
     // two CTAs per SM when at least three stages fit in half of the shared memory, else one CTA with all of it
     const int per_cta2 = (TC_SMEM_MAX / 2 - 2048) / xb;
     int ctas_per_sm = 2, nst = per_cta2;
-    int min2 = geom == 2 ? 2 : 3;
+    int min2 = (geom == 2 || geom == 5) ? 2 : 3;  // 10x20 tiles of a 5x5 layer: two CTAs x two stages beat one CTA x four (576ch: 78 -> 70 us)
     if (const char* ev = getenv("CF_DWT_MIN2")) min2 = atoi(ev);  // development probe: fewest stages worth two CTAs per SM
     if (nst < min2) ctas_per_sm = 1, nst = (TC_SMEM_MAX - 2048) / xb;
     if (const char* ev = getenv("CF_DWT_CTAS")) {  // development probe (tools/step_times.py)
