@@ -234,6 +234,9 @@ BLOCKS = [(32, 16, 1, 3, 1), (16, 24, 6, 3, 2), (24, 24, 6, 3, 1), (24, 32, 6, 5
           (64, 64, 6, 3, 1), (64, 96, 6, 5, 1), (96, 96, 6, 5, 1), (96, 160, 6, 5, 2), (160, 160, 6, 5, 1), (160, 320, 6, 3, 1)]
 
 
+TOPK_SMEM_MAX_HW = 51200  # csrc/k_decode.cuh
+
+
 def launch_table(h, w, fused=(), dwp=(), own=False):
     """(name, algorithmic bytes per image) of every launch of one forward + path-C decode, in launch order -- the same
     layer-wise accounting as cf_work_model (un-padded input once + output once + residual / low-res re-reads, fp32).
@@ -266,8 +269,11 @@ def launch_table(h, w, fused=(), dwp=(), own=False):
         hh, ww = hh * 2, ww * 2
         out.append((f"up{j + 1} {c}->24 (IDAUp)", (hh * ww * (c + 24) + lo * 24) * 4))
     out.append(("heads 3x3 24->15", hh * ww * (24 + 16) * 4))
-    out.append(("peak mask", hh * ww * 2 * 4))
-    out.append(("top-k + gather", hh * ww * 4 + 100 * 6 * 4))
+    if hh * ww <= TOPK_SMEM_MAX_HW:  # one launch: the peak keep runs on the top-k kernel's shared copy of the map
+        out.append(("peak mask + top-k + gather", hh * ww * 5 * 4 + 100 * 6 * 4))
+    else:
+        out.append(("peak mask", hh * ww * 2 * 4))
+        out.append(("top-k + gather", hh * ww * 4 + 100 * 6 * 4))
     return out
 
 

@@ -514,14 +514,21 @@ int build_plan(cf_engine* e, const void* input, int fmt, int B, int H, int W) {
     // path-C decode on the heads (entered through cf_decode_topk; listed for cf_replay_class)
     {
         const int hh = h, ww = wd;
-        P.push_back({CLS_DECODE, [=](cudaStream_t s) {
-                         const long long n = (long long)B * hh * ww;
-                         return launch_pdl(k_peak_mask, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, (const float*)e->hm_sig, e->peak, B,
-                                           hh, ww);
-                     }});
-        P.push_back({CLS_DECODE, [=](cudaStream_t s) {
-                         return launch_topk(e->peak, e->wh, e->reg, B, hh, ww, 100, e->o_dets, e->o_inds, s);
-                     }});
+        if (topk_fused(1, hh, ww)) {  // one launch: peak keep on the top-k kernel's shared copy of the map
+            P.push_back({CLS_DECODE, [=](cudaStream_t s) {
+                             return launch_topk(e->hm_sig, e->peak, e->wh, e->reg, B, hh, ww, 100, e->o_dets, e->o_inds, s);
+                         }});
+        } else {
+            P.push_back({CLS_DECODE, [=](cudaStream_t s) {
+                             const long long n = (long long)B * hh * ww;
+                             return launch_pdl(k_peak_mask, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, (const float*)e->hm_sig, e->peak, B,
+                                               hh, ww);
+                         }});
+            P.push_back({CLS_DECODE, [=](cudaStream_t s) {
+                             return launch_pdl(k_topk<false>, dim3(B), dim3(1024), 0, s, (const float*)e->peak, (const float*)e->wh, (const float*)e->reg, hh, ww,
+                                               100, e->o_dets, e->o_inds, 0, 1, 2);
+                         }});
+        }
     }
     e->in = input;
     e->fmt = fmt;
@@ -878,10 +885,9 @@ int cf_ctdet_decode_classes(const float* heat, const float* wh, const float* reg
     CF_CHECK(classes >= 1 && classes <= 1024 && (long long)classes * h * w <= (1ll << 30), CF_EINVAL, "cf_ctdet_decode: %d classes", classes);
     CF_CHECK(K >= 1 && K <= 1024 && K <= h * w, CF_EINVAL, "cf_ctdet_decode: K=%d outside [1,min(1024,h*w)]", K);
     cudaStream_t s = (cudaStream_t)stream;
-    const long long n = (long long)batch * classes * h * w;
-    // _nms works per (image, class) plane (max_pool2d, centerface_ext.py:44-50): B*C planes of h x w
-    CF_CUDA(launch_pdl(k_peak_mask, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, heat, scratch, batch * classes, h, w));
-    CF_CUDA(launch_topk(scratch, wh, reg, batch, h, w, K, out_dets, out_inds, s, classes, cat_spec_wh ? 2 * classes : 2));
+    // _nms works per (image, class) plane (max_pool2d, centerface_ext.py:44-50): fused into the top-k kernel when the image's
+    // classes*h*w keys fit its shared-memory cache, else k_peak_mask over the B*C planes into `scratch` first
+    CF_CUDA(launch_topk(heat, scratch, wh, reg, batch, h, w, K, out_dets, out_inds, s, classes, cat_spec_wh ? 2 * classes : 2));
     return CF_OK;
 }
 
@@ -895,7 +901,7 @@ int cf_decode_topk(cf_engine* e, int K, float* out_dets, int32_t* out_inds, void
     CF_CHECK(e->B > 0, CF_EINVAL, "cf_decode_topk: no cf_forward has run on this engine");
     CF_ON_DEVICE(e->device);
     int rc = cf_ctdet_decode(e->hm_sig, e->wh, e->reg, e->B, e->H / 4, e->W / 4, K, out_dets, out_inds, e->peak, stream);
-    if (rc == CF_OK) e->launches += 2;
+    if (rc == CF_OK) e->launches += topk_fused(1, e->H / 4, e->W / 4) ? 1 : 2;
     return rc;
 }
 

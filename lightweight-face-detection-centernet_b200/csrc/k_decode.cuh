@@ -70,8 +70,9 @@ __device__ __forceinline__ void bitonic_desc(unsigned long long* keys, int n) {
 // ---- K7+K8: per-image top-K of the peak map + gather + box assembly ------------------
 // grid = B, block = 1024.  4-pass MSB radix select of the K-th largest score, ordered
 // (lowest index first) admission of ties at the threshold, bitonic sort of the K winners.
-// SM: the image's H*W keys are read ONCE (all loads in flight together) into dynamic shared memory (4 B each, H*W <= 51 200)
-// and the four radix passes and the collection pass run on that copy; otherwise every pass re-reads the map from L2.
+// SM: the image's H*W keys are read ONCE (all loads in flight together) into dynamic shared memory (4 B each, H*W <= 51 200),
+// the 3x3 peak keep is applied to that copy (`pk` = the raw heat map), and the four radix passes and the collection pass run on
+// it; otherwise `pk` is the map k_peak_mask wrote and every pass re-reads it from L2.
 // The histogram increments are warp-aggregated (__match_any_sync): after the peak mask ~95 % of a map is +0.0, i.e. ONE
 // radix bin, and 25 600 shared-memory atomics on one address were most of this kernel's 68 us.
 constexpr int TOPK_SMEM_MAX_HW = 51200;
@@ -98,6 +99,35 @@ __global__ void __launch_bounds__(1024) k_topk(const float* __restrict__ pk, con
     if (SM) {
 #pragma unroll 8
         for (int i = tid; i < HW; i += 1024) skeys[i] = fkey(__ldcg(p + i));
+        __syncthreads();
+        // The 3x3 peak keep (_nms, centerface_ext.py:44-50; k_peak_mask above) on the shared copy: `pk` is the RAW heat map here.
+        // A pixel survives iff no in-bounds neighbour of its own plane is larger (max_pool2d pads with -inf; plateau neighbours
+        // all survive); the others become heat * 0.  The key order is the float order (-0 < +0 in keys only, and a suppressed
+        // +-0 stays +-0), so comparing keys decides exactly what comparing floats does.  One launch and one pass over the map
+        // less than k_peak_mask + k_topk (16 + 28 us -> 40 us at 32 x 160 x 160; the keep pass is ~45 instructions per pixel on ONE CTA per image).
+        unsigned long long kb = 0ull;  // keep bits of this thread's <= 50 pixels
+        int k = 0;
+        // (y, x, plane) of pixel i advance by 1024 pixels per iteration without a division; out-of-map neighbours are replaced by
+        // clamped ones, i.e. by other members of the same 3x3 window (or the pixel itself): branch-free, nine independent loads
+        const int stepy = 1024 / W, stepx = 1024 - stepy * W;
+        int pix = tid % HW1, plane0 = tid - pix;
+        int y = pix / W, x = pix - y * W;
+        for (int i = tid; i < HW; i += 1024, ++k) {
+            const uint32_t* pl = skeys + plane0;
+            const int ym = max(y - 1, 0) * W, y0 = y * W, yp = min(y + 1, H - 1) * W;
+            const int xm = max(x - 1, 0), xp = min(x + 1, W - 1);
+            const uint32_t v = pl[y0 + x];
+            uint32_t m = max(max(pl[ym + xm], pl[ym + x]), max(pl[ym + xp], pl[y0 + xm]));
+            m = max(max(m, pl[y0 + xp]), max(max(pl[yp + xm], pl[yp + x]), pl[yp + xp]));
+            if (!(m > v)) kb |= 1ull << k;
+            x += stepx, y += stepy;
+            if (x >= W) x -= W, ++y;
+            while (y >= H) y -= H, plane0 += HW1;  // next class plane (C > 1)
+        }
+        __syncthreads();
+        k = 0;
+        for (int i = tid; i < HW; i += 1024, ++k)
+            if (!((kb >> k) & 1ull)) skeys[i] = fkey(fkey_inv(skeys[i]) * 0.f);  // heat * keep.float()
         __syncthreads();
     }
     auto key_at = [&](int i) -> uint32_t { return SM ? skeys[i] : fkey(__ldcg(p + i)); };
@@ -336,9 +366,19 @@ __global__ void __launch_bounds__(1024) k_topk(const float* __restrict__ pk, con
     }
 }
 
-inline cudaError_t launch_topk(const float* pk, const float* wh, const float* reg, int B, int H, int W, int K, float* dets,
+// Maps that fit the shared-memory key cache take ONE launch: k_topk<true> reads the raw heat map and applies the peak keep on
+// its shared copy.  Larger maps: k_peak_mask into `scratch`, then k_topk<false> re-reads the masked map from L2 in every pass.
+inline bool topk_fused(int C, int H, int W) { return (long long)C * H * W <= TOPK_SMEM_MAX_HW; }
+inline cudaError_t launch_topk(const float* heat, float* scratch, const float* wh, const float* reg, int B, int H, int W, int K, float* dets,
                                int32_t* inds, cudaStream_t s, int C = 1, int wh_planes = 2) {
     const int HW = C * H * W;
+    const float* pk = heat;
+    if (!topk_fused(C, H, W)) {
+        const long long n = (long long)B * HW;
+        cudaError_t e = launch_pdl(k_peak_mask, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, heat, scratch, B * C, H, W);
+        if (e != cudaSuccess) return e;
+        pk = scratch;
+    }
     if (HW <= TOPK_SMEM_MAX_HW) {
         cudaError_t e = smem_optin((const void*)k_topk<true>, (TOPK_SMEM_MAX_HW + TOPK_SMEM_MAX_HW / 32) * 4);
         if (e != cudaSuccess) return e;

@@ -136,7 +136,7 @@ def test_time_steps_reports_every_launch(pkg, weights_path, variant_input):
     ms, cls = eng.time_steps(2)
     nf = len(pkg._lib.fused_blocks(pkg.CF_PW_TCGEN05))  # a fused MBConv block is one launch instead of three
     nd = len(pkg._lib.dwp_blocks(pkg.CF_PW_TCGEN05))    # depth-wise + projection as one launch instead of two
-    n = 43 - 2 * nf - nd                               # 41 layer-wise network launches + peak mask + top-k
+    n = 42 - 2 * nf - nd                               # 41 layer-wise network launches + the decode launch (peak keep + top-k, 80 x 96 map)
     assert len(ms) == len(cls) == n
     assert all(t > 0 for t in ms)
     assert cls[0] == pkg._lib.CLS_STEM and cls[-1] == pkg._lib.CLS_DECODE and cls.count(pkg._lib.CLS_PW) == 27 - 2 * nf - nd

@@ -20,6 +20,11 @@ def main():
     for r in rows:
         v = float(r["Metric Value"].replace(",", "")) * SCALE.get(r["Metric Unit"], 1)
         k.setdefault((int(r["ID"]), r["Kernel Name"], r["Grid Size"]), {})[r["Metric Name"]] = v
+    # a capture window longer than one step: keep the first COMPLETE step (first stem launch .. the top-k launch behind it)
+    ids = list(k.keys())
+    first = next((j for j, kk in enumerate(ids) if "k_stem" in kk[1]), 0)
+    last = next((j for j in range(first, len(ids)) if "k_topk" in ids[j][1]), len(ids) - 1)
+    k = OrderedDict((kk, k[kk]) for kk in ids[first:last + 1])
     agg = OrderedDict()
     print("| # | kernel | grid | time us | DRAM read MB | DRAM write MB | DRAM GB/s |")
     print("|---|---|---|---|---|---|---|")
