@@ -67,3 +67,18 @@ def test_shard_range_covers_everything():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         sh.shard_range(4, 2, 2)
+
+
+def test_bind_host_to_gpu_is_optional():
+    """bench.py pins every rank to its GPU's NUMA node before allocating pinned buffers; without NVML / without a GPU / inside a
+    cpuset that forbids it the helper reports (None, None) (or an unchanged set) and never raises or shrinks the set to nothing."""
+    import os
+    from conftest import PKG_NAME
+    import importlib
+    sh = importlib.import_module(PKG_NAME + ".sharding")
+    before = os.sched_getaffinity(0)
+    old, new = sh.bind_host_to_gpu(0)
+    try:
+        assert (old is None and new is None) or (len(new) >= 1 and new <= old == before)
+    finally:
+        os.sched_setaffinity(0, before)
