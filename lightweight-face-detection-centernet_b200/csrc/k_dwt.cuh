@@ -134,8 +134,9 @@ constexpr int DWT_THREADS = 256;
 template <int KS, int S, int GEOM>
 struct DwtGeom {
     // GEOM 5: 10 rows x 20 columns for the 5x5 stride-1 layers on the 40x40 / 20x20 maps (25 blocks of 2 x 4 outputs)
-    static constexpr int TH = (GEOM == 0 || GEOM == 5) ? 10 : (GEOM == 1 || GEOM == 3) ? 8 : 16;
-    static constexpr int TW = GEOM == 0 ? 10 : GEOM == 5 ? 20 : (GEOM == 1 || GEOM == 2) ? 16 : 32;
+    // GEOM 6: GEOM 1's 8 x 16 tile with 2 x 4 blocks (16 of the 32 block slots busy, a third fewer shared-memory loads per output): probe
+    static constexpr int TH = (GEOM == 0 || GEOM == 5) ? 10 : (GEOM == 1 || GEOM == 3 || GEOM == 6) ? 8 : 16;
+    static constexpr int TW = GEOM == 0 ? 10 : GEOM == 5 ? 20 : (GEOM == 1 || GEOM == 2 || GEOM == 6) ? 16 : 32;
     static constexpr int IH = (TH - 1) * S + KS, IW = (TW - 1) * S + KS;
     static constexpr int NPX = IH * IW;
     static constexpr int LO = (KS - S) / 2;
@@ -144,7 +145,7 @@ struct DwtGeom {
     // (3x3 stride 1: 24 window loads + 9 tap loads per 8 outputs instead of 32 + 18)
     // 5x5 stride 1 with 2 x 4 blocks: 48 window loads + 25 tap loads per 8 outputs instead of 36 + 25 per 4 -- the compute phase of
     // these layers is bound by the shared-memory pipe (one LDS.128 wavefront per quarter warp), not by the FMA pipe
-    static constexpr int XT = (S == 1 && (GEOM == 2 || GEOM == 5)) ? 4 : 2, YT = 2;
+    static constexpr int XT = ((S == 1 && (GEOM == 2 || GEOM == 5)) || GEOM == 6) ? 4 : 2, YT = 2;
 };
 
 struct DwtParams {
@@ -252,6 +253,7 @@ inline cudaError_t dwt_launch(const DwtLaunch& dl, cudaStream_t st) {
             case 3: return dwt_launch_t<K_, S_, 3>(dl, st);                   \
             case 4: return dwt_launch_t<K_, S_, 4>(dl, st);                   \
             case 5: return dwt_launch_t<K_, S_, 5>(dl, st);                   \
+            case 6: return dwt_launch_t<K_, S_, 6>(dl, st);                   \
             default: return dwt_launch_t<K_, S_, 0>(dl, st);                  \
         }                                                                     \
     }
@@ -276,7 +278,7 @@ inline int dwt_plan(PwTcState& st, int ks, int s, const float* X, const float* W
     // 144ch 215 -> 167), the 5x5 layers 8x16 (stride 1, 192ch: 118 -> 100; stride 2, 144ch: 138 -> 122); the 3x3 stride-2
     // layer is TMA/HBM-bound with any tile (209 of its 252 us are the bare tile stream) and the stride-16/32 maps
     // (40x40, 20x20) are not divisible: both keep 10x10.
-    const int gth[6] = {10, 8, 16, 8, 16, 10}, gtw[6] = {10, 16, 16, 32, 32, 20};
+    const int gth[7] = {10, 8, 16, 8, 16, 10, 8}, gtw[7] = {10, 16, 16, 32, 32, 20, 16};
     auto divides = [&](int g) {  // ... and one halo tile fits shared memory
         const int hh = (gth[g] - 1) * s + ks, hw = (gtw[g] - 1) * s + ks;
         return Ho % gth[g] == 0 && Wo % gtw[g] == 0 && (size_t)((hh * hw * 128 + 1023) / 1024 * 1024) + 2048 <= (size_t)TC_SMEM_MAX;
@@ -291,10 +293,11 @@ inline int dwt_plan(PwTcState& st, int ks, int s, const float* X, const float* W
     if (ks == 5 && s == 1 && (w4 & 1) && divides(2)) geom = 2;
     else if (ks == 5 && s == 1 && (w4 & 2) && divides(5)) geom = 5;
     else if (ks == 3 && s == 1 && (w4 & 4) && !divides(2) && divides(5)) geom = 5;
+    else if (ks == 5 && s == 2 && (w4 & 8) && divides(6)) geom = 6;  // probe
     if (const char* ev = getenv("CF_DWT_GEOM")) {  // development probe: geometry index wherever it divides the map
         const int g = atoi(ev);
         if (g == 0) geom = 0;
-        else if (g >= 1 && g <= 5) geom = divides(g) ? g : geom;
+        else if (g >= 1 && g <= 6) geom = divides(g) ? g : geom;
     }
     int th = 0, tw = 0, ih = 0, iw = 0, xb = 0;
 #define CF_DWT_GEOM_CASE(K_, S_)                                              \
@@ -305,6 +308,7 @@ inline int dwt_plan(PwTcState& st, int ks, int s, const float* X, const float* W
             case 3: dwt_geom<K_, S_, 3>(&th, &tw, &ih, &iw, &xb); break;      \
             case 4: dwt_geom<K_, S_, 4>(&th, &tw, &ih, &iw, &xb); break;      \
             case 5: dwt_geom<K_, S_, 5>(&th, &tw, &ih, &iw, &xb); break;      \
+            case 6: dwt_geom<K_, S_, 6>(&th, &tw, &ih, &iw, &xb); break;      \
             default: dwt_geom<K_, S_, 0>(&th, &tw, &ih, &iw, &xb); break;     \
         }                                                                     \
     }

@@ -896,8 +896,9 @@ inline int tc_plan(PwTcState& st, int passes, int epi, const float* A, const flo
     tl->passes = passes;
     // the one-K-block expand layers (24 -> 144: 115 -> 109 us, 32 -> 192: 44 -> 41) are MUFU-bound in the epilogue: one reciprocal
     // per four values there (a separate instantiation: as a run-time switch it cost every Swish layer 10 %); CF_TC_SWISHQ=0 = off
-    static const bool swq = [] { const char* ev = getenv("CF_TC_SWISHQ"); return !ev || atoi(ev) != 0; }();
-    tl->epi = (epi == EPI_SWISH && passes == 3 && p.single && swq) ? (int)EPI_SWISHQ : epi;
+    // (CF_TC_SWISHQ=2: every 3-pass Swish layer -- probe)
+    static const int swq = [] { const char* ev = getenv("CF_TC_SWISHQ"); return ev ? atoi(ev) : 1; }();
+    tl->epi = (epi == EPI_SWISH && passes == 3 && ((p.single && swq == 1) || swq == 2)) ? (int)EPI_SWISHQ : epi;
     return CF_OK;
 }
 

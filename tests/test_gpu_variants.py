@@ -65,7 +65,7 @@ def _heads(pkg, weights_path, x, env):
 
 
 SCHEDULE_ONLY = [{"CF_PWN": 0}, {"CF_DWT_GEOM": 0}, {"CF_DWT_GEOM": 1}, {"CF_DWT_CTAS": 1}, {"CF_TC_TABLE": 0}, {"CF_TC_RCHUNK": 0},
-                 {"CF_TC_DIRECT": 1}, {"CF_TC_DIRECT": 2}, {"CF_TC_DIRECT": 0, "CF_TC_STG": 4}, {"CF_TC_ATMEM": 0}, {"CF_STEM_TC": 1}, {"CF_STEM_TC": 2}, {"CF_TC_NACC": 3}, {"CF_PWN_CTAS": 3}, {"CF_PWN_CTAS": 2}, {"CF_PWN_NKB": 1}, {"CF_PWN_NKB": 6}, {"CF_DWT_W4": 0}, {"CF_DWT_W4": 3}]  # default 7
+                 {"CF_TC_DIRECT": 1}, {"CF_TC_DIRECT": 2}, {"CF_TC_DIRECT": 0, "CF_TC_STG": 4}, {"CF_TC_ATMEM": 0}, {"CF_STEM_TC": 1}, {"CF_STEM_TC": 2}, {"CF_TC_NACC": 3}, {"CF_PWN_CTAS": 3}, {"CF_PWN_CTAS": 2}, {"CF_PWN_NKB": 1}, {"CF_PWN_NKB": 6}, {"CF_DWT_W4": 0}, {"CF_DWT_W4": 3}, {"CF_DWT_W4": 15}]  # default 7
 
 
 @pytest.fixture(scope="module")
