@@ -206,3 +206,8 @@ def test_bench_launch_table_matches_work_model(pkg):
         tabf = bench.launch_table(h, w, fused, dwp)
         assert len(tabf) == 42 - sum(2 if bench.BLOCKS[i][2] != 1 else 1 for i in fused) - len(dwp)
         assert sum(b for n, b in tabf) == sum(b for n, b in tab)
+        # own=True: a fused launch counts its block input + output only -- the figure cf_work_model reports for the fused class
+        tabo = bench.launch_table(h, w, fused, dwp, own=True)
+        assert [n for n, _ in tabo] == [n for n, _ in tabf]
+        assert sum(b for n, b in tabo if "fused" in n) == L.work_model(h, w, L.CF_IN_U8_HWC, L.CLS_FUSED, L.CF_PW_TCGEN05)[0]
+        assert all(bo == bf for (n, bo), (_, bf) in zip(tabo, tabf) if "fused" not in n)
