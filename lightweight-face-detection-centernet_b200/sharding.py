@@ -8,9 +8,10 @@ from __future__ import annotations
 def bind_host_to_gpu(device_index):
     """Pin the calling process to the CPUs NVML reports as local to GPU ``device_index`` (its NUMA node), so that the pinned
     host buffers allocated afterwards -- the per-step H2D source of the end-to-end path -- sit behind the GPU's own PCIe root
-    complex instead of across the socket interconnect.  With eight ranks each copying 39 MB per 2.3 ms step this is the
-    difference between eight local streams and 120 GB/s through one socket.  Returns (previous affinity, new affinity), or
-    (None, None) when NVML, the affinity call or the container's cpuset do not allow it: purely an optimisation."""
+    complex instead of across the socket interconnect.  (Measured on the 8-GPU box of this pool: no change -- eight ranks x 39 MB
+    per 2.37 ms step = 133 GB/s is that box's aggregate host-to-device rate with or without the binding; kept because placement is
+    not guaranteed on other hosts.)  Returns (previous affinity, new affinity), or (None, None) when NVML, the affinity call or
+    the container's cpuset do not allow it: purely an optimisation."""
     import os
     try:
         import pynvml
