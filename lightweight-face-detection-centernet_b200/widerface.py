@@ -38,18 +38,7 @@ def bbox_overlap(boxes, query_boxes):
     if N == 0 or K == 0:
         return overlaps
     if boxes.dtype != query_boxes.dtype:
-        # Python's min()/max() return one of their operands WITH ITS OWN dtype, so with mixed float32/float64 inputs the
-        # reference's precision depends on which box wins each comparison: keep its scalar loop for that (unusual) case.
-        for k in range(K):
-            box_area = (query_boxes[k, 2] - query_boxes[k, 0] + 1) * (query_boxes[k, 3] - query_boxes[k, 1] + 1)
-            for n in range(N):
-                iw = min(boxes[n, 2], query_boxes[k, 2]) - max(boxes[n, 0], query_boxes[k, 0]) + 1
-                if iw > 0:
-                    ih = min(boxes[n, 3], query_boxes[k, 3]) - max(boxes[n, 1], query_boxes[k, 1]) + 1
-                    if ih > 0:
-                        ua = float((boxes[n, 2] - boxes[n, 0] + 1) * (boxes[n, 3] - boxes[n, 1] + 1) + box_area - iw * ih)
-                        overlaps[n, k] = iw * ih / ua
-        return overlaps
+        return _bbox_overlap_mixed(boxes, query_boxes, overlaps)
     b = boxes[:, None, :]
     q = query_boxes[None, :, :]
     box_area = (q[..., 2] - q[..., 0] + 1) * (q[..., 3] - q[..., 1] + 1)            # :52-55
@@ -59,6 +48,51 @@ def bbox_overlap(boxes, query_boxes):
     hit = (iw > 0) & (ih > 0)
     with np.errstate(divide="ignore", invalid="ignore"):
         val = iw * ih / ua                                                          # :72
+    overlaps[hit] = val[hit]
+    return overlaps
+
+
+def _bbox_overlap_mixed(boxes, query_boxes, overlaps):
+    """Mixed input dtypes (float32 detections against float64 annotations, say).  The reference's Python min() / max() hand
+    back one of their operands WITH ITS OWN dtype (the first one on a tie), so each difference `min - max + 1` is rounded in
+    the detection dtype, the annotation dtype or their common type depending on which box wins each comparison, and the
+    product iw * ih likewise.  Vectorised: every candidate expression is evaluated in its own dtype on whole arrays and the
+    per-element winner pattern selects among them (values are exact when widened to float64, so the selection is lossless)."""
+    tb, tq = boxes.dtype, query_boxes.dtype
+    tr = np.result_type(tb, tq)
+    b = boxes[:, None, :]
+    q = query_boxes[None, :, :]
+    one = 1  # a Python int: weak under NEP 50, keeps the operand dtype as in the reference's scalar arithmetic
+
+    def extent(lo, hi):
+        """min(b[hi], q[hi]) - max(b[lo], q[lo]) + 1 and the dtype class it was rounded in (0 detection, 1 annotation, 2 common)."""
+        mn_b = ~(q[..., hi] < b[..., hi])   # min(a, b) returns a unless b < a
+        mx_b = ~(q[..., lo] > b[..., lo])   # max(a, b) returns a unless b > a
+        shape = np.broadcast(b[..., hi], q[..., hi]).shape
+        bb = np.broadcast_to((b[..., hi] - b[..., lo] + one).astype(np.float64), shape)
+        qq = np.broadcast_to((q[..., hi] - q[..., lo] + one).astype(np.float64), shape)
+        bq = (b[..., hi].astype(tr) - q[..., lo].astype(tr) + one).astype(np.float64)
+        qb = (q[..., hi].astype(tr) - b[..., lo].astype(tr) + one).astype(np.float64)
+        val = np.where(mn_b, np.where(mx_b, bb, bq), np.where(mx_b, qb, qq))
+        cls = np.where(mn_b & mx_b, 0, np.where(~mn_b & ~mx_b, 1, 2))
+        return val, cls
+
+    iw, cw = extent(0, 2)                                                           # :57-60
+    ih, ch = extent(1, 3)                                                           # :62-65
+    pc = np.where((cw == 0) & (ch == 0), 0, np.where((cw == 1) & (ch == 1), 1, 2))  # dtype class of iw * ih
+    prod = np.where(pc == 0, (iw.astype(tb) * ih.astype(tb)).astype(np.float64),
+                    np.where(pc == 1, (iw.astype(tq) * ih.astype(tq)).astype(np.float64),
+                             (iw.astype(tr) * ih.astype(tr)).astype(np.float64)))
+    # a product of two same-class extents stays in that class; any other pairing is computed in the common type -- as is every
+    # later step, because the detection area (detection dtype) meets the annotation area (annotation dtype) in :67-71
+    area_b = ((b[..., 2] - b[..., 0] + one) * (b[..., 3] - b[..., 1] + one)).astype(tr)
+    area_q = ((q[..., 2] - q[..., 0] + one) * (q[..., 3] - q[..., 1] + one)).astype(tr)  # :52-55
+    ua = (area_b + area_q - prod.astype(tr)).astype(np.float64)
+    hit = (iw > 0) & (ih > 0)
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        # :72 divides the numpy scalar iw * ih by a PYTHON float (ua went through float()): the quotient keeps the scalar's dtype
+        val = np.where(pc == 0, (prod.astype(tb) / ua.astype(tb)).astype(np.float64),
+                       np.where(pc == 1, (prod.astype(tq) / ua.astype(tq)).astype(np.float64), prod / ua))
     overlaps[hit] = val[hit]
     return overlaps
 

@@ -51,6 +51,23 @@ def main():
         out[f"ov{ci}_query"] = q
         out[f"ov{ci}_out"] = ref.bbox_overlap(b, q)
         cases.append(ci)
+    # mixed dtypes in both directions, on a half-pixel grid as well (ties in min() / max(): the reference keeps the FIRST operand's
+    # dtype there); a separate generator, so that the cases above keep their bytes
+    rng2 = np.random.RandomState(20261017)
+    for j, (n, k, dt_b, dt_q, grid) in enumerate([(9, 7, np.float32, np.float64, 0), (9, 7, np.float64, np.float32, 0),
+                                                   (11, 6, np.float32, np.float64, 2), (11, 6, np.float64, np.float32, 2),
+                                                   (6, 8, np.float32, np.float64, 1), (6, 8, np.float64, np.float32, 1)]):
+        ci = 4 + j
+        b = synth_boxes(rng2, n, np.float64, size=120.0)
+        q = synth_boxes(rng2, k, np.float64, size=120.0)
+        q[0] = b[0]
+        if grid:
+            b, q = np.round(b * grid) / grid, np.round(q * grid) / grid
+        b, q = b.astype(dt_b), q.astype(dt_q)
+        out[f"ov{ci}_boxes"] = b
+        out[f"ov{ci}_query"] = q
+        out[f"ov{ci}_out"] = ref.bbox_overlap(b, q)
+        cases.append(ci)
     out["ov_cases"] = np.array(cases)
     # ---- evaluate: three batches of four images, stored detections stand in for the network
     batches = []

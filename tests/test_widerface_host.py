@@ -26,7 +26,8 @@ def test_bbox_overlap_is_bit_exact(wf, gold):
         want = gold[f"ov{ci}_out"]
         assert got.dtype == np.float64 and got.shape == want.shape
         assert np.array_equal(got, want), f"case {ci}: max diff {np.abs(got - want).max()}"
-        assert want[0, 0] == 1.0  # the identical pair
+        if ci < 4:
+            assert want[0, 0] == 1.0  # the identical pair (cases 4..: the pair differs by the float32 rounding of one side)
     assert wf.bbox_overlap(np.zeros((0, 4), np.float32), np.zeros((3, 4), np.float32)).shape == (0, 3)
     assert wf.bbox_overlap(np.zeros((2, 4), np.float32), np.zeros((0, 4), np.float32)).shape == (2, 0)
 
